@@ -1,0 +1,55 @@
+"""ctypes binding of libfmov_b200.so (the C-ABI declared in include/fmov_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, a RuntimeError is
+raised (north_star: "no CPU fallback, no multi-backend dispatch")."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfmov_b200.so")
+_lib = None
+
+c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(fmov_pose_b200 has no CPU fallback)")
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.fmov_last_error.restype = ctypes.c_char_p
+        _lib.fmov_sdf_fwd_blob_bytes.restype = c_ll
+        _lib.fmov_sdf_fwd_blob_offset.restype = c_ll
+        for name in ("fmov_fine_blob_bytes", "fmov_fine_workspace_bytes"):
+            if hasattr(_lib, name):
+                getattr(_lib, name).restype = c_ll
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what} failed (status {status}): {lib().fmov_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)"""
+    if t is None:
+        return c_void_p(0)
+    assert t.is_cuda, "fmov_pose_b200 kernels take CUDA tensors only"
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def f32c(t):
+    """contiguous fp32 view/copy"""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()

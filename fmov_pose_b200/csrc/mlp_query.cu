@@ -1,0 +1,281 @@
+// fmov_sdf_query: fused PE(6) -> 8 x Softplus(beta=100) layers -> sdf  (inference, value only).
+//
+// Replaces SDFNetwork.sdf on the no-grad paths of the reference: coarse + up-sample queries
+// (models/renderer.py:424-428, :230-232) and the dense grid query of extract_fields
+// (models/renderer.py:9-37, query_func = -sdf at :506).   Network semantics: models/fields.py:88-107.
+//
+// One persistent CTA per SM walks 128-point tiles through the chain engine (mlp_chain.cuh): the
+// activation tile never leaves shared memory, weights stream from L2 via TMA bulk copies, accumulators
+// live in TMEM.  The last linear layer only needs row 0 (the SDF), which is evaluated in fp32 by the
+// epilogue of layer 7 from the un-rounded activations.
+#include "mlp_chain.cuh"
+#include "../../include/fmov_b200.h"
+
+namespace fmov {
+
+using QL = ChainLayout<3, false>;
+
+struct QueryArgs {
+  // input modes: 0 = points [P,3]; 1 = rays (o,d [B,3]) x z [B, z_stride], S samples per ray;
+  //              2 = regular grid res^3 over [bmin,bmax] (torch.linspace semantics), x-major
+  int mode;
+  long long P;
+  const float* pts;
+  const float* rays_o;
+  const float* rays_d;
+  const float* z;
+  int S;
+  int z_stride;
+  int z_off;
+  int res;
+  long long grid_off;   // first flat grid index handled by this call (grid partitioning across ranks)
+  float bmin[3], bmax[3];
+  float in_scale;       // SDFNetwork.scale
+  float out_scale;      // sign / scale applied to the output (-1/scale for extract_fields)
+  const float* bias;    // [8][256] biases of layers 0..7 (padded with zeros)
+  const float* w8;      // [256] row 0 of lin8 (effective weight), fp32
+  float b8;             // lin8.bias[0]
+  float* out;           // [P]
+};
+
+__device__ __forceinline__ float linspace_at(float a, float b, int n, int i) {
+  // torch.linspace: step = (b-a)/(n-1); first half counts up from a, second half down from b
+  if (n <= 1) return a;
+  float step = (b - a) / (float)(n - 1);
+  return (i < n / 2) ? a + step * (float)i : b - step * (float)(n - 1 - i);
+}
+
+__device__ __forceinline__ void load_point(const QueryArgs& a, long long p, float x[3]) {
+  if (a.mode == 0) {
+    x[0] = a.pts[p * 3 + 0]; x[1] = a.pts[p * 3 + 1]; x[2] = a.pts[p * 3 + 2];
+  } else if (a.mode == 1) {
+    long long r = p / a.S;
+    int j = (int)(p - r * a.S);
+    float zz = a.z[r * a.z_stride + a.z_off + j];
+    x[0] = a.rays_o[r * 3 + 0] + a.rays_d[r * 3 + 0] * zz;
+    x[1] = a.rays_o[r * 3 + 1] + a.rays_d[r * 3 + 1] * zz;
+    x[2] = a.rays_o[r * 3 + 2] + a.rays_d[r * 3 + 2] * zz;
+  } else {
+    long long g = p + a.grid_off;
+    long long rr = (long long)a.res * a.res;
+    int ix = (int)(g / rr);
+    int iy = (int)((g - ix * rr) / a.res);
+    int iz = (int)(g - ix * rr - (long long)iy * a.res);
+    x[0] = linspace_at(a.bmin[0], a.bmax[0], a.res, ix);
+    x[1] = linspace_at(a.bmin[1], a.bmax[1], a.res, iy);
+    x[2] = linspace_at(a.bmin[2], a.bmax[2], a.res, iz);
+  }
+}
+
+// Positional encoding of one point into its row of a [128 x 64] fp16 block: 39 channels
+// [x, sin(2^k x), cos(2^k x)]_{k<6} (models/embedder.py:28-37), columns 39..63 zero.
+__device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float x[3]) {
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = s;
+      e[6 + 6 * k + c] = co;
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 v;
+    v.x = pack_h2(e[ch * 8 + 0], e[ch * 8 + 1]);
+    v.y = pack_h2(e[ch * 8 + 2], e[ch * 8 + 3]);
+    v.z = pack_h2(e[ch * 8 + 4], e[ch * 8 + 5]);
+    v.w = pack_h2(e[ch * 8 + 6], e[ch * 8 + 7]);
+    blk_st_chunk(blk, row, ch, v);
+  }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
+                 const __grid_constant__ QueryArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = chain_smem_base(smem_raw);
+  ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
+  uint8_t* act = base + QL::ACT;
+  uint8_t* aux = base + QL::AUX;
+  uint8_t* wst = base + QL::WST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
+  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (threadIdx.x == 0) chain_init_barriers<3>(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) chain_weight_producer<3>(tb, ptrs.weights, s, wst, n_my);
+  } else if (warp == 1) {
+    if (lane == 0) chain_mma_issuer<3>(tb, s, act, aux, wst, tmem, n_my);
+  } else if (warp >= EPI_WARP0) {
+    EpiCtx c;
+    epi_init(c, s, act, aux, nullptr, tmem);
+    for (int t = 0; t < n_my; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const long long p = tile * TILE_M + c.row;
+      const bool valid = p < a.P;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (valid) load_point(a, p, x);
+      x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
+      pe6_to_block(aux, c.row, x);
+      epi_signal_act(c);
+      float sdf = a.b8;
+      for (int l = 0; l < 8; ++l) {
+        const int n_valid = (l == 3) ? 217 : 256;
+        const float* bias = a.bias + l * 256;
+        epi_wait_acc(c);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64];
+          if (cb * 64 < tb.step[l].n) {
+            tmem_ld32(c.tmem + cb * 64, v);
+            if (cb * 64 + 32 < tb.step[l].n) tmem_ld32(c.tmem + cb * 64 + 32, v + 32);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const int col = cb * 64 + j;
+            float h = 0.f;
+            if (col < n_valid) h = softplus100(v[j] + __ldg(bias + col));
+            v[j] = h;
+          }
+          if (l == 7) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sdf = fmaf(v[j], __ldg(a.w8 + cb * 64 + j), sdf);
+          } else {
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              uint4 q;
+              q.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]);
+              q.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
+              q.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
+              q.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
+              blk_st_chunk(act + cb * BLK_BYTES, c.row, ch, q);
+            }
+          }
+        }
+        if (l < 7) epi_signal_act(c);
+        else tc_fence_before();
+      }
+      if (valid) a.out[p] = sdf * a.out_scale;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+}  // namespace fmov
+
+using namespace fmov;
+
+// Step table of the query chain. Weight blob layout (built by fmov_pack_sdf_weights):
+// layers 0..7 forward images, k-blocks consecutive.
+static void build_query_table(ChainTable& tb) {
+  memset(&tb, 0, sizeof(tb));
+  tb.n_steps = 8;
+  uint32_t off = 0;
+  for (int l = 0; l < 8; ++l) {
+    ChainStep& st = tb.step[l];
+    st.w_off = off;
+    st.n = (l == 3) ? 224 : 256;
+    st.nkb_a = (l == 0) ? 0 : 4;
+    st.nkb_aux = (l == 0 || l == 4) ? 1 : 0;
+    st.a_fmt = FMT_F16;
+    st.b_fmt = FMT_F16;
+    off += (uint32_t)st.n * 128u * (st.nkb_a + st.nkb_aux);
+  }
+}
+
+extern "C" long long fmov_sdf_fwd_blob_bytes(void) {
+  ChainTable tb;
+  build_query_table(tb);
+  const ChainStep& st = tb.step[7];
+  return (long long)st.w_off + (long long)st.n * 128 * (st.nkb_a + st.nkb_aux);
+}
+
+extern "C" long long fmov_sdf_fwd_blob_offset(int layer) {
+  ChainTable tb;
+  build_query_table(tb);
+  if (layer < 0 || layer > 7) return -1;
+  return tb.step[layer].w_off;
+}
+
+static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cudaStream_t stream) {
+  static ChainTable tb;
+  static bool init = false;
+  if (!init) { build_query_table(tb); init = true; }
+  ChainPtrs ptrs;
+  memset(&ptrs, 0, sizeof(ptrs));
+  ptrs.weights = reinterpret_cast<const uint8_t*>(wblob);
+  int dev = 0, sms = 0;
+  FMOV_CUDA(cudaGetDevice(&dev));
+  FMOV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static bool attr_set = false;
+  if (!attr_set) {
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    attr_set = true;
+  }
+  long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
+  if (n_tiles == 0) return OK;
+  int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  sdf_query_kernel<<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tb, ptrs, a);
+  FMOV_LAUNCH_CHECK("sdf_query_kernel");
+  return OK;
+}
+
+extern "C" int fmov_sdf_query_points(const float* pts, long long P, const void* wblob, const float* bias8x256,
+                                     const float* w8_row0, float b8, float in_scale, float out_scale, float* out,
+                                     void* stream) {
+  FMOV_REQUIRE(P >= 0 && (P == 0 || (pts && out && wblob && bias8x256 && w8_row0)), "fmov_sdf_query_points: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 0; a.P = P; a.pts = pts; a.in_scale = in_scale; a.out_scale = out_scale;
+  a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob, 0, (cudaStream_t)stream);
+}
+
+extern "C" int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z, long long B, int S,
+                                   int z_stride, int z_off, const void* wblob, const float* bias8x256,
+                                   const float* w8_row0, float b8, float in_scale, float out_scale, float* out,
+                                   void* stream) {
+  FMOV_REQUIRE(B >= 0 && S > 0 && z_stride >= S + z_off, "fmov_sdf_query_rays: bad shape B=%lld S=%d stride=%d off=%d", B, S,
+               z_stride, z_off);
+  FMOV_REQUIRE(B == 0 || (rays_o && rays_d && z && out && wblob && bias8x256 && w8_row0), "fmov_sdf_query_rays: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 1; a.P = B * S; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.S = S; a.z_stride = z_stride; a.z_off = z_off;
+  a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob, 0, (cudaStream_t)stream);
+}
+
+extern "C" int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
+                                   const void* wblob, const float* bias8x256, const float* w8_row0, float b8,
+                                   float in_scale, float out_scale, float* out, void* stream) {
+  FMOV_REQUIRE(res > 0 && first >= 0 && count >= 0 && first + count <= (long long)res * res * res,
+               "fmov_sdf_query_grid: bad range first=%lld count=%lld res=%d", first, count, res);
+  FMOV_REQUIRE(bmin3 && bmax3 && (count == 0 || (out && wblob && bias8x256 && w8_row0)), "fmov_sdf_query_grid: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 2; a.P = count; a.res = res; a.grid_off = first;
+  for (int i = 0; i < 3; ++i) { a.bmin[i] = bmin3[i]; a.bmax[i] = bmax3[i]; }
+  a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob, 0, (cudaStream_t)stream);
+}

@@ -1,0 +1,113 @@
+/* fmov_b200 — C ABI of the B200-native NeuS train-step hot path.
+ *
+ * Drop-in boundary for the path BASELINE.json `north_star` names.  The reference
+ * (diegointel/fmov_pose) has NO native/FFI layer: its seam is the Python interface of
+ * models/renderer.py, models/fields.py, models/dataset.py and the pose modules.
+ * The Python host code in fmov_pose_b200/models/ keeps those interfaces and calls the entry
+ * points below through ctypes; each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host";
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, <0 = error (fmov_last_error() gives the message); nothing throws,
+ *     nothing allocates, nothing is retained after the call returns (stream-ordered);
+ *   - fp32 tensors are dense row-major; "image" tensors are opaque fp16/bf16 tile images
+ *     (fmov_pose_b200/csrc/fmov_common.cuh) produced and consumed only by this library.
+ */
+#ifndef FMOV_B200_H_
+#define FMOV_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------- */
+const char* fmov_last_error(void);
+int fmov_version(void);
+
+/* ---- weight / tile images (host glue for the MLP kernels) ----------------------------- */
+/* fp32 matrix -> SW128 operand image [npad x 64*kblocks]; see api.cu. seg_* are HOST arrays. */
+int fmov_pack_image(const float* src, long long stride_n, long long stride_k, int n_valid, int row_off, int nseg,
+                    const int* seg_dst, const int* seg_src, const int* seg_len, float scale, int bf16, void* dst,
+                    int npad, int kblocks, void* stream);
+int fmov_ti_from_rowmajor(const float* src, long long P, int cols, int ld, int kblocks, int bf16, void* dst, void* stream);
+int fmov_ti_to_rowmajor(const void* src, long long P, int cols, int ld, int kblocks, int bf16, float* dst, void* stream);
+/* tcgen05 descriptor self-test (tests only). */
+int fmov_selftest_gemm(const void* a_img, const void* b_img, int n, int kblocks, int a_bf16, int b_bf16, int mode,
+                       float* out, void* stream);
+
+/* ---- SDF value query: SDFNetwork.sdf under no_grad ------------------------------------- */
+/* replaces models/fields.py:88-107 at the call sites models/renderer.py:424-428 (coarse),
+ * :230-232 (up-sample rounds) and :506 via extract_fields :9-37 (dense grid).
+ * wblob: forward weight images of lin0..lin7 (fmov_sdf_fwd_blob_bytes / _offset give the layout);
+ * bias8x256: biases of lin0..lin7 zero-padded to 256; w8_row0/b8: row 0 of lin8.             */
+long long fmov_sdf_fwd_blob_bytes(void);
+long long fmov_sdf_fwd_blob_offset(int layer);
+int fmov_sdf_query_points(const float* pts, long long P, const void* wblob, const float* bias8x256, const float* w8_row0,
+                          float b8, float in_scale, float out_scale, float* out, void* stream);
+int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z, long long B, int S, int z_stride,
+                        int z_off, const void* wblob, const float* bias8x256, const float* w8_row0, float b8,
+                        float in_scale, float out_scale, float* out, void* stream);
+/* bmin3/bmax3 are HOST float[3]; points first..first+count of the x-major res^3 grid. */
+int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
+                        const void* wblob, const float* bias8x256, const float* w8_row0, float b8, float in_scale,
+                        float out_scale, float* out, void* stream);
+
+/* ---- pose + ray generation ------------------------------------------------------------ */
+/* mode 1: LearnPoseGF tail  c2w = [Exp(rot)|trans] @ [R0 | scale*t0]  (models/picture_pose.py:176-186,
+ *         models/batch_lie_group_helper.py:19-47); init34 = rows 0..2 of init_c2w[cam] (row stride 4)
+ * mode 2: BARF  c2w = compose_pair(se3_to_SE3(se3), noise_pose)  (models/camera.py:89-102, 53-60;
+ *         exp_runner.py:419-424); init34 = noise pose rows (row stride 4)                           */
+int fmov_pose_fwd(int mode, const float* rot, const float* trans, const float* scale, const float* init34,
+                  const float* se3, float* c2w34, void* stream);
+int fmov_pose_bwd(int mode, const float* rot, const float* trans, const float* scale, const float* init34,
+                  const float* se3, const float* g_c2w34, float* g_rot, float* g_trans, float* g_scale, float* g_se3,
+                  void* stream);
+/* Dataset.gen_random_rays_at ray math (models/dataset.py:656-671) + near_far_from_sphere (:835-842), with the
+ * pose evaluated in-kernel (mode 0: c2w34 given). px/py are int64 pixel coordinates.                 */
+int fmov_raygen_fwd(int mode, const float* c2w34, const float* rot, const float* trans, const float* scale,
+                    const float* init34, const float* se3, const float* intr_inv, int intr_stride, const long long* px,
+                    const long long* py, long long B, float* rays_o, float* rays_d, float* near, float* far,
+                    float* c2w_out, void* stream);
+int fmov_raygen_bwd(const float* intr_inv, int intr_stride, const long long* px, const long long* py, long long B,
+                    const float* rays_o, const float* rays_d, const float* g_o, const float* g_d, const float* g_near,
+                    const float* g_far, float* g_c2w34, void* stream);
+
+/* ---- hierarchical sampling --------------------------------------------------------------- */
+/* coarse z + per-ray jitter (models/renderer.py:385-405); t_rand = the raw U[0,1) draw or NULL  */
+int fmov_sample_coarse(const float* near, const float* far, const float* t_rand, long long B, int n_samples,
+                       int z_stride, float* z, void* stream);
+/* one importance round: merge z[:, :n_sorted] with the sorted tail z[:, n_sorted:n_sorted+n_tail] (cat_z_vals,
+ * models/renderer.py:222-242; sdf permuted alongside when with_sdf), then up_sample + sample_pdf(det)
+ * (:168-220, :54-86) writing n_new samples after the merged ones.                                  */
+int fmov_sample_round(const float* rays_o, const float* rays_d, float* z, float* sdf, long long B, int z_stride,
+                      int n_sorted, int n_tail, int with_sdf, int n_new, float inv_s, void* stream);
+
+/* ---- compositing + losses ------------------------------------------------------------------ */
+/* render_core tail (models/renderer.py:261-272, 290-358) + render() reductions (:477-498).
+ * inv_s: device scalar, already clipped to [1e-6,1e6]; bg: device float[3] or NULL;
+ * eik_partial [B,2]: per-ray (sum relax*(|n|-1)^2, sum relax).                                      */
+int fmov_composite_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, const float* sdf,
+                       const float* nrm, const float* rgb, const float* inv_s, float sample_dist, float cos_anneal,
+                       const float* bg, float* color, float* weight_sum, float* weight_max, float* depth,
+                       float* weights, float* cdf, float* inside, float* mid_z, float* pts, float* eik_partial,
+                       void* stream);
+int fmov_composite_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, const float* sdf,
+                       const float* nrm, const float* rgb, const float* inv_s, float sample_dist, float cos_anneal,
+                       const float* bg, const float* g_color, const float* g_wsum, const float* g_depth,
+                       const float* g_weights, const float* g_eik, const float* eik_den, const float* g_nrm_ext,
+                       float* d_sdf, float* d_nrm, float* d_rgb, float* d_dir, float* d_dist, float* d_mid,
+                       float* d_invs, void* stream);
+/* exp_runner.py:562-599: per-ray masked-L1 and BCE terms + gradients for loss = colour + mask_weight*bce */
+int fmov_loss_fwd_bwd(const float* color, const float* weight_sum, const float* true_rgb, const float* mask, long long B,
+                      const float* mask_sum, long long n_rays_global, float mask_weight, float* partial, float* g_color,
+                      float* g_wsum, void* stream);
+/* autograd of pts = o + d*mid_z (models/renderer.py:269-272) reduced per ray */
+int fmov_ray_reduce_bwd(const float* d_pts, const float* d_dirs, const float* d_dir_tc, const float* d_dist,
+                        const float* d_mid, const float* rays_d, const float* z, long long B, int S, float sample_dist,
+                        float* d_o, float* d_d, float* d_z, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMOV_B200_H_ */

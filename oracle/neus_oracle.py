@@ -219,7 +219,23 @@ def render_core(sdf_p: Params, col_p: Params, variance, rays_o, rays_d, z_vals, 
     sampled_color = color_forward(col_p, pts, gradients, dirs, feat,
                                   multires_view=multires_view).reshape(B, S, 3)
 
-    inv_s = inv_s_from_variance(variance).reshape(1, 1).expand(B * S, 1)
+    ret = composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s_from_variance(variance),
+                    sample_dist, background_rgb=background_rgb, cos_anneal_ratio=cos_anneal_ratio)
+    ret["sdf"] = sdf
+    return ret
+
+
+def composite(rays_o, rays_d, z_vals, sdf, gradients, sampled_color, inv_s_scalar, sample_dist,
+              background_rgb=None, cos_anneal_ratio=0.0):
+    """The per-sample -> per-ray tail of render_core (models/renderer.py:261-272, 290-372) given the
+    network outputs: sdf [P,1], gradients [P,3], sampled_color [B,S,3], inv_s scalar (clipped)."""
+    B, S = z_vals.shape
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], sample_dist)], -1)
+    mid_z = z_vals + dists * 0.5
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z[..., :, None]).reshape(-1, 3)
+    dirs = rays_d[:, None, :].expand(B, S, 3).reshape(-1, 3)
+    inv_s = inv_s_scalar.reshape(1, 1).expand(B * S, 1)
     true_cos = (dirs * gradients).sum(-1, keepdim=True)
     iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - cos_anneal_ratio)
                  + F.relu(-true_cos) * cos_anneal_ratio)
@@ -246,10 +262,10 @@ def render_core(sdf_p: Params, col_p: Params, variance, rays_o, rays_d, z_vals, 
     gradient_error = (torch.linalg.norm(g, ord=2, dim=-1) - 1.0) ** 2
     gradient_error = (relax_inside * gradient_error).sum() / (relax_inside.sum() + 1e-5)
     return {
-        "color": color, "sdf": sdf, "dists": dists, "gradients": g, "s_val": 1.0 / inv_s,
+        "color": color, "dists": dists, "gradients": g, "s_val": 1.0 / inv_s,
         "mid_z_vals": mid_z, "weights": weights, "cdf": c_.reshape(B, S),
         "gradient_error": gradient_error, "inside_sphere": inside_sphere, "pts": pts,
-        "sampled_color": sampled_color, "alpha": alpha,
+        "sampled_color": sampled_color, "alpha": alpha, "relax_sum": relax_inside.sum(),
     }
 
 

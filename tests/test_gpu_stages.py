@@ -1,0 +1,212 @@
+"""GPU parity of the non-MLP stages (pose/ray-gen, hierarchical sampling, compositing + losses,
+ray reduction) against the CPU oracle, forward and backward."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neus_oracle as O
+from tests._util import load_golden, params_from, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(a, b, atol, rtol=1e-4, msg=""):
+    np.testing.assert_allclose(a.detach().cpu().double().numpy(), b.detach().cpu().double().numpy(), atol=atol,
+                               rtol=rtol, err_msg=msg)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_raygen_pose_fwd_bwd(mode):
+    from fmov_pose_b200 import ops
+    torch.manual_seed(mode)
+    B = 777
+    intr = torch.tensor([[600.0, 0, 320.0], [0, 600.0, 240.0], [0, 0, 1.0]])
+    intr_inv = torch.linalg.inv(intr).contiguous()
+    px = torch.randint(0, 640, [B]); py = torch.randint(0, 480, [B])
+    init = torch.eye(4); init[:3, :3] = O.rodrigues_exp(torch.tensor([[0.1, -0.2, 0.05]]))[0]; init[:3, 3] = torch.tensor([0.1, -0.2, -3.0])
+    rot = (torch.randn(3) * 0.3).requires_grad_(True)
+    trans = (torch.randn(3) * 0.1).requires_grad_(True)
+    scale = torch.tensor([1.1], requires_grad=True)
+    se3 = (torch.randn(6) * 0.2).requires_grad_(True)
+    if mode == 0:
+        pose = init[:3].clone().requires_grad_(True)
+        kw = dict(c2w34=pose.detach().to(DEV).contiguous())
+    elif mode == 1:
+        pose = O.pose_gf_compose(rot, trans, init[:3], scale[0])
+        kw = dict(rot=rot.detach().to(DEV), trans=trans.detach().to(DEV), scale=scale.detach().to(DEV), init34=init.to(DEV))
+    else:
+        pose = O.compose_pair(O.se3_to_SE3(se3[None]), init[None, :3])[0]
+        kw = dict(se3=se3.detach().to(DEV), init34=init.to(DEV))
+    ro, rd = O.gen_rays(pose, intr_inv, px, py)
+    near, far = O.near_far_from_sphere(ro, rd)
+    g_o, g_d, g_n, g_f = torch.randn(B, 3), torch.randn(B, 3), torch.randn(B, 1), torch.randn(B, 1)
+    leaves = {0: [pose], 1: [rot, trans, scale], 2: [se3]}[mode]
+    grads = torch.autograd.grad((ro * g_o).sum() + (rd * g_d).sum() + (near * g_n).sum() + (far * g_f).sum(), leaves)
+    o2, d2, n2, f2, c2w = ops.raygen_fwd(mode, intr_inv.to(DEV), px.to(DEV), py.to(DEV), **kw)
+    _close(o2, ro, 1e-6); _close(d2, rd, 2e-6); _close(n2, near, 1e-5); _close(f2, far, 1e-5)
+    _close(c2w, pose, 2e-6)
+    g34 = ops.raygen_bwd(intr_inv.to(DEV), px.to(DEV), py.to(DEV), o2, d2, g_o.to(DEV), g_d.to(DEV), g_n.to(DEV), g_f.to(DEV))
+    if mode == 0:
+        _close(g34, grads[0], 1e-3 * grads[0].abs().max().item())
+    else:
+        g_rot, g_trans, g_scale, g_se3 = ops.pose_bwd(mode, g34, **kw)
+        got = [g_rot, g_trans, g_scale] if mode == 1 else [g_se3]
+        for a, b in zip(got, grads):
+            _close(a, b, 2e-3 * b.abs().max().item() + 1e-6)
+
+
+def test_pose_kat_small_angles():
+    """Rodrigues at theta -> 0 and the Taylor se3 map against the reference's own outputs (kat.npz)."""
+    from fmov_pose_b200 import ops
+    d = load_golden("kat")
+    eye = torch.eye(4, device=DEV)
+    for r, R in zip(d["exp.r"], d["exp.R"]):
+        out = ops.pose_fwd(1, rot=torch.tensor(r, device=DEV), trans=torch.zeros(3, device=DEV), init34=eye)
+        np.testing.assert_allclose(out[:, :3].cpu().numpy(), R, atol=2e-6)
+    for wu, Rt in zip(d["se3.wu"], d["se3.Rt"]):
+        out = ops.pose_fwd(2, se3=torch.tensor(wu, device=DEV), init34=eye)
+        np.testing.assert_allclose(out.cpu().numpy(), Rt, atol=2e-6)
+
+
+def _rays(B, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    o = torch.tensor([0.0, 0.0, -3.0]).repeat(B, 1) + torch.randn(B, 3, generator=g) * 0.02
+    d = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 1.0]).repeat(B, 1) + torch.randn(B, 3, generator=g) * 0.12, dim=-1)
+    near, far = O.near_far_from_sphere(o, d)
+    return o, d, near, far, g
+
+
+def test_sample_pdf_kat_through_round_kernel():
+    """up_sample on the reference's KAT rays (all-outside ray, grazing ray), kat.npz 'up.*'."""
+    from fmov_pose_b200 import ops
+    d = load_golden("kat")
+    o, dd, z, sdf = t(d, "up.o"), t(d, "up.d"), t(d, "up.z"), t(d, "up.sdf")
+    for inv_s in (64, 512):
+        zz = torch.zeros(3, 80); zz[:, :64] = z
+        ss = torch.zeros(3, 80); ss[:, :64] = sdf
+        zz, ss = zz.to(DEV), ss.to(DEV)
+        ops.sample_round(o.to(DEV), dd.to(DEV), zz, ss, 64, 0, True, 16, float(inv_s))
+        np.testing.assert_allclose(zz[:, 64:80].cpu().numpy(), d[f"up.new{inv_s}"], atol=2e-5)
+
+
+@pytest.mark.parametrize("n,m,steps,perturb", [(64, 64, 4, True), (16, 32, 2, True), (32, 0, 4, False), (64, 64, 1, False)])
+def test_hierarchical_sampling_vs_oracle(n, m, steps, perturb):
+    """z_vals of renderer.py:385-446. The SDF used for importance sampling comes from the fp16 tensor-core
+    chain, so individual samples can move slightly; compare with the oracle driven by the SAME sdf
+    function (exact algorithmic parity) and with the fp32 oracle (tolerance)."""
+    from fmov_pose_b200 import ops, packing
+    d = load_golden("full_6464_gf")
+    p = params_from(d, "sdf.")
+    W = [O.eff_weight(p, "", l).to(DEV) for l in range(9)]
+    b = [p[f"lin{l}.bias"].to(DEV) for l in range(9)]
+    qw = packing.SdfQueryWeights(W, b)
+    B = 203
+    o, dd, near, far, g = _rays(B, 5)
+    t_rand = torch.rand(B, 1, generator=g) if perturb else None
+    z = ops.hierarchical_sample(qw, o.to(DEV), dd.to(DEV), near.to(DEV), far.to(DEV),
+                                None if t_rand is None else t_rand.to(DEV), n, m, steps)
+    torch.cuda.synchronize()
+    zc = z.cpu()
+    assert torch.all(zc[:, 1:] >= zc[:, :-1]), "z must be sorted"
+    # (a) exact-algorithm check: oracle sampling with the GPU sdf as the query function
+    def gpu_sdf(q):
+        return ops.sdf_query_points(qw, q.to(DEV)).cpu()
+    z_ref = O.coarse_z(near, far, n, t_rand)
+    if m > 0:
+        sdf = gpu_sdf((o[:, None] + dd[:, None] * z_ref[..., None]).reshape(-1, 3)).reshape(B, n)
+        for i in range(steps):
+            new_z = O.up_sample(o, dd, z_ref, sdf, m // steps, 64 * 2 ** i)
+            z_ref, sdf = O.cat_z_vals(gpu_sdf, o, dd, z_ref, new_z, sdf, last=(i + 1 == steps))
+    # The reference's inverse CDF is discontinuous where a bin's pdf sits at the `denom < 1e-5` switch
+    # (renderer.py:81-82): empty bins have pdf ~ 1e-5/sum, so ulp-level differences (expf, scan order) move
+    # a few samples inside their bin.  Moves are bounded by the bin width.
+    diff = (zc - z_ref).abs()
+    # (a moved sample also shifts the sorted positions between its old and new place, so compare as 1-D
+    # transport cost: mean |diff| tiny, max bounded by a coarse bin)
+    assert diff.mean().item() < 3e-4, diff.mean().item()
+    assert diff.max().item() < 2.5 / n, diff.max().item()
+    # (b) against the fp32 oracle end to end: samples are positions along the ray, tolerance 2e-3
+    z32 = O.sample_z(p, o, dd, near, far, n, m, steps, t_rand)
+    assert (zc - z32).abs().median().item() < 1e-4 and (zc - z32).abs().max().item() < 2.5 / n
+
+
+@pytest.mark.parametrize("S,bg,car", [(128, False, 1.0), (32, True, 0.4), (48, False, 0.0), (200, False, 1.0)])
+def test_composite_and_loss_fwd_bwd(S, bg, car):
+    from fmov_pose_b200 import ops
+    B = 150
+    o, dd, near, far, g = _rays(B, 7)
+    z = torch.sort(near + (far - near) * torch.rand(B, S, generator=g), dim=-1)[0]
+    z.requires_grad_(True); o.requires_grad_(True); dd.requires_grad_(True)
+    mid = (z.detach() + 0.01)
+    pts = o.detach()[:, None] + dd.detach()[:, None] * mid[..., None]
+    sdf = ((pts.norm(dim=-1) - 0.6).reshape(-1, 1) + torch.randn(B * S, 1, generator=g) * 0.01).requires_grad_(True)
+    nrm = (torch.nn.functional.normalize(pts.reshape(-1, 3), dim=-1) * (1 + 0.2 * torch.randn(B * S, 1, generator=g))).requires_grad_(True)
+    rgb = torch.rand(B, S, 3, generator=g).requires_grad_(True)
+    variance = torch.tensor(0.35, requires_grad=True)
+    inv_s = O.inv_s_from_variance(variance)
+    bgt = torch.tensor([[1.0, 0.5, 0.25]]) if bg else None
+    sd = 2.0 / 64
+    ref = O.composite(o, dd, z, sdf, nrm, rgb, inv_s, sd, background_rgb=bgt, cos_anneal_ratio=car)
+    true_rgb = torch.rand(B, 3, generator=g)
+    mask = (torch.rand(B, 1, generator=g) > 0.4).float()
+    out = {"color_fine": ref["color"], "gradient_error": ref["gradient_error"],
+           "weight_sum": ref["weights"].sum(-1, keepdim=True)}
+    losses = O.loss_block(out, true_rgb, mask, 0.1, 5.0)
+    depth = (ref["weights"] * ref["mid_z_vals"]).sum(-1, keepdim=True)
+    gw_ext = torch.randn(B, S, generator=g) * 1e-3
+    total = losses["loss"] + 0.01 * depth.sum() + (ref["weights"] * gw_ext).sum()
+    grads = torch.autograd.grad(total, [sdf, nrm, rgb, variance, o, dd, z], allow_unused=True)
+
+    D = lambda x: None if x is None else x.detach().to(DEV).contiguous()
+    inv_s_d = D(inv_s.reshape(1))
+    f = ops.composite_fwd(D(o), D(dd), D(z), D(sdf.reshape(-1)), D(nrm), D(rgb.reshape(-1, 3)), inv_s_d, sd, car,
+                          bg=None if bgt is None else D(bgt.reshape(3)))
+    _close(f["color"], ref["color"], 2e-5); _close(f["weights"], ref["weights"], 2e-5)
+    _close(f["cdf"], ref["cdf"], 2e-5); _close(f["mid_z"], ref["mid_z_vals"], 1e-5)
+    _close(f["inside"], ref["inside_sphere"], 0); _close(f["pts"], ref["pts"], 1e-5)
+    _close(f["depth"], depth, 2e-5)
+    _close(f["weight_max"], ref["weights"].max(-1, keepdim=True)[0], 2e-5)
+    eik = f["eik"].sum(0)
+    _close(eik[0] / (eik[1] + 1e-5), ref["gradient_error"], 1e-5)
+    mm = (mask > 0.5).float()
+    mask_sum = D((mm.sum() + 1e-5).reshape(1))
+    partial, g_color, g_wsum = ops.loss_fwd_bwd(f["color"], f["weight_sum"], D(true_rgb), D(mask), mask_sum, B, 5.0)
+    _close(partial[:, 0].sum(), losses["color_loss"], 1e-5); _close(partial[:, 1].sum(), losses["mask_loss"], 1e-5)
+    g_eik = torch.tensor([0.1], device=DEV)
+    bk = ops.composite_bwd(D(o), D(dd), D(z), D(sdf.reshape(-1)), D(nrm), D(rgb.reshape(-1, 3)), inv_s_d, sd, car,
+                           None if bgt is None else D(bgt.reshape(3)), g_color, g_wsum,
+                           torch.full((B,), 0.01, device=DEV), D(gw_ext), g_eik, eik[1:2].contiguous())
+    tol = lambda x: 2e-4 * x.abs().max().item() + 1e-9
+    _close(bk["d_sdf"], grads[0].reshape(-1), tol(grads[0]), rtol=2e-3, msg="d_sdf")
+    _close(bk["d_nrm"], grads[1], tol(grads[1]), rtol=2e-3, msg="d_nrm")
+    _close(bk["d_rgb"], grads[2].reshape(-1, 3), tol(grads[2]), rtol=2e-3, msg="d_rgb")
+    d_var = bk["d_invs"].sum() * 10.0 * inv_s_d[0]
+    _close(d_var, grads[3], 2e-3 * abs(grads[3].item()), msg="d_variance")
+    # rays / z gradients with zero point- and dir-gradients from the (absent) MLP
+    zero = torch.zeros(B * S, 3, device=DEV)
+    d_o, d_d, d_z = ops.ray_reduce_bwd(zero, None, bk["d_dir"], bk["d_dist"], bk["d_mid"], D(dd), D(z), sd, True)
+    # o and d also enter through pts -> relax/inside masks only (no gradient), so autograd grads are:
+    _close(d_d, grads[5], tol(grads[5]) + 1e-7, rtol=2e-3, msg="d_rays_d")
+    _close(d_z, grads[6], tol(grads[6]) + 1e-7, rtol=2e-3, msg="d_z")
+    assert grads[4] is None and d_o.abs().max().item() == 0.0
+
+
+def test_ray_reduce_bwd_points_path():
+    from fmov_pose_b200 import ops
+    B, S = 64, 96
+    o, dd, near, far, g = _rays(B, 9)
+    z = torch.sort(near + (far - near) * torch.rand(B, S, generator=g), dim=-1)[0].requires_grad_(True)
+    o.requires_grad_(True); dd.requires_grad_(True)
+    sd = 2.0 / 64
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((B, 1), sd)], -1)
+    mid = z + dists * 0.5
+    pts = o[:, None] + dd[:, None] * mid[..., None]
+    dirs = dd[:, None].expand(B, S, 3)
+    gp, gdirs = torch.randn(B, S, 3, generator=g), torch.randn(B, S, 3, generator=g)
+    grads = torch.autograd.grad((pts * gp).sum() + (dirs * gdirs).sum(), [o, dd, z])
+    D = lambda x: x.detach().to(DEV).contiguous()
+    zb = torch.zeros(B, S, device=DEV)
+    d_o, d_d, d_z = ops.ray_reduce_bwd(D(gp.reshape(-1, 3)), D(gdirs.reshape(-1, 3)), torch.zeros(B, 3, device=DEV), zb, zb,
+                                       D(dd), D(z), sd, True)
+    _close(d_o, grads[0], 1e-4); _close(d_d, grads[1], 2e-4); _close(d_z, grads[2], 1e-4)
