@@ -24,8 +24,8 @@ constexpr int EPI_THREADS = 128;
 constexpr int WSLOT_BYTES = 256 * 128;     // [256 rows x 64] fp16
 constexpr int SIDE_SLOTS = 4;
 constexpr int MAX_STEPS = 40;
-constexpr int MAX_SIDE = 96;
-constexpr int MAX_STASH = 48;
+constexpr int MAX_SIDE = 160;
+constexpr int MAX_STASH = 56;
 
 struct ChainStep {
   uint32_t w_off;       // byte offset of the first k-block of this step in the weight blob
@@ -37,7 +37,8 @@ struct ChainStep {
   uint8_t side_first;   // first entry in side[] consumed by this step's epilogue
   uint8_t side_cnt;     // number of side blocks
   uint8_t wait_stash;   // side producer waits for stash_bar before this step's side loads
-  uint8_t pad[3];
+  uint8_t no_mma;       // epilogue-only step (side loads but no weights / MMA / accumulator)
+  uint8_t pad[2];
 };
 struct SideRef {
   uint8_t tensor;       // index into stash[]
@@ -60,6 +61,7 @@ struct ChainSmem {
   uint64_t act_ready;
   uint64_t acc_ready;
   uint64_t stash_bar;
+  uint64_t misc_bar;    // epilogue-issued bulk loads (tile re-loads into ACT)
   uint64_t w_full[4];
   uint64_t w_empty[4];
   uint64_t side_full[SIDE_SLOTS];
@@ -91,6 +93,7 @@ __device__ __forceinline__ void chain_init_barriers(ChainSmem* s) {
   mbar_init(&s->act_ready, EPI_THREADS);
   mbar_init(&s->acc_ready, 1);
   mbar_init(&s->stash_bar, 1);
+  mbar_init(&s->misc_bar, 1);
   for (int i = 0; i < NS; ++i) {
     mbar_init(&s->w_full[i], 1);
     mbar_init(&s->w_empty[i], 1);
@@ -110,6 +113,7 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
   for (int t = 0; t < n_my_tiles; ++t) {
     for (int si = 0; si < tb.n_steps; ++si) {
       const ChainStep st = tb.step[si];
+      if (st.no_mma) continue;
       const uint32_t bytes = (uint32_t)st.n * 128u;
       const int nkb = st.nkb_a + st.nkb_aux;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -128,10 +132,12 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
                                                  uint8_t* wst, uint32_t tmem, int n_my_tiles) {
   uint32_t it = 0, nstep = 0;
   for (int t = 0; t < n_my_tiles; ++t) {
-    for (int si = 0; si < tb.n_steps; ++si, ++nstep) {
+    for (int si = 0; si < tb.n_steps; ++si) {
       const ChainStep st = tb.step[si];
+      if (st.no_mma) continue;
       const uint32_t idesc = umma_idesc(128, st.n, st.a_fmt, st.b_fmt, 0, 0);
       mbar_wait(&s->act_ready, nstep & 1);
+      ++nstep;
       tc_fence_after();
       const int nkb = st.nkb_a + st.nkb_aux;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -188,6 +194,7 @@ struct EpiCtx {
   uint32_t acc_n;      // accumulator phases consumed
   uint32_t side_n;     // side blocks consumed
   uint32_t stash_n;    // stash_bar signals issued (store thread only)
+  uint32_t misc_n;     // misc_bar phases consumed
   bool store_pending;  // store thread: a bulk store may still be reading ACT/AUX
 };
 
@@ -199,7 +206,7 @@ __device__ __forceinline__ void epi_init(EpiCtx& c, ChainSmem* s, uint8_t* act, 
   c.row = quarter * 32 + lane;
   c.etid = (warp - EPI_WARP0) * 32 + lane;
   c.tmem = tmem_base + ((uint32_t)(quarter * 32) << 16);
-  c.acc_n = 0; c.side_n = 0; c.stash_n = 0; c.store_pending = false;
+  c.acc_n = 0; c.side_n = 0; c.stash_n = 0; c.misc_n = 0; c.store_pending = false;
 }
 __device__ __forceinline__ void epi_wait_acc(EpiCtx& c) {
   mbar_wait(&c.s->acc_ready, c.acc_n & 1);
@@ -256,6 +263,66 @@ __device__ __forceinline__ uint4 blk_ld_chunk(const uint8_t* blk, int row, int c
 }
 __device__ __forceinline__ void blk_st_chunk(uint8_t* blk, int row, int chunk, uint4 v) {
   *reinterpret_cast<uint4*>(blk + ti_chunk_off(row, chunk)) = v;
+}
+
+
+// Publish variant that also covers plain st.global writes made by all epilogue threads (e.g. tile rows
+// written straight to HBM): every thread fences its writes towards the async proxy first.
+__device__ __forceinline__ void epi_publish_stash_all(EpiCtx& c) {
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  named_bar_sync(1, EPI_THREADS);
+  epi_publish_stash(c);
+}
+// Re-load `nkb` blocks of a stash tile into smem `dst` (ACT); all 128 threads call and wait.
+__device__ __forceinline__ void epi_reload_blocks(EpiCtx& c, uint8_t* dst, const uint8_t* src_tile, int nkb) {
+  if (c.etid == 0) {
+    mbar_expect_tx(&c.s->misc_bar, (uint32_t)nkb * BLK_BYTES);
+    for (int kb = 0; kb < nkb; ++kb) bulk_g2s(dst + kb * BLK_BYTES, src_tile + (size_t)kb * BLK_BYTES, BLK_BYTES, &c.s->misc_bar);
+  }
+  mbar_wait(&c.s->misc_bar, c.misc_n & 1);
+  ++c.misc_n;
+}
+// 64 accumulator columns [col0, col0+64) of this thread's row; columns >= n_mma read as zero.
+__device__ __forceinline__ void acc_load64(const EpiCtx& c, int col0, int n_mma, float* v) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (col0 + q * 16 < n_mma) {
+      tmem_ld16(c.tmem + col0 + q * 16, v + q * 16);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[q * 16 + j] = 0.f;
+    }
+  }
+  tmem_ld_wait();
+}
+// one 64-wide row of a block <-> 64 floats
+__device__ __forceinline__ void row_load64(const uint8_t* blk, int row, bool bf16, float* v) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const uint4 q = blk_ld_chunk(blk, row, ch);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = bf16 ? unpack_bf2(w[j]) : unpack_h2(w[j]);
+      v[ch * 8 + 2 * j] = f.x;
+      v[ch * 8 + 2 * j + 1] = f.y;
+    }
+  }
+}
+__device__ __forceinline__ void row_store64(uint8_t* blk, int row, bool bf16, const float* v) {
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 q;
+    if (bf16) {
+      q.x = pack_bf2(v[ch * 8 + 0], v[ch * 8 + 1]); q.y = pack_bf2(v[ch * 8 + 2], v[ch * 8 + 3]);
+      q.z = pack_bf2(v[ch * 8 + 4], v[ch * 8 + 5]); q.w = pack_bf2(v[ch * 8 + 6], v[ch * 8 + 7]);
+    } else {
+      q.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]); q.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
+      q.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]); q.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
+    }
+    blk_st_chunk(blk, row, ch, q);
+  }
 }
 
 }  // namespace fmov

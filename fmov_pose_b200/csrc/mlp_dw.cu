@@ -1,0 +1,371 @@
+// Weight / bias gradients of both MLPs from the activation- and gradient-tile stash written by
+// fmov_fine_fwd / fmov_fine_bwd  (the dW part of loss.backward(), exp_runner.py:802).
+//
+//   dW_l = Zbar_l^T U_l + Delta_l^T Vbar_l        (oracle/explicit_adjoint.py: sdf_backward)
+// Both products are GEMMs whose reduction dimension is the POINT index, so the tile images are used as
+// MN-major tcgen05 operands (no transposes): A = gradient tile (M = output features), B = input tile
+// (N = input features), K = 64 points per pipeline stage, fp32 accumulation of the whole point range of a
+// CTA in TMEM (2 x [128 x N] accumulators = all 512 columns for a 256 x 256 layer), one atomic flush at the end.
+// Bias gradients, lin8 row 0 and the 3-row colour output layer are column sums done by a CUDA-core kernel.
+#include "mlp_chain.cuh"
+#include "../../include/fmov_b200.h"
+
+namespace fmov {
+
+// stash ids (must match mlp_fine.cu)
+enum { S_PE = 0, S_H1 = 1, S_F = 9, S_D0 = 10, S_X = 18, S_C1 = 19, S_ZC0 = 23, S_FB = 27, S_GE = 28, S_V1 = 29,
+       S_Q0 = 37, S_Z0 = 45, S_COUNT = 53 };
+__host__ __device__ inline int s_kb(int id) { return (id == S_PE || id == S_X || id == S_GE) ? 1 : 4; }
+
+constexpr int DW_MAX_JOBS = 20;
+constexpr int DW_STAGES = 3;
+constexpr int DW_HALF = 64;                       // points per stage
+constexpr int DW_ABYTES = 4 * DW_HALF * 128;      // 32 KiB: [4 feature blocks][64 points x 128 B]
+constexpr int DW_STAGE_BYTES = 2 * DW_ABYTES;
+constexpr int DW_THREADS = 192;
+
+struct DwJob {
+  uint8_t npairs;
+  uint8_t a_id[2], b_id[2];        // stash tensors: A = gradient tile (4 blocks), B = input tile
+  uint8_t a_bf16[2], b_bf16[2];
+  uint8_t b_blocks;                // feature blocks of B used (N = 64*b_blocks)
+  uint8_t pad0;
+  int m_valid, n_valid;            // rows / cols of the fp32 output actually written
+  int ld, col_off;                 // out[m*ld + col_off + n]
+  long long out_off;               // offset (floats) into the flat gradient buffer
+  float scale;
+  int cta_first, cta_count;
+};
+struct DwPlan {
+  int n_jobs;
+  DwJob job[DW_MAX_JOBS];
+};
+struct DwPtrs {
+  const uint8_t* stash[S_COUNT];
+};
+
+__global__ void __launch_bounds__(DW_THREADS, 1)
+dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs ptrs, long long n_tiles, float* grads) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = chain_smem_base(smem_raw);
+  __shared__ uint64_t full[DW_STAGES], ready[DW_STAGES], empty[DW_STAGES], done_bar;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // which job / tile range
+  int ji = 0;
+  for (int j = 0; j < plan.n_jobs; ++j)
+    if ((int)blockIdx.x >= plan.job[j].cta_first && (int)blockIdx.x < plan.job[j].cta_first + plan.job[j].cta_count) ji = j;
+  const DwJob& jb = plan.job[ji];
+  const int local = blockIdx.x - jb.cta_first;
+  const long long per = (n_tiles + jb.cta_count - 1) / jb.cta_count;
+  const long long t0 = local * per, t1 = (t0 + per < n_tiles) ? t0 + per : n_tiles;
+  const int n_mma = jb.b_blocks * 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 128); mbar_init(&empty[i], 1); }
+    mbar_init(&done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const bool has_work = t1 > t0;
+
+  if (warp == 0 && lane == 0 && has_work) {
+    uint32_t it = 0;
+    for (long long t = t0; t < t1; ++t)
+      for (int pr = 0; pr < jb.npairs; ++pr) {
+        const uint8_t* asrc = ptrs.stash[jb.a_id[pr]] + (size_t)t * 4 * BLK_BYTES;
+        const uint8_t* bsrc = ptrs.stash[jb.b_id[pr]] + (size_t)t * s_kb(jb.b_id[pr]) * BLK_BYTES;
+        for (int h = 0; h < 2; ++h, ++it) {
+          const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
+          uint8_t* sa = base + slot * DW_STAGE_BYTES;
+          uint8_t* sb = sa + DW_ABYTES;
+          mbar_wait(&empty[slot], (n & 1) ^ 1);
+          mbar_expect_tx(&full[slot], (uint32_t)(4 + jb.b_blocks) * (DW_HALF * 128));
+          for (int kb = 0; kb < 4; ++kb)
+            bulk_g2s(sa + kb * (DW_HALF * 128), asrc + (size_t)kb * BLK_BYTES + h * (DW_HALF * 128), DW_HALF * 128, &full[slot]);
+          for (int kb = 0; kb < jb.b_blocks; ++kb)
+            bulk_g2s(sb + kb * (DW_HALF * 128), bsrc + (size_t)kb * BLK_BYTES + h * (DW_HALF * 128), DW_HALF * 128, &full[slot]);
+        }
+      }
+  } else if (warp == 1 && lane == 0 && has_work) {
+    uint32_t it = 0;
+    bool first = true;
+    for (long long t = t0; t < t1; ++t)
+      for (int pr = 0; pr < jb.npairs; ++pr) {
+        // tcgen05.mma kind::f16 cannot mix an fp16 with a bf16 operand (illegal instruction on sm_100a):
+        // the converter warps have rewritten the fp16 operand of the pair as bf16 in shared memory.
+        const uint32_t idesc = umma_idesc(128, n_mma, FMT_BF16, FMT_BF16, 1, 1);
+        for (int h = 0; h < 2; ++h, ++it) {
+          const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
+          const uint32_t sa = smem_u32(base + slot * DW_STAGE_BYTES);
+          const uint32_t sb = sa + DW_ABYTES;
+          mbar_wait(&ready[slot], n & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {        // 16 points per instruction = 2048 bytes of rows
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh) {
+              umma_f16(tmem + mh * 256, umma_desc_mnmajor(sa + mh * 2 * (DW_HALF * 128) + ks * 2048, DW_HALF * 128),
+                       umma_desc_mnmajor(sb + ks * 2048, DW_HALF * 128), idesc, (first && ks == 0) ? 0u : 1u);
+            }
+          }
+          first = false;
+          umma_commit(&empty[slot]);
+        }
+      }
+    umma_commit(&done_bar);
+  } else if (warp >= 2 && has_work) {
+    // converter: fp16 operand of each stage -> bf16, in place (element-wise, layout agnostic)
+    {
+      const int ctid = threadIdx.x - 64;
+      uint32_t it = 0;
+      for (long long t = t0; t < t1; ++t)
+        for (int pr = 0; pr < jb.npairs; ++pr)
+          for (int h = 0; h < 2; ++h, ++it) {
+            const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
+            uint8_t* sa = base + slot * DW_STAGE_BYTES;
+            mbar_wait(&full[slot], n & 1);
+            uint4* reg = nullptr;
+            int nchunks = 0;
+            if (!jb.a_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa); nchunks = DW_ABYTES / 16; }
+            else if (!jb.b_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa + DW_ABYTES); nchunks = jb.b_blocks * (DW_HALF * 128) / 16; }
+            for (int i = ctid; i < nchunks; i += 128) {
+              uint4 q = reg[i];
+              float2 f;
+              f = unpack_h2(q.x); q.x = pack_bf2(f.x, f.y);
+              f = unpack_h2(q.y); q.y = pack_bf2(f.x, f.y);
+              f = unpack_h2(q.z); q.z = pack_bf2(f.x, f.y);
+              f = unpack_h2(q.w); q.w = pack_bf2(f.x, f.y);
+              reg[i] = q;
+            }
+            fence_proxy_async();
+            mbar_arrive(&ready[slot]);
+          }
+    }
+    // epilogue: wait for the whole range, then flush the two [128 x N] accumulators with atomics
+    mbar_wait(&done_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    float* out = grads + jb.out_off;
+    for (int mh = 0; mh < 2; ++mh) {
+      const int m = mh * 128 + row;
+      for (int c0 = 0; c0 < n_mma; c0 += 16) {
+        float v[16];
+        tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + mh * 256 + c0, v);
+        tmem_ld_wait();
+        if (m < jb.m_valid) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + j < jb.n_valid) atomicAdd(out + (size_t)m * jb.ld + jb.col_off + c0 + j, v[j] * jb.scale);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---- column sums: biases, lin8 row 0, colour lin4 -----------------------------------------------------------
+struct ColsumArgs {
+  DwPtrs ptrs;
+  long long n_tiles, P;
+  const float* d_sdf;     // [P]
+  const float* zc4;       // [P,4]
+  float* grads;
+  long long off_b_sdf[9];  // float offsets of lin{l}.bias grads
+  long long off_b_col[5];
+  long long off_w8;        // lin8 weight grad [257,256] (row 0 written here)
+  long long off_wc4;       // colour lin4 weight grad [3,256]
+};
+
+__device__ __forceinline__ float ti_elem(const uint8_t* tile, int r, int m, bool bf16) {
+  const uint8_t* p = tile + (size_t)(m >> 6) * BLK_BYTES + ti_off(r, m & 63);
+  return bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)) : __half2float(*reinterpret_cast<const __half*>(p));
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
+  const int m = threadIdx.x;
+  float bz[8], bf = 0.f, bc[4], w8r = 0.f, wc4[3] = {0.f, 0.f, 0.f}, extra = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bz[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) bc[i] = 0.f;
+  __shared__ float s_sb[128], s_z4[128 * 3];
+  for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const long long p = t * 128 + threadIdx.x;
+      const bool ok = p < a.P;
+      s_sb[threadIdx.x] = ok ? a.d_sdf[p] : 0.f;
+      for (int j = 0; j < 3; ++j) s_z4[threadIdx.x * 3 + j] = ok ? a.zc4[p * 4 + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const uint8_t* tz = a.ptrs.stash[S_Z0 + l] + (size_t)t * 4 * BLK_BYTES;
+      float s = 0.f;
+      for (int r = 0; r < 128; ++r) s += ti_elem(tz, r, m, true);
+      bz[l] += s;
+    }
+    {
+      const uint8_t* tf = a.ptrs.stash[S_FB] + (size_t)t * 4 * BLK_BYTES;
+      const uint8_t* th = a.ptrs.stash[S_H1 + 7] + (size_t)t * 4 * BLK_BYTES;
+      const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + (size_t)t * 4 * BLK_BYTES;
+      const uint8_t* tc4 = a.ptrs.stash[S_C1 + 3] + (size_t)t * 4 * BLK_BYTES;
+      for (int r = 0; r < 128; ++r) {
+        bf += ti_elem(tf, r, m, true);
+        w8r += s_sb[r] * ti_elem(th, r, m, false) + ti_elem(tv, r, m, true);
+        const float c4 = ti_elem(tc4, r, m, false);
+        wc4[0] += s_z4[r * 3] * c4; wc4[1] += s_z4[r * 3 + 1] * c4; wc4[2] += s_z4[r * 3 + 2] * c4;
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const uint8_t* tz = a.ptrs.stash[S_ZC0 + l] + (size_t)t * 4 * BLK_BYTES;
+      float s = 0.f;
+      for (int r = 0; r < 128; ++r) s += ti_elem(tz, r, m, true);
+      bc[l] += s;
+    }
+    if (m < 4) {
+      float s = 0.f;
+      for (int r = 0; r < 128; ++r) s += (m == 0) ? s_sb[r] : s_z4[r * 3 + (m - 1)];
+      extra += s;
+    }
+  }
+  float* g = a.grads;
+#pragma unroll
+  for (int l = 0; l < 8; ++l)
+    if (l != 3 || m < 217) atomicAdd(g + a.off_b_sdf[l] + m, bz[l]);
+  atomicAdd(g + a.off_b_sdf[8] + 1 + m, bf);
+  atomicAdd(g + a.off_w8 + m, w8r);
+#pragma unroll
+  for (int l = 0; l < 4; ++l) atomicAdd(g + a.off_b_col[l] + m, bc[l]);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_wc4 + j * 256 + m, wc4[j]);
+  if (m == 0) atomicAdd(g + a.off_b_sdf[8], extra);
+  if (m >= 1 && m < 4) atomicAdd(g + a.off_b_col[4] + (m - 1), extra);
+}
+
+}  // namespace fmov
+using namespace fmov;
+
+// ---- flat gradient buffer layout (fp32), shapes = the reference parameters' effective weights -----------------
+static const int SDF_OUT[9] = {256, 256, 256, 217, 256, 256, 256, 256, 257};
+static const int SDF_IN[9] = {39, 256, 256, 256, 256, 256, 256, 256, 256};
+static const int COL_OUT[5] = {256, 256, 256, 256, 3};
+static const int COL_IN[5] = {289, 256, 256, 256, 256};
+
+// kind: 0 sdf weight, 1 sdf bias, 2 colour weight, 3 colour bias
+extern "C" long long fmov_grad_offset(int kind, int layer) {
+  long long off = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int nl = (k < 2) ? 9 : 5;
+    for (int l = 0; l < nl; ++l) {
+      if (k == kind && l == layer) return off;
+      const int o = (k < 2) ? SDF_OUT[l] : COL_OUT[l];
+      const int i = (k < 2) ? SDF_IN[l] : COL_IN[l];
+      off += (k == 0 || k == 2) ? (long long)o * i : o;
+    }
+  }
+  return (kind == 4) ? off : -1;
+}
+extern "C" long long fmov_grad_floats(void) { return fmov_grad_offset(4, 0); }
+
+static void add_job(DwPlan& pl, int npairs, int a0, int b0, int a0bf, int b0bf, int a1, int b1, int a1bf, int b1bf,
+                    int b_blocks, int m_valid, int n_valid, int ld, int col_off, long long out_off, float scale) {
+  DwJob& j = pl.job[pl.n_jobs++];
+  memset(&j, 0, sizeof(j));
+  j.npairs = (uint8_t)npairs;
+  j.a_id[0] = (uint8_t)a0; j.b_id[0] = (uint8_t)b0; j.a_bf16[0] = (uint8_t)a0bf; j.b_bf16[0] = (uint8_t)b0bf;
+  j.a_id[1] = (uint8_t)a1; j.b_id[1] = (uint8_t)b1; j.a_bf16[1] = (uint8_t)a1bf; j.b_bf16[1] = (uint8_t)b1bf;
+  j.b_blocks = (uint8_t)b_blocks; j.m_valid = m_valid; j.n_valid = n_valid; j.ld = ld; j.col_off = col_off;
+  j.out_off = out_off; j.scale = scale;
+}
+
+static void build_plan(DwPlan& pl, int n_ctas) {
+  memset(&pl, 0, sizeof(pl));
+  const float rs2 = 0.70710678118654752f;
+  // SDF layers 1..7: (Zbar_l, H_l) + (Delta_l, Vbar_l)
+  for (int l = 1; l <= 7; ++l) {
+    const int nv = (l == 4) ? 217 : 256;
+    add_job(pl, 2, S_Z0 + l, S_H1 + (l - 1), 1, 0, S_D0 + l, S_V1 + (l - 1), 0, 1, 4, SDF_OUT[l], nv, 256, 0,
+            fmov_grad_offset(0, l), l == 4 ? rs2 : 1.f);
+  }
+  // layer 4, PE columns 217..255: (Zbar_4, PE) + (Delta_4, GE)
+  add_job(pl, 2, S_Z0 + 4, S_PE, 1, 0, S_D0 + 4, S_GE, 0, 1, 1, 256, 39, 256, 217, fmov_grad_offset(0, 4), rs2);
+  // layer 0: (Zbar_0, PE) + (Delta_0, GE)
+  add_job(pl, 2, S_Z0 + 0, S_PE, 1, 0, S_D0 + 0, S_GE, 0, 1, 1, 256, 39, 39, 0, fmov_grad_offset(0, 0), 1.f);
+  // layer 8 feature rows 1..256: (fbar, H8)
+  add_job(pl, 1, S_FB, S_H1 + 7, 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(0, 8) + 256, 1.f);
+  // colour layers 1..3: (Zbar_cl, C_l); layer 0: (Zbar_c0, F) -> cols 33.., (Zbar_c0, X) -> cols 0..32
+  for (int l = 1; l <= 3; ++l)
+    add_job(pl, 1, S_ZC0 + l, S_C1 + (l - 1), 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(2, l), 1.f);
+  add_job(pl, 1, S_ZC0 + 0, S_F, 1, 0, 0, 0, 0, 0, 4, 256, 256, 289, 33, fmov_grad_offset(2, 0), 1.f);
+  add_job(pl, 1, S_ZC0 + 0, S_X, 1, 0, 0, 0, 0, 0, 1, 256, 33, 289, 0, fmov_grad_offset(2, 0), 1.f);
+  // distribute CTAs proportionally to cost (bytes streamed per tile)
+  float cost[DW_MAX_JOBS], total = 0.f;
+  for (int j = 0; j < pl.n_jobs; ++j) {
+    cost[j] = pl.job[j].npairs * (4.f + pl.job[j].b_blocks);
+    total += cost[j];
+  }
+  int used = 0;
+  for (int j = 0; j < pl.n_jobs; ++j) {
+    int c = (int)(cost[j] / total * n_ctas);
+    if (c < 1) c = 1;
+    pl.job[j].cta_count = c;
+    used += c;
+  }
+  // hand leftovers to / take excess from the biggest jobs
+  for (int j = 0; used != n_ctas; j = (j + 1) % pl.n_jobs) {
+    if (used < n_ctas && pl.job[j].npairs == 2 && pl.job[j].b_blocks == 4) { ++pl.job[j].cta_count; ++used; }
+    else if (used > n_ctas && pl.job[j].cta_count > 1) { --pl.job[j].cta_count; --used; }
+  }
+  int first = 0;
+  for (int j = 0; j < pl.n_jobs; ++j) { pl.job[j].cta_first = first; first += pl.job[j].cta_count; }
+}
+
+/* grads: flat fp32 buffer of fmov_grad_floats() floats, zeroed by this call. stash: HOST array of device pointers. */
+extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, float* grads, void* stream) {
+  FMOV_REQUIRE(P > 0 && stash && d_sdf && zc4 && grads, "fmov_dw: bad arguments");
+  static DwPlan plan;
+  static bool init = false;
+  static int n_ctas = 148;
+  if (!init) {
+    int dev = 0, sms = 148;
+    FMOV_CUDA(cudaGetDevice(&dev));
+    FMOV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    n_ctas = sms;
+    build_plan(plan, n_ctas);
+    FMOV_CUDA(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_STAGES * DW_STAGE_BYTES + 1024));
+    init = true;
+  }
+  DwPtrs ptrs;
+  for (int i = 0; i < S_COUNT; ++i) {
+    FMOV_REQUIRE(stash[i], "fmov_dw: stash tensor %d is null", i);
+    ptrs.stash[i] = reinterpret_cast<const uint8_t*>(stash[i]);
+  }
+  const long long n_tiles = (P + 127) / 128;
+  FMOV_CUDA(cudaMemsetAsync(grads, 0, (size_t)fmov_grad_floats() * sizeof(float), (cudaStream_t)stream));
+  dw_kernel<<<n_ctas, DW_THREADS, DW_STAGES * DW_STAGE_BYTES + 1024, (cudaStream_t)stream>>>(plan, ptrs, n_tiles, grads);
+  FMOV_LAUNCH_CHECK("dw_kernel");
+  ColsumArgs ca;
+  ca.ptrs = ptrs; ca.n_tiles = n_tiles; ca.P = P; ca.d_sdf = d_sdf; ca.zc4 = zc4; ca.grads = grads;
+  for (int l = 0; l < 9; ++l) ca.off_b_sdf[l] = fmov_grad_offset(1, l);
+  for (int l = 0; l < 5; ++l) ca.off_b_col[l] = fmov_grad_offset(3, l);
+  ca.off_w8 = fmov_grad_offset(0, 8);
+  ca.off_wc4 = fmov_grad_offset(2, 4);
+  const int cs_grid = (int)(n_tiles < 2 * n_ctas ? n_tiles : 2 * n_ctas);
+  colsum_kernel<<<cs_grid, 256, 0, (cudaStream_t)stream>>>(ca);
+  FMOV_LAUNCH_CHECK("colsum_kernel");
+  return OK;
+}

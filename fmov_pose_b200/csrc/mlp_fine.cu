@@ -1,0 +1,728 @@
+// Fine stage of NeuSRenderer.render_core as two fused chain kernels (forward, backward).
+//
+//   fmov_fine_fwd   per sample: SDF value + 256-d feature (SDFNetwork.forward, models/fields.py:88-104),
+//                   analytic normal d sdf/dx (replaces the second forward + autograd.grad of
+//                   SDFNetwork.gradient, models/fields.py:112-124), colour MLP (RenderingNetwork.forward,
+//                   models/fields.py:166-193); call sites models/renderer.py:277-288.
+//   fmov_fine_bwd   the matching part of loss.backward() (exp_runner.py:802): given dL/d{sdf, normal, rgb} per
+//                   sample it produces dL/d{point, view dir} and every activation-gradient tile the weight
+//                   gradient GEMMs (mlp_dw.cu) need, including the second-order path through the normal.
+//
+// Math: oracle/explicit_adjoint.py (checked against autograd) — same symbols:
+//   value pass   z_l = W_l u_l + b_l, h_{l+1} = softplus_100(z_l), sigma_l = 1 - exp(-100 h_{l+1})
+//   reverse sweep delta_7 = W_8[0,:]*sigma_7;  v_l = W_l^T delta_l;  delta_{l-1} = v_l*sigma_{l-1};  n = J_e^T g_e
+//   adjoint pass dbar_l = W_l vbar_l;  vbar_{l+1} = dbar_l*sigma_l;  q_l = 100*dbar_l*delta_l*(1-sigma_l)
+//   backward     zbar_{l-1} = (W_l^T zbar_l)*sigma_{l-1} + q_{l-1}
+// fp16 operands in the forward (value pass, reverse sweep, colour net), bf16 for every gradient tile; fp32
+// accumulation in TMEM; fp32 epilogue math.
+#include "mlp_chain.cuh"
+#include "../../include/fmov_b200.h"
+
+namespace fmov {
+
+using FL = ChainLayout<2, true>;
+
+// ---- weight image directory ---------------------------------------------------------------------
+enum ImgId {
+  IMG_F0 = 0,          // F0..F8   forward images (fp16): lin0..lin7, lin8 feature rows
+  IMG_T0 = 9,          // T0..T7   transposed images (fp16) for the reverse sweep
+  IMG_C0 = 17,         // C0..C4   colour net forward images (fp16)
+  IMG_CT0A = 22, IMG_CT0B = 23, IMG_CT1 = 24, IMG_CT2 = 25, IMG_CT3 = 26,   // colour transposed (bf16)
+  IMG_FB0 = 27,        // FB0..FB7 forward images in bf16 (adjoint pass)
+  IMG_TB0 = 35,        // TB0..TB8 transposed images in bf16 (backward pass; TB8 = lin8 feature rows^T)
+  IMG_COUNT = 44
+};
+struct ImgInfo { int npad, kblocks; };
+__host__ __device__ inline ImgInfo img_info(int id) {
+  if (id >= IMG_F0 && id < IMG_F0 + 9) {
+    const int l = id - IMG_F0;
+    return l == 0 ? ImgInfo{256, 1} : l == 3 ? ImgInfo{224, 4} : l == 4 ? ImgInfo{256, 5} : ImgInfo{256, 4};
+  }
+  if (id >= IMG_T0 && id < IMG_T0 + 8) return (id - IMG_T0) == 0 ? ImgInfo{48, 4} : ImgInfo{256, 4};
+  if (id >= IMG_C0 && id < IMG_C0 + 5) {
+    const int l = id - IMG_C0;
+    return l == 0 ? ImgInfo{256, 5} : l == 4 ? ImgInfo{16, 4} : ImgInfo{256, 4};
+  }
+  if (id == IMG_CT0B) return ImgInfo{48, 4};
+  if (id >= IMG_CT0A && id <= IMG_CT3) return ImgInfo{256, 4};
+  if (id >= IMG_FB0 && id < IMG_FB0 + 8) return img_info(IMG_F0 + (id - IMG_FB0));
+  if (id >= IMG_TB0 && id < IMG_TB0 + 9) return (id - IMG_TB0) == 0 ? ImgInfo{48, 4} : ImgInfo{256, 4};
+  return ImgInfo{0, 0};
+}
+static long long img_offset(int id) {
+  long long off = 0;
+  for (int i = 0; i < id; ++i) {
+    const ImgInfo ii = img_info(i);
+    off += (long long)ii.npad * 128 * ii.kblocks;
+  }
+  return off;
+}
+
+// ---- stash tensors --------------------------------------------------------------------------------
+enum StashId {
+  ST_PE = 0, ST_H1 = 1 /*..H8=8*/, ST_F = 9, ST_D0 = 10 /*..D7=17*/, ST_X = 18, ST_C1 = 19 /*..C4=22*/,
+  ST_ZC0 = 23 /*..ZC3=26*/, ST_FB = 27, ST_GE = 28, ST_V1 = 29 /*..V8=36*/, ST_Q0 = 37 /*..Q7=44*/,
+  ST_Z0 = 45 /*..Z7=52*/, ST_COUNT = 53
+};
+__host__ __device__ inline int stash_kb(int id) { return (id == ST_PE || id == ST_X || id == ST_GE) ? 1 : 4; }
+
+struct FineArgs {
+  long long B;
+  int S;
+  const float* rays_o; const float* rays_d; const float* z;   // [B,3],[B,3],[B,S]
+  float sample_dist;
+  // fp32 side parameters
+  const float* bias_sdf;   // [8][256]
+  const float* b8;         // [257]
+  const float* w8row;      // [256]  lin8 row 0 (effective)
+  const float* bias_col;   // [4][256]
+  const float* bc4;        // [3]
+  const float* wc4;        // [3][256]  colour lin4 (effective), fp32 (backward only)
+  // per-sample fp32 tensors
+  float* sdf; float* nrm; float* rgb; float* ge;              // fwd outputs: [P],[P,3],[P,3],[P,40]
+  const float* d_sdf; const float* d_nrm; const float* d_rgb; // bwd inputs
+  float* d_pts; float* d_dirs; float* zc4;                    // bwd outputs: [P,3],[P,3],[P,4]
+};
+
+__device__ __forceinline__ uint8_t* stash_tile(const ChainPtrs& ptrs, int id, long long tile) {
+  return ptrs.stash[id] + (size_t)tile * stash_kb(id) * BLK_BYTES;
+}
+
+struct PointCtx { bool valid; long long p; float x[3]; float d[3]; };
+__device__ __forceinline__ PointCtx load_sample(const FineArgs& a, long long tile, int row) {
+  PointCtx c;
+  c.p = tile * TILE_M + row;
+  c.valid = c.p < a.B * a.S;
+  c.x[0] = c.x[1] = c.x[2] = 0.f;
+  c.d[0] = c.d[1] = c.d[2] = 0.f;
+  if (c.valid) {
+    const long long r = c.p / a.S;
+    const int j = (int)(c.p - r * a.S);
+    const float z0 = a.z[c.p];
+    const float dist = (j + 1 < a.S) ? a.z[c.p + 1] - z0 : a.sample_dist;
+    const float mid = z0 + dist * 0.5f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      c.d[i] = a.rays_d[r * 3 + i];
+      c.x[i] = a.rays_o[r * 3 + i] + c.d[i] * mid;
+    }
+  }
+  return c;
+}
+
+// PE(L) of a 3-vector into e[3+6L]: [x, sin(2^k x), cos(2^k x)]  (models/embedder.py:28-37)
+template <int L>
+__device__ __forceinline__ void pe_eval(const float x[3], float* e) {
+  e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = s;
+      e[6 + 6 * k + c] = co;
+    }
+  }
+}
+// n = J_e^T g   (g has 3+6L entries)
+template <int L>
+__device__ __forceinline__ void pe_jt(const float x[3], const float* g, float n[3]) {
+  n[0] = g[0]; n[1] = g[1]; n[2] = g[2];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      n[c] += g[3 + 6 * k + c] * f * co - g[6 + 6 * k + c] * f * s;
+    }
+  }
+}
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+__global__ void __launch_bounds__(CH_THREADS, 1)
+fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
+                const __grid_constant__ FineArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = chain_smem_base(smem_raw);
+  ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
+  uint8_t* act = base + FL::ACT;
+  uint8_t* aux = base + FL::AUX;
+  uint8_t* side = base + FL::SIDE;
+  uint8_t* wst = base + FL::WST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long P = a.B * a.S;
+  const long long n_tiles = (P + TILE_M - 1) / TILE_M;
+  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (threadIdx.x == 0) chain_init_barriers<2>(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) chain_weight_producer<2>(tb, ptrs.weights, s, wst, n_my);
+  } else if (warp == 1) {
+    if (lane == 0) chain_mma_issuer<2>(tb, s, act, aux, wst, tmem, n_my);
+  } else if (warp == 2) {
+    if (lane == 0) chain_side_producer(tb, ptrs, s, side, blockIdx.x, gridDim.x, n_my);
+  } else {
+    EpiCtx c;
+    epi_init(c, s, act, aux, side, tmem);
+    for (int t = 0; t < n_my; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const PointCtx pc = load_sample(a, tile, c.row);
+      // ---- input: PE6(x) -> AUX, stash ---------------------------------------------------------
+      {
+        float e[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        pe_eval<6>(pc.x, e);
+        epi_before_write(c);
+        row_store64(aux, c.row, false, e);
+        epi_store_blocks(c, aux, stash_tile(ptrs, ST_PE, tile), 1);
+        epi_signal_act(c);
+      }
+      // ---- value pass: layers 0..7 -----------------------------------------------------------------
+      float sdf = __ldg(a.b8);
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const int n_valid = (l == 3) ? 217 : 256;
+        const int n_mma = (l == 3) ? 224 : 256;
+        const float* bias = a.bias_sdf + l * 256;
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64];
+          acc_load64(c, cb * 64, n_mma, v);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const int col = cb * 64 + j;
+            v[j] = (col < n_valid) ? softplus100(v[j] + __ldg(bias + col)) : 0.f;
+          }
+          if (l == 7) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sdf = fmaf(v[j], __ldg(a.w8row + cb * 64 + j), sdf);
+          }
+          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_H1 + l, tile), 4);
+        epi_signal_act(c);
+      }
+      if (pc.valid) a.sdf[pc.p] = sdf;
+      // ---- lin8 feature rows -> SIDE (staging) ; delta_7 = W8[0,:]*sigma_7 in place ----------------
+      epi_wait_acc(c);
+      epi_before_write(c);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[64], h[64];
+        acc_load64(c, cb * 64, 256, v);
+        row_load64(act + cb * BLK_BYTES, c.row, false, h);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int col = cb * 64 + j;
+          v[j] += __ldg(a.b8 + 1 + col);
+          h[j] = __ldg(a.w8row + col) * sigma_from_h(h[j]);
+        }
+        row_store64(side + cb * BLK_BYTES, c.row, false, v);
+        row_store64(act + cb * BLK_BYTES, c.row, false, h);
+      }
+      epi_store_blocks(c, side, stash_tile(ptrs, ST_F, tile), 4);
+      epi_store_blocks(c, act, stash_tile(ptrs, ST_D0 + 7, tile), 4);
+      epi_publish_stash(c);          // H1..H8, F have landed; SIDE staging buffer is free again
+      epi_signal_act(c);
+      // ---- reverse sweep l = 7..1 ------------------------------------------------------------------
+      float ge[40];
+#pragma unroll
+      for (int i = 0; i < 40; ++i) ge[i] = 0.f;
+#pragma unroll 1
+      for (int l = 7; l >= 1; --l) {
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64], h[64];
+          acc_load64(c, cb * 64, 256, v);
+          const uint8_t* sb = epi_side_wait(c);       // H_l block cb  -> sigma_{l-1}
+          row_load64(sb, c.row, false, h);
+          epi_side_release(c);
+          if (l == 4 && cb == 3) {
+            // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image)
+#pragma unroll
+            for (int j = 25; j < 64; ++j) ge[j - 25] += v[j];
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] *= sigma_from_h(h[j]);   // H_4 is zero beyond col 216 -> delta_3 too
+          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_D0 + (l - 1), tile), 4);
+        epi_signal_act(c);
+      }
+      // ---- g_e += W_0^T delta_0 ; normal ; colour-net extras -----------------------------------------
+      float nrm[3];
+      {
+        float v[64];
+        epi_wait_acc(c);
+        acc_load64(c, 0, 48, v);
+#pragma unroll
+        for (int i = 0; i < 39; ++i) ge[i] += v[i];
+        pe_jt<6>(pc.x, ge, nrm);
+        if (pc.valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) a.nrm[pc.p * 3 + i] = nrm[i];
+#pragma unroll
+          for (int i = 0; i < 40; ++i) a.ge[pc.p * 40 + i] = ge[i];
+        }
+        // extras = [pts(3), PE4(dirs)(27), normals(3)]   (models/fields.py:172-175)
+        float e[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        e[0] = pc.x[0]; e[1] = pc.x[1]; e[2] = pc.x[2];
+        pe_eval<4>(pc.d, e + 3);
+        e[30] = nrm[0]; e[31] = nrm[1]; e[32] = nrm[2];
+        epi_before_write(c);
+        row_store64(aux, c.row, false, e);
+        epi_store_blocks(c, aux, stash_tile(ptrs, ST_X, tile), 1);
+        epi_before_write(c);                                  // D0 store must have finished reading ACT
+        epi_reload_blocks(c, act, stash_tile(ptrs, ST_F, tile), 4);
+        epi_signal_act(c);
+      }
+      // ---- colour net: 4 ReLU layers ------------------------------------------------------------------
+#pragma unroll 1
+      for (int l = 0; l < 4; ++l) {
+        const float* bias = a.bias_col + l * 256;
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64];
+          acc_load64(c, cb * 64, 256, v);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j] + __ldg(bias + cb * 64 + j), 0.f);
+          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_C1 + l, tile), 4);
+        epi_signal_act(c);
+      }
+      // ---- colour output: sigmoid --------------------------------------------------------------------
+      {
+        float v[64];
+        epi_wait_acc(c);
+        acc_load64(c, 0, 16, v);
+        if (pc.valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) a.rgb[pc.p * 3 + i] = sigmoidf_(v[i] + __ldg(a.bc4 + i));
+        }
+        tc_fence_before();
+      }
+    }
+    if (c.etid == 0) bulk_wait_all0();     // all stash stores complete before the CTA exits
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// =====================================================================================================
+// backward
+// =====================================================================================================
+__global__ void __launch_bounds__(CH_THREADS, 1)
+fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
+                const __grid_constant__ FineArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = chain_smem_base(smem_raw);
+  ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
+  uint8_t* act = base + FL::ACT;
+  uint8_t* aux = base + FL::AUX;
+  uint8_t* side = base + FL::SIDE;
+  uint8_t* wst = base + FL::WST;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long P = a.B * a.S;
+  const long long n_tiles = (P + TILE_M - 1) / TILE_M;
+  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+
+  if (threadIdx.x == 0) chain_init_barriers<2>(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = s->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) chain_weight_producer<2>(tb, ptrs.weights, s, wst, n_my);
+  } else if (warp == 1) {
+    if (lane == 0) chain_mma_issuer<2>(tb, s, act, aux, wst, tmem, n_my);
+  } else if (warp == 2) {
+    if (lane == 0) chain_side_producer(tb, ptrs, s, side, blockIdx.x, gridDim.x, n_my);
+  } else {
+    EpiCtx c;
+    epi_init(c, s, act, aux, side, tmem);
+    for (int t = 0; t < n_my; ++t) {
+      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+      const PointCtx pc = load_sample(a, tile, c.row);
+      float sbar = 0.f, nbar[3] = {0.f, 0.f, 0.f}, zc4[3] = {0.f, 0.f, 0.f}, xbar[3] = {0.f, 0.f, 0.f};
+      if (pc.valid) {
+        sbar = a.d_sdf[pc.p];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          nbar[i] = a.d_nrm[pc.p * 3 + i];
+          const float r = a.rgb[pc.p * 3 + i];
+          zc4[i] = a.d_rgb[pc.p * 3 + i] * r * (1.f - r);     // sigmoid backward
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a.zc4[pc.p * 4 + i] = zc4[i];
+        a.zc4[pc.p * 4 + 3] = 0.f;
+      }
+      // ---- colour lin4 backward on CUDA cores (3 x 256) + ReLU mask of C4 -> zbar_c3 ---------------------
+      epi_before_write(c);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[64], h[64];
+        const uint8_t* sb = epi_side_wait(c);          // C4 block cb
+        row_load64(sb, c.row, false, h);
+        epi_side_release(c);
+#pragma unroll
+        for (int j = 0; j < 64; ++j) {
+          const int col = cb * 64 + j;
+          const float ab = zc4[0] * __ldg(a.wc4 + col) + zc4[1] * __ldg(a.wc4 + 256 + col) + zc4[2] * __ldg(a.wc4 + 512 + col);
+          v[j] = h[j] > 0.f ? ab : 0.f;
+        }
+        row_store64(act + cb * BLK_BYTES, c.row, true, v);
+      }
+      epi_store_blocks(c, act, stash_tile(ptrs, ST_ZC0 + 3, tile), 4);
+      epi_signal_act(c);
+      // ---- colour layers 3..1:  zbar_c{l-1} = (zbar_cl W_cl) * [C_l > 0] -----------------------------------
+#pragma unroll 1
+      for (int l = 3; l >= 1; --l) {
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64], h[64];
+          acc_load64(c, cb * 64, 256, v);
+          const uint8_t* sb = epi_side_wait(c);        // C_l block cb
+          row_load64(sb, c.row, false, h);
+          epi_side_release(c);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
+          row_store64(act + cb * BLK_BYTES, c.row, true, v);
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_ZC0 + (l - 1), tile), 4);
+        epi_signal_act(c);
+      }
+      // ---- colour lin0 backward, extras part: pts-bar, PE4(dirs)-bar, normals-bar -------------------------
+      {
+        float v[64];
+        epi_wait_acc(c);
+        acc_load64(c, 0, 48, v);
+        xbar[0] = v[0]; xbar[1] = v[1]; xbar[2] = v[2];
+        nbar[0] += v[30]; nbar[1] += v[31]; nbar[2] += v[32];
+        float dd[3];
+        pe_jt<4>(pc.d, v + 3, dd);
+        if (pc.valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) a.d_dirs[pc.p * 3 + i] = dd[i];
+        }
+        epi_signal_act(c);                 // ACT (zbar_c0) untouched: next step re-uses it
+      }
+      // ---- colour lin0 backward, feature part -> fbar (bf16) -> stash -----------------------------------
+      epi_wait_acc(c);
+      epi_before_write(c);
+#pragma unroll 1
+      for (int cb = 0; cb < 4; ++cb) {
+        float v[64];
+        acc_load64(c, cb * 64, 256, v);
+        row_store64(act + cb * BLK_BYTES, c.row, true, v);
+      }
+      epi_store_blocks(c, act, stash_tile(ptrs, ST_FB, tile), 4);
+      // ---- adjoint of n = J_e^T g_e: gbar_e = J_e nbar -> AUX ; PE-Hessian term into xbar -------------------
+      {
+        float e[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) e[i] = 0.f;
+        e[0] = nbar[0]; e[1] = nbar[1]; e[2] = nbar[2];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const float f = (float)(1 << k);
+#pragma unroll
+          for (int ci = 0; ci < 3; ++ci) {
+            float sn, co;
+            sincosf(pc.x[ci] * f, &sn, &co);
+            e[3 + 6 * k + ci] = nbar[ci] * f * co;
+            e[6 + 6 * k + ci] = -nbar[ci] * f * sn;
+            if (pc.valid) {
+              const float gs = a.ge[pc.p * 40 + 3 + 6 * k + ci], gc = a.ge[pc.p * 40 + 6 + 6 * k + ci];
+              xbar[ci] -= (gs * sn + gc * co) * f * f * nbar[ci];
+            }
+          }
+        }
+        row_store64(aux, c.row, true, e);          // AUX's previous store (GE of the last tile) is covered
+        epi_store_blocks(c, aux, stash_tile(ptrs, ST_GE, tile), 1);   //   by the epi_before_write above
+        epi_signal_act(c);
+      }
+      // ---- adjoint pass l = 0..7:  dbar_l = W_l vbar_l ; vbar_{l+1} = dbar_l*sigma_l ; q_l -------------------
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const int n_mma = (l == 3) ? 224 : 256;
+        uint8_t* qdst = stash_tile(ptrs, ST_Q0 + l, tile);
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll 1
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64], h[64], dl[64];
+          acc_load64(c, cb * 64, n_mma, v);
+          const uint8_t* sb = epi_side_wait(c);        // H_{l+1} block cb -> sigma_l
+          row_load64(sb, c.row, false, h);
+          epi_side_release(c);
+          sb = epi_side_wait(c);                       // D_l block cb -> delta_l
+          row_load64(sb, c.row, false, dl);
+          epi_side_release(c);
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const float sg = sigma_from_h(h[j]);
+            const float db = v[j];
+            v[j] = db * sg;                                       // vbar_{l+1}
+            dl[j] = SP_BETA * db * dl[j] * (1.f - sg);            // q_l
+          }
+          row_store64(act + cb * BLK_BYTES, c.row, true, v);
+          row_store64(qdst + cb * BLK_BYTES, c.row, true, dl);    // straight to HBM (tile image rows)
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_V1 + l, tile), 4);
+        if (l < 7) epi_signal_act(c);
+      }
+      epi_publish_stash_all(c);            // Q0..Q7 (st.global) and every bulk store are visible
+      epi_before_write(c);
+      epi_reload_blocks(c, act, stash_tile(ptrs, ST_FB, tile), 4);
+      epi_signal_act(c);
+      // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------
+      float eb[40];
+#pragma unroll
+      for (int i = 0; i < 40; ++i) eb[i] = 0.f;
+#pragma unroll 1
+      for (int l = 8; l >= 1; --l) {
+        epi_wait_acc(c);
+        epi_before_write(c);
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          float v[64], h[64], q[64];
+          acc_load64(c, cb * 64, 256, v);
+          const uint8_t* sb = epi_side_wait(c);        // H_l block cb -> sigma_{l-1}
+          row_load64(sb, c.row, false, h);
+          epi_side_release(c);
+          sb = epi_side_wait(c);                       // Q_{l-1} block cb
+          row_load64(sb, c.row, true, q);
+          epi_side_release(c);
+          if (l == 8) {
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + cb * 64 + j), v[j]);
+          }
+          if (l == 4 && cb == 3) {
+#pragma unroll
+            for (int j = 25; j < 64; ++j) eb[j - 25] += v[j];      // PE part of the skip input
+          }
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
+          row_store64(act + cb * BLK_BYTES, c.row, true, v);
+        }
+        epi_store_blocks(c, act, stash_tile(ptrs, ST_Z0 + (l - 1), tile), 4);
+        epi_signal_act(c);
+      }
+      // ---- e-bar += W_0^T zbar_0 ; xbar += J_e^T e-bar -----------------------------------------------------------
+      {
+        float v[64];
+        epi_wait_acc(c);
+        acc_load64(c, 0, 48, v);
+#pragma unroll
+        for (int i = 0; i < 39; ++i) eb[i] += v[i];
+        float xe[3];
+        pe_jt<6>(pc.x, eb, xe);
+        if (pc.valid) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) a.d_pts[pc.p * 3 + i] = xbar[i] + xe[i];
+        }
+        tc_fence_before();
+      }
+    }
+    if (c.etid == 0) bulk_wait_all0();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+}  // namespace fmov
+using namespace fmov;
+
+// ---- tables ---------------------------------------------------------------------------------------------
+static void set_step(ChainStep& st, int img, int nkb_a, int nkb_aux, uint32_t a_fmt, uint32_t b_fmt) {
+  const ImgInfo ii = img_info(img);
+  st.w_off = (uint32_t)img_offset(img);
+  st.n = (uint16_t)ii.npad;
+  st.nkb_a = (uint8_t)nkb_a;
+  st.nkb_aux = (uint8_t)nkb_aux;
+  st.a_fmt = (uint8_t)a_fmt;
+  st.b_fmt = (uint8_t)b_fmt;
+}
+static void add_side(ChainTable& tb, ChainStep& st, int tensor, int kb) {
+  if (st.side_cnt == 0) st.side_first = (uint8_t)tb.n_side;
+  tb.side[tb.n_side].tensor = (uint8_t)tensor;
+  tb.side[tb.n_side].kb = (uint8_t)kb;
+  ++tb.n_side;
+  ++st.side_cnt;
+}
+static void init_table(ChainTable& tb) {
+  memset(&tb, 0, sizeof(tb));
+  for (int i = 0; i < ST_COUNT; ++i) tb.stash_kb[i] = (uint8_t)stash_kb(i);
+}
+
+static void build_fwd_table(ChainTable& tb) {
+  init_table(tb);
+  int n = 0;
+  for (int l = 0; l < 8; ++l) set_step(tb.step[n++], IMG_F0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_F16, FMT_F16);
+  set_step(tb.step[n++], IMG_F0 + 8, 4, 0, FMT_F16, FMT_F16);                 // lin8 feature rows
+  for (int l = 7; l >= 1; --l) {                                                // reverse sweep
+    ChainStep& st = tb.step[n++];
+    set_step(st, IMG_T0 + l, 4, 0, FMT_F16, FMT_F16);
+    if (l == 7) st.wait_stash = 1;
+    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_H1 + (l - 1), cb);      // H_l
+  }
+  set_step(tb.step[n++], IMG_T0 + 0, 4, 0, FMT_F16, FMT_F16);                  // W_0^T delta_0 (N = 48)
+  set_step(tb.step[n++], IMG_C0 + 0, 4, 1, FMT_F16, FMT_F16);                  // colour lin0: feat + extras
+  for (int l = 1; l < 4; ++l) set_step(tb.step[n++], IMG_C0 + l, 4, 0, FMT_F16, FMT_F16);
+  set_step(tb.step[n++], IMG_C0 + 4, 4, 0, FMT_F16, FMT_F16);                  // colour lin4 (N = 16)
+  tb.n_steps = n;
+}
+
+static void build_bwd_table(ChainTable& tb) {
+  init_table(tb);
+  int n = 0;
+  {  // colour lin4 backward: epilogue only, ReLU mask from C4
+    ChainStep& st = tb.step[n++];
+    st.no_mma = 1;
+    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_C1 + 3, cb);
+  }
+  for (int l = 3; l >= 1; --l) {
+    ChainStep& st = tb.step[n++];
+    set_step(st, l == 3 ? IMG_CT3 : l == 2 ? IMG_CT2 : IMG_CT1, 4, 0, FMT_BF16, FMT_BF16);
+    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_C1 + (l - 1), cb);      // C_l
+  }
+  set_step(tb.step[n++], IMG_CT0B, 4, 0, FMT_BF16, FMT_BF16);
+  set_step(tb.step[n++], IMG_CT0A, 4, 0, FMT_BF16, FMT_BF16);
+  for (int l = 0; l < 8; ++l) {                                                 // adjoint pass
+    ChainStep& st = tb.step[n++];
+    set_step(st, IMG_FB0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_BF16, FMT_BF16);
+    for (int cb = 0; cb < 4; ++cb) {
+      add_side(tb, st, ST_H1 + l, cb);     // H_{l+1}
+      add_side(tb, st, ST_D0 + l, cb);     // delta_l
+    }
+  }
+  for (int l = 8; l >= 1; --l) {                                                // ordinary backward
+    ChainStep& st = tb.step[n++];
+    set_step(st, IMG_TB0 + l, 4, 0, FMT_BF16, FMT_BF16);
+    if (l == 8) st.wait_stash = 1;
+    for (int cb = 0; cb < 4; ++cb) {
+      add_side(tb, st, ST_H1 + (l - 1), cb);   // H_l
+      add_side(tb, st, ST_Q0 + (l - 1), cb);   // q_{l-1}
+    }
+  }
+  set_step(tb.step[n++], IMG_TB0 + 0, 4, 0, FMT_BF16, FMT_BF16);
+  tb.n_steps = n;
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------------------
+extern "C" int fmov_fine_image_count(void) { return IMG_COUNT; }
+extern "C" int fmov_fine_image_info(int id, long long* offset, int* npad, int* kblocks) {
+  FMOV_REQUIRE(id >= 0 && id < IMG_COUNT && offset && npad && kblocks, "fmov_fine_image_info: bad id %d", id);
+  const ImgInfo ii = img_info(id);
+  *offset = img_offset(id);
+  *npad = ii.npad;
+  *kblocks = ii.kblocks;
+  return OK;
+}
+extern "C" long long fmov_fine_blob_bytes(void) { return img_offset(IMG_COUNT); }
+extern "C" int fmov_fine_stash_count(void) { return ST_COUNT; }
+extern "C" int fmov_fine_stash_blocks(int id) { return (id >= 0 && id < ST_COUNT) ? stash_kb(id) : -1; }
+
+static int fill_args(FineArgs& a, ChainPtrs& ptrs, long long B, int S, const float* rays_o, const float* rays_d,
+                     const float* z, float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
+                     const float* b8, const float* w8row, const float* bias_col, const float* bc4, const float* wc4) {
+  FMOV_REQUIRE(B > 0 && S > 0, "fine: bad sizes B=%lld S=%d", B, S);
+  FMOV_REQUIRE(rays_o && rays_d && z && wblob && stash && bias_sdf && b8 && w8row && bias_col && bc4, "fine: null argument");
+  memset(&a, 0, sizeof(a));
+  memset(&ptrs, 0, sizeof(ptrs));
+  a.B = B; a.S = S; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.sample_dist = sample_dist;
+  a.bias_sdf = bias_sdf; a.b8 = b8; a.w8row = w8row; a.bias_col = bias_col; a.bc4 = bc4; a.wc4 = wc4;
+  ptrs.weights = reinterpret_cast<const uint8_t*>(wblob);
+  for (int i = 0; i < ST_COUNT; ++i) ptrs.stash[i] = reinterpret_cast<uint8_t*>(stash[i]);
+  return OK;
+}
+static int grid_for(long long P, int max_ctas) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long n_tiles = (P + TILE_M - 1) / TILE_M;
+  int grid = (int)(n_tiles < sms ? n_tiles : sms);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  return grid;
+}
+
+/* stash: HOST array of ST_COUNT device pointers (tile-image tensors, fmov_fine_stash_blocks(id) blocks per tile) */
+extern "C" int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z,
+                             float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
+                             const float* b8, const float* w8row, const float* bias_col, const float* bc4, float* sdf,
+                             float* nrm, float* rgb, float* ge, void* stream) {
+  static ChainTable tb;
+  static bool init = false;
+  if (!init) {
+    build_fwd_table(tb);
+    FMOV_CUDA(cudaFuncSetAttribute(fine_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::DYN_BYTES));
+    init = true;
+  }
+  FineArgs a;
+  ChainPtrs ptrs;
+  int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, nullptr);
+  if (st) return st;
+  FMOV_REQUIRE(sdf && nrm && rgb && ge, "fmov_fine_fwd: null output");
+  for (int i = 0; i <= ST_C1 + 3; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_fwd: stash tensor %d is null", i);
+  a.sdf = sdf; a.nrm = nrm; a.rgb = rgb; a.ge = ge;
+  fine_fwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
+  FMOV_LAUNCH_CHECK("fine_fwd_kernel");
+  return OK;
+}
+
+extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z,
+                             float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
+                             const float* b8, const float* w8row, const float* bias_col, const float* bc4,
+                             const float* wc4, const float* rgb, const float* ge, const float* d_sdf, const float* d_nrm,
+                             const float* d_rgb, float* d_pts, float* d_dirs, float* zc4, void* stream) {
+  static ChainTable tb;
+  static bool init = false;
+  if (!init) {
+    build_bwd_table(tb);
+    FMOV_CUDA(cudaFuncSetAttribute(fine_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FL::DYN_BYTES));
+    init = true;
+  }
+  FineArgs a;
+  ChainPtrs ptrs;
+  int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, wc4);
+  if (st) return st;
+  FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && d_pts && d_dirs && zc4, "fmov_fine_bwd: null argument");
+  for (int i = 0; i < ST_COUNT; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);
+  a.rgb = const_cast<float*>(rgb); a.ge = const_cast<float*>(ge);
+  a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4;
+  fine_bwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
+  FMOV_LAUNCH_CHECK("fine_bwd_kernel");
+  return OK;
+}

@@ -1,0 +1,183 @@
+"""NeuSRenderer — drop-in for models/renderer.py:89-532 on the B200-native kernels.
+
+Same constructor, attributes, `render()` signature and output dict (keys and shapes of
+models/renderer.py:486-498), differentiable where the reference's outputs are: `color_fine`,
+`weight_sum`, `depth_fine`, `weights`, `gradients`, `gradient_error`, `s_val` carry gradients to the SDF /
+colour / variance parameters and to `rays_o`, `rays_d` (→ pose parameters); with `n_importance == 0`
+also through `near` / `far` (models/renderer.py:390).  Not supported (explicit errors, no fallback):
+`n_outside > 0`, network shapes other than the shipped confs'.
+
+The jitter draw `torch.rand([B,1])` (renderer.py:404) stays in host PyTorch so RNG parity with the
+reference is preserved; pass `t_rand=` to inject a given draw."""
+import numpy as np
+import torch
+
+from .. import fine as _fine
+from .. import ops as _ops
+from .. import packing as _packing
+
+
+def extract_fields(bound_min, bound_max, resolution, query_func):
+    """Generic chunked grid evaluation with the reference's traversal (models/renderer.py:9-37).
+    `NeuSRenderer.extract_fields` is the fused single-launch path; this one serves arbitrary callables."""
+    N = 64
+    dev = bound_min.device if torch.is_tensor(bound_min) else None
+    X = torch.linspace(float(bound_min[0]), float(bound_max[0]), resolution, device=dev).split(N)
+    Y = torch.linspace(float(bound_min[1]), float(bound_max[1]), resolution, device=dev).split(N)
+    Z = torch.linspace(float(bound_min[2]), float(bound_max[2]), resolution, device=dev).split(N)
+    u = np.zeros([resolution, resolution, resolution], dtype=np.float32)
+    with torch.no_grad():
+        for xi, xs in enumerate(X):
+            for yi, ys in enumerate(Y):
+                for zi, zs in enumerate(Z):
+                    xx, yy, zz = torch.meshgrid(xs, ys, zs, indexing="ij")
+                    pts = torch.cat([xx.reshape(-1, 1), yy.reshape(-1, 1), zz.reshape(-1, 1)], dim=-1)
+                    val = query_func(pts).reshape(len(xs), len(ys), len(zs)).detach().cpu().numpy()
+                    u[xi * N: xi * N + len(xs), yi * N: yi * N + len(ys), zi * N: zi * N + len(zs)] = val
+    return u
+
+
+def extract_geometry(bound_min, bound_max, resolution, threshold, query_func=None, u=None):
+    """models/renderer.py:40-51. Marching cubes itself is third-party CPU code (PyMCubes) and out of
+    scope; it is imported lazily so that everything up to the `u` grid works without it."""
+    if u is None:
+        u = extract_fields(bound_min, bound_max, resolution, query_func)
+    try:
+        import mcubes
+    except ImportError as e:  # pragma: no cover
+        raise RuntimeError("PyMCubes is required for marching cubes (the SDF grid itself is available via "
+                           "NeuSRenderer.extract_fields)") from e
+    vertices, triangles = mcubes.marching_cubes(u, threshold)
+    b_max_np = bound_max.detach().cpu().numpy()
+    b_min_np = bound_min.detach().cpu().numpy()
+    vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
+    return vertices, triangles
+
+
+class NeuSRenderer:
+    def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
+                 up_sample_steps, perturb):
+        self.nerf = nerf
+        self.sdf_network = sdf_network
+        self.deviation_network = deviation_network
+        self.color_network = color_network
+        self.n_samples = n_samples
+        self.n_importance = n_importance
+        self.n_outside = n_outside
+        self.up_sample_steps = up_sample_steps
+        self.perturb = perturb
+        self.process_group = None      # set for ray-sharded data parallel runs (global eikonal normaliser)
+
+    # ------------------------------------------------------------------------------------------------
+    def _check(self):
+        if self.n_outside > 0:
+            raise NotImplementedError("n_outside > 0 (NeRF++ background, render_core_outside) is out of scope: "
+                                      "every shipped conf has n_outside = 0")
+        if getattr(self.color_network, "mode", "idr") != "idr":
+            raise NotImplementedError("RenderingNetwork mode must be 'idr' (every shipped conf)")
+        if float(getattr(self.sdf_network, "scale", 1.0)) != 1.0:
+            raise NotImplementedError("SDFNetwork.scale must be 1.0 (every shipped conf)")
+
+    def sample_z(self, rays_o, rays_d, near, far, t_rand):
+        """z_vals [B, n_samples + n_importance] (models/renderer.py:385-446)."""
+        if self.n_importance > 0:
+            with torch.no_grad():
+                W, b = self.sdf_network.effective_weights()
+                qw = _packing.SdfQueryWeights(W, b)
+                return _ops.hierarchical_sample(qw, rays_o.detach().float().contiguous(),
+                                                rays_d.detach().float().contiguous(), near.detach(), far.detach(),
+                                                t_rand, self.n_samples, self.n_importance, self.up_sample_steps)
+        # n_importance == 0: z keeps its autograd link to near/far (renderer.py:389-390, 403-405)
+        lin = torch.linspace(0.0, 1.0, self.n_samples, device=near.device)
+        z = near + (far - near) * lin[None, :]
+        if t_rand is not None:
+            z = z + (t_rand - 0.5) * 2.0 / self.n_samples
+        return z
+
+    def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
+               eval=False, t_rand=None):
+        self._check()
+        if not rays_o.is_cuda:
+            raise RuntimeError("fmov_pose_b200 renders on CUDA tensors only (no CPU fallback)")
+        batch_size = len(rays_o)
+        sample_dist = 2.0 / self.n_samples
+        perturb = self.perturb
+        if perturb_overwrite >= 0:
+            perturb = perturb_overwrite
+        if perturb > 0:
+            if t_rand is None:
+                t_rand = torch.rand([batch_size, 1], device=rays_o.device)
+        else:
+            t_rand = None
+        z_vals = self.sample_z(rays_o, rays_d, near, far, t_rand)
+        n_samples = z_vals.shape[1]
+
+        W_s, b_s = self.sdf_network.effective_weights()
+        W_c, b_c = self.color_network.effective_weights()
+        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)   # fields.py:294, renderer.py:290
+        need_bwd = torch.is_grad_enabled() and not eval
+        cfg = dict(sample_dist=sample_dist, cos_anneal_ratio=cos_anneal_ratio, background_rgb=background_rgb,
+                   need_backward=need_bwd, group=self.process_group)
+        if not need_bwd:
+            with torch.no_grad():
+                outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)
+        else:
+            outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)
+        (color, weight_sum, weight_max, depth, weights, cdf, inside, mid_z, pts, sdf, gradients, grad_err) = outs
+        s_val = (1.0 / inv_s).reshape(1, 1).expand(batch_size, 1)     # mean over samples of a constant
+        return {
+            "color_fine": color,
+            "depth_fine": depth,
+            "s_val": s_val,
+            "cdf_fine": cdf,
+            "weight_sum": weight_sum,
+            "weight_max": weight_max,
+            "gradients": gradients,
+            "weights": weights,
+            "gradient_error": grad_err,
+            "inside_sphere": inside,
+            "pts": pts,
+            # extras (not in the reference dict)
+            "z_vals": z_vals, "mid_z_vals": mid_z, "sdf": sdf,
+        }
+
+    # ------------------------------------------------------------------------------------------------
+    def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None):
+        """u = -sdf on the res^3 grid (models/renderer.py:9-37 with query_func of :506) in one launch.
+        `first`/`count` select a contiguous x-major range (grid partitioning across ranks)."""
+        with torch.no_grad():
+            W, b = self.sdf_network.effective_weights()
+            qw = _packing.SdfQueryWeights(W, b)
+            total = resolution ** 3
+            if count is None:
+                count = total - first
+            if out is None:
+                out = torch.empty(count, dtype=torch.float32, device=W[0].device)
+            sc = float(self.sdf_network.scale)
+            _ops.sdf_query_grid(qw, [float(v) for v in bound_min], [float(v) for v in bound_max], resolution, first,
+                                count, out, in_scale=sc, out_scale=-1.0 / sc)
+        return out
+
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        u = self.extract_fields(bound_min, bound_max, resolution).reshape(resolution, resolution, resolution)
+        return extract_geometry(bound_min, bound_max, resolution, threshold, u=u.cpu().numpy())
+
+    def extract_color(self, vertices):
+        """models/renderer.py:509-532: colour at mesh vertices with view dir = -normal."""
+        pts = torch.as_tensor(vertices, dtype=torch.float32, device=self.deviation_network.variance.device)
+        out = []
+        with torch.no_grad():
+            W, b = self.sdf_network.effective_weights()
+            Wc, bc = self.color_network.effective_weights()
+            fw = _fine.FineWeights(W, b, Wc, bc, need_backward=False)
+            for chunk in pts.split(1 << 16):
+                N = chunk.shape[0]
+                st = _fine.Stash(N, chunk.device, with_backward=False)
+                z0 = torch.zeros(N, 1, device=chunk.device)
+                # pass 1: normals at the vertices (points as degenerate rays o = x, d = 0)
+                _, nrm, _, _ = _fine.fine_forward(fw, st, chunk.contiguous(), torch.zeros_like(chunk), z0, 0.0)
+                # pass 2: view direction = -normal; keep the point fixed by sampling at mid_z = 0
+                #         (z = 0 and sample_dist = 0  =>  pts = o + d*0)
+                _, _, rgb, _ = _fine.fine_forward(fw, st, chunk.contiguous(), (-nrm).contiguous(), z0, 0.0)
+                out.append(rgb.cpu().numpy())
+        return np.concatenate(out, axis=0)

@@ -107,6 +107,32 @@ int fmov_ray_reduce_bwd(const float* d_pts, const float* d_dirs, const float* d_
                         const float* d_mid, const float* rays_d, const float* z, long long B, int S, float sample_dist,
                         float* d_o, float* d_d, float* d_z, void* stream);
 
+/* ---- fine stage: SDF value + feature + analytic normal + colour MLP, forward and backward -------- */
+/* forward: replaces sdf_network(pts), sdf_network.gradient(pts), color_network(...) of render_core
+ * (models/renderer.py:277-288; models/fields.py:88-124, 166-193).  backward + fmov_dw: the matching part of
+ * loss.backward() (exp_runner.py:802).  Points are o + d*mid_z of the [B,S] samples (renderer.py:261-272).
+ * wblob: weight images (fmov_fine_image_info gives id -> offset/npad/kblocks; packed with fmov_pack_image);
+ * stash: HOST array of fmov_fine_stash_count() device pointers, tensor i holding
+ *        ceil(B*S/128) * fmov_fine_stash_blocks(i) * 16384 bytes (activation / gradient tile images).       */
+int fmov_fine_image_count(void);
+int fmov_fine_image_info(int id, long long* offset, int* npad, int* kblocks);
+long long fmov_fine_blob_bytes(void);
+int fmov_fine_stash_count(void);
+int fmov_fine_stash_blocks(int id);
+int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
+                  const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
+                  const float* bias_col, const float* bc4, float* sdf, float* nrm, float* rgb, float* ge, void* stream);
+int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
+                  const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
+                  const float* bias_col, const float* bc4, const float* wc4, const float* rgb, const float* ge,
+                  const float* d_sdf, const float* d_nrm, const float* d_rgb, float* d_pts, float* d_dirs, float* zc4,
+                  void* stream);
+/* weight / bias gradients into one flat fp32 buffer (zeroed by the call); fmov_grad_offset(kind, layer):
+ * kind 0 sdf weight [out,in], 1 sdf bias, 2 colour weight, 3 colour bias (effective weights, reference shapes) */
+long long fmov_grad_offset(int kind, int layer);
+long long fmov_grad_floats(void);
+int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, float* grads, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

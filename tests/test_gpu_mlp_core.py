@@ -14,8 +14,10 @@ def _dev():
 
 
 @pytest.mark.parametrize("n,kb,abf,bbf", [(256, 4, 0, 0), (224, 4, 0, 0), (128, 5, 0, 0), (256, 1, 0, 0), (48, 4, 0, 0),
-                                          (16, 4, 0, 0), (256, 4, 1, 1), (256, 4, 1, 0)])
+                                          (16, 4, 0, 0), (256, 4, 1, 1)])
 def test_selftest_gemm_kmajor(n, kb, abf, bbf):
+    # (mixing an fp16 with a bf16 operand in one tcgen05.mma raises "illegal instruction" on sm_100a — measured;
+    #  all kernels use same-format operand pairs)
     from fmov_pose_b200 import _lib as L, packing
     torch.manual_seed(0)
     A = torch.randn(128, 64 * kb, device=_dev())
@@ -33,7 +35,7 @@ def test_selftest_gemm_kmajor(n, kb, abf, bbf):
     assert err < 2e-3, err
 
 
-@pytest.mark.parametrize("n,abf,bbf", [(256, 0, 0), (64, 0, 0), (16, 0, 0), (256, 1, 0), (256, 1, 1)])
+@pytest.mark.parametrize("n,abf,bbf", [(256, 0, 0), (64, 0, 0), (16, 0, 0), (256, 1, 1)])
 def test_selftest_gemm_mnmajor(n, abf, bbf):
     """dW form: D[128 feats x n feats] = A^T B over K = 128 points (MN-major descriptors)."""
     from fmov_pose_b200 import _lib as L, packing

@@ -1,0 +1,137 @@
+"""End-to-end GPU parity of NeuSRenderer.render fwd+bwd (the train-step hot path) against
+(a) golden fixtures produced by the imported reference and (b) the CPU oracle on identical z samples.
+Tolerances are BASELINE.json north_star's: colour <= 2e-3, SDF <= 1e-3, gradients rel <= 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neus_oracle as O
+from tests._util import load_golden, params_from, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build_from_fixture(d):
+    from fmov_pose_b200.models.barf_fields import BarfRenderingNetwork, BarfSDFNetwork
+    from fmov_pose_b200.models.fields import SingleVarianceNetwork
+    from fmov_pose_b200.models.renderer import NeuSRenderer
+    B, n, m, steps, dh = [int(v) for v in d["cfg"]]
+    sdf_kw = dict(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=[4], multires=6, bias=0.5, scale=1.0,
+                  geometric_init=True, weight_norm=True)
+    col_kw = dict(d_feature=256, mode="idr", d_in=9, d_out=3, d_hidden=256, n_layers=4, weight_norm=True,
+                  multires_view=4, squeeze_out=True)
+    sdf_net = BarfSDFNetwork(t(d, "init_c2w"), n_images=6, **sdf_kw)
+    col_net = BarfRenderingNetwork(**col_kw)
+    var_net = SingleVarianceNetwork(0.3)
+    sd = {k[4:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("sdf.")}
+    sdf_net.load_state_dict(sd, strict=True)
+    cd = {k[4:]: torch.from_numpy(np.asarray(v)) for k, v in d.items() if k.startswith("col.")}
+    col_net.load_state_dict(cd, strict=True)
+    var_net.variance.data.copy_(t(d, "variance"))
+    sdf_net, col_net, var_net = sdf_net.to(DEV), col_net.to(DEV), var_net.to(DEV)
+    rend = NeuSRenderer(None, sdf_net, var_net, col_net, n, m, 0, steps, 1.0)
+    return rend, sdf_net, col_net, var_net
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+@pytest.mark.parametrize("name", ["full_6464_gf", "full_3200_seg"])
+def test_render_train_step_vs_reference_and_oracle(name):
+    d = load_golden(name)
+    B, n, m, steps, dh = [int(v) for v in d["cfg"]]
+    rend, sdf_net, col_net, var_net = build_from_fixture(d)
+    mw = float(d["mask_weight"])
+    rays_o = t(d, "rays_o").to(DEV).requires_grad_(True)
+    rays_d = t(d, "rays_d").to(DEV).requires_grad_(True)
+    near, far = O.near_far_from_sphere(rays_o, rays_d)
+    out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=float(d["cos_anneal"]), t_rand=t(d, "t_rand").to(DEV))
+    losses = O.loss_block(out, t(d, "true_rgb").to(DEV), t(d, "mask").to(DEV), 0.1, mw)
+    losses["loss"].backward()
+    torch.cuda.synchronize()
+
+    # ---- (b) oracle on the same z samples: strict parity of everything downstream of sampling ----------
+    z = out["z_vals"].detach().cpu()
+    sdf_p = params_from(d, "sdf.", requires_grad=True)
+    col_p = params_from(d, "col.", requires_grad=True)
+    var = t(d, "variance").requires_grad_(True)
+    ro, rd = t(d, "rays_o").requires_grad_(True), t(d, "rays_d").requires_grad_(True)
+    nr, fr = O.near_far_from_sphere(ro, rd)
+    if m == 0:
+        z_or = O.coarse_z(nr, fr, n, t(d, "t_rand"))       # carries grad to near/far
+        np.testing.assert_allclose(z.numpy(), z_or.detach().numpy(), atol=2e-6)
+    else:
+        z_or = z
+    ref = O.render(sdf_p, col_p, var, ro, rd, nr, fr, n_samples=n, n_importance=m, up_sample_steps=steps,
+                   cos_anneal_ratio=float(d["cos_anneal"]), z_vals=z_or)
+    rl = O.loss_block(ref, t(d, "true_rgb"), t(d, "mask"), 0.1, mw)
+    rl["loss"].backward()
+    c = lambda x: x.detach().cpu().numpy()
+    assert np.abs(c(out["sdf"]) - c(ref["sdf"])).max() <= 1e-3, "sdf"
+    assert np.abs(c(out["color_fine"]) - c(ref["color_fine"])).max() <= 2e-3, "colour"
+    assert np.abs(c(out["gradients"]) - c(ref["gradients"])).max() <= 5e-3, "normals"
+    assert np.abs(c(out["weights"]) - c(ref["weights"])).max() <= 5e-3, "weights"
+    assert np.abs(c(out["weight_sum"]) - c(ref["weight_sum"])).max() <= 5e-3
+    assert np.abs(c(out["depth_fine"]) - c(ref["depth_fine"])).max() <= 1e-2
+    assert abs(out["gradient_error"].item() - ref["gradient_error"].item()) <= 1e-3
+    np.testing.assert_array_equal(c(out["inside_sphere"]), c(ref["inside_sphere"]))
+    np.testing.assert_allclose(c(out["pts"]), c(ref["pts"]), atol=1e-5)
+    for k in ("loss", "color_loss", "eikonal_loss", "mask_loss"):
+        assert abs(losses[k].item() - rl[k].item()) <= 2e-3 * max(1.0, abs(rl[k].item())), k
+    # gradients: relative L2 error <= 1e-2 per tensor
+    worst = 0.0
+    for prefix, net, pd in (("sdf", sdf_net, sdf_p), ("col", col_net, col_p)):
+        for k, p in net.named_parameters():
+            if not k.startswith("lin"):
+                continue
+            e = rel(c(p.grad), c(pd[k].grad))
+            worst = max(worst, e)
+            assert e <= 1e-2, (prefix, k, e)
+    assert rel(c(var_net.variance.grad), c(var.grad)) <= 1e-2, "variance grad"
+    assert rel(c(rays_d.grad), c(rd.grad)) <= 1e-2, ("rays_d grad", rel(c(rays_d.grad), c(rd.grad)))
+    assert rel(c(rays_o.grad), c(ro.grad)) <= 1e-2, ("rays_o grad", rel(c(rays_o.grad), c(ro.grad)))
+
+    # ---- (a) reference golden (own sampling): colour / losses / gradient norms ---------------------------
+    col_err = np.abs(c(out["color_fine"]) - d["out.color_fine"])
+    assert np.median(col_err) <= 2e-3 and (col_err > 2e-3).mean() <= 0.05, (np.median(col_err), col_err.max())
+    assert abs(losses["loss"].item() - d["loss"][0]) <= 1e-2 * abs(d["loss"][0])
+    g_rd = rel(c(rays_d.grad), d["grad.rays_d"])
+    assert g_rd <= 5e-2, g_rd
+    for k, v in d.items():
+        if k.startswith("gnorm.") and ".lin" in k:
+            net = sdf_net if k.startswith("gnorm.sdf.") else col_net
+            p = dict(net.named_parameters())[k.split(".", 2)[2]]
+            got = float(np.linalg.norm(c(p.grad).astype(np.float64)))
+            assert abs(got - float(v)) <= 5e-2 * float(v) + 1e-9, (k, got, float(v))
+
+
+def test_direct_field_calls_and_grid():
+    """sdf(), gradient(), forward() on raw points and the fused grid query."""
+    d = load_golden("full_6464_gf")
+    rend, sdf_net, col_net, var_net = build_from_fixture(d)
+    p = params_from(d, "sdf.")
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(3000, 3, generator=g)
+    pts = v / v.norm(dim=1, keepdim=True) * torch.rand(3000, 1, generator=g) ** (1 / 3)
+    ref = O.sdf_forward(p, pts)
+    ref_n = O.sdf_gradient(p, pts, create_graph=False)
+    x = pts.to(DEV)
+    assert (sdf_net.sdf(x).cpu() - ref[:, :1]).abs().max().item() <= 1e-3
+    full = sdf_net(x).cpu()
+    assert (full[:, :1] - ref[:, :1]).abs().max().item() <= 1e-3
+    assert (full[:, 1:] - ref[:, 1:]).abs().max().item() <= 5e-3
+    n = sdf_net.gradient(x)
+    assert tuple(n.shape) == (3000, 1, 3)
+    assert (n[:, 0].cpu() - ref_n).abs().max().item() <= 5e-3
+    res = 24
+    u = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res).reshape(res, res, res).cpu()
+    u_ref = O.extract_fields(p, [-1.01] * 3, [1.01] * 3, res)
+    assert (u - u_ref).abs().max().item() <= 2e-3
+    # partitioned query (2 "ranks") equals the full one
+    half = res ** 3 // 2
+    a = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, first=0, count=half)
+    b = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, first=half, count=res ** 3 - half)
+    assert torch.equal(torch.cat([a, b]).cpu(), u.reshape(-1))
