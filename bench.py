@@ -1,0 +1,271 @@
+"""bench.py — NeuS train-step throughput (train rays/s, fwd+bwd+Adam) of the B200-native path.
+
+Contract: `python bench.py --gpus N --steps K --warmup W` (under torchrun for N>1) prints ONE JSON line.
+  value        whole-job rays/s with step inputs already resident in HBM
+  e2e          same metric through the public API with per-step pinned-host -> device copies of the step
+               inputs (pixel indices, jitter) and a device -> host read of the loss inside the timed region
+  roofline     dominant kernel of the step (CUDA-event timed live, algorithmic FLOPs / duration)
+  cpu_baseline the reference algorithm (oracle port, PyTorch CPU) timed on this box's host cores (rank 0, N=1)
+`--impl reference` times that CPU path alone with all host threads on a bounded sample of the workload.
+Workload: configs[1] — ho3d_virtual.conf-shaped joint shape+pose train step (SegLearnPose per-frame pose,
+BarfSDFNetwork 8x256, colour 4x256, eikonal+colour+mask loss, mask_weight 5) with the 64+64 sampling the
+north_star throughput target is quoted on, on synthetic 640x480 frames.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs
+F_S = 1_049_088
+F_C = 542_720
+
+
+def flops_per_ray(n, m):
+    s = n + m
+    samp = (n + (m - m // 4 if m > 0 else 0)) * F_S if m > 0 else 0   # coarse + 3 of 4 rounds queried
+    return samp + s * (6 * F_S + 3 * F_C)
+
+
+KERNEL_FLOPS_PER_POINT = {       # algorithmic FLOPs per fine-stage sample point of each MLP kernel
+    "fine_fwd": 2 * F_S + F_C,   # value pass + reverse sweep (normal) + colour forward
+    "fine_bwd": 2 * F_S + F_C,   # adjoint pass + ordinary backward (dX) + colour backward (dX)
+    "dw": 2 * F_S + F_C,         # two outer-product accumulations per SDF layer + colour
+}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(o[0]))
+                self.max_mhz = float(o[1])
+                for nm, v in zip(names, o[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_step_fn(B, n, m, steps_up, threads):
+    """The reference algorithm on CPU (oracle port, PyTorch): render + loss + backward + Adam, C1 shapes."""
+    import torch
+    from oracle import neus_oracle as O
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.models.barf_fields import BarfRenderingNetwork, BarfSDFNetwork
+    from fmov_pose_b200.models.fields import SingleVarianceNetwork
+    torch.set_num_threads(threads)
+    torch.manual_seed(2024)
+    init = synthetic.make_init_poses(20)
+    sdf = BarfSDFNetwork(init, n_images=20, **synthetic.SDF_KW)
+    col = BarfRenderingNetwork(**synthetic.COL_KW)
+    var = SingleVarianceNetwork(0.3)
+    params = [p for net in (sdf, col, var) for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    g = torch.Generator().manual_seed(1)
+    intr_inv = torch.linalg.inv(torch.tensor(synthetic.INTRINSICS))
+
+    def step():
+        sdf_p = {k: v for k, v in sdf.named_parameters()}
+        col_p = {k: v for k, v in col.named_parameters()}
+        px = torch.randint(170, 470, [B], generator=g)
+        py = torch.randint(90, 390, [B], generator=g)
+        pose = init[3, :3].clone().requires_grad_(True)
+        mask = (((px - 320) ** 2 + (py - 240) ** 2) < 150 ** 2).float()[:, None]
+        losses, _ = O.train_step(sdf_p, col_p, var.variance, pose, intr_inv, px, py, torch.rand(B, 3, generator=g), mask,
+                                 t_rand=torch.rand(B, 1, generator=g), n_samples=n, n_importance=m,
+                                 up_sample_steps=steps_up, cos_anneal_ratio=1.0, igr_weight=0.1, mask_weight=5.0)
+        opt.zero_grad()
+        losses["loss"].backward()
+        opt.step()
+        return float(losses["loss"])
+    return step
+
+
+def time_cpu(B, n, m, steps_up, warm, iters):
+    threads = os.cpu_count() or 1
+    fn = cpu_reference_step_fn(B, n, m, steps_up, threads)
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return B / med, med, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=8192, help="rays per GPU per step (weak scaling)")
+    ap.add_argument("--n_samples", type=int, default=64)
+    ap.add_argument("--n_importance", type=int, default=64)
+    ap.add_argument("--cpu_rays", type=int, default=512, help="rays per CPU-baseline step (config C1)")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n, m, up = args.n_samples, args.n_importance, 4
+    workload = (f"C2 ho3d_virtual-shaped joint shape+pose train step (SegLearnPose, 8x256 SDF + 4x256 colour, "
+                f"eikonal+colour+mask loss, Adam), {n}+{m} samples, synthetic 640x480 frames")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        warm, iters = max(1, min(args.warmup, 2)), max(1, min(args.steps, 5))
+        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, warm, iters)
+        line = {"impl": "reference", "metric": "train rays/s (fwd+bwd+Adam)", "value": rps, "unit": "rays/s",
+                "n_gpus": args.gpus, "steps": iters, "warmup": warm, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "rays_per_step": args.cpu_rays, "n_samples": n, "n_importance": m},
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                 "sample": f"{iters} steps of {args.cpu_rays} rays ({n}+{m}); oracle port of the "
+                                           "reference PyTorch path (the reference itself is not pip-installable and "
+                                           "/root/reference does not exist on the GPU box)"},
+                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    from fmov_pose_b200 import _lib as L
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    scene = synthetic.build_scene(device=dev, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
+    ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, group=group)
+    B = args.rays
+    total_steps = args.warmup + args.steps
+    g = torch.Generator().manual_seed(1234 + rank)
+    # step inputs: pixel draw inside the mask bbox (mask_guided_sampling), jitter, frame id
+    px_h = torch.randint(140, 500, [2 * total_steps, B], generator=g).pin_memory()
+    py_h = torch.randint(60, 420, [2 * total_steps, B], generator=g).pin_memory()
+    tr_h = torch.rand(2 * total_steps, B, 1, generator=g).pin_memory()
+    img_ids = [(7 * i + rank) % scene["n_images"] for i in range(2 * total_steps)]
+    px_d, py_d, tr_d = px_h.to(dev), py_h.to(dev), tr_h.to(dev)
+    h2d = B * (8 + 8 + 4)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if group is not None:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run(i, e2e):
+        if e2e:
+            px, py, tr = px_h[i].to(dev, non_blocking=True), py_h[i].to(dev, non_blocking=True), tr_h[i].to(dev, non_blocking=True)
+        else:
+            px, py, tr = px_d[i], py_d[i], tr_d[i]
+        ls, _ = ts.step(img_ids[i], B, pixels=(px, py), t_rand=tr)
+        if e2e:
+            loss_host.copy_(ls["loss"].detach().reshape(1), non_blocking=False)
+        return ls
+
+    def timed(e2e, first):
+        for i in range(args.warmup):
+            run(first + i, e2e)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            run(first + args.warmup + i, e2e)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if group is not None:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.profile_reset(True)
+    ms_dev = timed(False, 0)
+    prof = L.profile_summary()
+    L.profile_reset(False)
+    ms_e2e = timed(True, total_steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    value = world * B * args.steps / (ms_dev * 1e-3)
+    e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+    # roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    roof = None
+    launches = sum(v["count"] for v in prof.values()) // max(1, args.steps + args.warmup) * args.steps if prof else 0
+    mlp = {k: v for k, v in prof.items() if k in KERNEL_FLOPS_PER_POINT}
+    if mlp:
+        top = max(mlp, key=lambda k: mlp[k]["ms"])
+        avg_ms = mlp[top]["ms"] / mlp[top]["count"]
+        fl = KERNEL_FLOPS_PER_POINT[top] * B * (n + m)
+        ach = fl / (avg_ms * 1e-3) / 1e12
+        step_ms = ms_dev / args.steps
+        roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": None, "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "share_of_step": (mlp[top]["ms"] / (args.steps + args.warmup)) / step_ms,
+                "kernel_ms_per_step": {k: v["ms"] / (args.steps + args.warmup) for k, v in prof.items()}}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 1, 3)
+        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+               "sample": f"3 steps of {args.cpu_rays} rays ({n}+{m}), oracle port of the reference PyTorch CPU path"}
+    if rank == 0:
+        line = {"metric": "train rays/s (fwd+bwd+Adam)", "value": value, "unit": "rays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16/bf16 operands, f32 accumulate",
+                "data": "synthetic",
+                "config": {"workload": workload, "rays_per_gpu": B, "global_rays": world * B, "n_samples": n,
+                           "n_importance": m, "up_sample_steps": up, "parallelism": f"ray-sharded dp{world}",
+                           "l2": "per-step working set (activation/gradient stash ~26 KB/sample) >> 126 MB L2",
+                           "algorithmic_flops_per_ray": flops_per_ray(n, m)},
+                "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "tensor_frac_whole_step": flops_per_ray(n, m) * value / world / 1e12 / peak_tf}
+        print(json.dumps(line))
+    if group is not None:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,3 +52,39 @@ def f32c(t):
     if t.dtype != torch.float32:
         t = t.float()
     return t.contiguous()
+
+
+# ---- optional per-kernel CUDA-event profiling (bench.py roofline) -------------------------------------
+_profile = None
+
+
+def profile_reset(enable):
+    global _profile
+    _profile = {} if enable else None
+
+
+class timed:
+    """with timed("fine_fwd"): <launch>  — records CUDA events on the current stream when profiling is on"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _profile is not None:
+            self.e1.record()
+            _profile.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
+def profile_summary():
+    if _profile is None:
+        return {}
+    torch.cuda.synchronize()
+    return {k: {"ms": sum(a.elapsed_time(b) for a, b in v), "count": len(v)} for k, v in _profile.items()}

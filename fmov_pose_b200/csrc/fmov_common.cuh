@@ -228,13 +228,35 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // models/fields.py:86)
 // ----------------------------------------------------------------------------------------
 constexpr float SP_BETA = 100.0f;
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// softplus_100(z) = max(z,0) + log1p(exp(-100|z|))/100.  One MUFU (ex2) + a degree-5 polynomial for
+// log1p(w) = w*P(w) on w in (0,1] (max abs error 6e-6 -> 6e-8 on the activation; the reference's
+// threshold branch, beta*z > 20 -> z, differs from this by < 2.1e-11).  Branch-free so that the 64
+// evaluations of an epilogue block interleave.
 __device__ __forceinline__ float softplus100(float z) {
-  float t = z * SP_BETA;
-  return t > 20.0f ? z : log1pf(__expf(t)) * (1.0f / SP_BETA);
+  const float w = ex2_approx(fabsf(z) * (-SP_BETA * 1.4426950408889634f));
+  float p = fmaf(w, -0.02397957257926464f, 0.10150004923343658f);
+  p = fmaf(p, w, -0.2102936953306198f);
+  p = fmaf(p, w, 0.3252951502799988f);
+  p = fmaf(p, w, -0.49937260150909424f);
+  p = fmaf(p, w, 0.9999918341636658f);
+  return fmaf(p * w, 1.0f / SP_BETA, fmaxf(z, 0.f));
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 // sigma = softplus'(z) recovered from h = softplus(z):  sigma = 1 - exp(-beta*h)
-__device__ __forceinline__ float sigma_from_h(float h) { return 1.0f - __expf(-SP_BETA * h); }
+__device__ __forceinline__ float sigma_from_h(float h) { return 1.0f - ex2_approx(h * (-SP_BETA * 1.4426950408889634f)); }
+// sin/cos with a two-constant Cody-Waite reduction to [-pi, pi] followed by the SFU approximations
+// (|x| <= 2^5 * few here; abs error ~1e-6, far below the fp16 rounding of the encoded tile)
+__device__ __forceinline__ void fast_sincos(float x, float* s, float* c) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(-k, -1.7484555e-7f, r);
+  __sincosf(r, s, c);
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);

@@ -120,7 +120,7 @@ __device__ __forceinline__ void pe_eval(const float x[3], float* e) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s, co;
-      sincosf(x[c] * f, &s, &co);
+      fast_sincos(x[c] * f, &s, &co);
       e[3 + 6 * k + c] = s;
       e[6 + 6 * k + c] = co;
     }
@@ -136,7 +136,7 @@ __device__ __forceinline__ void pe_jt(const float x[3], const float* g, float n[
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s, co;
-      sincosf(x[c] * f, &s, &co);
+      fast_sincos(x[c] * f, &s, &co);
       n[c] += g[3 + 6 * k + c] * f * co - g[6 + 6 * k + c] * f * s;
     }
   }
@@ -204,13 +204,22 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           float v[64];
           acc_load64(c, cb * 64, n_mma, v);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const int col = cb * 64 + j;
-            v[j] = (col < n_valid) ? softplus100(v[j] + __ldg(bias + col)) : 0.f;
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 64) + j4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              v[j] = (cb * 64 + j < n_valid) ? softplus100(v[j] + bb[e]) : 0.f;
+            }
           }
           if (l == 7) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sdf = fmaf(v[j], __ldg(a.w8row + cb * 64 + j), sdf);
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + cb * 64) + j4);
+              sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
+              sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
+            }
           }
           row_store64(act + cb * BLK_BYTES, c.row, false, v);
         }
@@ -457,7 +466,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci) {
             float sn, co;
-            sincosf(pc.x[ci] * f, &sn, &co);
+            fast_sincos(pc.x[ci] * f, &sn, &co);
             e[3 + 6 * k + ci] = nbar[ci] * f * co;
             e[6 + 6 * k + ci] = -nbar[ci] * f * sn;
             if (pc.valid) {

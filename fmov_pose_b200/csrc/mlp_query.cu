@@ -80,7 +80,7 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       float s, co;
-      sincosf(x[c] * f, &s, &co);
+      fast_sincos(x[c] * f, &s, &co);
       e[3 + 6 * k + c] = s;
       e[6 + 6 * k + c] = co;
     }
@@ -147,15 +147,22 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
             tmem_ld_wait();
           }
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const int col = cb * 64 + j;
-            float h = 0.f;
-            if (col < n_valid) h = softplus100(v[j] + __ldg(bias + col));
-            v[j] = h;
+          for (int j4 = 0; j4 < 16; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 64) + j4);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              v[j] = (cb * 64 + j < n_valid) ? softplus100(v[j] + bb[e]) : 0.f;
+            }
           }
           if (l == 7) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) sdf = fmaf(v[j], __ldg(a.w8 + cb * 64 + j), sdf);
+            for (int j4 = 0; j4 < 16; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + cb * 64) + j4);
+              sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
+              sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
+            }
           } else {
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {

@@ -134,7 +134,8 @@ def fine_forward(fw, stash, rays_o, rays_d, z, sample_dist):
     nrm = torch.empty(P, 3, dtype=torch.float32, device=dev)
     rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
     ge = torch.empty(P, 40, dtype=torch.float32, device=dev)
-    L.check(L.lib().fmov_fine_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
+    with L.timed("fine_fwd"):
+      L.check(L.lib().fmov_fine_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),
                                   L.ptr(fw.bias_col), L.ptr(fw.bc4), L.ptr(sdf), L.ptr(nrm), L.ptr(rgb), L.ptr(ge),
                                   L.stream()), "fmov_fine_fwd")
@@ -148,7 +149,8 @@ def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_n
     d_pts = torch.empty(P, 3, dtype=torch.float32, device=dev)
     d_dirs = torch.empty(P, 3, dtype=torch.float32, device=dev)
     zc4 = torch.empty(P, 4, dtype=torch.float32, device=dev)
-    L.check(L.lib().fmov_fine_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
+    with L.timed("fine_bwd"):
+      L.check(L.lib().fmov_fine_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),
                                   L.ptr(fw.bias_col), L.ptr(fw.bc4), L.ptr(fw.wc4), L.ptr(rgb), L.ptr(ge), L.ptr(d_sdf),
                                   L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_pts), L.ptr(d_dirs), L.ptr(zc4), L.stream()),
@@ -165,7 +167,8 @@ def weight_grads(stash, P, d_sdf, zc4):
     lib = L.lib()
     dev = d_sdf.device
     flat = torch.empty(int(lib.fmov_grad_floats()), dtype=torch.float32, device=dev)
-    L.check(lib.fmov_dw(L.c_ll(P), stash.ptrs, L.ptr(d_sdf), L.ptr(zc4), L.ptr(flat), L.stream()), "fmov_dw")
+    with L.timed("dw"):
+        L.check(lib.fmov_dw(L.c_ll(P), stash.ptrs, L.ptr(d_sdf), L.ptr(zc4), L.ptr(flat), L.stream()), "fmov_dw")
 
     def view(kind, l, shape):
         off = int(lib.fmov_grad_offset(kind, l))

@@ -1,0 +1,95 @@
+"""Ray generation side of models/dataset.py — the math of `gen_random_rays_at` (dataset.py:634-681),
+`gen_rays_at` (:547-576) and `near_far_from_sphere` (:835-842) on the fused pose/ray-gen kernel.
+
+Loading images / masks / cameras from disk (Dataset.__init__, dataset.py:146-545) is out of scope
+(SURVEY.md §2 row 16): `RayDataset` is constructed from tensors that are already in memory (the
+benchmark uses synthetic frames) and exposes the attributes the train loop reads."""
+import numpy as np
+import torch
+
+from .. import ops as _ops
+
+
+class _RayGenFn(torch.autograd.Function):
+    """(pose[3,4], K^-1, px, py) -> rays_o [B,3], rays_d [B,3]; backward -> d pose[3,4]"""
+
+    @staticmethod
+    def forward(ctx, pose34, intr_inv, px, py):
+        p = pose34.detach().float().contiguous()
+        rays_o, rays_d, _, _, _ = _ops.raygen_fwd(0, intr_inv, px, py, c2w34=p)
+        ctx.save_for_backward(intr_inv, px, py, rays_o, rays_d)
+        return rays_o, rays_d
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        intr_inv, px, py, rays_o, rays_d = ctx.saved_tensors
+        g34 = _ops.raygen_bwd(intr_inv, px, py, rays_o, rays_d, None if g_o is None else g_o.float().contiguous(),
+                              None if g_d is None else g_d.float().contiguous(), None, None)
+        return g34, None, None, None
+
+
+class RayDataset:
+    def __init__(self, images, masks, intrinsics, device="cuda"):
+        """images [N,H,W,3] fp32 in [0,1], masks [N,H,W,3] fp32, intrinsics [N,3,3] or [3,3]."""
+        self.device = torch.device(device)
+        self.images = images.to(self.device)
+        self.masks = masks.to(self.device)
+        self.masks_np = None
+        self.n_images, self.H, self.W = images.shape[0], images.shape[1], images.shape[2]
+        intr = torch.as_tensor(intrinsics, dtype=torch.float32)
+        if intr.dim() == 2:
+            intr = intr[None].repeat(self.n_images, 1, 1)
+        self.intrinsics_all = intr.to(self.device)
+        self.intrinsics_all_inv = torch.linalg.inv(intr).contiguous().to(self.device)
+        self.use_mono_depth = False
+
+    def _bbox(self, img_idx, patch_size):
+        if self.masks_np is None:
+            self.masks_np = self.masks[..., 0].cpu().numpy()
+        ys, xs = np.where(self.masks_np[int(img_idx)] > 0.5)
+        return (max(ys.min() - patch_size, 0), min(ys.max() + patch_size, self.H),
+                max(xs.min() - patch_size, 0), min(xs.max() + patch_size, self.W))
+
+    def gen_random_rays_at(self, img_idx, batch_size, pose, mask_guided_sampling=False, patch_size=30, pixels=None):
+        """-> (data [B,10] = rays_o, rays_v, rgb, mask ; depth=None).  `pixels=(px,py)` injects the int64 pixel
+        draw (for RNG parity / pinned-host pipelines); otherwise torch.randint on the device as the reference."""
+        img_idx = int(img_idx)
+        if pixels is None:
+            if mask_guided_sampling and np.random.rand() < 0.7:
+                ys_min, ys_max, xs_min, xs_max = self._bbox(img_idx, patch_size)
+            else:
+                ys_min, ys_max, xs_min, xs_max = 0, self.H, 0, self.W
+            px = torch.randint(low=xs_min, high=xs_max, size=[batch_size], device=self.device)
+            py = torch.randint(low=ys_min, high=ys_max, size=[batch_size], device=self.device)
+        else:
+            px, py = pixels
+        color = self.images[img_idx][(py, px)]
+        mask = self.masks[img_idx][(py, px)]
+        rays_o, rays_v = _RayGenFn.apply(pose[:3, :4], self.intrinsics_all_inv[img_idx], px, py)
+        return torch.cat([rays_o, rays_v, color, mask[:, :1]], dim=-1), None
+
+    def gen_rays_at(self, img_idx, resolution_level=1, pose=None, with_mask=False):
+        """full-frame rays [H/l, W/l, 3] (dataset.py:547-576); pixel grid = linspace(0, W-1, W//l)."""
+        l = resolution_level
+        img_idx = int(img_idx)
+        tx = torch.linspace(0, self.W - 1, self.W // l, device=self.device)
+        ty = torch.linspace(0, self.H - 1, self.H // l, device=self.device)
+        if l != 1:
+            raise NotImplementedError("resolution_level > 1 produces non-integer pixel centres; the fused ray-gen "
+                                      "kernel takes integer pixels (resolution_level == 1)")
+        px, py = torch.meshgrid(tx.long(), ty.long(), indexing="ij")          # [W,H]
+        rays_o, rays_v = _RayGenFn.apply(pose[:3, :4], self.intrinsics_all_inv[img_idx], px.reshape(-1).contiguous(),
+                                         py.reshape(-1).contiguous())
+        Wl, Hl = px.shape
+        rays_o = rays_o.reshape(Wl, Hl, 3).transpose(0, 1)
+        rays_v = rays_v.reshape(Wl, Hl, 3).transpose(0, 1)
+        if with_mask:
+            mask = self.masks[img_idx][(py, px)][..., 0].transpose(0, 1)
+            return rays_o, rays_v, mask
+        return rays_o, rays_v
+
+    def near_far_from_sphere(self, rays_o, rays_d):
+        a = torch.sum(rays_d ** 2, dim=-1, keepdim=True)
+        b = 2.0 * torch.sum(rays_o * rays_d, dim=-1, keepdim=True)
+        mid = 0.5 * (-b) / a
+        return mid - 1.0, mid + 1.0

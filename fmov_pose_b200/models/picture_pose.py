@@ -1,0 +1,159 @@
+"""LearnPoseGF / SegLearnPose — drop-in for models/picture_pose.py:13-250.
+
+Same parameters (lin1, lin2, lin3 | lin3_rot / lin3_trans(frozen) / lin3_scale, init_c2w), same
+Gaussian-Fourier features (b ~ N(0, embedding_scale^2) drawn from np.random exactly like the reference,
+picture_pose.py:74-78), same control methods.  The 21 k-parameter MLP head stays in torch; its tail —
+Rodrigues exponential + composition with the (optionally scaled) initial pose, picture_pose.py:176-186 —
+runs in fmov_pose_fwd/_bwd (csrc/pose_raygen.cu)."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops as _ops
+
+
+class _GfTailFn(torch.autograd.Function):
+    """c2w[3,4] = [Exp(rot) | trans] @ [R0 | scale * t0]"""
+
+    @staticmethod
+    def forward(ctx, rot, trans, scale, init44):
+        rot_c, trans_c = rot.detach().float().contiguous(), trans.detach().float().contiguous()
+        scale_c = None if scale is None else scale.detach().float().contiguous()
+        init_c = init44.detach().float().contiguous()
+        ctx.has_scale = scale is not None
+        ctx.save_for_backward(rot_c, trans_c, init_c, *(() if scale_c is None else (scale_c,)))
+        return _ops.pose_fwd(1, rot=rot_c, trans=trans_c, scale=scale_c, init34=init_c)
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        rot_c, trans_c, init_c = saved[:3]
+        scale_c = saved[3] if ctx.has_scale else None
+        g_rot, g_trans, g_scale, _ = _ops.pose_bwd(1, g.float().contiguous(), rot=rot_c, trans=trans_c, scale=scale_c,
+                                                   init34=init_c)
+        return g_rot, g_trans, (g_scale if ctx.has_scale else None), None
+
+
+class LearnPoseGF(nn.Module):
+    def __init__(self, num_cams, init_c2w=None, pose_encoding=False, embedding_scale=10, emphasize_rot=False,
+                 small_rot=False):
+        super().__init__()
+        self.emphasize_rot = emphasize_rot
+        self.num_cams = num_cams
+        self.embedding_size = 128
+        self.init_c2w = nn.Parameter(init_c2w, requires_grad=False) if init_c2w is not None else None
+        self.lin1 = nn.Linear(self.embedding_size * 2, 64)
+        self.gelu1 = nn.GELU()
+        self.lin2 = nn.Linear(64, 64)
+        self.gelu2 = nn.GELU()
+        if not emphasize_rot:
+            self.lin3 = nn.Linear(64, 6)
+            nn.init.normal_(self.lin3.weight, mean=0, std=0.01)
+            nn.init.zeros_(self.lin3.bias)
+        else:
+            self.lin3_rot = nn.Linear(64, 3)
+            nn.init.normal_(self.lin3_rot.weight, mean=0, std=0.01)
+            nn.init.zeros_(self.lin3_rot.bias)
+            self.lin3_trans = nn.Linear(64, 3)
+            nn.init.zeros_(self.lin3_trans.weight)
+            nn.init.zeros_(self.lin3_trans.bias)
+            for p in self.lin3_trans.parameters():
+                p.requires_grad = False
+            self.lin3_scale = nn.Linear(64, 1)
+            nn.init.normal_(self.lin3_scale.weight, mean=0, std=0.01)
+            nn.init.ones_(self.lin3_scale.bias)
+        self.embedding_scale = embedding_scale
+        if pose_encoding:
+            b = 2.0 ** np.linspace(0, 5, self.embedding_size // 2) - 1.0
+            b = b[:, np.newaxis]
+            b = np.concatenate([b, np.roll(b, 1, axis=-1)], 0) + 0
+        else:
+            b = np.random.normal(loc=0.0, scale=self.embedding_scale, size=[self.embedding_size, 1])
+        # the reference ends up with `b` registered as a frozen Parameter (picture_pose.py:82: Parameter(...).to(dev)
+        # returns the Parameter itself when it already lives on `dev`), so it is part of the state_dict
+        self.b = nn.Parameter(torch.tensor(b).float(), requires_grad=False)
+        self.small_rot = small_rot
+
+    # ---- control surface used by exp_runner.py ----------------------------------------------------------
+    def finish_warmup(self):
+        pass
+
+    def disable_trans(self):
+        for p in self.lin3_scale.parameters():
+            p.requires_grad = False
+
+    def enable_trans(self):
+        for p in self.lin3_scale.parameters():
+            p.requires_grad = True
+
+    def _heads(self):
+        if not self.emphasize_rot:
+            return [self.lin1, self.lin2, self.lin3]
+        return [self.lin1, self.lin2, self.lin3_rot, self.lin3_trans, self.lin3_scale]
+
+    def disable_grad(self):
+        for m in self._heads():
+            for p in m.parameters():
+                p.requires_grad = False
+
+    def enable_grad(self):
+        for m in self._heads():
+            for p in m.parameters():
+                p.requires_grad = True
+
+    def forward(self, cam_id):
+        cid = torch.as_tensor(cam_id, device=self.b.device).reshape(1).float()
+        ang = (2.0 * np.pi * cid) @ self.b.T                   # [128]
+        ff = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1) / float(np.sqrt(self.embedding_size))
+        h = self.gelu2(self.lin2(self.gelu1(self.lin1(ff))))
+        k = np.pi / 6 if self.small_rot else np.pi
+        if not self.emphasize_rot:
+            o = self.lin3(h)
+            rot, trans, scale = o[:3] * k, o[3:], None
+        else:
+            rot, trans, scale = self.lin3_rot(h) * k, self.lin3_trans(h), self.lin3_scale(h)
+        idx = int(cam_id)
+        if self.init_c2w is not None:
+            init = self.init_c2w[idx]
+        else:
+            init = torch.eye(4, device=self.b.device)
+        c2w34 = _GfTailFn.apply(rot, trans, scale, init)
+        bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=c2w34.device)
+        return torch.cat([c2w34, bottom], dim=0)                # (4,4) like the reference
+
+
+class SegLearnPose(nn.Module):
+    def __init__(self, num_cams, segment_img_num, init_c2w=None, pose_encoding=False, embedding_scale=10,
+                 emphasize_rot=False, small_rot=False):
+        super().__init__()
+        self.num_cams = num_cams
+        self.segment_img_num = segment_img_num
+        n = init_c2w.shape[0] // segment_img_num + (1 if init_c2w.shape[0] % segment_img_num else 0)
+        self.pose_mlps = nn.ModuleList(
+            [LearnPoseGF(num_cams, init_c2w.clone(), pose_encoding, embedding_scale, emphasize_rot, small_rot)
+             for _ in range(n)])
+        self.initialized_flag = nn.Parameter(torch.tensor([True] + [False] * (n - 1)), requires_grad=False)
+        self.progress = nn.Parameter(torch.zeros(n), requires_grad=False)
+
+    def forward(self, cam_id):
+        cid = int(cam_id)
+        k = cid // self.segment_img_num
+        if not self.initialized_flag[k]:
+            self.initialized_flag[k] = True
+            with torch.no_grad():      # picture_pose.py:227-235: seed the new segment with the previous pose
+                last_pose = self.pose_mlps[k - 1](k * self.segment_img_num - 1)
+                last44 = torch.eye(4, device=last_pose.device)
+                last44[:3] = last_pose[:3]
+                self.pose_mlps[k].init_c2w.data.copy_(last44.clone().repeat(self.num_cams, 1, 1))
+        return self.pose_mlps[k](cid)
+
+    def set_pose(self, cam_id, pose, force_update=False):
+        k = cam_id // self.segment_img_num
+        if not self.initialized_flag[k] or force_update:
+            self.initialized_flag[k] = True
+            with torch.no_grad():
+                self.pose_mlps[k].init_c2w.data.copy_(pose.clone().repeat(self.num_cams, 1, 1))
+
+    def step_progress(self, pose_mlp_index):
+        self.progress[pose_mlp_index] += 1
+        return self.progress[pose_mlp_index]

@@ -57,7 +57,8 @@ def sample_coarse(near, far, t_rand, n_samples, z_stride):
 
 def sample_round(rays_o, rays_d, z, sdf, n_sorted, n_tail, with_sdf, n_new, inv_s):
     B = z.shape[0]
-    L.check(L.lib().fmov_sample_round(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.c_ll(B), z.shape[1],
+    with L.timed("sample_round"):
+      L.check(L.lib().fmov_sample_round(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.c_ll(B), z.shape[1],
                                       n_sorted, n_tail, int(with_sdf), n_new, L.c_float(inv_s), L.stream()),
             "fmov_sample_round")
 
@@ -75,6 +76,7 @@ def hierarchical_sample(qw, rays_o, rays_d, near, far, t_rand, n_samples, n_impo
     lib = L.lib()
 
     def query(z_off, cnt):
+      with L.timed("sdf_query"):
         L.check(lib.fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), cnt, S, z_off,
                                         L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.c_float(qw.b8),
                                         L.c_float(scale), L.c_float(1.0 / scale), L.ptr(sdf_tmp), L.stream()),
@@ -153,7 +155,8 @@ def composite_fwd(rays_o, rays_d, z, sdf, nrm, rgb, inv_s, sample_dist, cos_anne
     if full:
         out.update(weights=e(B, S), cdf=e(B, S), inside=e(B, S), mid_z=e(B, S), pts=e(B * S, 3))
     g = lambda k: L.ptr(out.get(k))
-    L.check(L.lib().fmov_composite_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.ptr(nrm),
+    with L.timed("composite_fwd"):
+      L.check(L.lib().fmov_composite_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.ptr(nrm),
                                        L.ptr(rgb), L.ptr(inv_s), L.c_float(sample_dist), L.c_float(cos_anneal),
                                        L.ptr(bg), g("color"), g("weight_sum"), g("weight_max"), g("depth"), g("weights"),
                                        g("cdf"), g("inside"), g("mid_z"), g("pts"), g("eik"), L.stream()),
@@ -168,7 +171,8 @@ def composite_bwd(rays_o, rays_d, z, sdf, nrm, rgb, inv_s, sample_dist, cos_anne
     e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
     out = dict(d_sdf=e(B * S), d_nrm=e(B * S, 3), d_rgb=e(B * S, 3), d_dir=e(B, 3), d_dist=e(B, S), d_mid=e(B, S),
                d_invs=e(B))
-    L.check(L.lib().fmov_composite_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.ptr(nrm),
+    with L.timed("composite_bwd"):
+      L.check(L.lib().fmov_composite_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.ptr(sdf), L.ptr(nrm),
                                        L.ptr(rgb), L.ptr(inv_s), L.c_float(sample_dist), L.c_float(cos_anneal),
                                        L.ptr(bg), L.ptr(g_color), L.ptr(g_wsum), L.ptr(g_depth), L.ptr(g_weights),
                                        L.ptr(g_eik), L.ptr(eik_den), L.ptr(g_nrm_ext), L.ptr(out["d_sdf"]),

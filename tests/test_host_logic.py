@@ -1,0 +1,152 @@
+"""CPU tests of the host-side mirror: module construction, checkpoint-key compatibility with the reference
+(state_dict keys/shapes recorded in the golden fixtures), explicit errors instead of fallbacks, and the
+ray-sharded (world_size 2, gloo) loss normalisers / gradient all-reduce of TrainStep."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests._util import load_golden
+
+
+def _nets():
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.models.barf_fields import BarfRenderingNetwork, BarfSDFNetwork
+    from fmov_pose_b200.models.fields import NeRF, SingleVarianceNetwork
+    init = synthetic.make_init_poses(6)
+    return (BarfSDFNetwork(init, n_images=6, **synthetic.SDF_KW), BarfRenderingNetwork(**synthetic.COL_KW),
+            SingleVarianceNetwork(0.3), NeRF(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, output_ch=4,
+                                             skips=[4], use_viewdirs=True))
+
+
+def test_state_dict_keys_and_shapes_match_reference_checkpoints():
+    d = load_golden("full_6464_gf")
+    sdf, col, var, nerf = _nets()
+    for prefix, net in (("sdf.", sdf), ("col.", col)):
+        ref = {k[len(prefix):]: v.shape for k, v in d.items() if k.startswith(prefix)}
+        mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        assert set(ref) == set(mine), set(ref) ^ set(mine)
+        for k in ref:
+            assert tuple(ref[k]) == mine[k], k
+    assert list(var.state_dict()) == ["variance"]
+    assert sum(p.numel() for p in nerf.parameters()) == 606_596
+
+
+def test_pose_module_state_dict_matches_reference():
+    from fmov_pose_b200.models.picture_pose import LearnPoseGF, SegLearnPose
+    for name, emph in (("full_6464_gf", False), ("full_3200_seg", True)):
+        d = load_golden(name)
+        ref = {k[5:]: v.shape for k, v in d.items() if k.startswith("pose.")}
+        m = LearnPoseGF(6, init_c2w=torch.eye(4).repeat(6, 1, 1), emphasize_rot=emph)
+        mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert set(ref) == set(mine), set(ref) ^ set(mine)
+    seg = SegLearnPose(6, 1, init_c2w=torch.eye(4).repeat(6, 1, 1), emphasize_rot=True)
+    assert len(seg.pose_mlps) == 6 and bool(seg.initialized_flag[0]) and not bool(seg.initialized_flag[1])
+    trainable = sum(p.numel() for p in seg.pose_mlps[0].parameters() if p.requires_grad)
+    assert trainable == 20_868
+
+
+def test_geometric_init_statistics():
+    """fields.py:47-79: last layer ~ N(sqrt(pi)/16, 1e-4), bias -0.5; lin0 only xyz columns; lin4 PE columns 0."""
+    sdf, _, _, _ = _nets()
+    W, b = sdf.effective_weights()
+    assert abs(W[8].mean().item() - np.sqrt(np.pi) / 16) < 1e-3 and abs(b[8][0].item() + 0.5) < 1e-6
+    assert W[0][:, 3:].abs().max().item() == 0.0 and W[0][:, :3].abs().max().item() > 0
+    assert W[4][:, -36:].abs().max().item() == 0.0
+    assert tuple(W[3].shape) == (217, 256)
+
+
+def test_unsupported_configs_raise_instead_of_falling_back():
+    from fmov_pose_b200 import fine
+    from fmov_pose_b200.models.fields import RenderingNetwork, SDFNetwork
+    from fmov_pose_b200.models.renderer import NeuSRenderer
+    sdf, col, var, nerf = _nets()
+    r = NeuSRenderer(nerf, sdf, var, col, 64, 64, 32, 4, 1.0)
+    with pytest.raises(NotImplementedError):
+        r._check()
+    small = SDFNetwork(d_in=3, d_out=65, d_hidden=64, n_layers=4, skip_in=(2,), multires=6)
+    Ws, _ = small.effective_weights()
+    Wc, _ = col.effective_weights()
+    with pytest.raises(NotImplementedError):
+        fine.check_supported(Ws, Wc)
+    r2 = NeuSRenderer(None, sdf, var, col, 64, 64, 0, 4, 1.0)
+    o = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError):          # CPU tensors: no CPU fallback
+        r2.render(o, o, torch.zeros(4, 1), torch.ones(4, 1))
+    with pytest.raises(NotImplementedError):
+        col(o, o, o, torch.zeros(4, 256))
+
+
+def test_embedder_matches_reference_layout():
+    from fmov_pose_b200.models.embedder import get_embedder
+    d = load_golden("kat")
+    e6, n6 = get_embedder(6)
+    e4, n4 = get_embedder(4)
+    x = torch.from_numpy(d["pe.x"])
+    assert (n6, n4) == (39, 27)
+    np.testing.assert_array_equal(e6(x).numpy(), d["pe.e6"])
+    np.testing.assert_array_equal(e4(x).numpy(), d["pe.e4"])
+
+
+def test_camera_host_mirror_matches_reference_kats():
+    from fmov_pose_b200.models import camera
+    from fmov_pose_b200.models.batch_lie_group_helper import Exp
+    d = load_golden("kat")
+    np.testing.assert_allclose(camera.lie.se3_to_SE3(torch.from_numpy(d["se3.wu"])).numpy(), d["se3.Rt"], atol=1e-7)
+    np.testing.assert_allclose(camera.pose.compose([torch.from_numpy(d["compose.a"]), torch.from_numpy(d["compose.b"])]).numpy(),
+                               d["compose.out"], atol=1e-7)
+    np.testing.assert_array_equal(Exp(torch.from_numpy(d["exp.r"])).numpy(), d["exp.R"])
+
+
+# ---- world_size-2 gloo: global normalisers + gradient all-reduce ------------------------------------------
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fmov_pose_b200.train import TrainStep
+    torch.manual_seed(0)
+    B = 64
+    g = torch.Generator().manual_seed(5)
+    color = torch.rand(B, 3, generator=g)
+    wsum = torch.rand(B, 1, generator=g)
+    rgb = torch.rand(B, 3, generator=g)
+    mask = (torch.rand(B, 1, generator=g) > 0.3).float()
+    lin = torch.nn.Linear(3, 3)
+    with torch.no_grad():
+        lin.weight.copy_(torch.eye(3)); lin.bias.zero_()
+
+    class _R:
+        process_group = None
+    scene = dict(renderer=_R(), sdf_network=lin, deviation_network=torch.nn.Module(), color_network=torch.nn.Module(),
+                 pose_network=None)
+    # single-process reference on the union batch
+    ts1 = TrainStep(scene, mask_weight=5.0, group=None, optimizer=False)
+    out = dict(color_fine=lin(color), weight_sum=wsum, gradient_error=torch.tensor(0.25))
+    l1 = ts1.losses(out, rgb, mask)
+    l1["loss"].backward()
+    g_full = lin.weight.grad.clone()
+    lin.weight.grad = None; lin.bias.grad = None
+    # sharded
+    ts2 = TrainStep(scene, mask_weight=5.0, group=dist.group.WORLD, optimizer=False)
+    sl = slice(rank * B // world, (rank + 1) * B // world)
+    out2 = dict(color_fine=lin(color[sl]), weight_sum=wsum[sl], gradient_error=torch.tensor(0.25))
+    l2 = ts2.losses(out2, rgb[sl], mask[sl])
+    # colour and bce terms are partial sums over the shard with GLOBAL denominators
+    parts = torch.stack([l2["color_loss"].detach(), l2["mask_loss"].detach()])
+    dist.all_reduce(parts)
+    (l2["color_loss"] + 5.0 * l2["mask_loss"]).backward()
+    ts2.allreduce_grads()
+    ok = (abs(parts[0].item() - l1["color_loss"].item()) < 1e-6 and abs(parts[1].item() - l1["mask_loss"].item()) < 1e-6
+          and torch.allclose(lin.weight.grad, g_full, atol=1e-6))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_ray_sharded_losses_and_grad_allreduce_gloo_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 500)
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1), dict(ret)
