@@ -104,15 +104,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap, not hang the GPU (a hung box is a lost GPU lease).
+// Bounded waits: a protocol bug must trap, not hang the GPU (a hung box is a lost GPU lease).
+static __device__ __noinline__ void mbar_timeout_trap(uint64_t* bar, uint32_t parity) {
+  printf("fmov: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+         smem_u32(bar), parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-      printf("fmov: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
-             (int)threadIdx.x, smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 0xFFF) == 0) {                       // look at the clock rarely
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout_trap(bar, parity);   // ~4 s
+    }
+  }
+}
+// For the single-lane control warps: sleep between polls so the spin does not steal issue slots from the
+// epilogue warps that share the scheduler.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if ((++spins & 0x3FF) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout_trap(bar, parity);
     }
   }
 }

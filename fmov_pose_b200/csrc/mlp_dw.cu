@@ -35,6 +35,8 @@ struct DwJob {
   long long out_off;               // offset (floats) into the flat gradient buffer
   float scale;
   int cta_first, cta_count;
+  long long bias_off;              // float offset of the bias gradient fed by column sums of pair 0's A tile, or -1
+  int bias_n;                      // number of valid columns
 };
 struct DwPlan {
   int n_jobs;
@@ -120,9 +122,14 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
       }
     umma_commit(&done_bar);
   } else if (warp >= 2 && has_work) {
-    // converter: fp16 operand of each stage -> bf16, in place (element-wise, layout agnostic)
+    // converter: fp16 operand of each stage -> bf16, in place (element-wise, layout agnostic); and column sums
+    // of the gradient tile (pair 0's A operand) = bias gradient, two columns per thread
+    float bsum0 = 0.f, bsum1 = 0.f;
     {
       const int ctid = threadIdx.x - 64;
+      const int bcol = 2 * ctid;                                   // columns bcol, bcol+1
+      const uint32_t boff = (uint32_t)(bcol >> 6) * (DW_HALF * 128) + (uint32_t)((bcol & 7) >> 1) * 4;
+      const int bchunk = (bcol & 63) >> 3;
       uint32_t it = 0;
       for (long long t = t0; t < t1; ++t)
         for (int pr = 0; pr < jb.npairs; ++pr)
@@ -143,9 +150,22 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
               f = unpack_h2(q.w); q.w = pack_bf2(f.x, f.y);
               reg[i] = q;
             }
+            if (jb.bias_off >= 0 && pr == 0) {                     // A operand is bf16 here (never converted)
+#pragma unroll 8
+              for (int r = 0; r < DW_HALF; ++r) {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(sa + boff + r * 128 + ((bchunk ^ (r & 7)) << 4));
+                const float2 f = unpack_bf2(w);
+                bsum0 += f.x;
+                bsum1 += f.y;
+              }
+            }
             fence_proxy_async();
             mbar_arrive(&ready[slot]);
           }
+      if (jb.bias_off >= 0) {
+        if (bcol < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol, bsum0);
+        if (bcol + 1 < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol + 1, bsum1);
+      }
     }
     // epilogue: wait for the whole range, then flush the two [128 x N] accumulators with atomics
     mbar_wait(&done_bar, 0);
@@ -188,72 +208,55 @@ struct ColsumArgs {
   long long off_wc4;       // colour lin4 weight grad [3,256]
 };
 
-__device__ __forceinline__ float ti_elem(const uint8_t* tile, int r, int m, bool bf16) {
-  const uint8_t* p = tile + (size_t)(m >> 6) * BLK_BYTES + ti_off(r, m & 63);
-  return bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)) : __half2float(*reinterpret_cast<const __half*>(p));
-}
-
+// lin8 row 0 (sum_p sbar_p*H8[p,:] + Vbar8[p,:]), colour lin4 (sum_p zc4[p,j]*C4[p,:]), and the two scalar-ish
+// biases. 256 threads: thread = (row group rg = tid/32, 16-byte chunk cidx = tid%32 -> 8 columns); a warp reads
+// whole 128-byte rows (coalesced).
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
-  const int m = threadIdx.x;
-  float bz[8], bf = 0.f, bc[4], w8r = 0.f, wc4[3] = {0.f, 0.f, 0.f}, extra = 0.f;
+  const int cidx = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int blk = cidx >> 3, ch = cidx & 7;
+  float w8[8], c4[3][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) bz[i] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) bc[i] = 0.f;
-  __shared__ float s_sb[128], s_z4[128 * 3];
+  for (int i = 0; i < 8; ++i) { w8[i] = 0.f; c4[0][i] = c4[1][i] = c4[2][i] = 0.f; }
+  float extra[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-    __syncthreads();
-    if (threadIdx.x < 128) {
-      const long long p = t * 128 + threadIdx.x;
+    const uint8_t* th = a.ptrs.stash[S_H1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
+    const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
+    const uint8_t* tc = a.ptrs.stash[S_C1 + 3] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
+#pragma unroll 4
+    for (int r = rg; r < 128; r += 8) {
+      const long long p = t * 128 + r;
       const bool ok = p < a.P;
-      s_sb[threadIdx.x] = ok ? a.d_sdf[p] : 0.f;
-      for (int j = 0; j < 3; ++j) s_z4[threadIdx.x * 3 + j] = ok ? a.zc4[p * 4 + j] : 0.f;
-    }
-    __syncthreads();
+      const float sb = ok ? a.d_sdf[p] : 0.f;
+      const float z0 = ok ? a.zc4[p * 4] : 0.f, z1 = ok ? a.zc4[p * 4 + 1] : 0.f, z2 = ok ? a.zc4[p * 4 + 2] : 0.f;
+      const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
+      const uint4 qh = *reinterpret_cast<const uint4*>(th + off);
+      const uint4 qv = *reinterpret_cast<const uint4*>(tv + off);
+      const uint4 qc = *reinterpret_cast<const uint4*>(tc + off);
+      const uint32_t hh[4] = {qh.x, qh.y, qh.z, qh.w}, vv[4] = {qv.x, qv.y, qv.z, qv.w}, cc[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
-    for (int l = 0; l < 8; ++l) {
-      const uint8_t* tz = a.ptrs.stash[S_Z0 + l] + (size_t)t * 4 * BLK_BYTES;
-      float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += ti_elem(tz, r, m, true);
-      bz[l] += s;
-    }
-    {
-      const uint8_t* tf = a.ptrs.stash[S_FB] + (size_t)t * 4 * BLK_BYTES;
-      const uint8_t* th = a.ptrs.stash[S_H1 + 7] + (size_t)t * 4 * BLK_BYTES;
-      const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + (size_t)t * 4 * BLK_BYTES;
-      const uint8_t* tc4 = a.ptrs.stash[S_C1 + 3] + (size_t)t * 4 * BLK_BYTES;
-      for (int r = 0; r < 128; ++r) {
-        bf += ti_elem(tf, r, m, true);
-        w8r += s_sb[r] * ti_elem(th, r, m, false) + ti_elem(tv, r, m, true);
-        const float c4 = ti_elem(tc4, r, m, false);
-        wc4[0] += s_z4[r * 3] * c4; wc4[1] += s_z4[r * 3 + 1] * c4; wc4[2] += s_z4[r * 3 + 2] * c4;
+      for (int j = 0; j < 4; ++j) {
+        const float2 fh = unpack_h2(hh[j]), fv = unpack_bf2(vv[j]), fc = unpack_h2(cc[j]);
+        w8[2 * j] += sb * fh.x + fv.x; w8[2 * j + 1] += sb * fh.y + fv.y;
+        c4[0][2 * j] += z0 * fc.x; c4[0][2 * j + 1] += z0 * fc.y;
+        c4[1][2 * j] += z1 * fc.x; c4[1][2 * j + 1] += z1 * fc.y;
+        c4[2][2 * j] += z2 * fc.x; c4[2][2 * j + 1] += z2 * fc.y;
       }
-    }
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const uint8_t* tz = a.ptrs.stash[S_ZC0 + l] + (size_t)t * 4 * BLK_BYTES;
-      float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += ti_elem(tz, r, m, true);
-      bc[l] += s;
-    }
-    if (m < 4) {
-      float s = 0.f;
-      for (int r = 0; r < 128; ++r) s += (m == 0) ? s_sb[r] : s_z4[r * 3 + (m - 1)];
-      extra += s;
+      if (cidx == 0) { extra[0] += sb; extra[1] += z0; extra[2] += z1; extra[3] += z2; }
     }
   }
   float* g = a.grads;
 #pragma unroll
-  for (int l = 0; l < 8; ++l)
-    if (l != 3 || m < 217) atomicAdd(g + a.off_b_sdf[l] + m, bz[l]);
-  atomicAdd(g + a.off_b_sdf[8] + 1 + m, bf);
-  atomicAdd(g + a.off_w8 + m, w8r);
+  for (int i = 0; i < 8; ++i) {
+    const int col = cidx * 8 + i;
+    atomicAdd(g + a.off_w8 + col, w8[i]);
 #pragma unroll
-  for (int l = 0; l < 4; ++l) atomicAdd(g + a.off_b_col[l] + m, bc[l]);
+    for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_wc4 + j * 256 + col, c4[j][i]);
+  }
+  if (cidx == 0) {
+    atomicAdd(g + a.off_b_sdf[8], extra[0]);
 #pragma unroll
-  for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_wc4 + j * 256 + m, wc4[j]);
-  if (m == 0) atomicAdd(g + a.off_b_sdf[8], extra);
-  if (m >= 1 && m < 4) atomicAdd(g + a.off_b_col[4] + (m - 1), extra);
+    for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_b_col[4] + j, extra[1 + j]);
+  }
 }
 
 }  // namespace fmov
@@ -282,14 +285,15 @@ extern "C" long long fmov_grad_offset(int kind, int layer) {
 extern "C" long long fmov_grad_floats(void) { return fmov_grad_offset(4, 0); }
 
 static void add_job(DwPlan& pl, int npairs, int a0, int b0, int a0bf, int b0bf, int a1, int b1, int a1bf, int b1bf,
-                    int b_blocks, int m_valid, int n_valid, int ld, int col_off, long long out_off, float scale) {
+                    int b_blocks, int m_valid, int n_valid, int ld, int col_off, long long out_off, float scale,
+                    long long bias_off = -1, int bias_n = 0) {
   DwJob& j = pl.job[pl.n_jobs++];
   memset(&j, 0, sizeof(j));
   j.npairs = (uint8_t)npairs;
   j.a_id[0] = (uint8_t)a0; j.b_id[0] = (uint8_t)b0; j.a_bf16[0] = (uint8_t)a0bf; j.b_bf16[0] = (uint8_t)b0bf;
   j.a_id[1] = (uint8_t)a1; j.b_id[1] = (uint8_t)b1; j.a_bf16[1] = (uint8_t)a1bf; j.b_bf16[1] = (uint8_t)b1bf;
   j.b_blocks = (uint8_t)b_blocks; j.m_valid = m_valid; j.n_valid = n_valid; j.ld = ld; j.col_off = col_off;
-  j.out_off = out_off; j.scale = scale;
+  j.out_off = out_off; j.scale = scale; j.bias_off = bias_off; j.bias_n = bias_n;
 }
 
 static void build_plan(DwPlan& pl, int n_ctas) {
@@ -299,18 +303,22 @@ static void build_plan(DwPlan& pl, int n_ctas) {
   for (int l = 1; l <= 7; ++l) {
     const int nv = (l == 4) ? 217 : 256;
     add_job(pl, 2, S_Z0 + l, S_H1 + (l - 1), 1, 0, S_D0 + l, S_V1 + (l - 1), 0, 1, 4, SDF_OUT[l], nv, 256, 0,
-            fmov_grad_offset(0, l), l == 4 ? rs2 : 1.f);
+            fmov_grad_offset(0, l), l == 4 ? rs2 : 1.f, fmov_grad_offset(1, l), SDF_OUT[l]);
   }
   // layer 4, PE columns 217..255: (Zbar_4, PE) + (Delta_4, GE)
   add_job(pl, 2, S_Z0 + 4, S_PE, 1, 0, S_D0 + 4, S_GE, 0, 1, 1, 256, 39, 256, 217, fmov_grad_offset(0, 4), rs2);
   // layer 0: (Zbar_0, PE) + (Delta_0, GE)
-  add_job(pl, 2, S_Z0 + 0, S_PE, 1, 0, S_D0 + 0, S_GE, 0, 1, 1, 256, 39, 39, 0, fmov_grad_offset(0, 0), 1.f);
+  add_job(pl, 2, S_Z0 + 0, S_PE, 1, 0, S_D0 + 0, S_GE, 0, 1, 1, 256, 39, 39, 0, fmov_grad_offset(0, 0), 1.f,
+          fmov_grad_offset(1, 0), 256);
   // layer 8 feature rows 1..256: (fbar, H8)
-  add_job(pl, 1, S_FB, S_H1 + 7, 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(0, 8) + 256, 1.f);
+  add_job(pl, 1, S_FB, S_H1 + 7, 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(0, 8) + 256, 1.f,
+          fmov_grad_offset(1, 8) + 1, 256);
   // colour layers 1..3: (Zbar_cl, C_l); layer 0: (Zbar_c0, F) -> cols 33.., (Zbar_c0, X) -> cols 0..32
   for (int l = 1; l <= 3; ++l)
-    add_job(pl, 1, S_ZC0 + l, S_C1 + (l - 1), 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(2, l), 1.f);
-  add_job(pl, 1, S_ZC0 + 0, S_F, 1, 0, 0, 0, 0, 0, 4, 256, 256, 289, 33, fmov_grad_offset(2, 0), 1.f);
+    add_job(pl, 1, S_ZC0 + l, S_C1 + (l - 1), 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(2, l), 1.f,
+            fmov_grad_offset(3, l), 256);
+  add_job(pl, 1, S_ZC0 + 0, S_F, 1, 0, 0, 0, 0, 0, 4, 256, 256, 289, 33, fmov_grad_offset(2, 0), 1.f,
+          fmov_grad_offset(3, 0), 256);
   add_job(pl, 1, S_ZC0 + 0, S_X, 1, 0, 0, 0, 0, 0, 1, 256, 33, 289, 0, fmov_grad_offset(2, 0), 1.f);
   // distribute CTAs proportionally to cost (bytes streamed per tile)
   float cost[DW_MAX_JOBS], total = 0.f;
@@ -364,7 +372,7 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
   for (int l = 0; l < 5; ++l) ca.off_b_col[l] = fmov_grad_offset(3, l);
   ca.off_w8 = fmov_grad_offset(0, 8);
   ca.off_wc4 = fmov_grad_offset(2, 4);
-  const int cs_grid = (int)(n_tiles < 2 * n_ctas ? n_tiles : 2 * n_ctas);
+  const int cs_grid = (int)(n_tiles < 4 * n_ctas ? n_tiles : 4 * n_ctas);
   colsum_kernel<<<cs_grid, 256, 0, (cudaStream_t)stream>>>(ca);
   FMOV_LAUNCH_CHECK("colsum_kernel");
   return OK;

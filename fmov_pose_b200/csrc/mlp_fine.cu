@@ -20,7 +20,7 @@
 
 namespace fmov {
 
-using FL = ChainLayout<2, true>;
+using FL = ChainLayout;
 
 // ---- weight image directory ---------------------------------------------------------------------
 enum ImgId {
@@ -82,6 +82,7 @@ struct FineArgs {
   float* sdf; float* nrm; float* rgb; float* ge;              // fwd outputs: [P],[P,3],[P,3],[P,40]
   const float* d_sdf; const float* d_nrm; const float* d_rgb; // bwd inputs
   float* d_pts; float* d_dirs; float* zc4;                    // bwd outputs: [P,3],[P,3],[P,4]
+  float* eb;                                                  // bwd scratch [P,40]
 };
 
 __device__ __forceinline__ uint8_t* stash_tile(const ChainPtrs& ptrs, int id, long long tile) {
@@ -142,6 +143,22 @@ __device__ __forceinline__ void pe_jt(const float x[3], const float* g, float n[
   }
 }
 
+__device__ __forceinline__ uint8_t* stash_row(const ChainPtrs& ptrs, int id, long long tile, int kb, int row) {
+  return ptrs.stash[id] + ((size_t)tile * stash_kb(id) + kb) * BLK_BYTES + (size_t)row * 128;
+}
+// store one 32-column chunk (index hb = 0..7 within a 256-wide tile) to the ACT operand and/or a stash tensor
+__device__ __forceinline__ void put_chunk(const EpiCtx& c, const ChainPtrs& ptrs, bool to_act, int stash_id,
+                                          long long tile, int hb, bool bf16, const float* v) {
+  uint4 q[4];
+  pack4(v, bf16, q);
+  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+}
+__device__ __forceinline__ void get_chunk_raw(const EpiCtx& c, const ChainPtrs& ptrs, int stash_id, long long tile,
+                                              int hb, uint4* q) {
+  row_half_load(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+}
+
 // =====================================================================================================
 // forward
 // =====================================================================================================
@@ -151,46 +168,47 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
-  uint8_t* act = base + FL::ACT;
-  uint8_t* aux = base + FL::AUX;
-  uint8_t* side = base + FL::SIDE;
+  uint8_t* act0 = base + FL::ACT;
+  uint8_t* aux0 = base + FL::AUX;
   uint8_t* wst = base + FL::WST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long P = a.B * a.S;
   const long long n_tiles = (P + TILE_M - 1) / TILE_M;
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (threadIdx.x == 0) chain_init_barriers<2>(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  if (threadIdx.x == 0) chain_init_barriers(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) chain_weight_producer<2>(tb, ptrs.weights, s, wst, n_my);
+    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
   } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer<2>(tb, s, act, aux, wst, tmem, n_my);
-  } else if (warp == 2) {
-    if (lane == 0) chain_side_producer(tb, ptrs, s, side, blockIdx.x, gridDim.x, n_my);
+    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
   } else {
     EpiCtx c;
-    epi_init(c, s, act, aux, side, tmem);
-    for (int t = 0; t < n_my; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+    epi_init(c, s, act0, aux0, tmem);
+    for (int k = c.slot; k < n_my; k += CH_SLOTS) {
+      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
-      // ---- input: PE6(x) -> AUX, stash ---------------------------------------------------------
+      // ---- input: PE6(x) -> AUX + stash ----------------------------------------------------------------
       {
         float e[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
         pe_eval<6>(pc.x, e);
-        epi_before_write(c);
-        row_store64(aux, c.row, false, e);
-        epi_store_blocks(c, aux, stash_tile(ptrs, ST_PE, tile), 1);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 q[4];
+          pack4(e + 32 * h, false, q);
+          row_half_store(c.aux + c.row * 128, c.swz, h, q);
+          row_half_store(stash_row(ptrs, ST_PE, tile, 0, c.row), c.swz, h, q);
+        }
         epi_signal_act(c);
       }
-      // ---- value pass: layers 0..7 -----------------------------------------------------------------
+      // ---- value pass: layers 0..7 -----------------------------------------------------------------------
       float sdf = __ldg(a.b8);
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
@@ -198,91 +216,100 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const int n_mma = (l == 3) ? 224 : 256;
         const float* bias = a.bias_sdf + l * 256;
         epi_wait_acc(c);
-        epi_before_write(c);
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64];
-          acc_load64(c, cb * 64, n_mma, v);
+#pragma unroll 2
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32];
+          if (hb * 32 < n_mma) {
+            acc_load32(c, hb * 32, v);
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 64) + j4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              v[j] = (cb * 64 + j < n_valid) ? softplus100(v[j] + bb[e]) : 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+              v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
+              v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
+              v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
+              v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
             }
+            if (hb * 32 + 32 > n_valid) {           // lin3: columns 217..223 are padding
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (hb * 32 + j < n_valid) ? v[j] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           if (l == 7) {
 #pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + cb * 64) + j4);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + hb * 32) + j4);
               sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
               sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
             }
           }
-          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+          put_chunk(c, ptrs, true, ST_H1 + l, tile, hb, false, v);
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_H1 + l, tile), 4);
         epi_signal_act(c);
       }
       if (pc.valid) a.sdf[pc.p] = sdf;
-      // ---- lin8 feature rows -> SIDE (staging) ; delta_7 = W8[0,:]*sigma_7 in place ----------------
+      // ---- lin8 feature rows -> stash F ; delta_7 = W8[0,:]*sigma_7 in place -------------------------------------
       epi_wait_acc(c);
-      epi_before_write(c);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        float v[64], h[64];
-        acc_load64(c, cb * 64, 256, v);
-        row_load64(act + cb * BLK_BYTES, c.row, false, h);
+#pragma unroll 2
+      for (int hb = 0; hb < 8; ++hb) {
+        float v[32], h[32];
+        uint4 q[4];
+        acc_load32(c, hb * 32, v);
+        row_half_load(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+        unpack4(q, false, h);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int col = cb * 64 + j;
+        for (int j = 0; j < 32; ++j) {
+          const int col = hb * 32 + j;
           v[j] += __ldg(a.b8 + 1 + col);
           h[j] = __ldg(a.w8row + col) * sigma_from_h(h[j]);
         }
-        row_store64(side + cb * BLK_BYTES, c.row, false, v);
-        row_store64(act + cb * BLK_BYTES, c.row, false, h);
+        put_chunk(c, ptrs, false, ST_F, tile, hb, false, v);
+        put_chunk(c, ptrs, true, ST_D0 + 7, tile, hb, false, h);
       }
-      epi_store_blocks(c, side, stash_tile(ptrs, ST_F, tile), 4);
-      epi_store_blocks(c, act, stash_tile(ptrs, ST_D0 + 7, tile), 4);
-      epi_publish_stash(c);          // H1..H8, F have landed; SIDE staging buffer is free again
       epi_signal_act(c);
-      // ---- reverse sweep l = 7..1 ------------------------------------------------------------------
-      float ge[40];
-#pragma unroll
-      for (int i = 0; i < 40; ++i) ge[i] = 0.f;
+      // ---- reverse sweep l = 7..1 -------------------------------------------------------------------------------
 #pragma unroll 1
       for (int l = 7; l >= 1; --l) {
+        uint4 sq[4], sn[4];
+        get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, 0, sq);        // H_l -> sigma_{l-1} (own rows)
         epi_wait_acc(c);
-        epi_before_write(c);
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64], h[64];
-          acc_load64(c, cb * 64, 256, v);
-          const uint8_t* sb = epi_side_wait(c);       // H_l block cb  -> sigma_{l-1}
-          row_load64(sb, c.row, false, h);
-          epi_side_release(c);
-          if (l == 4 && cb == 3) {
-            // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image)
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32], h[32];
+          if (hb < 7) get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, hb + 1, sn);
+          acc_load32(c, hb * 32, v);
+          unpack4(sq, false, h);
+          if (l == 4 && hb == 6 && pc.valid) {
+            // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image): parked in
+            // the g_e output row until the W_0^T delta_0 term arrives (keeps 39 registers free across the sweep)
 #pragma unroll
-            for (int j = 25; j < 64; ++j) ge[j - 25] += v[j];
+            for (int j = 25; j < 32; ++j) a.ge[pc.p * 40 + (j - 25)] = v[j];
+          }
+          if (l == 4 && hb == 7 && pc.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a.ge[pc.p * 40 + 7 + j] = v[j];
           }
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] *= sigma_from_h(h[j]);   // H_4 is zero beyond col 216 -> delta_3 too
-          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+          for (int j = 0; j < 32; ++j) v[j] *= sigma_from_h(h[j]);    // H_4 is zero beyond col 216 -> delta_3 too
+          put_chunk(c, ptrs, true, ST_D0 + (l - 1), tile, hb, false, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sq[i] = sn[i];
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_D0 + (l - 1), tile), 4);
         epi_signal_act(c);
       }
-      // ---- g_e += W_0^T delta_0 ; normal ; colour-net extras -----------------------------------------
-      float nrm[3];
+      // ---- g_e += W_0^T delta_0 ; normal ; colour-net extras ; feature tile back into ACT -----------------------------
       {
-        float v[64];
+        float v[48];
+        float nrm[3];
+        float ge[40];
         epi_wait_acc(c);
-        acc_load64(c, 0, 48, v);
+        acc_load32(c, 0, v);
+        acc_load16(c, 32, v + 32);
+        ge[39] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 39; ++i) ge[i] += v[i];
+        for (int i = 0; i < 39; ++i) ge[i] = v[i] + (pc.valid ? a.ge[pc.p * 40 + i] : 0.f);
         pe_jt<6>(pc.x, ge, nrm);
         if (pc.valid) {
 #pragma unroll
@@ -297,35 +324,47 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         e[0] = pc.x[0]; e[1] = pc.x[1]; e[2] = pc.x[2];
         pe_eval<4>(pc.d, e + 3);
         e[30] = nrm[0]; e[31] = nrm[1]; e[32] = nrm[2];
-        epi_before_write(c);
-        row_store64(aux, c.row, false, e);
-        epi_store_blocks(c, aux, stash_tile(ptrs, ST_X, tile), 1);
-        epi_before_write(c);                                  // D0 store must have finished reading ACT
-        epi_reload_blocks(c, act, stash_tile(ptrs, ST_F, tile), 4);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 q[4];
+          pack4(e + 32 * h, false, q);
+          row_half_store(c.aux + c.row * 128, c.swz, h, q);
+          row_half_store(stash_row(ptrs, ST_X, tile, 0, c.row), c.swz, h, q);
+        }
+#pragma unroll
+        for (int hb = 0; hb < 8; ++hb) {          // own rows of F: written above by this thread
+          uint4 q[4];
+          get_chunk_raw(c, ptrs, ST_F, tile, hb, q);
+          row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+        }
         epi_signal_act(c);
       }
-      // ---- colour net: 4 ReLU layers ------------------------------------------------------------------
+      // ---- colour net: 4 ReLU layers ------------------------------------------------------------------------------
 #pragma unroll 1
       for (int l = 0; l < 4; ++l) {
         const float* bias = a.bias_col + l * 256;
         epi_wait_acc(c);
-        epi_before_write(c);
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64];
-          acc_load64(c, cb * 64, 256, v);
+#pragma unroll 2
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32];
+          acc_load32(c, hb * 32, v);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j] + __ldg(bias + cb * 64 + j), 0.f);
-          row_store64(act + cb * BLK_BYTES, c.row, false, v);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+            v[j4 * 4 + 0] = fmaxf(v[j4 * 4 + 0] + b4.x, 0.f);
+            v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b4.y, 0.f);
+            v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b4.z, 0.f);
+            v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b4.w, 0.f);
+          }
+          put_chunk(c, ptrs, true, ST_C1 + l, tile, hb, false, v);
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_C1 + l, tile), 4);
         epi_signal_act(c);
       }
-      // ---- colour output: sigmoid --------------------------------------------------------------------
+      // ---- colour output: sigmoid ------------------------------------------------------------------------------------
       {
-        float v[64];
+        float v[16];
         epi_wait_acc(c);
-        acc_load64(c, 0, 16, v);
+        acc_load16(c, 0, v);
         if (pc.valid) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) a.rgb[pc.p * 3 + i] = sigmoidf_(v[i] + __ldg(a.bc4 + i));
@@ -333,12 +372,11 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         tc_fence_before();
       }
     }
-    if (c.etid == 0) bulk_wait_all0();     // all stash stores complete before the CTA exits
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -351,33 +389,30 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
-  uint8_t* act = base + FL::ACT;
-  uint8_t* aux = base + FL::AUX;
-  uint8_t* side = base + FL::SIDE;
+  uint8_t* act0 = base + FL::ACT;
+  uint8_t* aux0 = base + FL::AUX;
   uint8_t* wst = base + FL::WST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long P = a.B * a.S;
   const long long n_tiles = (P + TILE_M - 1) / TILE_M;
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (threadIdx.x == 0) chain_init_barriers<2>(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  if (threadIdx.x == 0) chain_init_barriers(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) chain_weight_producer<2>(tb, ptrs.weights, s, wst, n_my);
+    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
   } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer<2>(tb, s, act, aux, wst, tmem, n_my);
-  } else if (warp == 2) {
-    if (lane == 0) chain_side_producer(tb, ptrs, s, side, blockIdx.x, gridDim.x, n_my);
+    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
   } else {
     EpiCtx c;
-    epi_init(c, s, act, aux, side, tmem);
-    for (int t = 0; t < n_my; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+    epi_init(c, s, act0, aux0, tmem);
+    for (int k = c.slot; k < n_my; k += CH_SLOTS) {
+      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
       float sbar = 0.f, nbar[3] = {0.f, 0.f, 0.f}, zc4[3] = {0.f, 0.f, 0.f}, xbar[3] = {0.f, 0.f, 0.f};
       if (pc.valid) {
@@ -393,47 +428,47 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         a.zc4[pc.p * 4 + 3] = 0.f;
       }
       // ---- colour lin4 backward on CUDA cores (3 x 256) + ReLU mask of C4 -> zbar_c3 ---------------------
-      epi_before_write(c);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        float v[64], h[64];
-        const uint8_t* sb = epi_side_wait(c);          // C4 block cb
-        row_load64(sb, c.row, false, h);
-        epi_side_release(c);
+#pragma unroll 2
+      for (int hb = 0; hb < 8; ++hb) {
+        float v[32], h[32];
+        uint4 q[4];
+        get_chunk_raw(c, ptrs, ST_C1 + 3, tile, hb, q);
+        unpack4(q, false, h);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int col = cb * 64 + j;
+        for (int j = 0; j < 32; ++j) {
+          const int col = hb * 32 + j;
           const float ab = zc4[0] * __ldg(a.wc4 + col) + zc4[1] * __ldg(a.wc4 + 256 + col) + zc4[2] * __ldg(a.wc4 + 512 + col);
           v[j] = h[j] > 0.f ? ab : 0.f;
         }
-        row_store64(act + cb * BLK_BYTES, c.row, true, v);
+        put_chunk(c, ptrs, true, ST_ZC0 + 3, tile, hb, true, v);
       }
-      epi_store_blocks(c, act, stash_tile(ptrs, ST_ZC0 + 3, tile), 4);
       epi_signal_act(c);
       // ---- colour layers 3..1:  zbar_c{l-1} = (zbar_cl W_cl) * [C_l > 0] -----------------------------------
 #pragma unroll 1
       for (int l = 3; l >= 1; --l) {
+        uint4 sq[4], sn[4];
+        get_chunk_raw(c, ptrs, ST_C1 + (l - 1), tile, 0, sq);
         epi_wait_acc(c);
-        epi_before_write(c);
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64], h[64];
-          acc_load64(c, cb * 64, 256, v);
-          const uint8_t* sb = epi_side_wait(c);        // C_l block cb
-          row_load64(sb, c.row, false, h);
-          epi_side_release(c);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
-          row_store64(act + cb * BLK_BYTES, c.row, true, v);
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32], h[32];
+          if (hb < 7) get_chunk_raw(c, ptrs, ST_C1 + (l - 1), tile, hb + 1, sn);
+          acc_load32(c, hb * 32, v);
+          unpack4(sq, false, h);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
+          put_chunk(c, ptrs, true, ST_ZC0 + (l - 1), tile, hb, true, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sq[i] = sn[i];
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_ZC0 + (l - 1), tile), 4);
         epi_signal_act(c);
       }
       // ---- colour lin0 backward, extras part: pts-bar, PE4(dirs)-bar, normals-bar -------------------------
       {
-        float v[64];
+        float v[48];
         epi_wait_acc(c);
-        acc_load64(c, 0, 48, v);
+        acc_load32(c, 0, v);
+        acc_load16(c, 32, v + 32);
         xbar[0] = v[0]; xbar[1] = v[1]; xbar[2] = v[2];
         nbar[0] += v[30]; nbar[1] += v[31]; nbar[2] += v[32];
         float dd[3];
@@ -444,16 +479,14 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         }
         epi_signal_act(c);                 // ACT (zbar_c0) untouched: next step re-uses it
       }
-      // ---- colour lin0 backward, feature part -> fbar (bf16) -> stash -----------------------------------
+      // ---- colour lin0 backward, feature part -> fbar (bf16) -> stash only -----------------------------------
       epi_wait_acc(c);
-      epi_before_write(c);
-#pragma unroll 1
-      for (int cb = 0; cb < 4; ++cb) {
-        float v[64];
-        acc_load64(c, cb * 64, 256, v);
-        row_store64(act + cb * BLK_BYTES, c.row, true, v);
+#pragma unroll 2
+      for (int hb = 0; hb < 8; ++hb) {
+        float v[32];
+        acc_load32(c, hb * 32, v);
+        put_chunk(c, ptrs, false, ST_FB, tile, hb, true, v);
       }
-      epi_store_blocks(c, act, stash_tile(ptrs, ST_FB, tile), 4);
       // ---- adjoint of n = J_e^T g_e: gbar_e = J_e nbar -> AUX ; PE-Hessian term into xbar -------------------
       {
         float e[64];
@@ -461,98 +494,121 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
         e[0] = nbar[0]; e[1] = nbar[1]; e[2] = nbar[2];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const float f = (float)(1 << k);
+        for (int kk = 0; kk < 6; ++kk) {
+          const float f = (float)(1 << kk);
 #pragma unroll
           for (int ci = 0; ci < 3; ++ci) {
             float sn, co;
             fast_sincos(pc.x[ci] * f, &sn, &co);
-            e[3 + 6 * k + ci] = nbar[ci] * f * co;
-            e[6 + 6 * k + ci] = -nbar[ci] * f * sn;
+            e[3 + 6 * kk + ci] = nbar[ci] * f * co;
+            e[6 + 6 * kk + ci] = -nbar[ci] * f * sn;
             if (pc.valid) {
-              const float gs = a.ge[pc.p * 40 + 3 + 6 * k + ci], gc = a.ge[pc.p * 40 + 6 + 6 * k + ci];
+              const float gs = a.ge[pc.p * 40 + 3 + 6 * kk + ci], gc = a.ge[pc.p * 40 + 6 + 6 * kk + ci];
               xbar[ci] -= (gs * sn + gc * co) * f * f * nbar[ci];
             }
           }
         }
-        row_store64(aux, c.row, true, e);          // AUX's previous store (GE of the last tile) is covered
-        epi_store_blocks(c, aux, stash_tile(ptrs, ST_GE, tile), 1);   //   by the epi_before_write above
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint4 q[4];
+          pack4(e + 32 * h, true, q);
+          row_half_store(c.aux + c.row * 128, c.swz, h, q);
+          row_half_store(stash_row(ptrs, ST_GE, tile, 0, c.row), c.swz, h, q);
+        }
         epi_signal_act(c);
       }
       // ---- adjoint pass l = 0..7:  dbar_l = W_l vbar_l ; vbar_{l+1} = dbar_l*sigma_l ; q_l -------------------
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int n_mma = (l == 3) ? 224 : 256;
-        uint8_t* qdst = stash_tile(ptrs, ST_Q0 + l, tile);
+        uint4 sq[4], sn[4], dq[4], dn[4];
+        get_chunk_raw(c, ptrs, ST_H1 + l, tile, 0, sq);      // H_{l+1} -> sigma_l
+        get_chunk_raw(c, ptrs, ST_D0 + l, tile, 0, dq);      // delta_l
         epi_wait_acc(c);
-        epi_before_write(c);
-#pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64], h[64], dl[64];
-          acc_load64(c, cb * 64, n_mma, v);
-          const uint8_t* sb = epi_side_wait(c);        // H_{l+1} block cb -> sigma_l
-          row_load64(sb, c.row, false, h);
-          epi_side_release(c);
-          sb = epi_side_wait(c);                       // D_l block cb -> delta_l
-          row_load64(sb, c.row, false, dl);
-          epi_side_release(c);
 #pragma unroll
-          for (int j = 0; j < 64; ++j) {
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32], h[32], dl[32];
+          if (hb < 7) {
+            get_chunk_raw(c, ptrs, ST_H1 + l, tile, hb + 1, sn);
+            get_chunk_raw(c, ptrs, ST_D0 + l, tile, hb + 1, dn);
+          }
+          if (hb * 32 < n_mma) {
+            acc_load32(c, hb * 32, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          unpack4(sq, false, h);
+          unpack4(dq, false, dl);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
             const float sg = sigma_from_h(h[j]);
             const float db = v[j];
             v[j] = db * sg;                                       // vbar_{l+1}
             dl[j] = SP_BETA * db * dl[j] * (1.f - sg);            // q_l
           }
-          row_store64(act + cb * BLK_BYTES, c.row, true, v);
-          row_store64(qdst + cb * BLK_BYTES, c.row, true, dl);    // straight to HBM (tile image rows)
+          put_chunk(c, ptrs, true, ST_V1 + l, tile, hb, true, v);
+          put_chunk(c, ptrs, false, ST_Q0 + l, tile, hb, true, dl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_V1 + l, tile), 4);
         if (l < 7) epi_signal_act(c);
       }
-      epi_publish_stash_all(c);            // Q0..Q7 (st.global) and every bulk store are visible
-      epi_before_write(c);
-      epi_reload_blocks(c, act, stash_tile(ptrs, ST_FB, tile), 4);
+      // ---- fbar back into ACT (own rows) -----------------------------------------------------------------------
+#pragma unroll
+      for (int hb = 0; hb < 8; ++hb) {
+        uint4 q[4];
+        get_chunk_raw(c, ptrs, ST_FB, tile, hb, q);
+        row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+      }
       epi_signal_act(c);
       // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------
-      float eb[40];
-#pragma unroll
-      for (int i = 0; i < 40; ++i) eb[i] = 0.f;
 #pragma unroll 1
       for (int l = 8; l >= 1; --l) {
+        uint4 sq[4], sn[4], dq[4], dn[4];
+        get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, 0, sq);    // H_l -> sigma_{l-1}
+        get_chunk_raw(c, ptrs, ST_Q0 + (l - 1), tile, 0, dq);    // q_{l-1} (own rows, written above)
         epi_wait_acc(c);
-        epi_before_write(c);
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64], h[64], q[64];
-          acc_load64(c, cb * 64, 256, v);
-          const uint8_t* sb = epi_side_wait(c);        // H_l block cb -> sigma_{l-1}
-          row_load64(sb, c.row, false, h);
-          epi_side_release(c);
-          sb = epi_side_wait(c);                       // Q_{l-1} block cb
-          row_load64(sb, c.row, true, q);
-          epi_side_release(c);
+        for (int hb = 0; hb < 8; ++hb) {
+          float v[32], h[32], q[32];
+          if (hb < 7) {
+            get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, hb + 1, sn);
+            get_chunk_raw(c, ptrs, ST_Q0 + (l - 1), tile, hb + 1, dn);
+          }
+          acc_load32(c, hb * 32, v);
+          unpack4(sq, false, h);
+          unpack4(dq, true, q);
           if (l == 8) {
 #pragma unroll
-            for (int j = 0; j < 64; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + cb * 64 + j), v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + hb * 32 + j), v[j]);
           }
-          if (l == 4 && cb == 3) {
+          if (l == 4 && hb == 6 && pc.valid) {                     // PE part of the skip input -> scratch row
 #pragma unroll
-            for (int j = 25; j < 64; ++j) eb[j - 25] += v[j];      // PE part of the skip input
+            for (int j = 25; j < 32; ++j) a.eb[pc.p * 40 + (j - 25)] = v[j];
+          }
+          if (l == 4 && hb == 7 && pc.valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a.eb[pc.p * 40 + 7 + j] = v[j];
           }
 #pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
-          row_store64(act + cb * BLK_BYTES, c.row, true, v);
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
+          put_chunk(c, ptrs, true, ST_Z0 + (l - 1), tile, hb, true, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
         }
-        epi_store_blocks(c, act, stash_tile(ptrs, ST_Z0 + (l - 1), tile), 4);
         epi_signal_act(c);
       }
       // ---- e-bar += W_0^T zbar_0 ; xbar += J_e^T e-bar -----------------------------------------------------------
       {
-        float v[64];
+        float v[48];
+        float eb[40];
         epi_wait_acc(c);
-        acc_load64(c, 0, 48, v);
+        acc_load32(c, 0, v);
+        acc_load16(c, 32, v + 32);
+        eb[39] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 39; ++i) eb[i] += v[i];
+        for (int i = 0; i < 39; ++i) eb[i] = v[i] + (pc.valid ? a.eb[pc.p * 40 + i] : 0.f);
         float xe[3];
         pe_jt<6>(pc.x, eb, xe);
         if (pc.valid) {
@@ -562,12 +618,11 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         tc_fence_before();
       }
     }
-    if (c.etid == 0) bulk_wait_all0();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -584,29 +639,22 @@ static void set_step(ChainStep& st, int img, int nkb_a, int nkb_aux, uint32_t a_
   st.a_fmt = (uint8_t)a_fmt;
   st.b_fmt = (uint8_t)b_fmt;
 }
-static void add_side(ChainTable& tb, ChainStep& st, int tensor, int kb) {
-  if (st.side_cnt == 0) st.side_first = (uint8_t)tb.n_side;
-  tb.side[tb.n_side].tensor = (uint8_t)tensor;
-  tb.side[tb.n_side].kb = (uint8_t)kb;
-  ++tb.n_side;
-  ++st.side_cnt;
-}
 static void init_table(ChainTable& tb) {
   memset(&tb, 0, sizeof(tb));
-  for (int i = 0; i < ST_COUNT; ++i) tb.stash_kb[i] = (uint8_t)stash_kb(i);
+  for (int i = 0; i < MAX_STEPS; ++i) tb.step[i].pf[0] = tb.step[i].pf[1] = 0xFF;
 }
+static void set_pf(ChainStep& st, int t0, int t1 = 0xFF) { st.pf[0] = (uint8_t)t0; st.pf[1] = (uint8_t)t1; }
 
 static void build_fwd_table(ChainTable& tb) {
   init_table(tb);
   int n = 0;
   for (int l = 0; l < 8; ++l) set_step(tb.step[n++], IMG_F0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_F16, FMT_F16);
   set_step(tb.step[n++], IMG_F0 + 8, 4, 0, FMT_F16, FMT_F16);                 // lin8 feature rows
-  for (int l = 7; l >= 1; --l) {                                                // reverse sweep
-    ChainStep& st = tb.step[n++];
-    set_step(st, IMG_T0 + l, 4, 0, FMT_F16, FMT_F16);
-    if (l == 7) st.wait_stash = 1;
-    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_H1 + (l - 1), cb);      // H_l
+  for (int l = 7; l >= 1; --l) {                                                // reverse sweep: reads H_l
+    set_pf(tb.step[n], ST_H1 + (l - 1));
+    set_step(tb.step[n++], IMG_T0 + l, 4, 0, FMT_F16, FMT_F16);
   }
+  set_pf(tb.step[n], ST_F);                                                     // F goes back into ACT here
   set_step(tb.step[n++], IMG_T0 + 0, 4, 0, FMT_F16, FMT_F16);                  // W_0^T delta_0 (N = 48)
   set_step(tb.step[n++], IMG_C0 + 0, 4, 1, FMT_F16, FMT_F16);                  // colour lin0: feat + extras
   for (int l = 1; l < 4; ++l) set_step(tb.step[n++], IMG_C0 + l, 4, 0, FMT_F16, FMT_F16);
@@ -617,34 +665,21 @@ static void build_fwd_table(ChainTable& tb) {
 static void build_bwd_table(ChainTable& tb) {
   init_table(tb);
   int n = 0;
-  {  // colour lin4 backward: epilogue only, ReLU mask from C4
-    ChainStep& st = tb.step[n++];
-    st.no_mma = 1;
-    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_C1 + 3, cb);
-  }
+  set_pf(tb.step[n], ST_C1 + 3);
+  tb.step[n++].no_mma = 1;          // colour lin4 backward: epilogue only (CUDA cores, 3 x 256)
   for (int l = 3; l >= 1; --l) {
-    ChainStep& st = tb.step[n++];
-    set_step(st, l == 3 ? IMG_CT3 : l == 2 ? IMG_CT2 : IMG_CT1, 4, 0, FMT_BF16, FMT_BF16);
-    for (int cb = 0; cb < 4; ++cb) add_side(tb, st, ST_C1 + (l - 1), cb);      // C_l
+    set_pf(tb.step[n], ST_C1 + (l - 1));
+    set_step(tb.step[n++], l == 3 ? IMG_CT3 : l == 2 ? IMG_CT2 : IMG_CT1, 4, 0, FMT_BF16, FMT_BF16);
   }
   set_step(tb.step[n++], IMG_CT0B, 4, 0, FMT_BF16, FMT_BF16);
   set_step(tb.step[n++], IMG_CT0A, 4, 0, FMT_BF16, FMT_BF16);
-  for (int l = 0; l < 8; ++l) {                                                 // adjoint pass
-    ChainStep& st = tb.step[n++];
-    set_step(st, IMG_FB0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_BF16, FMT_BF16);
-    for (int cb = 0; cb < 4; ++cb) {
-      add_side(tb, st, ST_H1 + l, cb);     // H_{l+1}
-      add_side(tb, st, ST_D0 + l, cb);     // delta_l
-    }
+  for (int l = 0; l < 8; ++l) {                                                 // adjoint pass: reads H_{l+1}, delta_l
+    set_pf(tb.step[n], ST_H1 + l, ST_D0 + l);
+    set_step(tb.step[n++], IMG_FB0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_BF16, FMT_BF16);
   }
-  for (int l = 8; l >= 1; --l) {                                                // ordinary backward
-    ChainStep& st = tb.step[n++];
-    set_step(st, IMG_TB0 + l, 4, 0, FMT_BF16, FMT_BF16);
-    if (l == 8) st.wait_stash = 1;
-    for (int cb = 0; cb < 4; ++cb) {
-      add_side(tb, st, ST_H1 + (l - 1), cb);   // H_l
-      add_side(tb, st, ST_Q0 + (l - 1), cb);   // q_{l-1}
-    }
+  for (int l = 8; l >= 1; --l) {                                                // ordinary backward: reads H_l, q_{l-1}
+    set_pf(tb.step[n], ST_H1 + (l - 1), ST_Q0 + (l - 1));
+    set_step(tb.step[n++], IMG_TB0 + l, 4, 0, FMT_BF16, FMT_BF16);
   }
   set_step(tb.step[n++], IMG_TB0 + 0, 4, 0, FMT_BF16, FMT_BF16);
   tb.n_steps = n;
@@ -715,7 +750,7 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
                              float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
                              const float* b8, const float* w8row, const float* bias_col, const float* bc4,
                              const float* wc4, const float* rgb, const float* ge, const float* d_sdf, const float* d_nrm,
-                             const float* d_rgb, float* d_pts, float* d_dirs, float* zc4, void* stream) {
+                             const float* d_rgb, float* d_pts, float* d_dirs, float* zc4, float* eb_scratch, void* stream) {
   static ChainTable tb;
   static bool init = false;
   if (!init) {
@@ -727,10 +762,10 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
   ChainPtrs ptrs;
   int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, wc4);
   if (st) return st;
-  FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && d_pts && d_dirs && zc4, "fmov_fine_bwd: null argument");
+  FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && d_pts && d_dirs && zc4 && eb_scratch, "fmov_fine_bwd: null argument");
   for (int i = 0; i < ST_COUNT; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);
   a.rgb = const_cast<float*>(rgb); a.ge = const_cast<float*>(ge);
-  a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4;
+  a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4; a.eb = eb_scratch;
   fine_bwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
   FMOV_LAUNCH_CHECK("fine_bwd_kernel");
   return OK;

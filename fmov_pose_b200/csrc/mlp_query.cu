@@ -13,7 +13,7 @@
 
 namespace fmov {
 
-using QL = ChainLayout<3, false>;
+using QL = ChainLayout;
 
 struct QueryArgs {
   // input modes: 0 = points [P,3]; 1 = rays (o,d [B,3]) x z [B, z_stride], S samples per ray;
@@ -34,7 +34,7 @@ struct QueryArgs {
   float out_scale;      // sign / scale applied to the output (-1/scale for extract_fields)
   const float* bias;    // [8][256] biases of layers 0..7 (padded with zeros)
   const float* w8;      // [256] row 0 of lin8 (effective weight), fp32
-  float b8;             // lin8.bias[0]
+  const float* b8;      // lin8.bias (device), element 0 used
   float* out;           // [P]
 };
 
@@ -86,13 +86,10 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
     }
   }
 #pragma unroll
-  for (int ch = 0; ch < 8; ++ch) {
-    uint4 v;
-    v.x = pack_h2(e[ch * 8 + 0], e[ch * 8 + 1]);
-    v.y = pack_h2(e[ch * 8 + 2], e[ch * 8 + 3]);
-    v.z = pack_h2(e[ch * 8 + 4], e[ch * 8 + 5]);
-    v.w = pack_h2(e[ch * 8 + 6], e[ch * 8 + 7]);
-    blk_st_chunk(blk, row, ch, v);
+  for (int h = 0; h < 2; ++h) {
+    uint4 q[4];
+    pack4(e + 32 * h, false, q);
+    row_half_store(blk + row * 128, row & 7, h, q);
   }
 }
 
@@ -102,77 +99,68 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
-  uint8_t* act = base + QL::ACT;
-  uint8_t* aux = base + QL::AUX;
+  uint8_t* act0 = base + QL::ACT;
+  uint8_t* aux0 = base + QL::AUX;
   uint8_t* wst = base + QL::WST;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (threadIdx.x == 0) chain_init_barriers<3>(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 256);
+  if (threadIdx.x == 0) chain_init_barriers(s);
+  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) chain_weight_producer<3>(tb, ptrs.weights, s, wst, n_my);
+    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
   } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer<3>(tb, s, act, aux, wst, tmem, n_my);
-  } else if (warp >= EPI_WARP0) {
+    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+  } else {
     EpiCtx c;
-    epi_init(c, s, act, aux, nullptr, tmem);
-    for (int t = 0; t < n_my; ++t) {
-      const long long tile = (long long)blockIdx.x + (long long)t * gridDim.x;
+    epi_init(c, s, act0, aux0, tmem);
+    const float b8 = __ldg(a.b8);
+    for (int k = c.slot; k < n_my; k += CH_SLOTS) {
+      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const long long p = tile * TILE_M + c.row;
       const bool valid = p < a.P;
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) load_point(a, p, x);
       x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
-      pe6_to_block(aux, c.row, x);
+      pe6_to_block(c.aux, c.row, x);
       epi_signal_act(c);
-      float sdf = a.b8;
-      for (int l = 0; l < 8; ++l) {
-        const int n_valid = (l == 3) ? 217 : 256;
-        const float* bias = a.bias + l * 256;
-        epi_wait_acc(c);
+      float sdf = b8;
 #pragma unroll 1
-        for (int cb = 0; cb < 4; ++cb) {
-          float v[64];
-          if (cb * 64 < tb.step[l].n) {
-            tmem_ld32(c.tmem + cb * 64, v);
-            if (cb * 64 + 32 < tb.step[l].n) tmem_ld32(c.tmem + cb * 64 + 32, v + 32);
-            tmem_ld_wait();
-          }
+      for (int l = 0; l < 8; ++l) {
+        const float* bias = a.bias + l * 256;
+        const int n_mma = (l == 3) ? 224 : 256;       // lin3 has 217 outputs; columns 217.. meet zero weights next
+        epi_wait_acc(c);
+#pragma unroll 2
+        for (int hb = 0; hb < 8; ++hb) {
+          if (hb * 32 >= n_mma) break;
+          float v[32];
+          acc_load32(c, hb * 32, v);
 #pragma unroll
-          for (int j4 = 0; j4 < 16; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + cb * 64) + j4);
-            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              v[j] = (cb * 64 + j < n_valid) ? softplus100(v[j] + bb[e]) : 0.f;
-            }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+            v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
+            v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
+            v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
+            v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
           }
           if (l == 7) {
 #pragma unroll
-            for (int j4 = 0; j4 < 16; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + cb * 64) + j4);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + hb * 32) + j4);
               sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
               sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
             }
           } else {
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              uint4 q;
-              q.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]);
-              q.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
-              q.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
-              q.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
-              blk_st_chunk(act + cb * BLK_BYTES, c.row, ch, q);
-            }
+            uint4 q[4];
+            pack4(v, false, q);
+            row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
           }
         }
         if (l < 7) epi_signal_act(c);
@@ -184,7 +172,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -206,6 +194,7 @@ static void build_query_table(ChainTable& tb) {
     st.nkb_aux = (l == 0 || l == 4) ? 1 : 0;
     st.a_fmt = FMT_F16;
     st.b_fmt = FMT_F16;
+    st.pf[0] = st.pf[1] = 0xFF;
     off += (uint32_t)st.n * 128u * (st.nkb_a + st.nkb_aux);
   }
 }
@@ -249,7 +238,7 @@ static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cud
 }
 
 extern "C" int fmov_sdf_query_points(const float* pts, long long P, const void* wblob, const float* bias8x256,
-                                     const float* w8_row0, float b8, float in_scale, float out_scale, float* out,
+                                     const float* w8_row0, const float* b8, float in_scale, float out_scale, float* out,
                                      void* stream) {
   FMOV_REQUIRE(P >= 0 && (P == 0 || (pts && out && wblob && bias8x256 && w8_row0)), "fmov_sdf_query_points: null argument");
   QueryArgs a;
@@ -261,7 +250,7 @@ extern "C" int fmov_sdf_query_points(const float* pts, long long P, const void* 
 
 extern "C" int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z, long long B, int S,
                                    int z_stride, int z_off, const void* wblob, const float* bias8x256,
-                                   const float* w8_row0, float b8, float in_scale, float out_scale, float* out,
+                                   const float* w8_row0, const float* b8, float in_scale, float out_scale, float* out,
                                    void* stream) {
   FMOV_REQUIRE(B >= 0 && S > 0 && z_stride >= S + z_off, "fmov_sdf_query_rays: bad shape B=%lld S=%d stride=%d off=%d", B, S,
                z_stride, z_off);
@@ -274,7 +263,7 @@ extern "C" int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, con
 }
 
 extern "C" int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
-                                   const void* wblob, const float* bias8x256, const float* w8_row0, float b8,
+                                   const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8,
                                    float in_scale, float out_scale, float* out, void* stream) {
   FMOV_REQUIRE(res > 0 && first >= 0 && count >= 0 && first + count <= (long long)res * res * res,
                "fmov_sdf_query_grid: bad range first=%lld count=%lld res=%d", first, count, res);

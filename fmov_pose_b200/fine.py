@@ -149,11 +149,12 @@ def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_n
     d_pts = torch.empty(P, 3, dtype=torch.float32, device=dev)
     d_dirs = torch.empty(P, 3, dtype=torch.float32, device=dev)
     zc4 = torch.empty(P, 4, dtype=torch.float32, device=dev)
+    eb = torch.empty(P, 40, dtype=torch.float32, device=dev)
     with L.timed("fine_bwd"):
       L.check(L.lib().fmov_fine_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),
                                   L.ptr(fw.bias_col), L.ptr(fw.bc4), L.ptr(fw.wc4), L.ptr(rgb), L.ptr(ge), L.ptr(d_sdf),
-                                  L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_pts), L.ptr(d_dirs), L.ptr(zc4), L.stream()),
+                                  L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_pts), L.ptr(d_dirs), L.ptr(zc4), L.ptr(eb), L.stream()),
             "fmov_fine_bwd")
     return d_pts, d_dirs, zc4
 

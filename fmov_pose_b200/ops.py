@@ -13,7 +13,7 @@ def sdf_query_points(qw, pts, in_scale=1.0, out_scale=1.0):
     out = torch.empty(P, 1, dtype=torch.float32, device=pts.device)
     if P:
         L.check(L.lib().fmov_sdf_query_points(L.ptr(pts), L.c_ll(P), L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8),
-                                              L.c_float(qw.b8), L.c_float(in_scale), L.c_float(out_scale), L.ptr(out),
+                                              L.ptr(qw.b8), L.c_float(in_scale), L.c_float(out_scale), L.ptr(out),
                                               L.stream()), "fmov_sdf_query_points")
     return out
 
@@ -25,7 +25,7 @@ def sdf_query_rays(qw, rays_o, rays_d, z, S, z_off=0, in_scale=1.0, out_scale=1.
     out = torch.empty(B, S, dtype=torch.float32, device=z.device)
     if B:
         L.check(L.lib().fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), S, z.shape[1], z_off,
-                                            L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.c_float(qw.b8),
+                                            L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
                                             L.c_float(in_scale), L.c_float(out_scale), L.ptr(out), L.stream()),
                 "fmov_sdf_query_rays")
     return out
@@ -36,7 +36,7 @@ def sdf_query_grid(qw, bmin, bmax, res, first, count, out, in_scale=1.0, out_sca
     bm = (ctypes.c_float * 3)(*[float(v) for v in bmin])
     bx = (ctypes.c_float * 3)(*[float(v) for v in bmax])
     L.check(L.lib().fmov_sdf_query_grid(bm, bx, int(res), L.c_ll(first), L.c_ll(count), L.ptr(qw.blob), L.ptr(qw.bias),
-                                        L.ptr(qw.w8), L.c_float(qw.b8), L.c_float(in_scale), L.c_float(out_scale),
+                                        L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(in_scale), L.c_float(out_scale),
                                         L.ptr(out), L.stream()), "fmov_sdf_query_grid")
     return out
 
@@ -78,7 +78,7 @@ def hierarchical_sample(qw, rays_o, rays_d, near, far, t_rand, n_samples, n_impo
     def query(z_off, cnt):
       with L.timed("sdf_query"):
         L.check(lib.fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), cnt, S, z_off,
-                                        L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.c_float(qw.b8),
+                                        L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
                                         L.c_float(scale), L.c_float(1.0 / scale), L.ptr(sdf_tmp), L.stream()),
                 "fmov_sdf_query_rays")
 

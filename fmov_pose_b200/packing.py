@@ -82,4 +82,4 @@ class SdfQueryWeights:
         for l in range(8):
             self.bias[l, : b[l].numel()] = b[l].detach().float()
         self.w8 = W[8][0].detach().float().contiguous()
-        self.b8 = float(b[8][0])
+        self.b8 = b[8].detach().float().contiguous()

@@ -40,17 +40,17 @@ int fmov_selftest_gemm(const void* a_img, const void* b_img, int n, int kblocks,
 /* replaces models/fields.py:88-107 at the call sites models/renderer.py:424-428 (coarse),
  * :230-232 (up-sample rounds) and :506 via extract_fields :9-37 (dense grid).
  * wblob: forward weight images of lin0..lin7 (fmov_sdf_fwd_blob_bytes / _offset give the layout);
- * bias8x256: biases of lin0..lin7 zero-padded to 256; w8_row0/b8: row 0 of lin8.             */
+ * bias8x256: biases of lin0..lin7 zero-padded to 256; w8_row0: row 0 of lin8; b8: lin8.bias (device, [0] used).             */
 long long fmov_sdf_fwd_blob_bytes(void);
 long long fmov_sdf_fwd_blob_offset(int layer);
 int fmov_sdf_query_points(const float* pts, long long P, const void* wblob, const float* bias8x256, const float* w8_row0,
-                          float b8, float in_scale, float out_scale, float* out, void* stream);
+                          const float* b8, float in_scale, float out_scale, float* out, void* stream);
 int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z, long long B, int S, int z_stride,
-                        int z_off, const void* wblob, const float* bias8x256, const float* w8_row0, float b8,
+                        int z_off, const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8,
                         float in_scale, float out_scale, float* out, void* stream);
 /* bmin3/bmax3 are HOST float[3]; points first..first+count of the x-major res^3 grid. */
 int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
-                        const void* wblob, const float* bias8x256, const float* w8_row0, float b8, float in_scale,
+                        const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
                         float out_scale, float* out, void* stream);
 
 /* ---- pose + ray generation ------------------------------------------------------------ */
@@ -126,7 +126,7 @@ int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, 
                   const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
                   const float* bias_col, const float* bc4, const float* wc4, const float* rgb, const float* ge,
                   const float* d_sdf, const float* d_nrm, const float* d_rgb, float* d_pts, float* d_dirs, float* zc4,
-                  void* stream);
+                  float* eb_scratch /* [P,40] */, void* stream);
 /* weight / bias gradients into one flat fp32 buffer (zeroed by the call); fmov_grad_offset(kind, layer):
  * kind 0 sdf weight [out,in], 1 sdf bias, 2 colour weight, 3 colour bias (effective weights, reference shapes) */
 long long fmov_grad_offset(int kind, int layer);
