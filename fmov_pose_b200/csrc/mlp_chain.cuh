@@ -222,6 +222,18 @@ __device__ __forceinline__ void acc_load16(const EpiCtx& c, int col0, float* v) 
 
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------
 // chunk ch (0..7) of row r sits at 16-byte position (ch ^ (r & 7)) of the 128-byte row.
+__device__ __forceinline__ void pack4_grad(const float* v, uint4* q) {   // gradient tile format
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (kGradBf16) {
+      q[i].x = pack_bf2(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_bf2(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_bf2(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_bf2(v[i * 8 + 6], v[i * 8 + 7]);
+    } else {
+      q[i].x = pack_h2_sat(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_h2_sat(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_h2_sat(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_h2_sat(v[i * 8 + 6], v[i * 8 + 7]);
+    }
+  }
+}
 __device__ __forceinline__ void pack4(const float* v, bool bf16, uint4* q) {   // 32 floats -> 4 chunks
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

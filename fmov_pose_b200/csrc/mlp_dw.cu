@@ -47,7 +47,8 @@ struct DwPtrs {
 };
 
 __global__ void __launch_bounds__(DW_THREADS, 1)
-dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs ptrs, long long n_tiles, float* grads) {
+dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs ptrs, long long n_tiles, float* grads,
+          const float* amax) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   __shared__ uint64_t full[DW_STAGES], ready[DW_STAGES], empty[DW_STAGES], done_bar;
@@ -101,7 +102,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
       for (int pr = 0; pr < jb.npairs; ++pr) {
         // tcgen05.mma kind::f16 cannot mix an fp16 with a bf16 operand (illegal instruction on sm_100a):
         // the converter warps have rewritten the fp16 operand of the pair as bf16 in shared memory.
-        const uint32_t idesc = umma_idesc(128, n_mma, FMT_BF16, FMT_BF16, 1, 1);
+        const uint32_t idesc = umma_idesc(128, n_mma, kGradFmt, kGradFmt, 1, 1);
         for (int h = 0; h < 2; ++h, ++it) {
           const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
           const uint32_t sa = smem_u32(base + slot * DW_STAGE_BYTES);
@@ -139,8 +140,10 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
             mbar_wait(&full[slot], n & 1);
             uint4* reg = nullptr;
             int nchunks = 0;
-            if (!jb.a_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa); nchunks = DW_ABYTES / 16; }
-            else if (!jb.b_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa + DW_ABYTES); nchunks = jb.b_blocks * (DW_HALF * 128) / 16; }
+            if (kGradBf16) {      // fp16 gradient tiles need no conversion: every operand is fp16 already
+              if (!jb.a_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa); nchunks = DW_ABYTES / 16; }
+              else if (!jb.b_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa + DW_ABYTES); nchunks = jb.b_blocks * (DW_HALF * 128) / 16; }
+            }
             for (int i = ctid; i < nchunks; i += 128) {
               uint4 q = reg[i];
               float2 f;
@@ -154,7 +157,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
 #pragma unroll 8
               for (int r = 0; r < DW_HALF; ++r) {
                 const uint32_t w = *reinterpret_cast<const uint32_t*>(sa + boff + r * 128 + ((bchunk ^ (r & 7)) << 4));
-                const float2 f = unpack_bf2(w);
+                const float2 f = kGradBf16 ? unpack_bf2(w) : unpack_h2(w);
                 bsum0 += f.x;
                 bsum1 += f.y;
               }
@@ -163,8 +166,9 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
             mbar_arrive(&ready[slot]);
           }
       if (jb.bias_off >= 0) {
-        if (bcol < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol, bsum0);
-        if (bcol + 1 < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol + 1, bsum1);
+        const float ginv_b = 1.0f / grad_scale_from_amax(__ldg(amax));
+        if (bcol < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol, bsum0 * ginv_b);
+        if (bcol + 1 < jb.bias_n) atomicAdd(grads + jb.bias_off + bcol + 1, bsum1 * ginv_b);
       }
     }
     // epilogue: wait for the whole range, then flush the two [128 x N] accumulators with atomics
@@ -173,6 +177,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     float* out = grads + jb.out_off;
+    const float oscale = jb.scale / grad_scale_from_amax(__ldg(amax));
     for (int mh = 0; mh < 2; ++mh) {
       const int m = mh * 128 + row;
       for (int c0 = 0; c0 < n_mma; c0 += 16) {
@@ -182,7 +187,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
         if (m < jb.m_valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (c0 + j < jb.n_valid) atomicAdd(out + (size_t)m * jb.ld + jb.col_off + c0 + j, v[j] * jb.scale);
+            if (c0 + j < jb.n_valid) atomicAdd(out + (size_t)m * jb.ld + jb.col_off + c0 + j, v[j] * oscale);
         }
       }
     }
@@ -200,7 +205,8 @@ struct ColsumArgs {
   DwPtrs ptrs;
   long long n_tiles, P;
   const float* d_sdf;     // [P]
-  const float* zc4;       // [P,4]
+  const float* zc4;       // [P,4]  (loss-scaled)
+  const float* amax;
   float* grads;
   long long off_b_sdf[9];  // float offsets of lin{l}.bias grads
   long long off_b_col[5];
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) { w8[i] = 0.f; c4[0][i] = c4[1][i] = c4[2][i] = 0.f; }
   float extra[4] = {0.f, 0.f, 0.f, 0.f};
+  const float ginv = 1.0f / grad_scale_from_amax(__ldg(a.amax));
   for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const uint8_t* th = a.ptrs.stash[S_H1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
     const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
       const long long p = t * 128 + r;
       const bool ok = p < a.P;
       const float sb = ok ? a.d_sdf[p] : 0.f;
-      const float z0 = ok ? a.zc4[p * 4] : 0.f, z1 = ok ? a.zc4[p * 4 + 1] : 0.f, z2 = ok ? a.zc4[p * 4 + 2] : 0.f;
+      const float z0 = ok ? a.zc4[p * 4] * ginv : 0.f, z1 = ok ? a.zc4[p * 4 + 1] * ginv : 0.f, z2 = ok ? a.zc4[p * 4 + 2] * ginv : 0.f;
       const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
       const uint4 qh = *reinterpret_cast<const uint4*>(th + off);
       const uint4 qv = *reinterpret_cast<const uint4*>(tv + off);
@@ -235,8 +242,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
       const uint32_t hh[4] = {qh.x, qh.y, qh.z, qh.w}, vv[4] = {qv.x, qv.y, qv.z, qv.w}, cc[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 fh = unpack_h2(hh[j]), fv = unpack_bf2(vv[j]), fc = unpack_h2(cc[j]);
-        w8[2 * j] += sb * fh.x + fv.x; w8[2 * j + 1] += sb * fh.y + fv.y;
+        const float2 fh = unpack_h2(hh[j]), fv = kGradBf16 ? unpack_bf2(vv[j]) : unpack_h2(vv[j]), fc = unpack_h2(cc[j]);
+        w8[2 * j] += sb * fh.x + fv.x * ginv; w8[2 * j + 1] += sb * fh.y + fv.y * ginv;
         c4[0][2 * j] += z0 * fc.x; c4[0][2 * j + 1] += z0 * fc.y;
         c4[1][2 * j] += z1 * fc.x; c4[1][2 * j + 1] += z1 * fc.y;
         c4[2][2 * j] += z2 * fc.x; c4[2][2 * j + 1] += z2 * fc.y;
@@ -259,8 +266,32 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
   }
 }
 
+// max |x| over the three upstream per-sample gradient arrays -> device scalar (float bits, non-negative)
+__global__ void grad_amax_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
+                                 const float* __restrict__ c, long long nc, unsigned int* out) {
+  float m = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nc; i += stride) m = fmaxf(m, fabsf(c[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && isfinite(m)) atomicMax(out, __float_as_uint(m));
+}
+
 }  // namespace fmov
 using namespace fmov;
+
+/* amax (device float) = max |d_sdf|, |d_nrm|, |d_rgb| : fixes the loss scale of the fp16 gradient tiles */
+extern "C" int fmov_grad_amax(const float* d_sdf, const float* d_nrm, const float* d_rgb, long long P, float* amax,
+                              void* stream) {
+  FMOV_REQUIRE(P > 0 && d_sdf && d_nrm && d_rgb && amax, "fmov_grad_amax: bad arguments");
+  FMOV_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), (cudaStream_t)stream));
+  grad_amax_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(d_sdf, P, d_nrm, 3 * P, d_rgb, 3 * P,
+                                                         reinterpret_cast<unsigned int*>(amax));
+  FMOV_LAUNCH_CHECK("grad_amax_kernel");
+  return OK;
+}
 
 // ---- flat gradient buffer layout (fp32), shapes = the reference parameters' effective weights -----------------
 static const int SDF_OUT[9] = {256, 256, 256, 217, 256, 256, 256, 256, 257};
@@ -299,27 +330,28 @@ static void add_job(DwPlan& pl, int npairs, int a0, int b0, int a0bf, int b0bf, 
 static void build_plan(DwPlan& pl, int n_ctas) {
   memset(&pl, 0, sizeof(pl));
   const float rs2 = 0.70710678118654752f;
+  const int G = kGradBf16 ? 1 : 0;     // format flag of gradient tiles
   // SDF layers 1..7: (Zbar_l, H_l) + (Delta_l, Vbar_l)
   for (int l = 1; l <= 7; ++l) {
     const int nv = (l == 4) ? 217 : 256;
-    add_job(pl, 2, S_Z0 + l, S_H1 + (l - 1), 1, 0, S_D0 + l, S_V1 + (l - 1), 0, 1, 4, SDF_OUT[l], nv, 256, 0,
+    add_job(pl, 2, S_Z0 + l, S_H1 + (l - 1), G, 0, S_D0 + l, S_V1 + (l - 1), 0, G, 4, SDF_OUT[l], nv, 256, 0,
             fmov_grad_offset(0, l), l == 4 ? rs2 : 1.f, fmov_grad_offset(1, l), SDF_OUT[l]);
   }
   // layer 4, PE columns 217..255: (Zbar_4, PE) + (Delta_4, GE)
-  add_job(pl, 2, S_Z0 + 4, S_PE, 1, 0, S_D0 + 4, S_GE, 0, 1, 1, 256, 39, 256, 217, fmov_grad_offset(0, 4), rs2);
+  add_job(pl, 2, S_Z0 + 4, S_PE, G, 0, S_D0 + 4, S_GE, 0, G, 1, 256, 39, 256, 217, fmov_grad_offset(0, 4), rs2);
   // layer 0: (Zbar_0, PE) + (Delta_0, GE)
-  add_job(pl, 2, S_Z0 + 0, S_PE, 1, 0, S_D0 + 0, S_GE, 0, 1, 1, 256, 39, 39, 0, fmov_grad_offset(0, 0), 1.f,
+  add_job(pl, 2, S_Z0 + 0, S_PE, G, 0, S_D0 + 0, S_GE, 0, G, 1, 256, 39, 39, 0, fmov_grad_offset(0, 0), 1.f,
           fmov_grad_offset(1, 0), 256);
   // layer 8 feature rows 1..256: (fbar, H8)
-  add_job(pl, 1, S_FB, S_H1 + 7, 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(0, 8) + 256, 1.f,
+  add_job(pl, 1, S_FB, S_H1 + 7, G, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(0, 8) + 256, 1.f,
           fmov_grad_offset(1, 8) + 1, 256);
   // colour layers 1..3: (Zbar_cl, C_l); layer 0: (Zbar_c0, F) -> cols 33.., (Zbar_c0, X) -> cols 0..32
   for (int l = 1; l <= 3; ++l)
-    add_job(pl, 1, S_ZC0 + l, S_C1 + (l - 1), 1, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(2, l), 1.f,
+    add_job(pl, 1, S_ZC0 + l, S_C1 + (l - 1), G, 0, 0, 0, 0, 0, 4, 256, 256, 256, 0, fmov_grad_offset(2, l), 1.f,
             fmov_grad_offset(3, l), 256);
-  add_job(pl, 1, S_ZC0 + 0, S_F, 1, 0, 0, 0, 0, 0, 4, 256, 256, 289, 33, fmov_grad_offset(2, 0), 1.f,
+  add_job(pl, 1, S_ZC0 + 0, S_F, G, 0, 0, 0, 0, 0, 4, 256, 256, 289, 33, fmov_grad_offset(2, 0), 1.f,
           fmov_grad_offset(3, 0), 256);
-  add_job(pl, 1, S_ZC0 + 0, S_X, 1, 0, 0, 0, 0, 0, 1, 256, 33, 289, 0, fmov_grad_offset(2, 0), 1.f);
+  add_job(pl, 1, S_ZC0 + 0, S_X, G, 0, 0, 0, 0, 0, 1, 256, 33, 289, 0, fmov_grad_offset(2, 0), 1.f);
   // distribute CTAs proportionally to cost (bytes streamed per tile)
   float cost[DW_MAX_JOBS], total = 0.f;
   for (int j = 0; j < pl.n_jobs; ++j) {
@@ -343,8 +375,9 @@ static void build_plan(DwPlan& pl, int n_ctas) {
 }
 
 /* grads: flat fp32 buffer of fmov_grad_floats() floats, zeroed by this call. stash: HOST array of device pointers. */
-extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, float* grads, void* stream) {
-  FMOV_REQUIRE(P > 0 && stash && d_sdf && zc4 && grads, "fmov_dw: bad arguments");
+extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, const float* amax, float* grads,
+                       void* stream) {
+  FMOV_REQUIRE(P > 0 && stash && d_sdf && zc4 && amax && grads, "fmov_dw: bad arguments");
   static DwPlan plan;
   static bool init = false;
   static int n_ctas = 148;
@@ -364,10 +397,10 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
   }
   const long long n_tiles = (P + 127) / 128;
   FMOV_CUDA(cudaMemsetAsync(grads, 0, (size_t)fmov_grad_floats() * sizeof(float), (cudaStream_t)stream));
-  dw_kernel<<<n_ctas, DW_THREADS, DW_STAGES * DW_STAGE_BYTES + 1024, (cudaStream_t)stream>>>(plan, ptrs, n_tiles, grads);
+  dw_kernel<<<n_ctas, DW_THREADS, DW_STAGES * DW_STAGE_BYTES + 1024, (cudaStream_t)stream>>>(plan, ptrs, n_tiles, grads, amax);
   FMOV_LAUNCH_CHECK("dw_kernel");
   ColsumArgs ca;
-  ca.ptrs = ptrs; ca.n_tiles = n_tiles; ca.P = P; ca.d_sdf = d_sdf; ca.zc4 = zc4; ca.grads = grads;
+  ca.ptrs = ptrs; ca.n_tiles = n_tiles; ca.P = P; ca.d_sdf = d_sdf; ca.zc4 = zc4; ca.amax = amax; ca.grads = grads;
   for (int l = 0; l < 9; ++l) ca.off_b_sdf[l] = fmov_grad_offset(1, l);
   for (int l = 0; l < 5; ++l) ca.off_b_col[l] = fmov_grad_offset(3, l);
   ca.off_w8 = fmov_grad_offset(0, 8);

@@ -83,6 +83,7 @@ struct FineArgs {
   const float* d_sdf; const float* d_nrm; const float* d_rgb; // bwd inputs
   float* d_pts; float* d_dirs; float* zc4;                    // bwd outputs: [P,3],[P,3],[P,4]
   float* eb;                                                  // bwd scratch [P,40]
+  const float* amax;                                          // bwd: device scalar, max |upstream gradient|
 };
 
 __device__ __forceinline__ uint8_t* stash_tile(const ChainPtrs& ptrs, int id, long long tile) {
@@ -151,6 +152,13 @@ __device__ __forceinline__ void put_chunk(const EpiCtx& c, const ChainPtrs& ptrs
                                           long long tile, int hb, bool bf16, const float* v) {
   uint4 q[4];
   pack4(v, bf16, q);
+  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+}
+__device__ __forceinline__ void put_chunk_grad(const EpiCtx& c, const ChainPtrs& ptrs, bool to_act, int stash_id,
+                                               long long tile, int hb, const float* v) {
+  uint4 q[4];
+  pack4_grad(v, q);
   if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
   if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
 }
@@ -411,17 +419,19 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   } else {
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
+    const float gscale = grad_scale_from_amax(__ldg(a.amax));
+    const float ginv = 1.0f / gscale;
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
       float sbar = 0.f, nbar[3] = {0.f, 0.f, 0.f}, zc4[3] = {0.f, 0.f, 0.f}, xbar[3] = {0.f, 0.f, 0.f};
       if (pc.valid) {
-        sbar = a.d_sdf[pc.p];
+        sbar = a.d_sdf[pc.p] * gscale;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          nbar[i] = a.d_nrm[pc.p * 3 + i];
+          nbar[i] = a.d_nrm[pc.p * 3 + i] * gscale;
           const float r = a.rgb[pc.p * 3 + i];
-          zc4[i] = a.d_rgb[pc.p * 3 + i] * r * (1.f - r);     // sigmoid backward
+          zc4[i] = a.d_rgb[pc.p * 3 + i] * gscale * r * (1.f - r);     // sigmoid backward (loss-scaled)
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) a.zc4[pc.p * 4 + i] = zc4[i];
@@ -440,7 +450,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           const float ab = zc4[0] * __ldg(a.wc4 + col) + zc4[1] * __ldg(a.wc4 + 256 + col) + zc4[2] * __ldg(a.wc4 + 512 + col);
           v[j] = h[j] > 0.f ? ab : 0.f;
         }
-        put_chunk(c, ptrs, true, ST_ZC0 + 3, tile, hb, true, v);
+        put_chunk_grad(c, ptrs, true, ST_ZC0 + 3, tile, hb, v);
       }
       epi_signal_act(c);
       // ---- colour layers 3..1:  zbar_c{l-1} = (zbar_cl W_cl) * [C_l > 0] -----------------------------------
@@ -457,7 +467,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           unpack4(sq, false, h);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
-          put_chunk(c, ptrs, true, ST_ZC0 + (l - 1), tile, hb, true, v);
+          put_chunk_grad(c, ptrs, true, ST_ZC0 + (l - 1), tile, hb, v);
 #pragma unroll
           for (int i = 0; i < 4; ++i) sq[i] = sn[i];
         }
@@ -475,7 +485,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         pe_jt<4>(pc.d, v + 3, dd);
         if (pc.valid) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) a.d_dirs[pc.p * 3 + i] = dd[i];
+          for (int i = 0; i < 3; ++i) a.d_dirs[pc.p * 3 + i] = dd[i] * ginv;
         }
         epi_signal_act(c);                 // ACT (zbar_c0) untouched: next step re-uses it
       }
@@ -485,7 +495,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       for (int hb = 0; hb < 8; ++hb) {
         float v[32];
         acc_load32(c, hb * 32, v);
-        put_chunk(c, ptrs, false, ST_FB, tile, hb, true, v);
+        put_chunk_grad(c, ptrs, false, ST_FB, tile, hb, v);
       }
       // ---- adjoint of n = J_e^T g_e: gbar_e = J_e nbar -> AUX ; PE-Hessian term into xbar -------------------
       {
@@ -511,7 +521,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint4 q[4];
-          pack4(e + 32 * h, true, q);
+          pack4_grad(e + 32 * h, q);
           row_half_store(c.aux + c.row * 128, c.swz, h, q);
           row_half_store(stash_row(ptrs, ST_GE, tile, 0, c.row), c.swz, h, q);
         }
@@ -547,8 +557,8 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             v[j] = db * sg;                                       // vbar_{l+1}
             dl[j] = SP_BETA * db * dl[j] * (1.f - sg);            // q_l
           }
-          put_chunk(c, ptrs, true, ST_V1 + l, tile, hb, true, v);
-          put_chunk(c, ptrs, false, ST_Q0 + l, tile, hb, true, dl);
+          put_chunk_grad(c, ptrs, true, ST_V1 + l, tile, hb, v);
+          put_chunk_grad(c, ptrs, false, ST_Q0 + l, tile, hb, dl);
 #pragma unroll
           for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
         }
@@ -578,7 +588,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           }
           acc_load32(c, hb * 32, v);
           unpack4(sq, false, h);
-          unpack4(dq, true, q);
+          unpack4(dq, kGradBf16, q);
           if (l == 8) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + hb * 32 + j), v[j]);
@@ -593,7 +603,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
-          put_chunk(c, ptrs, true, ST_Z0 + (l - 1), tile, hb, true, v);
+          put_chunk_grad(c, ptrs, true, ST_Z0 + (l - 1), tile, hb, v);
 #pragma unroll
           for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
         }
@@ -613,7 +623,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         pe_jt<6>(pc.x, eb, xe);
         if (pc.valid) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) a.d_pts[pc.p * 3 + i] = xbar[i] + xe[i];
+          for (int i = 0; i < 3; ++i) a.d_pts[pc.p * 3 + i] = (xbar[i] + xe[i]) * ginv;
         }
         tc_fence_before();
       }
@@ -669,19 +679,19 @@ static void build_bwd_table(ChainTable& tb) {
   tb.step[n++].no_mma = 1;          // colour lin4 backward: epilogue only (CUDA cores, 3 x 256)
   for (int l = 3; l >= 1; --l) {
     set_pf(tb.step[n], ST_C1 + (l - 1));
-    set_step(tb.step[n++], l == 3 ? IMG_CT3 : l == 2 ? IMG_CT2 : IMG_CT1, 4, 0, FMT_BF16, FMT_BF16);
+    set_step(tb.step[n++], l == 3 ? IMG_CT3 : l == 2 ? IMG_CT2 : IMG_CT1, 4, 0, kGradFmt, kGradFmt);
   }
-  set_step(tb.step[n++], IMG_CT0B, 4, 0, FMT_BF16, FMT_BF16);
-  set_step(tb.step[n++], IMG_CT0A, 4, 0, FMT_BF16, FMT_BF16);
+  set_step(tb.step[n++], IMG_CT0B, 4, 0, kGradFmt, kGradFmt);
+  set_step(tb.step[n++], IMG_CT0A, 4, 0, kGradFmt, kGradFmt);
   for (int l = 0; l < 8; ++l) {                                                 // adjoint pass: reads H_{l+1}, delta_l
     set_pf(tb.step[n], ST_H1 + l, ST_D0 + l);
-    set_step(tb.step[n++], IMG_FB0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_BF16, FMT_BF16);
+    set_step(tb.step[n++], (kGradBf16 ? IMG_FB0 : IMG_F0) + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, kGradFmt, kGradFmt);
   }
   for (int l = 8; l >= 1; --l) {                                                // ordinary backward: reads H_l, q_{l-1}
     set_pf(tb.step[n], ST_H1 + (l - 1), ST_Q0 + (l - 1));
-    set_step(tb.step[n++], IMG_TB0 + l, 4, 0, FMT_BF16, FMT_BF16);
+    set_step(tb.step[n++], (kGradBf16 || l == 8 ? IMG_TB0 : IMG_T0) + l, 4, 0, kGradFmt, kGradFmt);   // (T8 only exists in the TB range)
   }
-  set_step(tb.step[n++], IMG_TB0 + 0, 4, 0, FMT_BF16, FMT_BF16);
+  set_step(tb.step[n++], (kGradBf16 ? IMG_TB0 : IMG_T0) + 0, 4, 0, kGradFmt, kGradFmt);
   tb.n_steps = n;
 }
 
@@ -696,6 +706,7 @@ extern "C" int fmov_fine_image_info(int id, long long* offset, int* npad, int* k
   return OK;
 }
 extern "C" long long fmov_fine_blob_bytes(void) { return img_offset(IMG_COUNT); }
+extern "C" int fmov_grad_is_bf16(void) { return kGradBf16 ? 1 : 0; }
 extern "C" int fmov_fine_stash_count(void) { return ST_COUNT; }
 extern "C" int fmov_fine_stash_blocks(int id) { return (id >= 0 && id < ST_COUNT) ? stash_kb(id) : -1; }
 
@@ -750,7 +761,8 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
                              float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
                              const float* b8, const float* w8row, const float* bias_col, const float* bc4,
                              const float* wc4, const float* rgb, const float* ge, const float* d_sdf, const float* d_nrm,
-                             const float* d_rgb, float* d_pts, float* d_dirs, float* zc4, float* eb_scratch, void* stream) {
+                             const float* d_rgb, const float* amax, float* d_pts, float* d_dirs, float* zc4, float* eb_scratch,
+                             void* stream) {
   static ChainTable tb;
   static bool init = false;
   if (!init) {
@@ -762,10 +774,10 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
   ChainPtrs ptrs;
   int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, wc4);
   if (st) return st;
-  FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && d_pts && d_dirs && zc4 && eb_scratch, "fmov_fine_bwd: null argument");
+  FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && amax && d_pts && d_dirs && zc4 && eb_scratch, "fmov_fine_bwd: null argument");
   for (int i = 0; i < ST_COUNT; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);
   a.rgb = const_cast<float*>(rgb); a.ge = const_cast<float*>(ge);
-  a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4; a.eb = eb_scratch;
+  a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4; a.eb = eb_scratch; a.amax = amax;
   fine_bwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
   FMOV_LAUNCH_CHECK("fine_bwd_kernel");
   return OK;

@@ -84,14 +84,18 @@ class FineWeights:
             pk(IMG_C0 + l, Wc[l], [(0, 0, 256)])
         pk(IMG_C0 + 4, Wc[4], [(0, 0, 256)], n_valid=3)
         if need_backward:
-            pk(IMG_CT0A, Wc[0], [(0, 0, 256)], transpose=True, row_off=33, n_valid=256, bf16=True)
-            pk(IMG_CT0B, Wc[0], [(0, 0, 256)], transpose=True, n_valid=33, bf16=True)
+            gbf = bool(L.lib().fmov_grad_is_bf16())     # gradient passes: bf16 copies, or the fp16 images (loss-scaled)
+            pk(IMG_CT0A, Wc[0], [(0, 0, 256)], transpose=True, row_off=33, n_valid=256, bf16=gbf)
+            pk(IMG_CT0B, Wc[0], [(0, 0, 256)], transpose=True, n_valid=33, bf16=gbf)
             for img, l in ((IMG_CT1, 1), (IMG_CT2, 2), (IMG_CT3, 3)):
-                pk(img, Wc[l], [(0, 0, 256)], transpose=True, bf16=True)
-            for l in range(8):
-                fwd_image(IMG_FB0 + l, l, True)
-            for l in range(9):
-                tr_image(IMG_TB0 + l, l, True)
+                pk(img, Wc[l], [(0, 0, 256)], transpose=True, bf16=gbf)
+            if gbf:
+                for l in range(8):
+                    fwd_image(IMG_FB0 + l, l, True)
+                for l in range(9):
+                    tr_image(IMG_TB0 + l, l, True)
+            else:
+                tr_image(IMG_TB0 + 8, 8, False)        # lin8 feature rows^T (only needed by the backward)
         self.bias_sdf = torch.zeros(8, 256, dtype=torch.float32, device=dev)
         for l in range(8):
             self.bias_sdf[l, : b_sdf[l].numel()] = b_sdf[l].detach().float()
@@ -142,7 +146,7 @@ def fine_forward(fw, stash, rays_o, rays_d, z, sample_dist):
     return sdf, nrm, rgb, ge
 
 
-def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_nrm, d_rgb):
+def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_nrm, d_rgb, amax):
     B, S = z.shape
     dev = z.device
     P = B * S
@@ -154,7 +158,7 @@ def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_n
       L.check(L.lib().fmov_fine_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),
                                   L.ptr(fw.bias_col), L.ptr(fw.bc4), L.ptr(fw.wc4), L.ptr(rgb), L.ptr(ge), L.ptr(d_sdf),
-                                  L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(d_pts), L.ptr(d_dirs), L.ptr(zc4), L.ptr(eb), L.stream()),
+                                  L.ptr(d_nrm), L.ptr(d_rgb), L.ptr(amax), L.ptr(d_pts), L.ptr(d_dirs), L.ptr(zc4), L.ptr(eb), L.stream()),
             "fmov_fine_bwd")
     return d_pts, d_dirs, zc4
 
@@ -163,13 +167,13 @@ _SDF_SHAPES = [(256, 39), (256, 256), (256, 256), (217, 256), (256, 256), (256, 
 _COL_SHAPES = [(256, 289), (256, 256), (256, 256), (256, 256), (3, 256)]
 
 
-def weight_grads(stash, P, d_sdf, zc4):
+def weight_grads(stash, P, d_sdf, zc4, amax):
     """-> (dW_sdf[9], db_sdf[9], dW_col[5], db_col[5]) as views of one flat fp32 buffer"""
     lib = L.lib()
     dev = d_sdf.device
     flat = torch.empty(int(lib.fmov_grad_floats()), dtype=torch.float32, device=dev)
     with L.timed("dw"):
-        L.check(lib.fmov_dw(L.c_ll(P), stash.ptrs, L.ptr(d_sdf), L.ptr(zc4), L.ptr(flat), L.stream()), "fmov_dw")
+        L.check(lib.fmov_dw(L.c_ll(P), stash.ptrs, L.ptr(d_sdf), L.ptr(zc4), L.ptr(amax), L.ptr(flat), L.stream()), "fmov_dw")
 
     def view(kind, l, shape):
         off = int(lib.fmov_grad_offset(kind, l))
@@ -236,8 +240,11 @@ class RenderCoreFunction(torch.autograd.Function):
         bk = ops.composite_bwd(rays_o, rays_d, z, sdf, nrm, rgb, inv_s_d, sd, car, ctx.bg, c(g_color), c(g_wsum),
                                c(g_depth), c(g_weights), g_eik_d, ctx.eik_den,
                                None if g_nrm is None else L.f32c(g_nrm.reshape(-1, 3)))
-        d_pts, d_dirs, zc4 = fine_backward(fw, stash, rays_o, rays_d, z, sd, rgb, ge, bk["d_sdf"], bk["d_nrm"], bk["d_rgb"])
-        dW_s, db_s, dW_c, db_c, flat = weight_grads(stash, B * S, bk["d_sdf"], zc4)
+        amax = torch.empty(1, dtype=torch.float32, device=dev)
+        L.check(L.lib().fmov_grad_amax(L.ptr(bk["d_sdf"]), L.ptr(bk["d_nrm"]), L.ptr(bk["d_rgb"]), L.c_ll(B * S), L.ptr(amax),
+                                       L.stream()), "fmov_grad_amax")
+        d_pts, d_dirs, zc4 = fine_backward(fw, stash, rays_o, rays_d, z, sd, rgb, ge, bk["d_sdf"], bk["d_nrm"], bk["d_rgb"], amax)
+        dW_s, db_s, dW_c, db_c, flat = weight_grads(stash, B * S, bk["d_sdf"], zc4, amax)
         want_dz = ctx.needs_input_grad[2]
         d_o, d_d, d_z = ops.ray_reduce_bwd(d_pts, d_dirs, bk["d_dir"], bk["d_dist"], bk["d_mid"], rays_d, z, sd, want_dz)
         d_inv_s = bk["d_invs"].sum().reshape(())

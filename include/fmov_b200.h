@@ -125,13 +125,17 @@ int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, 
 int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
                   const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
                   const float* bias_col, const float* bc4, const float* wc4, const float* rgb, const float* ge,
-                  const float* d_sdf, const float* d_nrm, const float* d_rgb, float* d_pts, float* d_dirs, float* zc4,
-                  float* eb_scratch /* [P,40] */, void* stream);
+                  const float* d_sdf, const float* d_nrm, const float* d_rgb, const float* amax, float* d_pts, float* d_dirs,
+                  float* zc4, float* eb_scratch /* [P,40] */, void* stream);
 /* weight / bias gradients into one flat fp32 buffer (zeroed by the call); fmov_grad_offset(kind, layer):
  * kind 0 sdf weight [out,in], 1 sdf bias, 2 colour weight, 3 colour bias (effective weights, reference shapes) */
 long long fmov_grad_offset(int kind, int layer);
 long long fmov_grad_floats(void);
-int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, float* grads, void* stream);
+int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc4, const float* amax, float* grads,
+            void* stream);
+/* device scalar amax = max|upstream per-sample gradient|: sets the power-of-two loss scale of the fp16 gradient tiles */
+int fmov_grad_amax(const float* d_sdf, const float* d_nrm, const float* d_rgb, long long P, float* amax, void* stream);
+int fmov_grad_is_bf16(void);
 
 #ifdef __cplusplus
 }
