@@ -26,7 +26,7 @@ extern "C" const char* fmov_last_error(void) { return g_err; }
 extern "C" int fmov_version(void) { return 100; }
 
 // ----------------------------------------------------------------------------------------
-// Weight image packing: fp32 matrix -> [npad rows x 64*kblocks] fp16/bf16 SW128 image.
+// Weight image packing: fp32 matrix -> [npad rows x 64*kblocks] fp16/bf16 no-swizzle operand image.
 // dst(n, k) = scale * src[(n + row_off)*stride_n + kmap(k)*stride_k] for n < n_valid and k inside a
 // segment, else 0.  Segments let the caller permute / split input columns (skip connection,
 // colour-net input order) without materialising a permuted matrix.
@@ -71,7 +71,7 @@ __global__ void pack_image_kernel(PackArgs a) {
       q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);
     }
     uint8_t* blk = a.dst + (size_t)kb * a.npad * 128;
-    *reinterpret_cast<uint4*>(blk + ti_chunk_off(n, ch)) = q;
+    *reinterpret_cast<uint4*>(blk + (size_t)ch * a.npad * 16 + (size_t)n * 16) = q;   // [chunk][row][16 B]
   }
 }
 
@@ -207,13 +207,14 @@ selftest_gemm_kernel(const uint8_t* a_img, const uint8_t* b_img, int n, int kblo
       const uint32_t idesc = umma_idesc(128, n, a_fmt, b_fmt, 0, 0);
       for (int kb = 0; kb < kblocks; ++kb)
         for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem, umma_desc_kmajor(smem_u32(sa + kb * BLK_BYTES) + ks * 32),
-                   umma_desc_kmajor(smem_u32(sb + (size_t)kb * n * 128) + ks * 32), idesc, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem, umma_desc_kmajor(smem_u32(sa + kb * BLK_BYTES) + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                   umma_desc_kmajor(smem_u32(sb + (size_t)kb * n * 128) + ks * 2 * (n * 16), n * 16), idesc,
+                   (kb | ks) ? 1u : 0u);
     } else {
       const uint32_t idesc = umma_idesc(128, n, a_fmt, b_fmt, 1, 1);
-      for (int ks = 0; ks < 8; ++ks)   // K = 128 points, 16 per instruction = 2048 bytes of rows
-        umma_f16(tmem, umma_desc_mnmajor(smem_u32(sa) + ks * 2048, BLK_BYTES),
-                 umma_desc_mnmajor(smem_u32(sb) + ks * 2048, BLK_BYTES), idesc, ks ? 1u : 0u);
+      for (int ks = 0; ks < 8; ++ks)   // K = 128 points, 16 per instruction = 2 groups of 8 rows = 256 bytes
+        umma_f16(tmem, umma_desc_mnmajor(smem_u32(sa) + ks * 256, TI_CHUNK_STRIDE),
+                 umma_desc_mnmajor(smem_u32(sb) + ks * 256, TI_CHUNK_STRIDE), idesc, ks ? 1u : 0u);
     }
     umma_commit(&bar_mma);
   }

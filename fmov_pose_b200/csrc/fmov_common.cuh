@@ -5,13 +5,17 @@
 //    ld / fences), UMMA shared-memory + instruction descriptors
 //  * the "tile image" layout shared by every MLP kernel
 //
-// Tile image (TI): activations of 128 points x 64 features (fp16 or bf16) are stored as one
-// 16 KiB block that is byte-for-byte the SWIZZLE_128B shared-memory operand of tcgen05.mma:
-//     byte(r, c) = r*128 + ((c/8) ^ (r & 7))*16 + (c%8)*2          r in [0,128), c in [0,64)
+// Tile image (TI): activations of 128 points x 64 features (fp16 or bf16) are stored as one 16 KiB
+// block in tcgen05's canonical NO-SWIZZLE ("interleaved") operand layout, 8 chunk-columns of 16 bytes:
+//     byte(r, c) = (c/8)*2048 + r*16 + (c%8)*2                     r in [0,128), c in [0,64)
+// i.e. [chunk column][row][8 features].  8 rows x 16 B = one 128-byte UMMA core matrix, so the same bytes
+// are a K-major operand (layer GEMMs: M = points, K = features; LBO = 2048, SBO = 128) and an MN-major
+// operand (weight-gradient GEMMs: K = points; SBO = 2048, LBO = 128) — no re-layout, no tensor maps.
+// A warp whose lanes own 32 consecutive rows reads/writes chunk column c as 512 CONTIGUOUS bytes, in shared
+// memory (conflict-free) and in HBM (4 cache lines per instruction; the SWIZZLE_128B row-major image needed
+// 32 — measured as the L1 bottleneck of the first version).
 // A [128 x 64*KB] tensor is KB consecutive blocks; a [P x 64*KB] tensor is P/128 such tiles.
-// Used K-major (A operand of the layer GEMMs: M = points, K = features) and MN-major
-// (operands of the weight-gradient GEMMs: K = points) without any re-layout.
-// Weight images use the same block format with N rows instead of 128.
+// Weight images: same format with N rows: byte(n, k) = (k/8)*(N*16) + n*16 + (k%8)*2 per 64-wide k-block.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -63,11 +67,12 @@ constexpr int BLK_BYTES = TILE_M * KBLK * 2;   // 16384
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ uint32_t ti_off(int r, int c) {   // byte offset inside one block
-  return (uint32_t)(r * 128 + ((((c >> 3) ^ (r & 7)) << 4) | ((c & 7) << 1)));
+constexpr int TI_CHUNK_STRIDE = TILE_M * 16;   // 2048: distance between 16-byte chunk columns of a block
+__device__ __forceinline__ uint32_t ti_off(int r, int c) {   // byte offset inside one 128-row block
+  return (uint32_t)((c >> 3) * TI_CHUNK_STRIDE + r * 16 + ((c & 7) << 1));
 }
 __device__ __forceinline__ uint32_t ti_chunk_off(int r, int chunk) {  // 16-byte chunk offset
-  return (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+  return (uint32_t)(chunk * TI_CHUNK_STRIDE + r * 16);
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -180,22 +185,26 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm100 "version 1"):
-//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (0 = SWIZZLE_NONE)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
   return d;
 }
-// K-major SW128 operand: rows at 128 B, 8-row groups at 1024 B; LBO unused (encoded 1).
-__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) { return umma_desc(saddr, 16, 1024); }
-// MN-major SW128 operand: 64 MN-elements per 128 B row, k-rows at 128 B, 8-k groups at 1024 B (SBO),
-// next 64 MN-elements at `lbo_bytes`.
-__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t lbo_bytes) {
-  return umma_desc(saddr, lbo_bytes, 1024);
+// Canonical no-swizzle layouts (cute mma_traits_sm100.hpp, make_umma_desc): 128-byte core matrices of
+// 8 rows x 16 bytes.
+//   K-major  ((8,m),(T,2)):((1T,SBO),(1,LBO)) : LBO = distance between the two 16-byte K chunks of one MMA,
+//                                               SBO = distance between 8-row groups (= 128 here)
+//   MN-major ((T,1,m),(8,k)):((1,T,SBO),(1T,LBO)) : SBO = distance between 8-element MN groups (chunk columns),
+//                                               LBO = distance between 8-row K groups (= 128 here)
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t chunk_stride) {
+  return umma_desc(saddr, chunk_stride, 128);
+}
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t saddr, uint32_t chunk_stride) {
+  return umma_desc(saddr, 128, chunk_stride);
 }
 
 enum : uint32_t { FMT_F16 = 0, FMT_BF16 = 1 };

@@ -164,7 +164,8 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
           const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
+            umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                     umma_desc_kmajor(b_base + ks * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
                      (kb | ks) != 0 ? 1u : 0u);
           }
           umma_commit(&s->w_empty[stage]);   // stage reusable once these MMAs have read it
@@ -183,7 +184,6 @@ struct EpiCtx {
   uint32_t tmem;       // TMEM address of this slot's accumulator with the warp's lane quarter folded in
   int slot;
   int row;             // 0..127 (tile row == TMEM lane)
-  int swz;             // row & 7
   uint32_t acc_n;      // accumulator phases consumed
 };
 
@@ -195,7 +195,6 @@ __device__ __forceinline__ void epi_init(EpiCtx& c, ChainSmem* s, uint8_t* act0,
   c.act = act0 + c.slot * 4 * BLK_BYTES;
   c.aux = aux0 + c.slot * BLK_BYTES;
   c.row = quarter * 32 + lane;
-  c.swz = c.row & 7;
   c.tmem = tmem_base + c.slot * 256 + ((uint32_t)(quarter * 32) << 16);
   c.acc_n = 0;
 }
@@ -221,7 +220,7 @@ __device__ __forceinline__ void acc_load16(const EpiCtx& c, int col0, float* v) 
 }
 
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------
-// chunk ch (0..7) of row r sits at 16-byte position (ch ^ (r & 7)) of the 128-byte row.
+// chunk ch (0..7) of row r sits at blk + ch*2048 + r*16: the 32 lanes of a warp touch 512 contiguous bytes.
 __device__ __forceinline__ void pack4_grad(const float* v, uint4* q) {   // gradient tile format
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -258,18 +257,14 @@ __device__ __forceinline__ void unpack4(const uint4* q, bool bf16, float* v) {
     }
   }
 }
-// half h (0/1) of a block row: chunks 4h..4h+3.  `rowp` points at the 128-byte row (shared or global).
-__device__ __forceinline__ void row_half_store(uint8_t* rowp, int swz, int h, const uint4* q) {
+// half h (0/1) of a block row: chunks 4h..4h+3.  `rowp` = block base + row*16 (shared or global).
+__device__ __forceinline__ void row_half_store(uint8_t* rowp, int h, const uint4* q) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(rowp + (((4 * h + i) ^ swz) << 4)) = q[i];
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(rowp + (4 * h + i) * TI_CHUNK_STRIDE) = q[i];
 }
-__device__ __forceinline__ void row_half_load(const uint8_t* rowp, int swz, int h, uint4* q) {
+__device__ __forceinline__ void row_half_load(const uint8_t* rowp, int h, uint4* q) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(rowp + (((4 * h + i) ^ swz) << 4));
-}
-__device__ __forceinline__ void row_half_load_nc(const uint8_t* rowp, int swz, int h, uint4* q) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) q[i] = __ldg(reinterpret_cast<const uint4*>(rowp + (((4 * h + i) ^ swz) << 4)));
+  for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const uint4*>(rowp + (4 * h + i) * TI_CHUNK_STRIDE);
 }
 
 }  // namespace fmov

@@ -18,10 +18,8 @@ enum { S_PE = 0, S_H1 = 1, S_F = 9, S_D0 = 10, S_X = 18, S_C1 = 19, S_ZC0 = 23, 
 __host__ __device__ inline int s_kb(int id) { return (id == S_PE || id == S_X || id == S_GE) ? 1 : 4; }
 
 constexpr int DW_MAX_JOBS = 20;
-constexpr int DW_STAGES = 3;
-constexpr int DW_HALF = 64;                       // points per stage
-constexpr int DW_ABYTES = 4 * DW_HALF * 128;      // 32 KiB: [4 feature blocks][64 points x 128 B]
-constexpr int DW_STAGE_BYTES = 2 * DW_ABYTES;
+constexpr int DW_ENTRIES = 3;                     // ring of whole 128-point tiles (64 KiB each): A, B, A, B, ...
+constexpr int DW_ENTRY_BYTES = 4 * BLK_BYTES;
 constexpr int DW_THREADS = 192;
 
 struct DwJob {
@@ -51,7 +49,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
           const float* amax) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
-  __shared__ uint64_t full[DW_STAGES], ready[DW_STAGES], empty[DW_STAGES], done_bar;
+  __shared__ uint64_t full[DW_ENTRIES], ready[DW_ENTRIES], empty[DW_ENTRIES], done_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -66,7 +64,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
   const int n_mma = jb.b_blocks * 64;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < DW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 128); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < DW_ENTRIES; ++i) { mbar_init(&full[i], 1); mbar_init(&ready[i], 128); mbar_init(&empty[i], 1); }
     mbar_init(&done_bar, 1);
     fence_mbar_init();
   }
@@ -76,94 +74,91 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const bool has_work = t1 > t0;
+  // ring entry sequence: (tile, pair) -> A entry then B entry
 
   if (warp == 0 && lane == 0 && has_work) {
     uint32_t it = 0;
     for (long long t = t0; t < t1; ++t)
-      for (int pr = 0; pr < jb.npairs; ++pr) {
-        const uint8_t* asrc = ptrs.stash[jb.a_id[pr]] + (size_t)t * 4 * BLK_BYTES;
-        const uint8_t* bsrc = ptrs.stash[jb.b_id[pr]] + (size_t)t * s_kb(jb.b_id[pr]) * BLK_BYTES;
-        for (int h = 0; h < 2; ++h, ++it) {
-          const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
-          uint8_t* sa = base + slot * DW_STAGE_BYTES;
-          uint8_t* sb = sa + DW_ABYTES;
-          mbar_wait(&empty[slot], (n & 1) ^ 1);
-          mbar_expect_tx(&full[slot], (uint32_t)(4 + jb.b_blocks) * (DW_HALF * 128));
-          for (int kb = 0; kb < 4; ++kb)
-            bulk_g2s(sa + kb * (DW_HALF * 128), asrc + (size_t)kb * BLK_BYTES + h * (DW_HALF * 128), DW_HALF * 128, &full[slot]);
-          for (int kb = 0; kb < jb.b_blocks; ++kb)
-            bulk_g2s(sb + kb * (DW_HALF * 128), bsrc + (size_t)kb * BLK_BYTES + h * (DW_HALF * 128), DW_HALF * 128, &full[slot]);
+      for (int pr = 0; pr < jb.npairs; ++pr)
+        for (int ab = 0; ab < 2; ++ab, ++it) {
+          const uint32_t e = it % DW_ENTRIES, n = it / DW_ENTRIES;
+          const int id = ab ? jb.b_id[pr] : jb.a_id[pr];
+          const uint32_t bytes = (uint32_t)(ab ? jb.b_blocks : 4) * BLK_BYTES;
+          const uint8_t* src = ptrs.stash[id] + (size_t)t * s_kb(id) * BLK_BYTES;
+          mbar_wait_backoff(&empty[e], (n & 1) ^ 1);
+          mbar_expect_tx(&full[e], bytes);
+          for (uint32_t off = 0; off < bytes; off += BLK_BYTES)
+            bulk_g2s(base + e * DW_ENTRY_BYTES + off, src + off, BLK_BYTES, &full[e]);
         }
-      }
   } else if (warp == 1 && lane == 0 && has_work) {
     uint32_t it = 0;
     bool first = true;
+    // tcgen05.mma kind::f16 cannot mix an fp16 with a bf16 operand (illegal instruction on sm_100a): in bf16
+    // gradient mode the converter warps rewrite the fp16 operand of the pair as bf16 in shared memory.
+    const uint32_t idesc = umma_idesc(128, n_mma, kGradFmt, kGradFmt, 1, 1);
     for (long long t = t0; t < t1; ++t)
-      for (int pr = 0; pr < jb.npairs; ++pr) {
-        // tcgen05.mma kind::f16 cannot mix an fp16 with a bf16 operand (illegal instruction on sm_100a):
-        // the converter warps have rewritten the fp16 operand of the pair as bf16 in shared memory.
-        const uint32_t idesc = umma_idesc(128, n_mma, kGradFmt, kGradFmt, 1, 1);
-        for (int h = 0; h < 2; ++h, ++it) {
-          const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
-          const uint32_t sa = smem_u32(base + slot * DW_STAGE_BYTES);
-          const uint32_t sb = sa + DW_ABYTES;
-          mbar_wait(&ready[slot], n & 1);
-          tc_fence_after();
+      for (int pr = 0; pr < jb.npairs; ++pr, it += 2) {
+        const uint32_t ea = it % DW_ENTRIES, na = it / DW_ENTRIES;
+        const uint32_t eb = (it + 1) % DW_ENTRIES, nb = (it + 1) / DW_ENTRIES;
+        const uint32_t sa = smem_u32(base + ea * DW_ENTRY_BYTES);
+        const uint32_t sb = smem_u32(base + eb * DW_ENTRY_BYTES);
+        mbar_wait_backoff(&ready[ea], na & 1);
+        mbar_wait_backoff(&ready[eb], nb & 1);
+        tc_fence_after();
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {        // 16 points per instruction = 2048 bytes of rows
+        for (int ks = 0; ks < 8; ++ks) {        // 16 points per instruction = two 8-row groups = 256 bytes
 #pragma unroll
-            for (int mh = 0; mh < 2; ++mh) {
-              umma_f16(tmem + mh * 256, umma_desc_mnmajor(sa + mh * 2 * (DW_HALF * 128) + ks * 2048, DW_HALF * 128),
-                       umma_desc_mnmajor(sb + ks * 2048, DW_HALF * 128), idesc, (first && ks == 0) ? 0u : 1u);
-            }
+          for (int mh = 0; mh < 2; ++mh) {      // 128 output features = 16 chunk columns
+            umma_f16(tmem + mh * 256, umma_desc_mnmajor(sa + mh * 16 * TI_CHUNK_STRIDE + ks * 256, TI_CHUNK_STRIDE),
+                     umma_desc_mnmajor(sb + ks * 256, TI_CHUNK_STRIDE), idesc, (first && ks == 0) ? 0u : 1u);
           }
-          first = false;
-          umma_commit(&empty[slot]);
         }
+        first = false;
+        umma_commit(&empty[ea]);
+        umma_commit(&empty[eb]);
       }
     umma_commit(&done_bar);
   } else if (warp >= 2 && has_work) {
-    // converter: fp16 operand of each stage -> bf16, in place (element-wise, layout agnostic); and column sums
-    // of the gradient tile (pair 0's A operand) = bias gradient, two columns per thread
+    // helper warps: (bf16 mode) fp16 operand -> bf16 in place; column sums of the gradient tile (pair 0's A
+    // operand) = bias gradient, two columns per thread
     float bsum0 = 0.f, bsum1 = 0.f;
     {
       const int ctid = threadIdx.x - 64;
       const int bcol = 2 * ctid;                                   // columns bcol, bcol+1
-      const uint32_t boff = (uint32_t)(bcol >> 6) * (DW_HALF * 128) + (uint32_t)((bcol & 7) >> 1) * 4;
-      const int bchunk = (bcol & 63) >> 3;
+      const int bcc = bcol >> 3;                                   // chunk column
+      const uint32_t boff = (uint32_t)bcc * TI_CHUNK_STRIDE + (uint32_t)((bcol & 7) >> 1) * 4;
       uint32_t it = 0;
       for (long long t = t0; t < t1; ++t)
         for (int pr = 0; pr < jb.npairs; ++pr)
-          for (int h = 0; h < 2; ++h, ++it) {
-            const uint32_t slot = it % DW_STAGES, n = it / DW_STAGES;
-            uint8_t* sa = base + slot * DW_STAGE_BYTES;
-            mbar_wait(&full[slot], n & 1);
-            uint4* reg = nullptr;
-            int nchunks = 0;
-            if (kGradBf16) {      // fp16 gradient tiles need no conversion: every operand is fp16 already
-              if (!jb.a_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa); nchunks = DW_ABYTES / 16; }
-              else if (!jb.b_bf16[pr]) { reg = reinterpret_cast<uint4*>(sa + DW_ABYTES); nchunks = jb.b_blocks * (DW_HALF * 128) / 16; }
+          for (int ab = 0; ab < 2; ++ab, ++it) {
+            const uint32_t e = it % DW_ENTRIES, n = it / DW_ENTRIES;
+            uint8_t* se = base + e * DW_ENTRY_BYTES;
+            mbar_wait(&full[e], n & 1);
+            if (kGradBf16 && !(ab ? jb.b_bf16[pr] : jb.a_bf16[pr])) {
+              uint4* reg = reinterpret_cast<uint4*>(se);
+              const int nchunks = (ab ? jb.b_blocks : 4) * BLK_BYTES / 16;
+              for (int i = ctid; i < nchunks; i += 128) {
+                uint4 q = reg[i];
+                float2 f;
+                f = unpack_h2(q.x); q.x = pack_bf2(f.x, f.y);
+                f = unpack_h2(q.y); q.y = pack_bf2(f.x, f.y);
+                f = unpack_h2(q.z); q.z = pack_bf2(f.x, f.y);
+                f = unpack_h2(q.w); q.w = pack_bf2(f.x, f.y);
+                reg[i] = q;
+              }
+              fence_proxy_async();
             }
-            for (int i = ctid; i < nchunks; i += 128) {
-              uint4 q = reg[i];
-              float2 f;
-              f = unpack_h2(q.x); q.x = pack_bf2(f.x, f.y);
-              f = unpack_h2(q.y); q.y = pack_bf2(f.x, f.y);
-              f = unpack_h2(q.z); q.z = pack_bf2(f.x, f.y);
-              f = unpack_h2(q.w); q.w = pack_bf2(f.x, f.y);
-              reg[i] = q;
-            }
-            if (jb.bias_off >= 0 && pr == 0) {                     // A operand is bf16 here (never converted)
+            if (jb.bias_off >= 0 && pr == 0 && ab == 0) {
 #pragma unroll 8
-              for (int r = 0; r < DW_HALF; ++r) {
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(sa + boff + r * 128 + ((bchunk ^ (r & 7)) << 4));
+              for (int i = 0; i < TILE_M; ++i) {
+                const int r = (i + (bcc & 7)) & (TILE_M - 1);      // staggered start row: conflict-free across chunk columns
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(se + boff + r * 16);
                 const float2 f = kGradBf16 ? unpack_bf2(w) : unpack_h2(w);
                 bsum0 += f.x;
                 bsum1 += f.y;
               }
             }
-            fence_proxy_async();
-            mbar_arrive(&ready[slot]);
+            mbar_arrive(&ready[e]);
           }
       if (jb.bias_off >= 0) {
         const float ginv_b = 1.0f / grad_scale_from_amax(__ldg(amax));
@@ -200,7 +195,7 @@ dw_kernel(const __grid_constant__ DwPlan plan, const __grid_constant__ DwPtrs pt
   }
 }
 
-// ---- column sums: biases, lin8 row 0, colour lin4 -----------------------------------------------------------
+// ---- column sums: lin8 row 0, colour lin4, scalar biases ---------------------------------------------------------
 struct ColsumArgs {
   DwPtrs ptrs;
   long long n_tiles, P;
@@ -215,54 +210,70 @@ struct ColsumArgs {
 };
 
 // lin8 row 0 (sum_p sbar_p*H8[p,:] + Vbar8[p,:]), colour lin4 (sum_p zc4[p,j]*C4[p,:]), and the two scalar-ish
-// biases. 256 threads: thread = (row group rg = tid/32, 16-byte chunk cidx = tid%32 -> 8 columns); a warp reads
-// whole 128-byte rows (coalesced).
+// biases.  grid = (tile groups, 4): a warp owns ONE 16-byte chunk column (8 features) of the three tiles and its
+// lanes own consecutive rows, so every load instruction covers 512 contiguous bytes.
 __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
-  const int cidx = threadIdx.x & 31, rg = threadIdx.x >> 5;
-  const int blk = cidx >> 3, ch = cidx & 7;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cc = blockIdx.y * 8 + warp;           // chunk column 0..31 -> features 8cc .. 8cc+7
   float w8[8], c4[3][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { w8[i] = 0.f; c4[0][i] = c4[1][i] = c4[2][i] = 0.f; }
   float extra[4] = {0.f, 0.f, 0.f, 0.f};
   const float ginv = 1.0f / grad_scale_from_amax(__ldg(a.amax));
   for (long long t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
-    const uint8_t* th = a.ptrs.stash[S_H1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
-    const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
-    const uint8_t* tc = a.ptrs.stash[S_C1 + 3] + (size_t)t * 4 * BLK_BYTES + (size_t)blk * BLK_BYTES;
-#pragma unroll 4
-    for (int r = rg; r < 128; r += 8) {
+    const size_t toff = (size_t)t * 4 * BLK_BYTES + (size_t)cc * TI_CHUNK_STRIDE;
+    const uint8_t* th = a.ptrs.stash[S_H1 + 7] + toff;
+    const uint8_t* tv = a.ptrs.stash[S_V1 + 7] + toff;
+    const uint8_t* tc = a.ptrs.stash[S_C1 + 3] + toff;
+#pragma unroll
+    for (int rgp = 0; rgp < 4; ++rgp) {
+      const int r = rgp * 32 + lane;
       const long long p = t * 128 + r;
       const bool ok = p < a.P;
       const float sb = ok ? a.d_sdf[p] : 0.f;
-      const float z0 = ok ? a.zc4[p * 4] * ginv : 0.f, z1 = ok ? a.zc4[p * 4 + 1] * ginv : 0.f, z2 = ok ? a.zc4[p * 4 + 2] * ginv : 0.f;
-      const uint32_t off = r * 128 + ((ch ^ (r & 7)) << 4);
-      const uint4 qh = *reinterpret_cast<const uint4*>(th + off);
-      const uint4 qv = *reinterpret_cast<const uint4*>(tv + off);
-      const uint4 qc = *reinterpret_cast<const uint4*>(tc + off);
-      const uint32_t hh[4] = {qh.x, qh.y, qh.z, qh.w}, vv[4] = {qv.x, qv.y, qv.z, qv.w}, cc[4] = {qc.x, qc.y, qc.z, qc.w};
+      float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) z4 = *reinterpret_cast<const float4*>(a.zc4 + p * 4);
+      const float z0 = z4.x * ginv, z1 = z4.y * ginv, z2 = z4.z * ginv;
+      const uint4 qh = *reinterpret_cast<const uint4*>(th + r * 16);
+      const uint4 qv = *reinterpret_cast<const uint4*>(tv + r * 16);
+      const uint4 qc = *reinterpret_cast<const uint4*>(tc + r * 16);
+      const uint32_t hh[4] = {qh.x, qh.y, qh.z, qh.w}, vv[4] = {qv.x, qv.y, qv.z, qv.w}, cw[4] = {qc.x, qc.y, qc.z, qc.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 fh = unpack_h2(hh[j]), fv = kGradBf16 ? unpack_bf2(vv[j]) : unpack_h2(vv[j]), fc = unpack_h2(cc[j]);
+        const float2 fh = unpack_h2(hh[j]), fv = kGradBf16 ? unpack_bf2(vv[j]) : unpack_h2(vv[j]), fc = unpack_h2(cw[j]);
         w8[2 * j] += sb * fh.x + fv.x * ginv; w8[2 * j + 1] += sb * fh.y + fv.y * ginv;
         c4[0][2 * j] += z0 * fc.x; c4[0][2 * j + 1] += z0 * fc.y;
         c4[1][2 * j] += z1 * fc.x; c4[1][2 * j + 1] += z1 * fc.y;
         c4[2][2 * j] += z2 * fc.x; c4[2][2 * j + 1] += z2 * fc.y;
       }
-      if (cidx == 0) { extra[0] += sb; extra[1] += z0; extra[2] += z1; extra[3] += z2; }
+      if (cc == 0) { extra[0] += sb; extra[1] += z0; extra[2] += z1; extra[3] += z2; }
     }
   }
   float* g = a.grads;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int col = cidx * 8 + i;
-    atomicAdd(g + a.off_w8 + col, w8[i]);
+    float s0 = w8[i], s1 = c4[0][i], s2 = c4[1][i], s3 = c4[2][i];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_wc4 + j * 256 + col, c4[j][i]);
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    }
+    if (lane == 0) {
+      const int col = cc * 8 + i;
+      atomicAdd(g + a.off_w8 + col, s0);
+      atomicAdd(g + a.off_wc4 + col, s1);
+      atomicAdd(g + a.off_wc4 + 256 + col, s2);
+      atomicAdd(g + a.off_wc4 + 512 + col, s3);
+    }
   }
-  if (cidx == 0) {
-    atomicAdd(g + a.off_b_sdf[8], extra[0]);
+  if (cc == 0) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) atomicAdd(g + a.off_b_col[4] + j, extra[1 + j]);
+    for (int j = 0; j < 4; ++j) {
+      float e = extra[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      if (lane == 0) atomicAdd(j == 0 ? g + a.off_b_sdf[8] : g + a.off_b_col[4] + (j - 1), e);
+    }
   }
 }
 
@@ -355,7 +366,7 @@ static void build_plan(DwPlan& pl, int n_ctas) {
   // distribute CTAs proportionally to cost (bytes streamed per tile)
   float cost[DW_MAX_JOBS], total = 0.f;
   for (int j = 0; j < pl.n_jobs; ++j) {
-    cost[j] = pl.job[j].npairs * (4.f + pl.job[j].b_blocks);
+    cost[j] = pl.job[j].npairs * (4.f + pl.job[j].b_blocks);   // 16 KiB blocks streamed per tile
     total += cost[j];
   }
   int used = 0;
@@ -387,7 +398,7 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
     FMOV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     n_ctas = sms;
     build_plan(plan, n_ctas);
-    FMOV_CUDA(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_STAGES * DW_STAGE_BYTES + 1024));
+    FMOV_CUDA(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_ENTRIES * DW_ENTRY_BYTES + 1024));
     init = true;
   }
   DwPtrs ptrs;
@@ -397,7 +408,7 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
   }
   const long long n_tiles = (P + 127) / 128;
   FMOV_CUDA(cudaMemsetAsync(grads, 0, (size_t)fmov_grad_floats() * sizeof(float), (cudaStream_t)stream));
-  dw_kernel<<<n_ctas, DW_THREADS, DW_STAGES * DW_STAGE_BYTES + 1024, (cudaStream_t)stream>>>(plan, ptrs, n_tiles, grads, amax);
+  dw_kernel<<<n_ctas, DW_THREADS, DW_ENTRIES * DW_ENTRY_BYTES + 1024, (cudaStream_t)stream>>>(plan, ptrs, n_tiles, grads, amax);
   FMOV_LAUNCH_CHECK("dw_kernel");
   ColsumArgs ca;
   ca.ptrs = ptrs; ca.n_tiles = n_tiles; ca.P = P; ca.d_sdf = d_sdf; ca.zc4 = zc4; ca.amax = amax; ca.grads = grads;
@@ -405,8 +416,8 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
   for (int l = 0; l < 5; ++l) ca.off_b_col[l] = fmov_grad_offset(3, l);
   ca.off_w8 = fmov_grad_offset(0, 8);
   ca.off_wc4 = fmov_grad_offset(2, 4);
-  const int cs_grid = (int)(n_tiles < 4 * n_ctas ? n_tiles : 4 * n_ctas);
-  colsum_kernel<<<cs_grid, 256, 0, (cudaStream_t)stream>>>(ca);
+  const int cs_grid = (int)(n_tiles < 2 * n_ctas ? n_tiles : 2 * n_ctas);
+  colsum_kernel<<<dim3(cs_grid, 4), 256, 0, (cudaStream_t)stream>>>(ca);
   FMOV_LAUNCH_CHECK("colsum_kernel");
   return OK;
 }

@@ -145,26 +145,26 @@ __device__ __forceinline__ void pe_jt(const float x[3], const float* g, float n[
 }
 
 __device__ __forceinline__ uint8_t* stash_row(const ChainPtrs& ptrs, int id, long long tile, int kb, int row) {
-  return ptrs.stash[id] + ((size_t)tile * stash_kb(id) + kb) * BLK_BYTES + (size_t)row * 128;
+  return ptrs.stash[id] + ((size_t)tile * stash_kb(id) + kb) * BLK_BYTES + (size_t)row * 16;
 }
 // store one 32-column chunk (index hb = 0..7 within a 256-wide tile) to the ACT operand and/or a stash tensor
 __device__ __forceinline__ void put_chunk(const EpiCtx& c, const ChainPtrs& ptrs, bool to_act, int stash_id,
                                           long long tile, int hb, bool bf16, const float* v) {
   uint4 q[4];
   pack4(v, bf16, q);
-  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
-  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
+  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), hb & 1, q);
 }
 __device__ __forceinline__ void put_chunk_grad(const EpiCtx& c, const ChainPtrs& ptrs, bool to_act, int stash_id,
                                                long long tile, int hb, const float* v) {
   uint4 q[4];
   pack4_grad(v, q);
-  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
-  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+  if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
+  if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), hb & 1, q);
 }
 __device__ __forceinline__ void get_chunk_raw(const EpiCtx& c, const ChainPtrs& ptrs, int stash_id, long long tile,
                                               int hb, uint4* q) {
-  row_half_load(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), c.swz, hb & 1, q);
+  row_half_load(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), hb & 1, q);
 }
 
 // =====================================================================================================
@@ -211,8 +211,8 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int h = 0; h < 2; ++h) {
           uint4 q[4];
           pack4(e + 32 * h, false, q);
-          row_half_store(c.aux + c.row * 128, c.swz, h, q);
-          row_half_store(stash_row(ptrs, ST_PE, tile, 0, c.row), c.swz, h, q);
+          row_half_store(c.aux + c.row * 16, h, q);
+          row_half_store(stash_row(ptrs, ST_PE, tile, 0, c.row), h, q);
         }
         epi_signal_act(c);
       }
@@ -265,7 +265,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         float v[32], h[32];
         uint4 q[4];
         acc_load32(c, hb * 32, v);
-        row_half_load(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+        row_half_load(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
         unpack4(q, false, h);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -336,14 +336,14 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int h = 0; h < 2; ++h) {
           uint4 q[4];
           pack4(e + 32 * h, false, q);
-          row_half_store(c.aux + c.row * 128, c.swz, h, q);
-          row_half_store(stash_row(ptrs, ST_X, tile, 0, c.row), c.swz, h, q);
+          row_half_store(c.aux + c.row * 16, h, q);
+          row_half_store(stash_row(ptrs, ST_X, tile, 0, c.row), h, q);
         }
 #pragma unroll
         for (int hb = 0; hb < 8; ++hb) {          // own rows of F: written above by this thread
           uint4 q[4];
           get_chunk_raw(c, ptrs, ST_F, tile, hb, q);
-          row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+          row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
         }
         epi_signal_act(c);
       }
@@ -522,8 +522,8 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int h = 0; h < 2; ++h) {
           uint4 q[4];
           pack4_grad(e + 32 * h, q);
-          row_half_store(c.aux + c.row * 128, c.swz, h, q);
-          row_half_store(stash_row(ptrs, ST_GE, tile, 0, c.row), c.swz, h, q);
+          row_half_store(c.aux + c.row * 16, h, q);
+          row_half_store(stash_row(ptrs, ST_GE, tile, 0, c.row), h, q);
         }
         epi_signal_act(c);
       }
@@ -569,7 +569,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       for (int hb = 0; hb < 8; ++hb) {
         uint4 q[4];
         get_chunk_raw(c, ptrs, ST_FB, tile, hb, q);
-        row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+        row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
       }
       epi_signal_act(c);
       // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------

@@ -89,7 +89,7 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
   for (int h = 0; h < 2; ++h) {
     uint4 q[4];
     pack4(e + 32 * h, false, q);
-    row_half_store(blk + row * 128, row & 7, h, q);
+    row_half_store(blk + row * 16, h, q);
   }
 }
 
@@ -160,7 +160,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
           } else {
             uint4 q[4];
             pack4(v, false, q);
-            row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 128, c.swz, hb & 1, q);
+            row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
           }
         }
         if (l < 7) epi_signal_act(c);
