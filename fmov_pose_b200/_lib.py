@@ -30,7 +30,12 @@ def lib():
     return _lib
 
 
+n_calls = 0      # successful C-ABI calls (each launches >= 1 kernel); bench.py reports it as gpu_launches
+
+
 def check(status, what):
+    global n_calls
+    n_calls += 1
     if status != 0:
         raise RuntimeError(f"{what} failed (status {status}): {lib().fmov_last_error().decode()}")
 

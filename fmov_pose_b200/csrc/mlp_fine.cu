@@ -49,6 +49,8 @@ __host__ __device__ inline ImgInfo img_info(int id) {
   if (id >= IMG_TB0 && id < IMG_TB0 + 9) return (id - IMG_TB0) == 0 ? ImgInfo{48, 4} : ImgInfo{256, 4};
   return ImgInfo{0, 0};
 }
+__constant__ long long c_img_offset[IMG_COUNT + 1];
+__device__ __forceinline__ long long img_offset_dev(int id) { return c_img_offset[id]; }
 static long long img_offset(int id) {
   long long off = 0;
   for (int i = 0; i < id; ++i) {
@@ -636,6 +638,75 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   }
 }
 
+
+// =====================================================================================================
+// one-launch packing of every weight image + the fp32 side arrays from the 28 effective-weight tensors
+// =====================================================================================================
+struct PackSpec {
+  int img;             // image id
+  int src;             // 0..8 W_sdf[l], 14..18 -> W_col[l]  (index into PackAllArgs::src)
+  int src_rows, src_cols;
+  int transpose;       // image row n <-> source column
+  int row_off, n_valid;
+  int nseg, seg_dst[2], seg_src[2], seg_len[2];
+  float scale;
+  int bf16;
+  int chunk0;          // first 16-byte chunk of this image in the global chunk numbering
+};
+constexpr int PACK_MAX = 48;
+struct PackAllArgs {
+  const float* src[28];        // W_sdf[9], b_sdf[9], W_col[5], b_col[5]
+  uint8_t* blob;
+  float* side;                 // [bias_sdf 8x256 | b8 257(+pad to 264) | w8row 256 | bias_col 4x256 | bc4 4 | wc4 3x256]
+  int n_spec;
+  int total_chunks;
+  PackSpec spec[PACK_MAX];
+};
+constexpr int SIDE_BIAS_SDF = 0, SIDE_B8 = 2048, SIDE_W8ROW = 2048 + 264, SIDE_BIAS_COL = SIDE_W8ROW + 256,
+              SIDE_BC4 = SIDE_BIAS_COL + 1024, SIDE_WC4 = SIDE_BC4 + 4, SIDE_FLOATS = SIDE_WC4 + 768;
+
+__global__ void pack_all_kernel(const __grid_constant__ PackAllArgs a) {
+  // ---- fp32 side arrays (block 0 .. few) ---------------------------------------------------------------
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < SIDE_FLOATS; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < SIDE_B8) { const int l = i >> 8, c = i & 255; v = (l != 3 || c < 217) ? a.src[9 + l][c] : 0.f; }
+    else if (i < SIDE_W8ROW) { const int c = i - SIDE_B8; v = c < 257 ? a.src[17][c] : 0.f; }
+    else if (i < SIDE_BIAS_COL) v = a.src[8][i - SIDE_W8ROW];                       // lin8 row 0
+    else if (i < SIDE_BC4) { const int j = i - SIDE_BIAS_COL; v = a.src[23 + (j >> 8)][j & 255]; }
+    else if (i < SIDE_WC4) { const int c = i - SIDE_BC4; v = c < 3 ? a.src[27][c] : 0.f; }
+    else v = a.src[22][i - SIDE_WC4];                                               // colour lin4 [3,256]
+    a.side[i] = v;
+  }
+  // ---- operand images ----------------------------------------------------------------------------------
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < a.total_chunks; g += gridDim.x * blockDim.x) {
+    int si = 0;
+    while (si + 1 < a.n_spec && g >= a.spec[si + 1].chunk0) ++si;
+    const PackSpec& sp = a.spec[si];
+    const ImgInfo ii = img_info(sp.img);
+    const int i = g - sp.chunk0;
+    const int kb = i / (ii.npad * 8);
+    const int rem = i - kb * ii.npad * 8;
+    const int ch = rem / ii.npad, n = rem - ch * ii.npad;       // [k-block][chunk column][row]
+    const float* src = a.src[sp.src];
+    const long long sn = sp.transpose ? 1 : sp.src_cols, sk = sp.transpose ? sp.src_cols : 1;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kb * 64 + ch * 8 + j;
+      float x = 0.f;
+      if (n < sp.n_valid) {
+        for (int q = 0; q < sp.nseg; ++q)
+          if (k >= sp.seg_dst[q] && k < sp.seg_dst[q] + sp.seg_len[q])
+            x = sp.scale * src[(long long)(n + sp.row_off) * sn + (long long)(sp.seg_src[q] + k - sp.seg_dst[q]) * sk];
+      }
+      v[j] = x;
+    }
+    uint4 q4;
+    if (sp.bf16) { q4.x = pack_bf2(v[0], v[1]); q4.y = pack_bf2(v[2], v[3]); q4.z = pack_bf2(v[4], v[5]); q4.w = pack_bf2(v[6], v[7]); }
+    else { q4.x = pack_h2(v[0], v[1]); q4.y = pack_h2(v[2], v[3]); q4.z = pack_h2(v[4], v[5]); q4.w = pack_h2(v[6], v[7]); }
+    *reinterpret_cast<uint4*>(a.blob + img_offset_dev(sp.img) + (size_t)kb * ii.npad * 128 + (size_t)ch * ii.npad * 16 + (size_t)n * 16) = q4;
+  }
+}
 }  // namespace fmov
 using namespace fmov;
 
@@ -693,6 +764,89 @@ static void build_bwd_table(ChainTable& tb) {
   }
   set_step(tb.step[n++], (kGradBf16 ? IMG_TB0 : IMG_T0) + 0, 4, 0, kGradFmt, kGradFmt);
   tb.n_steps = n;
+}
+
+
+// ---- fused packing -----------------------------------------------------------------------------------------
+static void add_spec(PackAllArgs& a, int img, int src, int rows, int cols, bool tr, int row_off, int n_valid, int nseg,
+                     int d0, int s0, int l0, int d1, int s1, int l1, float scale, bool bf16) {
+  PackSpec& sp = a.spec[a.n_spec++];
+  sp.img = img; sp.src = src; sp.src_rows = rows; sp.src_cols = cols; sp.transpose = tr ? 1 : 0; sp.row_off = row_off;
+  sp.n_valid = n_valid; sp.nseg = nseg; sp.seg_dst[0] = d0; sp.seg_src[0] = s0; sp.seg_len[0] = l0;
+  sp.seg_dst[1] = d1; sp.seg_src[1] = s1; sp.seg_len[1] = l1; sp.scale = scale; sp.bf16 = bf16 ? 1 : 0;
+  const ImgInfo ii = img_info(img);
+  sp.chunk0 = a.total_chunks;
+  a.total_chunks += ii.npad * ii.kblocks * 8;
+}
+static void build_pack_specs(PackAllArgs& a, bool backward) {
+  a.n_spec = 0; a.total_chunks = 0;
+  const float rs2 = 0.70710678118654752f;
+  static const int so[9] = {256, 256, 256, 217, 256, 256, 256, 256, 257}, si[9] = {39, 256, 256, 256, 256, 256, 256, 256, 256};
+  auto fwd_img = [&](int img, int l, bool bf) {
+    if (l == 0) add_spec(a, img, 0, so[0], si[0], false, 0, 256, 1, 0, 0, 39, 0, 0, 0, 1.f, bf);
+    else if (l == 4) add_spec(a, img, 4, 256, 256, false, 0, 256, 2, 0, 0, 217, 256, 217, 39, rs2, bf);
+    else if (l == 8) add_spec(a, img, 8, 257, 256, false, 1, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
+    else add_spec(a, img, l, so[l], si[l], false, 0, so[l], 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
+  };
+  auto tr_img = [&](int img, int l, bool bf) {      // image rows = input index, K = output index
+    if (l == 0) add_spec(a, img, 0, 256, 39, true, 0, 39, 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
+    else if (l == 3) add_spec(a, img, 3, 217, 256, true, 0, 256, 1, 0, 0, 217, 0, 0, 0, 1.f, bf);
+    else if (l == 4) add_spec(a, img, 4, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, rs2, bf);
+    else if (l == 8) add_spec(a, img, 8, 257, 256, true, 0, 256, 1, 0, 1, 256, 0, 0, 0, 1.f, bf);
+    else add_spec(a, img, l, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
+  };
+  for (int l = 0; l < 9; ++l) fwd_img(IMG_F0 + l, l, false);
+  for (int l = 0; l < 8; ++l) tr_img(IMG_T0 + l, l, false);
+  // colour net: kernel K order is [feat(256) | extras(33)], reference order is [extras(33) | feat(256)]
+  add_spec(a, IMG_C0 + 0, 18, 256, 289, false, 0, 256, 2, 0, 33, 256, 256, 0, 33, 1.f, false);
+  for (int l = 1; l <= 3; ++l) add_spec(a, IMG_C0 + l, 18 + l, 256, 256, false, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, false);
+  add_spec(a, IMG_C0 + 4, 22, 3, 256, false, 0, 3, 1, 0, 0, 256, 0, 0, 0, 1.f, false);
+  if (backward) {
+    const bool g = kGradBf16;
+    add_spec(a, IMG_CT0A, 18, 256, 289, true, 33, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, g);
+    add_spec(a, IMG_CT0B, 18, 256, 289, true, 0, 33, 1, 0, 0, 256, 0, 0, 0, 1.f, g);
+    add_spec(a, IMG_CT1, 19, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, g);
+    add_spec(a, IMG_CT2, 20, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, g);
+    add_spec(a, IMG_CT3, 21, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, g);
+    if (g) {
+      for (int l = 0; l < 8; ++l) fwd_img(IMG_FB0 + l, l, true);
+      for (int l = 0; l < 9; ++l) tr_img(IMG_TB0 + l, l, true);
+    } else {
+      tr_img(IMG_TB0 + 8, 8, false);
+    }
+  }
+}
+
+extern "C" int fmov_side_floats(void) { return SIDE_FLOATS; }
+extern "C" int fmov_side_offset(int which) {
+  const int offs[6] = {SIDE_BIAS_SDF, SIDE_B8, SIDE_W8ROW, SIDE_BIAS_COL, SIDE_BC4, SIDE_WC4};
+  return (which >= 0 && which < 6) ? offs[which] : -1;
+}
+/* srcs: HOST array of 28 device pointers: W_sdf[0..8], b_sdf[0..8], W_col[0..4], b_col[0..4] (contiguous fp32,
+ * reference shapes).  One launch writes every operand image into `blob` (fmov_fine_blob_bytes()) and the fp32 side
+ * arrays into `side` (fmov_side_floats() floats; offsets from fmov_side_offset()). */
+extern "C" int fmov_pack_all(const float* const* srcs, void* blob, float* side, int need_backward, void* stream) {
+  FMOV_REQUIRE(srcs && blob && side, "fmov_pack_all: null argument");
+  static PackAllArgs tmpl[2];
+  static bool init = false;
+  if (!init) {
+    build_pack_specs(tmpl[0], false);
+    build_pack_specs(tmpl[1], true);
+    long long offs[IMG_COUNT + 1];
+    for (int i = 0; i <= IMG_COUNT; ++i) offs[i] = img_offset(i);
+    FMOV_CUDA(cudaMemcpyToSymbol(c_img_offset, offs, sizeof(offs)));
+    init = true;
+  }
+  PackAllArgs a = tmpl[need_backward ? 1 : 0];
+  for (int i = 0; i < 28; ++i) {
+    FMOV_REQUIRE(srcs[i], "fmov_pack_all: source tensor %d is null", i);
+    a.src[i] = srcs[i];
+  }
+  a.blob = reinterpret_cast<uint8_t*>(blob);
+  a.side = side;
+  pack_all_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(a);
+  FMOV_LAUNCH_CHECK("pack_all_kernel");
+  return OK;
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------------

@@ -38,72 +38,29 @@ def check_supported(W_sdf, W_col):
 
 
 class FineWeights:
-    """All operand images + fp32 side arrays for fmov_fine_fwd/_bwd, packed from effective weights."""
+    """All operand images + fp32 side arrays for the MLP kernels, packed from the effective weights by ONE
+    launch (fmov_pack_all).  The first fmov_sdf_fwd_blob_bytes() bytes are exactly the value-chain blob of
+    fmov_sdf_query_*, so hierarchical sampling shares it (`.query` is a packing.SdfQueryWeights view)."""
 
     def __init__(self, W_sdf, b_sdf, W_col, b_col, need_backward=True):
         check_supported(W_sdf, W_col)
+        lib = L.lib()
         dev = W_sdf[0].device
-        self.blob = torch.empty(int(L.lib().fmov_fine_blob_bytes()), dtype=torch.uint8, device=dev)
-        Ws = [w.detach().float().contiguous() for w in W_sdf]
-        Wc = [w.detach().float().contiguous() for w in W_col]
-
-        def pk(img, src, segs, **kw):
-            off, npad, kb = _img_info(img)
-            packing.pack_image(src, self.blob, off, npad, kb, segs, **kw)
-
-        def fwd_image(img, l, bf16):
-            if l == 0:
-                pk(img, Ws[0], [(0, 0, 39)], bf16=bf16)
-            elif l == 4:
-                pk(img, Ws[4], [(0, 0, 217), (256, 217, 39)], scale=1.0 / SQ2, bf16=bf16)
-            elif l == 8:
-                pk(img, Ws[8], [(0, 0, 256)], row_off=1, n_valid=256, bf16=bf16)
-            else:
-                pk(img, Ws[l], [(0, 0, 256)], bf16=bf16)
-
-        def tr_image(img, l, bf16):
-            # image rows n = input index of W_l, K = output index
-            if l == 0:
-                pk(img, Ws[0], [(0, 0, 256)], transpose=True, n_valid=39, bf16=bf16)
-            elif l == 3:
-                pk(img, Ws[3], [(0, 0, 217)], transpose=True, bf16=bf16)
-            elif l == 4:
-                pk(img, Ws[4], [(0, 0, 256)], transpose=True, scale=1.0 / SQ2, bf16=bf16)
-            elif l == 8:
-                pk(img, Ws[8], [(0, 1, 256)], transpose=True, bf16=bf16)      # feature rows 1..256
-            else:
-                pk(img, Ws[l], [(0, 0, 256)], transpose=True, bf16=bf16)
-
-        for l in range(9):
-            fwd_image(IMG_F0 + l, l, False)
-        for l in range(8):
-            tr_image(IMG_T0 + l, l, False)
-        # colour net: kernel K order is [feat(256) | extras(33)], reference order is [extras(33) | feat(256)]
-        pk(IMG_C0 + 0, Wc[0], [(0, 33, 256), (256, 0, 33)])
-        for l in (1, 2, 3):
-            pk(IMG_C0 + l, Wc[l], [(0, 0, 256)])
-        pk(IMG_C0 + 4, Wc[4], [(0, 0, 256)], n_valid=3)
-        if need_backward:
-            gbf = bool(L.lib().fmov_grad_is_bf16())     # gradient passes: bf16 copies, or the fp16 images (loss-scaled)
-            pk(IMG_CT0A, Wc[0], [(0, 0, 256)], transpose=True, row_off=33, n_valid=256, bf16=gbf)
-            pk(IMG_CT0B, Wc[0], [(0, 0, 256)], transpose=True, n_valid=33, bf16=gbf)
-            for img, l in ((IMG_CT1, 1), (IMG_CT2, 2), (IMG_CT3, 3)):
-                pk(img, Wc[l], [(0, 0, 256)], transpose=True, bf16=gbf)
-            if gbf:
-                for l in range(8):
-                    fwd_image(IMG_FB0 + l, l, True)
-                for l in range(9):
-                    tr_image(IMG_TB0 + l, l, True)
-            else:
-                tr_image(IMG_TB0 + 8, 8, False)        # lin8 feature rows^T (only needed by the backward)
-        self.bias_sdf = torch.zeros(8, 256, dtype=torch.float32, device=dev)
-        for l in range(8):
-            self.bias_sdf[l, : b_sdf[l].numel()] = b_sdf[l].detach().float()
-        self.b8 = b_sdf[8].detach().float().contiguous()
-        self.w8row = Ws[8][0].contiguous()
-        self.bias_col = torch.stack([b.detach().float() for b in b_col[:4]]).contiguous()
-        self.bc4 = b_col[4].detach().float().contiguous()
-        self.wc4 = Wc[4]
+        srcs = [t.detach().float().contiguous() for t in (list(W_sdf) + list(b_sdf) + list(W_col) + list(b_col))]
+        self._keep = srcs
+        self.blob = torch.empty(int(lib.fmov_fine_blob_bytes()), dtype=torch.uint8, device=dev)
+        self.side = torch.empty(int(lib.fmov_side_floats()), dtype=torch.float32, device=dev)
+        ptrs = (ctypes.c_void_p * 28)(*[t.data_ptr() for t in srcs])
+        L.check(lib.fmov_pack_all(ptrs, L.ptr(self.blob), L.ptr(self.side), int(bool(need_backward)), L.stream()),
+                "fmov_pack_all")
+        o = [int(lib.fmov_side_offset(i)) for i in range(6)]
+        self.bias_sdf = self.side[o[0]: o[0] + 2048]
+        self.b8 = self.side[o[1]: o[1] + 257]
+        self.w8row = self.side[o[2]: o[2] + 256]
+        self.bias_col = self.side[o[3]: o[3] + 1024]
+        self.bc4 = self.side[o[4]: o[4] + 3]
+        self.wc4 = self.side[o[5]: o[5] + 768]
+        self.query = packing.SdfQueryWeights.from_views(self.blob, self.bias_sdf, self.w8row, self.b8)
 
 
 class Stash:

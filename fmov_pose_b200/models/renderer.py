@@ -78,12 +78,13 @@ class NeuSRenderer:
         if float(getattr(self.sdf_network, "scale", 1.0)) != 1.0:
             raise NotImplementedError("SDFNetwork.scale must be 1.0 (every shipped conf)")
 
-    def sample_z(self, rays_o, rays_d, near, far, t_rand):
+    def sample_z(self, rays_o, rays_d, near, far, t_rand, qw=None):
         """z_vals [B, n_samples + n_importance] (models/renderer.py:385-446)."""
         if self.n_importance > 0:
             with torch.no_grad():
-                W, b = self.sdf_network.effective_weights()
-                qw = _packing.SdfQueryWeights(W, b)
+                if qw is None:
+                    W, b = self.sdf_network.effective_weights()
+                    qw = _packing.SdfQueryWeights(W, b)
                 return _ops.hierarchical_sample(qw, rays_o.detach().float().contiguous(),
                                                 rays_d.detach().float().contiguous(), near.detach(), far.detach(),
                                                 t_rand, self.n_samples, self.n_importance, self.up_sample_steps)
@@ -109,15 +110,16 @@ class NeuSRenderer:
                 t_rand = torch.rand([batch_size, 1], device=rays_o.device)
         else:
             t_rand = None
-        z_vals = self.sample_z(rays_o, rays_d, near, far, t_rand)
-        n_samples = z_vals.shape[1]
-
         W_s, b_s = self.sdf_network.effective_weights()
         W_c, b_c = self.color_network.effective_weights()
-        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)   # fields.py:294, renderer.py:290
         need_bwd = torch.is_grad_enabled() and not eval
+        with torch.no_grad():      # one packing launch serves the sampling queries and the fine stage
+            fw = _fine.FineWeights(W_s, b_s, W_c, b_c, need_backward=need_bwd)
+        z_vals = self.sample_z(rays_o, rays_d, near, far, t_rand, qw=fw.query)
+        n_samples = z_vals.shape[1]
+        inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)   # fields.py:294, renderer.py:290
         cfg = dict(sample_dist=sample_dist, cos_anneal_ratio=cos_anneal_ratio, background_rgb=background_rgb,
-                   need_backward=need_bwd, group=self.process_group)
+                   need_backward=need_bwd, group=self.process_group, fine_weights=fw)
         if not need_bwd:
             with torch.no_grad():
                 outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)

@@ -60,6 +60,12 @@ def ti_to_rowmajor(img, P, cols, kblocks, bf16=False):
 class SdfQueryWeights:
     """Forward images of lin0..lin7 + fp32 side arrays for fmov_sdf_query_* (value-only chain)."""
 
+    @classmethod
+    def from_views(cls, blob, bias, w8, b8):
+        self = cls.__new__(cls)
+        self.blob, self.bias, self.w8, self.b8 = blob, bias, w8, b8
+        return self
+
     def __init__(self, W, b):
         """W, b: lists of the 9 effective fp32 weights / biases of the SDF net (CUDA)."""
         dev = W[0].device

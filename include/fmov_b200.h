@@ -117,6 +117,12 @@ int fmov_ray_reduce_bwd(const float* d_pts, const float* d_dirs, const float* d_
 int fmov_fine_image_count(void);
 int fmov_fine_image_info(int id, long long* offset, int* npad, int* kblocks);
 long long fmov_fine_blob_bytes(void);
+/* one launch: every operand image + the fp32 side arrays from the 28 effective-weight tensors (HOST array of device
+ * pointers W_sdf[9], b_sdf[9], W_col[5], b_col[5]); side layout via fmov_side_offset(0..5) =
+ * bias_sdf[8x256], b8[257], w8row[256], bias_col[4x256], bc4[3], wc4[3x256] */
+int fmov_pack_all(const float* const* srcs, void* blob, float* side, int need_backward, void* stream);
+int fmov_side_floats(void);
+int fmov_side_offset(int which);
 int fmov_fine_stash_count(void);
 int fmov_fine_stash_blocks(int id);
 int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
