@@ -64,27 +64,62 @@ class FineWeights:
 
 
 class Stash:
-    """Tile-image tensors in HBM (activations of the forward, gradient tiles of the backward)."""
+    """Tile-image tensors in HBM (activations of the forward, gradient tiles of the backward) carved out of ONE
+    buffer.  Buffers are recycled through a small free-list so that a train loop does not allocate/free tens of
+    GB per step (a Stash is returned to the pool at the end of backward or when its autograd node dies)."""
+    _pool = {}
 
     def __init__(self, P, device, with_backward=True):
         lib = L.lib()
         n = lib.fmov_fine_stash_count()
-        nt = (P + 127) // 128
-        self.tensors = []
-        for i in range(n):
-            if i > ST_FWD_LAST and not with_backward:
+        self.nt = (P + 127) // 128
+        self.device = device
+        self.blocks = [lib.fmov_fine_stash_blocks(i) for i in range(n)]
+        n_fwd = sum(self.blocks[: ST_FWD_LAST + 1])
+        n_all = sum(self.blocks)
+        self.key = (str(device), self.nt)
+        self.buf = None
+        free = Stash._pool.get(self.key, [])
+        while free:
+            cand = free.pop()
+            if cand.numel() >= (n_all if with_backward else n_fwd) * self.nt * 16384:
+                self.buf = cand
+                break
+        if self.buf is None:
+            self.buf = torch.empty((n_all if with_backward else n_fwd) * self.nt * 16384, dtype=torch.uint8, device=device)
+        self._carve()
+
+    def _carve(self):
+        have = self.buf.numel() // (self.nt * 16384)
+        self.tensors, off = [], 0
+        for nb in self.blocks:
+            if off + nb <= have:
+                self.tensors.append(self.buf[off * self.nt * 16384: (off + nb) * self.nt * 16384])
+            else:
                 self.tensors.append(None)
-                continue
-            self.tensors.append(torch.empty(nt * lib.fmov_fine_stash_blocks(i) * 16384, dtype=torch.uint8, device=device))
-        self.ptrs = (ctypes.c_void_p * n)(*[(t.data_ptr() if t is not None else 0) for t in self.tensors])
+            off += nb
+        self.ptrs = (ctypes.c_void_p * len(self.blocks))(*[(t.data_ptr() if t is not None else 0) for t in self.tensors])
 
     def ensure_backward(self, P, device):
-        lib = L.lib()
-        nt = (P + 127) // 128
-        for i, t in enumerate(self.tensors):
-            if t is None:
-                self.tensors[i] = torch.empty(nt * lib.fmov_fine_stash_blocks(i) * 16384, dtype=torch.uint8, device=device)
-        self.ptrs = (ctypes.c_void_p * len(self.tensors))(*[t.data_ptr() for t in self.tensors])
+        if any(t is None for t in self.tensors):
+            # forward-only stash asked to run backward: grow (keeps the forward part)
+            big = torch.empty(sum(self.blocks) * self.nt * 16384, dtype=torch.uint8, device=device)
+            big[: self.buf.numel()].copy_(self.buf)
+            self.buf = big
+            self._carve()
+
+    def release(self):
+        if self.buf is not None:
+            lst = Stash._pool.setdefault(self.key, [])
+            if len(lst) < 2:
+                lst.append(self.buf)
+            self.buf, self.tensors = None, []
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
 
 
 def fine_forward(fw, stash, rays_o, rays_d, z, sample_dist):
@@ -205,5 +240,6 @@ class RenderCoreFunction(torch.autograd.Function):
         want_dz = ctx.needs_input_grad[2]
         d_o, d_d, d_z = ops.ray_reduce_bwd(d_pts, d_dirs, bk["d_dir"], bk["d_dist"], bk["d_mid"], rays_d, z, sd, want_dz)
         d_inv_s = bk["d_invs"].sum().reshape(())
-        ctx.stash = None          # free the stash as soon as the gradients exist
+        stash.release()           # recycle the stash as soon as the gradients exist
+        ctx.stash = None
         return (d_o, d_d, d_z, d_inv_s, None) + tuple(dW_s) + tuple(db_s) + tuple(dW_c) + tuple(db_c)

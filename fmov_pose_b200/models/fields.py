@@ -101,6 +101,7 @@ class SDFNetwork(_WeightNormMLP):
             # points as degenerate rays: o = x, d = 0, one sample each
             sdf, nrm, rgb, _ = _fine.fine_forward(fw, st, x, torch.zeros_like(x), torch.zeros(N, 1, device=x.device), 0.0)
             feat = _packing.ti_to_rowmajor(st.tensors[9], N, 256, 4)
+            st.release()
         return sdf.view(-1, 1), nrm, feat, rgb
 
     def forward(self, inputs):
