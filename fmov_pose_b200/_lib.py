@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfmov_b200.so")
+LIB_PATH = os.environ.get("FMOV_LIB", os.path.join(_HERE, "libfmov_b200.so"))   # FMOV_LIB: A/B-testing builds
 _lib = None
 
 c_void_p, c_int, c_ll, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float

@@ -3,11 +3,14 @@
 // accumulators in TMEM and a per-kernel epilogue between steps.  TWO tiles are in flight per CTA so that
 // the tensor core works on one tile while the other tile's epilogue runs.
 //
-// Warp roles (10 warps, 320 threads):
-//   warp 0      weight producer   cp.async.bulk  weight-image k-blocks -> WST ring            (1 lane)
-//   warp 1      MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage        (1 lane) + TMEM alloc
-//   warps 2..5  epilogue of tile slot 0   } tcgen05.ld -> fp32 math -> st.shared (next A operand)
-//   warps 6..9  epilogue of tile slot 1   }             + st.global / ld.global of the stash rows
+// Warp roles (18 warps, 576 threads):
+//   warp 0        weight producer   cp.async.bulk  weight-image k-blocks -> WST ring            (1 lane)
+//   warp 1        MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage        (1 lane) + TMEM alloc
+//   warps 2..9    epilogue of tile slot 0: two warpgroups, columns 0..127 and 128..255 of the tile
+//   warps 10..17  epilogue of tile slot 1        (tcgen05.ld -> fp32 math -> st.shared next A operand
+//                                                 + st.global / ld.global of the stash rows)
+// 4 epilogue warps per scheduler: the epilogues are latency bound (TMEM / HBM loads, MUFU chains), measured
+// 0.24 eligible warps per cycle with 8 epilogue warps.
 //
 // Stash traffic is done by the row-owning thread: in the tile-image layout a tile row is 128 contiguous
 // bytes per 64-feature block, so a warp reads/writes 4 KiB contiguous per block (fully coalesced), and a
@@ -22,9 +25,14 @@
 namespace fmov {
 
 constexpr int CH_SLOTS = 2;
-constexpr int CH_THREADS = 64 + CH_SLOTS * 128;   // 320
+#ifndef FMOV_CH_WGS
+#define FMOV_CH_WGS 1
+#endif
+constexpr int CH_WGS = FMOV_CH_WGS;                // epilogue warpgroups (column ranges) per tile slot: 1 or 2
+constexpr int CH_CHUNKS = 16 / CH_WGS;             // 16-column chunks handled by one warpgroup
+constexpr int CH_THREADS = 64 + CH_SLOTS * CH_WGS * 128;   // 576
 constexpr int EPI_WARP0 = 2;
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_THREADS = CH_WGS * 128;          // threads arriving per slot
 constexpr int WSLOT_BYTES = 256 * 128;            // [256 rows x 64] 16-bit
 constexpr int CH_WSTAGES = 2;
 constexpr int MAX_STEPS = 40;
@@ -59,16 +67,17 @@ struct ChainSmem {
   uint64_t w_empty[CH_WSTAGES];
   uint32_t tmem_base;
   uint32_t pad_;
+  float scratch[CH_SLOTS][128];   // per-row partial sums exchanged between the two column warpgroups of a slot
 };
 
 // Dynamic smem: [ChainSmem | pad to 1024][ACT0 64K][ACT1 64K][AUX0 16K][AUX1 16K][WST 2 x 32K]
 struct ChainLayout {
-  static constexpr int HDR = 1024;
+  static constexpr int HDR = 2048;
   static constexpr int ACT = HDR;
   static constexpr int AUX = ACT + CH_SLOTS * 4 * BLK_BYTES;
   static constexpr int WST = AUX + CH_SLOTS * BLK_BYTES;
   static constexpr int TOTAL = WST + CH_WSTAGES * WSLOT_BYTES;
-  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024-alignment
+  static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024-alignment (dynamic smem base is >= 16 B aligned)
 };
 static_assert(ChainLayout::DYN_BYTES <= 227 * 1024, "chain engine exceeds the 227 KiB shared-memory limit");
 
@@ -183,6 +192,7 @@ struct EpiCtx {
   uint8_t* aux;        // this slot's AUX (1 block)
   uint32_t tmem;       // TMEM address of this slot's accumulator with the warp's lane quarter folded in
   int slot;
+  int wg;              // column half handled by this warpgroup: chunks of columns [128*wg, 128*wg + 128)
   int row;             // 0..127 (tile row == TMEM lane)
   uint32_t acc_n;      // accumulator phases consumed
 };
@@ -190,7 +200,8 @@ struct EpiCtx {
 __device__ __forceinline__ void epi_init(EpiCtx& c, ChainSmem* s, uint8_t* act0, uint8_t* aux0, uint32_t tmem_base) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int quarter = warp & 3;                  // TMEM lanes this warp may access
-  c.slot = (warp - EPI_WARP0) >> 2;
+  c.slot = (warp - EPI_WARP0) / (4 * CH_WGS);
+  c.wg = ((warp - EPI_WARP0) >> 2) % CH_WGS;
   c.s = s;
   c.act = act0 + c.slot * 4 * BLK_BYTES;
   c.aux = aux0 + c.slot * BLK_BYTES;
@@ -217,6 +228,51 @@ __device__ __forceinline__ void acc_load32(const EpiCtx& c, int col0, float* v) 
 __device__ __forceinline__ void acc_load16(const EpiCtx& c, int col0, float* v) {
   tmem_ld16(c.tmem + col0, v);
   tmem_ld_wait();
+}
+// all 256 threads of a tile slot (both column warpgroups); orders their shared/global writes
+__device__ __forceinline__ void slot_sync(const EpiCtx& c) { named_bar_sync(1 + c.slot, EPI_THREADS); }
+
+// ---- 16-column chunks (index ck = 0..15 within a 256-wide tile): 2 x 16-byte pieces of a row -----------------
+__device__ __forceinline__ void pack2(const float* v, bool bf16, uint4* q) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (bf16) {
+      q[i].x = pack_bf2(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_bf2(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_bf2(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_bf2(v[i * 8 + 6], v[i * 8 + 7]);
+    } else {
+      q[i].x = pack_h2(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_h2(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_h2(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_h2(v[i * 8 + 6], v[i * 8 + 7]);
+    }
+  }
+}
+__device__ __forceinline__ void pack2_grad(const float* v, uint4* q) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (kGradBf16) {
+      q[i].x = pack_bf2(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_bf2(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_bf2(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_bf2(v[i * 8 + 6], v[i * 8 + 7]);
+    } else {
+      q[i].x = pack_h2_sat(v[i * 8 + 0], v[i * 8 + 1]); q[i].y = pack_h2_sat(v[i * 8 + 2], v[i * 8 + 3]);
+      q[i].z = pack_h2_sat(v[i * 8 + 4], v[i * 8 + 5]); q[i].w = pack_h2_sat(v[i * 8 + 6], v[i * 8 + 7]);
+    }
+  }
+}
+// element j (0..15) of a packed 16-column chunk
+__device__ __forceinline__ float2 chunk_pair(const uint4* q, int jp, bool bf16) {   // jp = pair index 0..7
+  const uint4 w = q[jp >> 2];
+  const uint32_t u = (jp & 3) == 0 ? w.x : (jp & 3) == 1 ? w.y : (jp & 3) == 2 ? w.z : w.w;
+  return bf16 ? unpack_bf2(u) : unpack_h2(u);
+}
+// `tilep` = base of a 256-wide tile (4 blocks) + row*16, shared or global; chunk ck -> block ck/4, pieces 2*(ck%4)..
+__device__ __forceinline__ void chunk_store(uint8_t* tilep, int ck, const uint4* q) {
+  uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+  *reinterpret_cast<uint4*>(p) = q[0];
+  *reinterpret_cast<uint4*>(p + TI_CHUNK_STRIDE) = q[1];
+}
+__device__ __forceinline__ void chunk_load(const uint8_t* tilep, int ck, uint4* q) {
+  const uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+  q[0] = *reinterpret_cast<const uint4*>(p);
+  q[1] = *reinterpret_cast<const uint4*>(p + TI_CHUNK_STRIDE);
 }
 
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------

@@ -164,6 +164,16 @@ __device__ __forceinline__ void put_chunk_grad(const EpiCtx& c, const ChainPtrs&
   if (to_act) row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
   if (stash_id >= 0) row_half_store(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), hb & 1, q);
 }
+// hoisted-base variants: `tp` = stash tile base + row*16 (or ACT base + row*16); chunk hb = 32 columns
+__device__ __forceinline__ uint8_t* tile_base(const ChainPtrs& ptrs, int id, long long tile, int row) {
+  return ptrs.stash[id] + (size_t)tile * stash_kb(id) * BLK_BYTES + (size_t)row * 16;
+}
+__device__ __forceinline__ void ld_half(const uint8_t* tp, int hb, uint4* q) {
+  row_half_load(tp + (hb >> 1) * BLK_BYTES, hb & 1, q);
+}
+__device__ __forceinline__ void st_half(uint8_t* tp, int hb, const uint4* q) {
+  row_half_store(tp + (hb >> 1) * BLK_BYTES, hb & 1, q);
+}
 __device__ __forceinline__ void get_chunk_raw(const EpiCtx& c, const ChainPtrs& ptrs, int stash_id, long long tile,
                                               int hb, uint4* q) {
   row_half_load(stash_row(ptrs, stash_id, tile, hb >> 1, c.row), hb & 1, q);
@@ -282,15 +292,18 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       // ---- reverse sweep l = 7..1 -------------------------------------------------------------------------------
 #pragma unroll 1
       for (int l = 7; l >= 1; --l) {
-        uint4 sq[4], sn[4];
-        get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, 0, sq);        // H_l -> sigma_{l-1} (own rows)
+        const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);      // H_l -> sigma_{l-1} (own rows)
+        uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);
+        uint8_t* ap = c.act + c.row * 16;
+        uint4 sb[2][4];
+        ld_half(hp, 0, sb[0]);
         epi_wait_acc(c);
 #pragma unroll
         for (int hb = 0; hb < 8; ++hb) {
           float v[32], h[32];
-          if (hb < 7) get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, hb + 1, sn);
+          if (hb < 7) ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
           acc_load32(c, hb * 32, v);
-          unpack4(sq, false, h);
+          unpack4(sb[hb & 1], false, h);
           if (l == 4 && hb == 6 && pc.valid) {
             // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image): parked in
             // the g_e output row until the W_0^T delta_0 term arrives (keeps 39 registers free across the sweep)
@@ -303,9 +316,10 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= sigma_from_h(h[j]);    // H_4 is zero beyond col 216 -> delta_3 too
-          put_chunk(c, ptrs, true, ST_D0 + (l - 1), tile, hb, false, v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sq[i] = sn[i];
+          uint4 q[4];
+          pack4(v, false, q);
+          st_half(ap, hb, q);
+          st_half(dp, hb, q);
         }
         epi_signal_act(c);
       }
@@ -458,20 +472,24 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       // ---- colour layers 3..1:  zbar_c{l-1} = (zbar_cl W_cl) * [C_l > 0] -----------------------------------
 #pragma unroll 1
       for (int l = 3; l >= 1; --l) {
-        uint4 sq[4], sn[4];
-        get_chunk_raw(c, ptrs, ST_C1 + (l - 1), tile, 0, sq);
+        const uint8_t* cp = tile_base(ptrs, ST_C1 + (l - 1), tile, c.row);
+        uint8_t* zp = tile_base(ptrs, ST_ZC0 + (l - 1), tile, c.row);
+        uint8_t* ap = c.act + c.row * 16;
+        uint4 sb[2][4];
+        ld_half(cp, 0, sb[0]);
         epi_wait_acc(c);
 #pragma unroll
         for (int hb = 0; hb < 8; ++hb) {
           float v[32], h[32];
-          if (hb < 7) get_chunk_raw(c, ptrs, ST_C1 + (l - 1), tile, hb + 1, sn);
+          if (hb < 7) ld_half(cp, hb + 1, sb[(hb + 1) & 1]);
           acc_load32(c, hb * 32, v);
-          unpack4(sq, false, h);
+          unpack4(sb[hb & 1], false, h);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
-          put_chunk_grad(c, ptrs, true, ST_ZC0 + (l - 1), tile, hb, v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sq[i] = sn[i];
+          uint4 q[4];
+          pack4_grad(v, q);
+          st_half(ap, hb, q);
+          st_half(zp, hb, q);
         }
         epi_signal_act(c);
       }
@@ -533,16 +551,21 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int n_mma = (l == 3) ? 224 : 256;
-        uint4 sq[4], sn[4], dq[4], dn[4];
-        get_chunk_raw(c, ptrs, ST_H1 + l, tile, 0, sq);      // H_{l+1} -> sigma_l
-        get_chunk_raw(c, ptrs, ST_D0 + l, tile, 0, dq);      // delta_l
+        const uint8_t* hp = tile_base(ptrs, ST_H1 + l, tile, c.row);      // H_{l+1} -> sigma_l
+        const uint8_t* dp = tile_base(ptrs, ST_D0 + l, tile, c.row);      // delta_l
+        uint8_t* vp = tile_base(ptrs, ST_V1 + l, tile, c.row);
+        uint8_t* qp = tile_base(ptrs, ST_Q0 + l, tile, c.row);
+        uint8_t* ap = c.act + c.row * 16;
+        uint4 sb[2][4], db[2][4];
+        ld_half(hp, 0, sb[0]);
+        ld_half(dp, 0, db[0]);
         epi_wait_acc(c);
 #pragma unroll
         for (int hb = 0; hb < 8; ++hb) {
           float v[32], h[32], dl[32];
           if (hb < 7) {
-            get_chunk_raw(c, ptrs, ST_H1 + l, tile, hb + 1, sn);
-            get_chunk_raw(c, ptrs, ST_D0 + l, tile, hb + 1, dn);
+            ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
+            ld_half(dp, hb + 1, db[(hb + 1) & 1]);
           }
           if (hb * 32 < n_mma) {
             acc_load32(c, hb * 32, v);
@@ -550,19 +573,21 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          unpack4(sq, false, h);
-          unpack4(dq, false, dl);
+          unpack4(sb[hb & 1], false, h);
+          unpack4(db[hb & 1], false, dl);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float sg = sigma_from_h(h[j]);
-            const float db = v[j];
-            v[j] = db * sg;                                       // vbar_{l+1}
-            dl[j] = SP_BETA * db * dl[j] * (1.f - sg);            // q_l
+            const float dbar = v[j];
+            v[j] = dbar * sg;                                       // vbar_{l+1}
+            dl[j] = SP_BETA * dbar * dl[j] * (1.f - sg);            // q_l
           }
-          put_chunk_grad(c, ptrs, true, ST_V1 + l, tile, hb, v);
-          put_chunk_grad(c, ptrs, false, ST_Q0 + l, tile, hb, dl);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
+          uint4 q[4];
+          pack4_grad(v, q);
+          st_half(ap, hb, q);
+          st_half(vp, hb, q);
+          pack4_grad(dl, q);
+          st_half(qp, hb, q);
         }
         if (l < 7) epi_signal_act(c);
       }
@@ -577,20 +602,24 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------
 #pragma unroll 1
       for (int l = 8; l >= 1; --l) {
-        uint4 sq[4], sn[4], dq[4], dn[4];
-        get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, 0, sq);    // H_l -> sigma_{l-1}
-        get_chunk_raw(c, ptrs, ST_Q0 + (l - 1), tile, 0, dq);    // q_{l-1} (own rows, written above)
+        const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);    // H_l -> sigma_{l-1}
+        const uint8_t* qp = tile_base(ptrs, ST_Q0 + (l - 1), tile, c.row);    // q_{l-1} (own rows, written above)
+        uint8_t* zp = tile_base(ptrs, ST_Z0 + (l - 1), tile, c.row);
+        uint8_t* ap = c.act + c.row * 16;
+        uint4 sb[2][4], db[2][4];
+        ld_half(hp, 0, sb[0]);
+        ld_half(qp, 0, db[0]);
         epi_wait_acc(c);
 #pragma unroll
         for (int hb = 0; hb < 8; ++hb) {
           float v[32], h[32], q[32];
           if (hb < 7) {
-            get_chunk_raw(c, ptrs, ST_H1 + (l - 1), tile, hb + 1, sn);
-            get_chunk_raw(c, ptrs, ST_Q0 + (l - 1), tile, hb + 1, dn);
+            ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
+            ld_half(qp, hb + 1, db[(hb + 1) & 1]);
           }
           acc_load32(c, hb * 32, v);
-          unpack4(sq, false, h);
-          unpack4(dq, kGradBf16, q);
+          unpack4(sb[hb & 1], false, h);
+          unpack4(db[hb & 1], kGradBf16, q);
           if (l == 8) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + hb * 32 + j), v[j]);
@@ -605,9 +634,10 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
-          put_chunk_grad(c, ptrs, true, ST_Z0 + (l - 1), tile, hb, v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { sq[i] = sn[i]; dq[i] = dn[i]; }
+          uint4 qq[4];
+          pack4_grad(v, qq);
+          st_half(ap, hb, qq);
+          st_half(zp, hb, qq);
         }
         epi_signal_act(c);
       }

@@ -8,6 +8,9 @@
 // activation tile never leaves shared memory, weights stream from L2 via TMA bulk copies, accumulators
 // live in TMEM.  The last linear layer only needs row 0 (the SDF), which is evaluated in fp32 by the
 // epilogue of layer 7 from the un-rounded activations.
+// the value-only chain has no HBM traffic in its epilogue and fits 96 registers: two column warpgroups per tile slot
+// (16 epilogue warps) measured 1.45 -> 1.33 ms per 1M points; the fine-stage kernels keep one (register bound)
+#define FMOV_CH_WGS 2
 #include "mlp_chain.cuh"
 #include "../../include/fmov_b200.h"
 
@@ -92,6 +95,26 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
     row_half_store(blk + row * 16, h, q);
   }
 }
+__device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const float x[3], int h) {
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      fast_sincos(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = s;
+      e[6 + 6 * k + c] = co;
+    }
+  }
+  uint4 q[4];
+  if (h == 0) pack4(e, false, q); else pack4(e + 32, false, q);
+  row_half_store(blk + row * 16, h, q);
+}
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
@@ -129,22 +152,25 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) load_point(a, p, x);
       x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
-      pe6_to_block(c.aux, c.row, x);
+      if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
+      else pe6_to_block(c.aux, c.row, x);
       epi_signal_act(c);
-      float sdf = b8;
+      float sdf = 0.f;
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const float* bias = a.bias + l * 256;
         const int n_mma = (l == 3) ? 224 : 256;       // lin3 has 217 outputs; columns 217.. meet zero weights next
+        uint8_t* actp = c.act + c.row * 16;
         epi_wait_acc(c);
 #pragma unroll 2
-        for (int hb = 0; hb < 8; ++hb) {
-          if (hb * 32 >= n_mma) break;
-          float v[32];
-          acc_load32(c, hb * 32, v);
+        for (int i = 0; i < CH_CHUNKS; ++i) {
+          const int ck = c.wg * CH_CHUNKS + i;
+          if (ck * 16 >= n_mma) break;
+          float v[16];
+          acc_load16(c, ck * 16, v);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
             v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
             v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
             v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
@@ -152,21 +178,28 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
           }
           if (l == 7) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + hb * 32) + j4);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + ck * 16) + j4);
               sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
               sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
             }
           } else {
-            uint4 q[4];
-            pack4(v, false, q);
-            row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
+            uint4 q2[2];
+            pack2(v, false, q2);
+            chunk_store(actp, ck, q2);
           }
         }
         if (l < 7) epi_signal_act(c);
         else tc_fence_before();
       }
-      if (valid) a.out[p] = sdf * a.out_scale;
+      // combine the two column halves of the lin8-row-0 dot product
+      if (CH_WGS == 2) {
+        if (c.wg == 0) s->scratch[c.slot][c.row] = sdf;
+        slot_sync(c);
+        if (c.wg == 1) sdf += s->scratch[c.slot][c.row];
+        slot_sync(c);      // scratch may be rewritten by the next tile
+      }
+      if (c.wg == CH_WGS - 1 && valid) a.out[p] = (sdf + b8) * a.out_scale;
     }
   }
   __syncthreads();
