@@ -118,8 +118,8 @@ def time_cpu(B, n, m, steps_up, warm, iters):
 
 
 # DRAM traffic of the MLP kernels per sample point, from `ncu --set full` (dram__bytes_read + dram__bytes_write,
-# profiles/r1_v2_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 3.94 GB, fine_bwd 8.94 GB, dw 5.91 GB
-NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 3.942e9 / 262144, "fine_bwd": 8.936e9 / 262144, "dw": 5.908e9 / 262144}
+# profiles/r1_final_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 3.94 GB, fine_bwd 8.94 GB, dw 5.91 GB
+NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 3.924e9 / 262144, "fine_bwd": 8.890e9 / 262144, "dw": 5.893e9 / 262144}
 
 
 def measure_extras(scene, dev):
@@ -301,7 +301,7 @@ def main():
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B * (n + m) or None,
                 "traffic_note": "dram bytes per launch from ncu --set full at 2048 rays, scaled by points "
-                                "(profiles/r1_v2_ncu_full.txt); HBM view: %.0f GB/s of %.1f measured" % (
+                                "(profiles/r1_final_ncu_full.txt); HBM view: %.0f GB/s of %.1f measured" % (
                                     NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B * (n + m) / (avg_ms * 1e-3) / 1e9,
                                     peaks.get("hbm_gbs", 6650.0)),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
