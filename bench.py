@@ -102,6 +102,56 @@ def cpu_reference_step_fn(B, n, m, steps_up, threads):
     return step
 
 
+def time_torch_gpu(B, n, m, steps_up, dev, warm=2, iters=5):
+    """The same PyTorch restatement of the reference (fp32 eager autograd, double backward through
+    sdf_network.gradient) run on THIS GPU — the "reference-PyTorch on one B200" arm of north_star's 50x target.
+    Baseline only: nothing of it is on the product path."""
+    import torch
+    from oracle import neus_oracle as O
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.models.barf_fields import BarfRenderingNetwork, BarfSDFNetwork
+    from fmov_pose_b200.models.fields import SingleVarianceNetwork
+    torch.manual_seed(2024)
+    init = synthetic.make_init_poses(20)
+    sdf = BarfSDFNetwork(init, n_images=20, **synthetic.SDF_KW).to(dev)
+    col = BarfRenderingNetwork(**synthetic.COL_KW).to(dev)
+    var = SingleVarianceNetwork(0.3).to(dev)
+    params = [p for net in (sdf, col, var) for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=5e-4)
+    g = torch.Generator(device=dev).manual_seed(1)
+    intr_inv = torch.linalg.inv(torch.tensor(synthetic.INTRINSICS)).to(dev)
+    init = init.to(dev)
+
+    def step():
+        with torch.device(dev):      # the oracle's factory calls (linspace/ones/zeros) follow the default device
+            sdf_p = {k: v for k, v in sdf.named_parameters()}
+            col_p = {k: v for k, v in col.named_parameters()}
+            px = torch.randint(170, 470, [B], generator=g, device=dev)
+            py = torch.randint(90, 390, [B], generator=g, device=dev)
+            pose = init[3, :3].clone().requires_grad_(True)
+            mask = (((px - 320) ** 2 + (py - 240) ** 2) < 150 ** 2).float()[:, None]
+            losses, _ = O.train_step(sdf_p, col_p, var.variance, pose, intr_inv, px, py,
+                                     torch.rand(B, 3, generator=g, device=dev), mask,
+                                     t_rand=torch.rand(B, 1, generator=g, device=dev), n_samples=n, n_importance=m,
+                                     up_sample_steps=steps_up, cos_anneal_ratio=1.0, igr_weight=0.1, mask_weight=5.0)
+            opt.zero_grad()
+            losses["loss"].backward()
+            opt.step()
+        return losses["loss"]
+
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return B / ms * 1e3, ms
+
+
 def time_cpu(B, n, m, steps_up, warm, iters):
     threads = os.cpu_count() or 1
     fn = cpu_reference_step_fn(B, n, m, steps_up, threads)
@@ -122,7 +172,7 @@ def time_cpu(B, n, m, steps_up, warm, iters):
 NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 3.924e9 / 262144, "fine_bwd": 8.890e9 / 262144, "dw": 5.893e9 / 262144}
 
 
-def measure_extras(scene, dev):
+def measure_extras(scene, dev, use_graph=True):
     """Secondary numbers of BASELINE.json's metric (not the headline): dense SDF grid query rate (config C5 shape,
     one GPU's 1/8 slab of the 512^3 grid) and the literal ho3d_virtual.conf step (2 x 512 rays, 32+0 samples)."""
     import torch
@@ -146,25 +196,43 @@ def measure_extras(scene, dev):
     out["c5_grid_query"] = {"points": count, "ms": ms, "sdf_queries_per_s": count / ms * 1e3,
                             "tflops_algorithmic": count * F_S / ms / 1e9,
                             "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing"}
+    tg = {}
+    for rays_t in (512, 4096):      # the reference's own batch size, and a large batch that amortises its launches
+        try:
+            rps, ms_t = time_torch_gpu(rays_t, 64, 64, 4, dev)
+            tg[f"{rays_t}_rays"] = {"rays_per_s": rps, "ms_per_step": ms_t}
+        except Exception as e:      # e.g. out of memory at the large batch: report, do not fail the bench
+            tg[f"{rays_t}_rays"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        torch.cuda.empty_cache()
+    out["torch_fp32_port_on_this_gpu"] = dict(tg, note="oracle port of the reference (PyTorch fp32 eager autograd, 64+64, "
+                                              "fwd+bwd+Adam) on the same B200: baseline for north_star's 50x target")
     sc2 = synthetic.build_scene(device=dev, n_samples=32, n_importance=0, up_sample_steps=4, pose_type="seg")
-    ts2 = TrainStep(sc2, mask_weight=5.0)
+    ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph)
     g = torch.Generator().manual_seed(3)
     B2 = 1024
-    px = torch.randint(140, 500, [8, B2], generator=g).to(dev)
-    py = torch.randint(60, 420, [8, B2], generator=g).to(dev)
-    tr = torch.rand(8, B2, 1, generator=g).to(dev)
-    for i in range(3):
-        ts2.step(i, B2, pixels=(px[i], py[i]), t_rand=tr[i])
+    n_it = 24
+    px = torch.randint(140, 500, [n_it, B2], generator=g).to(dev)
+    py = torch.randint(60, 420, [n_it, B2], generator=g).to(dev)
+    tr = torch.rand(n_it, B2, 1, generator=g).to(dev)
+    if use_graph:
+        from fmov_pose_b200.train import GraphedTrainStep
+        g2 = GraphedTrainStep(ts2, B2)
+        step2 = lambda i: g2.step(i % 4, px[i], py[i], tr[i])
+    else:
+        step2 = lambda i: ts2.step(i % 4, B2, pixels=(px[i], py[i]), t_rand=tr[i])
+    for i in range(8):
+        step2(i)
     torch.cuda.synchronize()
     e0.record()
-    for i in range(3, 8):
-        ts2.step(i, B2, pixels=(px[i], py[i]), t_rand=tr[i])
+    for i in range(8, n_it):
+        step2(i)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    ms = e0.elapsed_time(e1) / (n_it - 8)
     out["c2_literal_1024rays_32+0"] = {"ms_per_step": ms, "rays_per_s": B2 / ms * 1e3,
                                        "note": "confs/ho3d_virtual.conf as shipped (n_samples 32, n_importance 0, "
-                                               "maintain_shape 2x512 rays); host-launch bound at this size"}
+                                               "maintain_shape 2x512 rays); " +
+                                               ("CUDA-graph replay" if use_graph else "eager, host-launch bound")}
     return out
 
 
@@ -180,6 +248,7 @@ def main():
     ap.add_argument("--cpu_rays", type=int, default=512, help="rays per CPU-baseline step (config C1)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_extras", action="store_true")
+    ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,10 +286,12 @@ def main():
         group = dist.group.WORLD
     from fmov_pose_b200 import _lib as L
     from fmov_pose_b200 import synthetic
-    from fmov_pose_b200.train import TrainStep
+    from fmov_pose_b200.train import GraphedTrainStep, TrainStep
+    use_graph = not args.no_graph
     scene = synthetic.build_scene(device=dev, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
-    ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, group=group)
+    ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, group=group, capturable=use_graph)
     B = args.rays
+    gts = GraphedTrainStep(ts, B) if use_graph else None
     total_steps = args.warmup + args.steps
     g = torch.Generator().manual_seed(1234 + rank)
     # step inputs: pixel draw inside the mask bbox (mask_guided_sampling), jitter, frame id
@@ -237,12 +308,18 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def run(i, e2e):
-        if e2e:
-            px, py, tr = px_h[i].to(dev, non_blocking=True), py_h[i].to(dev, non_blocking=True), tr_h[i].to(dev, non_blocking=True)
+    def run(i, e2e, eager=False):
+        if gts is not None and not eager:
+            # replay of the captured step; its static input buffers are refilled from pinned host memory (e2e) or
+            # from device-resident tensors (value)
+            src = (px_h[i], py_h[i], tr_h[i]) if e2e else (px_d[i], py_d[i], tr_d[i])
+            ls, _ = gts.step(img_ids[i], *src)
         else:
-            px, py, tr = px_d[i], py_d[i], tr_d[i]
-        ls, _ = ts.step(img_ids[i], B, pixels=(px, py), t_rand=tr)
+            if e2e:
+                px, py, tr = px_h[i].to(dev, non_blocking=True), py_h[i].to(dev, non_blocking=True), tr_h[i].to(dev, non_blocking=True)
+            else:
+                px, py, tr = px_d[i], py_d[i], tr_d[i]
+            ls, _ = ts.step(img_ids[i], B, pixels=(px, py), t_rand=tr)
         if e2e:
             loss_host[i:i + 1].copy_(ls["loss"].detach().reshape(1), non_blocking=True)
         return ls
@@ -265,16 +342,28 @@ def main():
     # initialisation (not part of the W warm-up steps of the contract): first-use work that a long training run pays
     # once — CUDA module loading, the caching allocator growing to the 27 GB activation stash, NCCL channel setup
     for i in range(5):
-        run(2 * total_steps - 1 - (i % 2), False)
+        run(2 * total_steps - 1 - (i % 2), False, eager=True)
+    if gts is not None:          # capture one graph per pose-parameter set (here: per frame) before anything is timed
+        seen = set()
+        for i in range(2 * total_steps):
+            if ts.graph_key(img_ids[i]) not in seen:
+                seen.add(ts.graph_key(img_ids[i]))
+                run(i, False)
+    barrier()
+    # per-kernel CUDA-event profile (roofline of the dominant kernel): eager launches of the same step, outside the
+    # timed regions (events cannot be recorded inside a graph replay)
+    L.profile_reset(True)
+    calls0 = L.n_calls
+    n_prof = max(3, min(args.steps, 10))
+    for i in range(n_prof):
+        run(i, False, eager=True)
+    calls_per_step = (L.n_calls - calls0) // n_prof
+    prof = L.profile_summary()
+    L.profile_reset(False)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    L.profile_reset(True)
-    calls0 = L.n_calls
     ms_dev = timed(False, 0)
-    calls_per_step = (L.n_calls - calls0) // (args.steps + args.warmup)
-    prof = L.profile_summary()
-    L.profile_reset(False)
     ms_e2e = timed(True, total_steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -305,11 +394,11 @@ def main():
                                     NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B * (n + m) / (avg_ms * 1e-3) / 1e9,
                                     peaks.get("hbm_gbs", 6650.0)),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
-                "share_of_step": (mlp[top]["ms"] / (args.steps + args.warmup)) / step_ms,
-                "kernel_ms_per_step": {k: v["ms"] / (args.steps + args.warmup) for k, v in prof.items()}}
+                "share_of_step": (mlp[top]["ms"] / n_prof) / step_ms,
+                "kernel_ms_per_step": {k: v["ms"] / n_prof for k, v in prof.items()}}
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = measure_extras(scene, dev)
+        extras = measure_extras(scene, dev, use_graph)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 1, 3)
@@ -322,6 +411,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload, "rays_per_gpu": B, "global_rays": world * B, "n_samples": n,
                            "n_importance": m, "up_sample_steps": up, "parallelism": f"ray-sharded dp{world}",
+                           "launch": "CUDA-graph replay of the whole step" if use_graph else "eager",
                            "l2": "per-step working set (activation/gradient stash ~26 KB/sample) >> 126 MB L2",
                            "algorithmic_flops_per_ray": flops_per_ray(n, m)},
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -103,7 +103,9 @@ def barf_pose(se3_row, noise_pose):
     """compose([se3_to_SE3(se3_row), noise_pose[:3]]) for one frame (exp_runner.py:419-424) -> [3,4]"""
     n = noise_pose
     if n.shape[-2] == 3:
-        n = torch.cat([n, torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=n.device)], dim=0)
+        # device-side fills only (CUDA-graph capturable; torch.tensor([...], device=...) is a pageable H2D copy)
+        bottom = torch.cat([torch.zeros(1, 3, device=n.device), torch.ones(1, 1, device=n.device)], dim=1)
+        n = torch.cat([n, bottom], dim=0)
     return _BarfPoseFn.apply(se3_row, n)
 
 

@@ -50,9 +50,11 @@ class RayDataset:
         return (max(ys.min() - patch_size, 0), min(ys.max() + patch_size, self.H),
                 max(xs.min() - patch_size, 0), min(xs.max() + patch_size, self.W))
 
-    def gen_random_rays_at(self, img_idx, batch_size, pose, mask_guided_sampling=False, patch_size=30, pixels=None):
+    def gen_random_rays_at(self, img_idx, batch_size, pose, mask_guided_sampling=False, patch_size=30, pixels=None,
+                           img_idx_t=None):
         """-> (data [B,10] = rays_o, rays_v, rgb, mask ; depth=None).  `pixels=(px,py)` injects the int64 pixel
-        draw (for RNG parity / pinned-host pipelines); otherwise torch.randint on the device as the reference."""
+        draw (for RNG parity / pinned-host pipelines); otherwise torch.randint on the device as the reference.
+        `img_idx_t` (int64 device tensor [1]) makes the frame a device-side input (CUDA-graph replay)."""
         img_idx = int(img_idx)
         if pixels is None:
             if mask_guided_sampling and np.random.rand() < 0.7:
@@ -63,9 +65,16 @@ class RayDataset:
             py = torch.randint(low=ys_min, high=ys_max, size=[batch_size], device=self.device)
         else:
             px, py = pixels
-        color = self.images[img_idx][(py, px)]
-        mask = self.masks[img_idx][(py, px)]
-        rays_o, rays_v = _RayGenFn.apply(pose[:3, :4], self.intrinsics_all_inv[img_idx], px, py)
+        if img_idx_t is not None:
+            it = img_idx_t.reshape(1)
+            color = self.images[it, py, px]
+            mask = self.masks[it, py, px]
+            intr_inv = self.intrinsics_all_inv.index_select(0, it)[0]
+        else:
+            color = self.images[img_idx][(py, px)]
+            mask = self.masks[img_idx][(py, px)]
+            intr_inv = self.intrinsics_all_inv[img_idx]
+        rays_o, rays_v = _RayGenFn.apply(pose[:3, :4], intr_inv, px, py)
         return torch.cat([rays_o, rays_v, color, mask[:, :1]], dim=-1), None
 
     def gen_rays_at(self, img_idx, resolution_level=1, pose=None, with_mask=False):

@@ -73,6 +73,7 @@ class LearnPoseGF(nn.Module):
         # returns the Parameter itself when it already lives on `dev`), so it is part of the state_dict
         self.b = nn.Parameter(torch.tensor(b).float(), requires_grad=False)
         self.small_rot = small_rot
+        self._bottom = None         # cached [[0,0,0,1]] row on the module's device (no H2D copy per call)
 
     # ---- control surface used by exp_runner.py ----------------------------------------------------------
     def finish_warmup(self):
@@ -101,8 +102,14 @@ class LearnPoseGF(nn.Module):
             for p in m.parameters():
                 p.requires_grad = True
 
-    def forward(self, cam_id):
-        cid = torch.as_tensor(cam_id, device=self.b.device).reshape(1).float()
+    def forward(self, cam_id, cam_id_t=None):
+        """`cam_id_t`: optional int64 device tensor [1] holding cam_id.  When given, the frame index is read on the
+        device only (Fourier features and the init_c2w row), which keeps the call CUDA-graph capturable with the
+        frame as a replay-time input (train.GraphedTrainStep)."""
+        if cam_id_t is not None:
+            cid = cam_id_t.reshape(1).float()
+        else:
+            cid = torch.as_tensor(cam_id, device=self.b.device).reshape(1).float()
         ang = (2.0 * np.pi * cid) @ self.b.T                   # [128]
         ff = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1) / float(np.sqrt(self.embedding_size))
         h = self.gelu2(self.lin2(self.gelu1(self.lin1(ff))))
@@ -112,14 +119,14 @@ class LearnPoseGF(nn.Module):
             rot, trans, scale = o[:3] * k, o[3:], None
         else:
             rot, trans, scale = self.lin3_rot(h) * k, self.lin3_trans(h), self.lin3_scale(h)
-        idx = int(cam_id)
         if self.init_c2w is not None:
-            init = self.init_c2w[idx]
+            init = self.init_c2w.index_select(0, cam_id_t.reshape(1))[0] if cam_id_t is not None else self.init_c2w[int(cam_id)]
         else:
             init = torch.eye(4, device=self.b.device)
         c2w34 = _GfTailFn.apply(rot, trans, scale, init)
-        bottom = torch.tensor([[0.0, 0.0, 0.0, 1.0]], device=c2w34.device)
-        return torch.cat([c2w34, bottom], dim=0)                # (4,4) like the reference
+        if self._bottom is None or self._bottom.device != c2w34.device:
+            self._bottom = torch.cat([torch.zeros(1, 3, device=c2w34.device), torch.ones(1, 1, device=c2w34.device)], 1)
+        return torch.cat([c2w34, self._bottom], dim=0)          # (4,4) like the reference
 
 
 class SegLearnPose(nn.Module):
@@ -134,23 +141,38 @@ class SegLearnPose(nn.Module):
              for _ in range(n)])
         self.initialized_flag = nn.Parameter(torch.tensor([True] + [False] * (n - 1)), requires_grad=False)
         self.progress = nn.Parameter(torch.zeros(n), requires_grad=False)
+        self._flags_host = None      # host mirror of initialized_flag (no device read-back per call)
 
-    def forward(self, cam_id):
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._flags_host = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _flag(self, k):
+        if self._flags_host is None:
+            self._flags_host = [bool(v) for v in self.initialized_flag.tolist()]
+        return self._flags_host[k]
+
+    def _set_flag(self, k):
+        self._flag(k)
+        self._flags_host[k] = True
+        self.initialized_flag[k] = True
+
+    def forward(self, cam_id, cam_id_t=None):
         cid = int(cam_id)
         k = cid // self.segment_img_num
-        if not self.initialized_flag[k]:
-            self.initialized_flag[k] = True
+        if not self._flag(k):
+            self._set_flag(k)
             with torch.no_grad():      # picture_pose.py:227-235: seed the new segment with the previous pose
                 last_pose = self.pose_mlps[k - 1](k * self.segment_img_num - 1)
                 last44 = torch.eye(4, device=last_pose.device)
                 last44[:3] = last_pose[:3]
                 self.pose_mlps[k].init_c2w.data.copy_(last44.clone().repeat(self.num_cams, 1, 1))
-        return self.pose_mlps[k](cid)
+        return self.pose_mlps[k](cid, cam_id_t)
 
     def set_pose(self, cam_id, pose, force_update=False):
         k = cam_id // self.segment_img_num
-        if not self.initialized_flag[k] or force_update:
-            self.initialized_flag[k] = True
+        if not self._flag(k) or force_update:
+            self._set_flag(k)
             with torch.no_grad():
                 self.pose_mlps[k].init_c2w.data.copy_(pose.clone().repeat(self.num_cams, 1, 1))
 

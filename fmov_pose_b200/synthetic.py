@@ -44,6 +44,7 @@ def build_scene(device="cuda", n_images=20, n_samples=64, n_importance=64, up_sa
     if pose_type == "seg":           # ho3d_virtual.conf: pose_type = seg, image_interval = 1, emphasize_rot
         pose = SegLearnPose(n_images, 1, init_c2w=init.clone(), emphasize_rot=True)
         pose.initialized_flag.data[:] = True
+        pose._flags_host = None
     elif pose_type == "gf":          # ho3d_barf.conf / ho3d_global_womask.conf
         pose = LearnPoseGF(n_images, init_c2w=init.clone())
     elif pose_type == "se3":         # BARF se3_refine (exp_runner.py:419-424)

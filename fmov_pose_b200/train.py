@@ -9,7 +9,8 @@ from .models import camera as _camera
 
 
 class TrainStep:
-    def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True):
+    def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True,
+                 capturable=False):
         self.s = scene
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
         self.group = group
@@ -24,17 +25,46 @@ class TrainStep:
         self.all_params = self.params + self.pose_params
         self.optimizer = None
         if optimizer:       # exp_runner.py:264-269 (nets) and :258-262 (pose MLPs)
+            dev = self.params[0].device
+            if capturable:        # learning rates live on the device so a captured step follows the LR schedule
+                lr = torch.tensor(float(lr), device=dev)
+                pose_lr = torch.tensor(float(pose_lr), device=dev)
             groups = [dict(params=self.params, lr=lr)]
             if self.pose_params:
                 groups.append(dict(params=self.pose_params, lr=pose_lr))
-            self.optimizer = torch.optim.Adam(groups, fused=True)
+            self.optimizer = torch.optim.Adam(groups, fused=True, capturable=capturable)
+            if capturable:        # state is created up front: lazy creation inside a capture would be replayed
+                for grp in self.optimizer.param_groups:
+                    for p in grp["params"]:
+                        self.optimizer.state[p] = dict(step=torch.zeros((), dtype=torch.float32, device=p.device),
+                                                       exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
+        self.capturable = capturable
 
-    def pose_of(self, img_id):
+    def set_lr(self, lr, pose_lr=None):
+        """exp_runner.py:1049-1087 writes param_group['lr'] every iteration; device-side when capturable."""
+        vals = [lr, lr if pose_lr is None else pose_lr]
+        for grp, v in zip(self.optimizer.param_groups, vals):
+            if torch.is_tensor(grp["lr"]):
+                grp["lr"].fill_(float(v))
+            else:
+                grp["lr"] = float(v)
+
+    def pose_of(self, img_id, img_t=None):
         s = self.s
         if s["pose_network"] is not None:
-            return s["pose_network"](img_id)[:3]
+            return s["pose_network"](img_id, img_t)[:3] if img_t is not None else s["pose_network"](img_id)[:3]
         sdf = s["sdf_network"]
+        if img_t is not None:
+            it = img_t.reshape(1)
+            return _camera.barf_pose(sdf.se3_refine.weight.index_select(0, it)[0],
+                                     sdf.noise_poses.index_select(0, it)[0, :3, :])
         return _camera.barf_pose(sdf.se3_refine.weight[int(img_id)], sdf.noise_poses[int(img_id), :3, :])
+
+    def graph_key(self, img_id):
+        """frames that share trainable pose parameters share one captured graph"""
+        pn = self.s["pose_network"]
+        seg = getattr(pn, "segment_img_num", None)
+        return int(img_id) // seg if seg else 0
 
     def losses(self, out, true_rgb, mask):
         """exp_runner.py:562-599, 772-779 with global normalisers when ray-sharded."""
@@ -43,7 +73,7 @@ class TrainStep:
         else:
             mask = torch.ones_like(mask)
         msum = mask.sum()
-        n_rays = torch.tensor(float(mask.shape[0]), device=mask.device)
+        n_rays = torch.full((), float(mask.shape[0]), device=mask.device)
         if self.group is not None:
             pack = torch.stack([msum, n_rays])
             torch.distributed.all_reduce(pack, group=self.group)
@@ -56,11 +86,11 @@ class TrainStep:
         loss = color_loss + eik * self.igr_weight + bce * self.mask_weight
         return dict(loss=loss, color_loss=color_loss, eikonal_loss=eik, mask_loss=bce)
 
-    def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0):
+    def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None):
         s = self.s
         ds, rend = s["dataset"], s["renderer"]
-        pose = self.pose_of(img_id)
-        data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels)
+        pose = self.pose_of(img_id, img_t)
+        data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         near, far = ds.near_far_from_sphere(rays_o, rays_d)
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand)
@@ -80,8 +110,76 @@ class TrainStep:
         for p, g in zip(self.all_params, torch._utils._unflatten_dense_tensors(flat, grads)):
             p.grad = g
 
-    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0):
-        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio)
+    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None):
+        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t)
         if self.optimizer is not None:
             self.optimizer.step()
+        return ls, out
+
+
+class GraphedTrainStep:
+    """TrainStep.step captured once per pose-parameter set as a CUDA graph and replayed.
+
+    A step is ~220 launches of this library plus the torch glue (weight-norm, pose MLP head, losses, fused Adam, NCCL
+    all-reduce): eager execution is host-bound for the shipped 512/1024-ray batches and leaves launch gaps at 8 K rays.
+    The captured step has static shapes: `batch_size` rays, pixel indices / jitter / frame index are device buffers that
+    `step()` refills before each replay (from pinned host memory or device tensors), the learning rates are device
+    scalars (`TrainStep.set_lr`), the activation stash is the recycled Stash pool buffer.  Nothing in the step reads
+    back to the host, so one replay == one reference iteration (exp_runner.py:497-599, 772-816)."""
+
+    def __init__(self, ts, batch_size, cos_anneal_ratio=1.0):
+        assert ts.optimizer is None or ts.capturable, "build the TrainStep with capturable=True"
+        self.ts, self.B, self.car = ts, int(batch_size), float(cos_anneal_ratio)
+        dev = ts.params[0].device
+        self.dev = dev
+        self.px = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.py = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.tr = torch.zeros(self.B, 1, dtype=torch.float32, device=dev)
+        self.img = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.graphs = {}
+        self.pool = None
+        self.launches_per_step = 0
+        self._keep = []
+
+    def _body(self, img_id):
+        return self.ts.step(img_id, self.B, pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car,
+                            img_t=self.img)
+
+    def _capture(self, key, img_id):
+        from . import _lib as L
+        from .fine import Stash
+        ts = self.ts
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            # eager pass without the optimizer: one-time library/cuBLAS initialisation and the stash allocation
+            ts.forward_backward(img_id, self.B, pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car,
+                                img_t=self.img)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        for p in ts.all_params:
+            p.grad = None
+        self._keep = [b for lst in Stash._pool.values() for b in lst]      # keep the stash buffer alive with the graph
+        g = torch.cuda.CUDAGraph()
+        n0 = L.n_calls
+        with torch.cuda.graph(g, pool=self.pool):
+            ls, out = self._body(img_id)
+        self.launches_per_step = L.n_calls - n0
+        if self.pool is None:
+            self.pool = g.pool()
+        self.graphs[key] = (g, ls, out)
+
+    def step(self, img_id, px, py, t_rand):
+        """px, py int64 [B], t_rand fp32 [B,1] (device or pinned host tensors) -> (losses, render dict): static
+        tensors that the next replay overwrites."""
+        self.px.copy_(px, non_blocking=True)
+        self.py.copy_(py, non_blocking=True)
+        self.tr.copy_(t_rand.reshape(self.B, 1), non_blocking=True)
+        self.img.fill_(int(img_id))
+        key = self.ts.graph_key(img_id)
+        if key not in self.graphs:
+            self._capture(key, img_id)
+        g, ls, out = self.graphs[key]
+        g.replay()
         return ls, out

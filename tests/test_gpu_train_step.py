@@ -63,3 +63,46 @@ def test_barf_se3_pose_path():
     # batched host-side torch mirror agrees too (all frames at once, as the reference computes them)
     all_p = camera.pose.compose([camera.lie.se3_to_SE3(se3.detach()), noise[:, :3, :]])
     np.testing.assert_allclose(all_p.cpu().numpy(), d["pose_all"], atol=3e-6)
+
+
+@pytest.mark.parametrize("pose_type", ["seg", "se3"])
+def test_graphed_step_equals_eager_step(pose_type):
+    """CUDA-graph replay of the train step (train.GraphedTrainStep) == the eager launches of the same step:
+    same losses and the same parameters after several Adam updates, with the frame index, pixels, jitter and
+    learning rate as replay-time inputs."""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import GraphedTrainStep, TrainStep
+    B, n_steps = 256, 5
+    g = torch.Generator().manual_seed(11)
+    px = torch.randint(200, 440, [n_steps, B], generator=g)
+    py = torch.randint(120, 360, [n_steps, B], generator=g)
+    tr = torch.rand(n_steps, B, 1, generator=g)
+    imgs = [3, 3, 5, 3, 5]
+    lrs = [5e-4, 4e-4, 3e-4, 2e-4, 1e-4]
+    res = []
+    for graphed in (False, True):
+        sc = synthetic.build_scene(device=DEV, n_images=8, n_samples=16, n_importance=16, up_sample_steps=2,
+                                   pose_type=pose_type)
+        ts = TrainStep(sc, mask_weight=5.0, capturable=graphed)
+        gts = GraphedTrainStep(ts, B) if graphed else None
+        losses = []
+        for i in range(n_steps):
+            ts.set_lr(lrs[i])
+            if graphed:
+                ls, _ = gts.step(imgs[i], px[i].pin_memory(), py[i].pin_memory(), tr[i].pin_memory())
+            else:
+                ls, _ = ts.step(imgs[i], B, pixels=(px[i].to(DEV), py[i].to(DEV)), t_rand=tr[i].to(DEV))
+            losses.append(float(ls["loss"]))
+        res.append((losses, [p.detach().clone() for p in ts.all_params]))
+        if graphed:
+            assert gts.launches_per_step > 10 and len(gts.graphs) == (2 if pose_type == "seg" else 1)
+    (l0, p0), (l1, p1) = res
+    np.testing.assert_allclose(l1, l0, rtol=2e-3)
+    moved = 0.0
+    for a, b in zip(p0, p1):
+        # Adam's sign-like first steps amplify fp16 rounding noise on near-zero gradients: compare on the scale of
+        # the accumulated update (5 steps x lr), not bitwise
+        assert float((a - b).abs().max()) <= 3e-3, float((a - b).abs().max())
+        assert float((a - b).abs().mean()) <= 1e-4, float((a - b).abs().mean())
+        moved = max(moved, float(a.abs().max()))
+    assert moved > 0
