@@ -11,6 +11,8 @@ LIB = os.path.join(HERE, "libfmov_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math_off_placeholder"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.endswith("placeholder")]
+NVCC_FLAGS += os.environ.get("FMOV_NVCC_EXTRA", "").split()      # experiment switches (-DFMOV_...), A/B builds
+LIB = os.environ.get("FMOV_LIB_OUT", LIB)
 
 
 def _nvcc():

@@ -142,6 +142,20 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     }
   }
 }
+// Weight-ring waits of the control warps: these sit on the critical path of every MMA step (slot free -> refill ->
+// slot full -> MMA), so they poll without sleeping; try_wait itself suspends the thread for a HW-bounded time.
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout_trap(bar, parity);
+    }
+  }
+}
 __device__ __forceinline__ void fence_proxy_async() {   // generic-proxy smem writes -> async proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }

@@ -3,12 +3,13 @@
 // accumulators in TMEM and a per-kernel epilogue between steps.  TWO tiles are in flight per CTA so that
 // the tensor core works on one tile while the other tile's epilogue runs.
 //
-// Warp roles (18 warps, 576 threads):
-//   warp 0        weight producer   cp.async.bulk  weight-image k-blocks -> WST ring            (1 lane)
-//   warp 1        MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage        (1 lane) + TMEM alloc
-//   warps 2..9    epilogue of tile slot 0: two warpgroups, columns 0..127 and 128..255 of the tile
-//   warps 10..17  epilogue of tile slot 1        (tcgen05.ld -> fp32 math -> st.shared next A operand
+// Warp roles (CH_WGS = 2: 20 warps, 640 threads):
+//   warps 0..7    epilogue of tile slot 0: two warpgroups, columns 0..127 and 128..255 of the tile
+//   warps 8..15   epilogue of tile slot 1        (tcgen05.ld -> fp32 math -> st.shared next A operand
 //                                                 + st.global / ld.global of the stash rows)
+//   warp 16       weight producer   cp.async.bulk  weight-image k-blocks -> WST ring            (1 lane)
+//   warp 17       MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage        (1 lane) + TMEM alloc
+//   warps 18,19   idle (complete the control warpgroup for setmaxnreg)
 // 4 epilogue warps per scheduler: the epilogues are latency bound (TMEM / HBM loads, MUFU chains), measured
 // 0.24 eligible warps per cycle with 8 epilogue warps.
 //
@@ -30,13 +31,45 @@ constexpr int CH_SLOTS = 2;
 #endif
 constexpr int CH_WGS = FMOV_CH_WGS;                // epilogue warpgroups (column ranges) per tile slot: 1 or 2
 constexpr int CH_CHUNKS = 16 / CH_WGS;             // 16-column chunks handled by one warpgroup
-constexpr int CH_THREADS = 64 + CH_SLOTS * CH_WGS * 128;   // 576
-constexpr int EPI_WARP0 = 2;
+// Warp layout: epilogue warps first (whole warpgroups, so that setmaxnreg can be applied per role), then one control
+// warpgroup whose warps 0/1 are the weight producer / MMA issuer (warps 2/3 idle).  Registers are allocated per SM
+// sub-partition (16 K each, warp w lives in partition w % 4): with 5 warps per partition the launch allocation is
+// <= 96 registers/thread; the control warpgroup then shrinks to 24 and the epilogue warps grow (chain_regs_*).
+constexpr int EPI_WARP0 = 0;
+constexpr int CTRL_WARP0 = CH_SLOTS * CH_WGS * 4;
+constexpr int PRODUCER_WARP = CTRL_WARP0;
+constexpr int ISSUER_WARP = CTRL_WARP0 + 1;
+constexpr int CH_THREADS = (CTRL_WARP0 + 4) * 32;           // 640 (two warpgroups per slot) / 384
 constexpr int EPI_THREADS = CH_WGS * 128;          // threads arriving per slot
-constexpr int WSLOT_BYTES = 256 * 128;            // [256 rows x 64] 16-bit
-constexpr int CH_WSTAGES = 2;
+// Weight ring: 64 KiB of shared memory in CH_WSTAGES slots of 1/CH_WSPLIT k-block each (a K = 64/CH_WSPLIT slice of
+// all N rows is contiguous in the weight image).  The ring is refilled from L2 with ~1.5 us latency per slot; with two
+// 32 KiB slots the MMA issuer waited on weights for half of every step (measured: 5.1 K cycles per 128x256x256 step
+// against 2 K of tensor time); four 16 KiB slots keep three copies in flight behind the one being read.
+#ifndef FMOV_CH_WSPLIT
+#define FMOV_CH_WSPLIT 2
+#endif
+constexpr int CH_WSPLIT = FMOV_CH_WSPLIT;          // ring slots per 64-wide k-block: 1, 2 or 4
+constexpr int WSLOT_BYTES = 256 * 128 / CH_WSPLIT; // [256 rows x 64/CH_WSPLIT] 16-bit
+constexpr int CH_WSTAGES = 2 * CH_WSPLIT;
 constexpr int MAX_STEPS = 40;
 constexpr int MAX_STASH = 56;
+
+// ---- optional timeline trace (-DFMOV_TRACE): CTA 0 records (tag, clock64) pairs; read back with fmov_debug_trace ----
+#ifdef FMOV_TRACE
+__device__ long long g_trace[2 * 32768];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_ev(int kind, int who, int idx) {
+  if (blockIdx.x != 0) return;
+  const unsigned int i = atomicAdd(&g_trace_n, 1u);
+  if (i < 32768u) {
+    g_trace[2 * i] = ((long long)kind << 32) | ((long long)who << 16) | (long long)(idx & 0xFFFF);
+    g_trace[2 * i + 1] = clock64();
+  }
+}
+#define FMOV_TR(kind, who, idx) trace_ev(kind, who, idx)
+#else
+#define FMOV_TR(kind, who, idx)
+#endif
 
 struct ChainStep {
   uint32_t w_off;       // byte offset of the first k-block of this step in the weight blob
@@ -102,7 +135,12 @@ __device__ __forceinline__ void chain_init_barriers(ChainSmem* s) {
 // Tiles of this CTA: global tile index = blockIdx.x + k*gridDim.x, k = 0..n_my-1; slot = k & 1.
 // Producer and issuer walk (pair, step, slot, k-block) in the same order.
 
-// ---- warp 0 -----------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void chain_regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void chain_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// ---- producer warp -------------------------------------------------------------------------
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
@@ -134,14 +172,14 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
           chain_prefetch_step(tb, ptrs, 0, tile0 + (long long)(k0 + CH_SLOTS + slot) * tile_stride);
       }
       if (st.no_mma) continue;
-      const uint32_t bytes = (uint32_t)st.n * 128u;
-      const int nkb = st.nkb_a + st.nkb_aux;
+      const uint32_t bytes = (uint32_t)st.n * (128u / CH_WSPLIT);
+      const int nsl = (st.nkb_a + st.nkb_aux) * CH_WSPLIT;      // consecutive slices of this step's weight image
       for (int slot = 0; slot < nslot; ++slot)
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int sl = 0; sl < nsl; ++sl, ++it) {
           const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
-          mbar_wait_backoff(&s->w_empty[stage], (n & 1) ^ 1);
+          mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
           mbar_expect_tx(&s->w_full[stage], bytes);
-          bulk_g2s(wst + stage * WSLOT_BYTES, wblob + st.w_off + (size_t)kb * bytes, bytes, &s->w_full[stage]);
+          bulk_g2s(wst + stage * WSLOT_BYTES, wblob + st.w_off + (size_t)sl * bytes, bytes, &s->w_full[stage]);
         }
     }
   }
@@ -162,24 +200,31 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
       for (int slot = 0; slot < nslot; ++slot) {
         uint8_t* act = act0 + slot * 4 * BLK_BYTES;
         uint8_t* aux = aux0 + slot * BLK_BYTES;
-        mbar_wait_backoff(&s->act_ready[slot], nstep[slot] & 1);
+        FMOV_TR(1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
+        mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
+        FMOV_TR(2, slot, nstep[slot]);            // operand ready seen
         ++nstep[slot];
         tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
-          mbar_wait_backoff(&s->w_full[stage], n & 1);
-          tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t a_base = smem_u32(kb < st.nkb_a ? act + kb * BLK_BYTES : aux + (kb - st.nkb_a) * BLK_BYTES);
-          const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
-                     umma_desc_kmajor(b_base + ks * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
-                     (kb | ks) != 0 ? 1u : 0u);
+          for (int part = 0; part < CH_WSPLIT; ++part, ++it) {
+            const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
+            mbar_wait_poll(&s->w_full[stage], n & 1);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 4 / CH_WSPLIT; ++kk) {
+              const int ks = part * (4 / CH_WSPLIT) + kk;            // K = 16 slice of the k-block
+              umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                       umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
+                       (kb | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&s->w_empty[stage]);   // slot reusable once these MMAs have read it
           }
-          umma_commit(&s->w_empty[stage]);   // stage reusable once these MMAs have read it
         }
         umma_commit(&s->acc_ready[slot]);
+        FMOV_TR(3, slot, nstep[slot] - 1);        // all MMAs of the step issued
       }
     }
   }
@@ -210,7 +255,9 @@ __device__ __forceinline__ void epi_init(EpiCtx& c, ChainSmem* s, uint8_t* act0,
   c.acc_n = 0;
 }
 __device__ __forceinline__ void epi_wait_acc(EpiCtx& c) {
+  if ((threadIdx.x & 31) == 0) FMOV_TR(4, threadIdx.x >> 5, c.acc_n);      // epilogue warp starts waiting
   mbar_wait(&c.s->acc_ready[c.slot], c.acc_n & 1);
+  if ((threadIdx.x & 31) == 0) FMOV_TR(5, threadIdx.x >> 5, c.acc_n);      // accumulator ready
   ++c.acc_n;
   tc_fence_after();
 }
@@ -219,6 +266,7 @@ __device__ __forceinline__ void epi_signal_act(EpiCtx& c) {
   tc_fence_before();
   fence_proxy_async();
   mbar_arrive(&c.s->act_ready[c.slot]);
+  if ((threadIdx.x & 31) == 0) FMOV_TR(6, threadIdx.x >> 5, c.acc_n);      // epilogue warp done with the step
 }
 // 32 accumulator columns [col0, col0+32) of this thread's row
 __device__ __forceinline__ void acc_load32(const EpiCtx& c, int col0, float* v) {
@@ -273,6 +321,23 @@ __device__ __forceinline__ void chunk_load(const uint8_t* tilep, int ck, uint4* 
   const uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
   q[0] = *reinterpret_cast<const uint4*>(p);
   q[1] = *reinterpret_cast<const uint4*>(p + TI_CHUNK_STRIDE);
+}
+
+// L2 prefetch of this warp's rows of chunk columns [ck_first*2, (ck_first+n_ck)*2) of a 256-wide tile: a warp's 32 rows
+// of one 16-byte chunk column are 512 contiguous bytes = 4 lines, so every 8th lane prefetches one line.  Issued by the
+// epilogue threads when they start waiting for the accumulator: the MMA time (4-5 K cycles) is the lead that turns the
+// HBM latency of the step's stash reads into L2 hits without holding registers.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void tile_prefetch_l2(const uint8_t* tilep, int ck_first, int n_ck) {
+  if ((threadIdx.x & 7) == 0) {
+    for (int ck = ck_first; ck < ck_first + n_ck; ++ck) {
+      const uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+      prefetch_l2(p);
+      prefetch_l2(p + TI_CHUNK_STRIDE);
+    }
+  }
 }
 
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------

@@ -15,12 +15,44 @@
 //   backward     zbar_{l-1} = (W_l^T zbar_l)*sigma_{l-1} + q_{l-1}
 // fp16 operands in the forward (value pass, reverse sweep, colour net), bf16 for every gradient tile; fp32
 // accumulation in TMEM; fp32 epilogue math.
+// Epilogue warpgroups per tile slot (FMOV_FINE_WGS, default 2): with two, warpgroup w owns columns [128w, 128w+128) of
+// every 256-wide tile (32-column chunks hb = 4w..4w+3); warpgroup WGS-1 additionally owns the per-row state (normal,
+// x-bar, PE adjoints) and the narrow N=48 / N=16 steps.  A thread still only re-reads stash rows/chunks it wrote itself.
+#ifndef FMOV_FINE_WGS
+#define FMOV_FINE_WGS 2
+#endif
+#define FMOV_CH_WGS FMOV_FINE_WGS
 #include "mlp_chain.cuh"
 #include "../../include/fmov_b200.h"
 
 namespace fmov {
 
 using FL = ChainLayout;
+constexpr int HPW = 8 / CH_WGS;          // 32-column chunks per warpgroup
+constexpr int NCK = CH_CHUNKS;           // 16-column chunks per warpgroup
+#ifndef FMOV_FINE_PFD
+#define FMOV_FINE_PFD 1
+#endif
+#ifdef FMOV_NO_STASH_PREFETCH
+constexpr bool kStashPrefetch = false;
+#else
+constexpr bool kStashPrefetch = true;
+#endif
+#ifdef FMOV_PREFETCH_NEXT
+constexpr bool kPrefetchNext = true;
+#else
+constexpr bool kPrefetchNext = false;
+#endif
+constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks) in the backward hot loops
+#define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)
+// Register budget: 640 threads put 5 warps on every SM sub-partition (16 K registers each), so ptxas caps the kernels
+// at 96 registers/thread.  setmaxnreg re-balancing (control warpgroup -> 24..56, epilogue -> 104..120) was tried at
+// compile time and dropped: ptxas 12.9 either fails (C7600, control <= 32) or compiles the epilogue region against
+// the SMALLER budget (spill bytes tracked the control value: 5.6 KB at 40, 1.5 KB at 56 against 0.4 KB for the plain
+// 96-register build), so it never reached the GPU.  The hot loops are written in 16-column chunks so that they fit 96
+// registers without spills; the remaining spills (ptxas -v) sit in the once-per-tile positional-encoding steps.
+#define FINE_CTRL_REGS()
+#define FINE_EPI_REGS()
 
 // ---- weight image directory ---------------------------------------------------------------------
 enum ImgId {
@@ -182,7 +214,7 @@ __device__ __forceinline__ void get_chunk_raw(const EpiCtx& c, const ChainPtrs& 
 // =====================================================================================================
 // forward
 // =====================================================================================================
-__global__ void __launch_bounds__(CH_THREADS, 1)
+__global__ void FINE_BOUNDS
 fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
                 const __grid_constant__ FineArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -197,19 +229,26 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) chain_init_barriers(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
+  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
-  if (warp == 0) {
-    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
-  } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+  if (warp >= CTRL_WARP0) {
+    FINE_CTRL_REGS();
+    if (warp == PRODUCER_WARP) {
+      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+    } else if (warp == ISSUER_WARP) {
+      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+    }
   } else {
+    FINE_EPI_REGS();
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
+    const int hb0 = c.wg * HPW;
+    const int ck0 = c.wg * NCK;
+    const bool owner = c.wg == CH_WGS - 1;      // warpgroup that owns the per-row state and the narrow steps
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
@@ -221,6 +260,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         pe_eval<6>(pc.x, e);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+          if (CH_WGS == 2 && h != c.wg) continue;        // each warpgroup stores one 32-column half
           uint4 q[4];
           pack4(e + 32 * h, false, q);
           row_half_store(c.aux + c.row * 16, h, q);
@@ -229,51 +269,67 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         epi_signal_act(c);
       }
       // ---- value pass: layers 0..7 -----------------------------------------------------------------------
-      float sdf = __ldg(a.b8);
+      float sdf = owner ? __ldg(a.b8) : 0.f;
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int n_valid = (l == 3) ? 217 : 256;
         const int n_mma = (l == 3) ? 224 : 256;
         const float* bias = a.bias_sdf + l * 256;
         epi_wait_acc(c);
-#pragma unroll 2
-        for (int hb = 0; hb < 8; ++hb) {
-          float v[32];
-          if (hb * 32 < n_mma) {
-            acc_load32(c, hb * 32, v);
+        // 16-column chunks; the TMEM load of chunk i+1 is in flight while chunk i is evaluated (two register buffers)
+        uint8_t* actp = c.act + c.row * 16;
+        uint8_t* hsp = tile_base(ptrs, ST_H1 + l, tile, c.row);
+        float vbuf[2][16];
+        tmem_ld16(c.tmem + ck0 * 16, vbuf[0]);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+        for (int i = 0; i < NCK; ++i) {
+          const int ck = ck0 + i;
+          float* v = vbuf[i & 1];
+          tmem_ld_wait();
+          if (i + 1 < NCK && (ck + 1) * 16 < n_mma) tmem_ld16(c.tmem + (ck + 1) * 16, vbuf[(i + 1) & 1]);
+          if (ck * 16 < n_mma) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
               v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
               v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
               v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
               v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
             }
-            if (hb * 32 + 32 > n_valid) {           // lin3: columns 217..223 are padding
+            if (ck * 16 + 16 > n_valid) {           // lin3: columns 217..223 are padding
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (hb * 32 + j < n_valid) ? v[j] : 0.f;
+              for (int jj = 0; jj < 16; ++jj) v[jj] = (ck * 16 + jj < n_valid) ? v[jj] : 0.f;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
           }
           if (l == 7) {
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + hb * 32) + j4);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + ck * 16) + j4);
               sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
               sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
             }
           }
-          put_chunk(c, ptrs, true, ST_H1 + l, tile, hb, false, v);
+          uint4 q2[2];
+          pack2(v, false, q2);
+          chunk_store(actp, ck, q2);
+          chunk_store(hsp, ck, q2);
         }
         epi_signal_act(c);
       }
-      if (pc.valid) a.sdf[pc.p] = sdf;
+      if (CH_WGS == 2) {       // combine the two column halves of the lin8-row-0 dot product
+        if (!owner) s->scratch[c.slot][c.row] = sdf;
+        slot_sync(c);
+        if (owner) sdf += s->scratch[c.slot][c.row];
+      }
+      if (owner && pc.valid) a.sdf[pc.p] = sdf;
       // ---- lin8 feature rows -> stash F ; delta_7 = W8[0,:]*sigma_7 in place -------------------------------------
       epi_wait_acc(c);
 #pragma unroll 2
-      for (int hb = 0; hb < 8; ++hb) {
+      for (int hi = 0; hi < HPW; ++hi) {
+        const int hb = hb0 + hi;
         float v[32], h[32];
         uint4 q[4];
         acc_load32(c, hb * 32, v);
@@ -296,14 +352,16 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
         uint4 sb[2][4];
-        ld_half(hp, 0, sb[0]);
+        ld_half(hp, hb0, sb[0]);
+        if (kStashPrefetch) tile_prefetch_l2(hp, ck0 + 2, NCK - 2);
         epi_wait_acc(c);
 #pragma unroll
-        for (int hb = 0; hb < 8; ++hb) {
+        for (int hi = 0; hi < HPW; ++hi) {
+          const int hb = hb0 + hi;
           float v[32], h[32];
-          if (hb < 7) ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
+          if (hi < HPW - 1) ld_half(hp, hb + 1, sb[(hi + 1) & 1]);
           acc_load32(c, hb * 32, v);
-          unpack4(sb[hb & 1], false, h);
+          unpack4(sb[hi & 1], false, h);
           if (l == 4 && hb == 6 && pc.valid) {
             // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image): parked in
             // the g_e output row until the W_0^T delta_0 term arrives (keeps 39 registers free across the sweep)
@@ -324,11 +382,11 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         epi_signal_act(c);
       }
       // ---- g_e += W_0^T delta_0 ; normal ; colour-net extras ; feature tile back into ACT -----------------------------
-      {
+      epi_wait_acc(c);
+      if (owner) {
         float v[48];
         float nrm[3];
         float ge[40];
-        epi_wait_acc(c);
         acc_load32(c, 0, v);
         acc_load16(c, 32, v + 32);
         ge[39] = 0.f;
@@ -355,8 +413,11 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           row_half_store(c.aux + c.row * 16, h, q);
           row_half_store(stash_row(ptrs, ST_X, tile, 0, c.row), h, q);
         }
+      }
+      {
 #pragma unroll
-        for (int hb = 0; hb < 8; ++hb) {          // own rows of F: written above by this thread
+        for (int hi = 0; hi < HPW; ++hi) {        // own chunks of F: written above by this thread
+          const int hb = hb0 + hi;
           uint4 q[4];
           get_chunk_raw(c, ptrs, ST_F, tile, hb, q);
           row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
@@ -369,7 +430,8 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const float* bias = a.bias_col + l * 256;
         epi_wait_acc(c);
 #pragma unroll 2
-        for (int hb = 0; hb < 8; ++hb) {
+        for (int hi = 0; hi < HPW; ++hi) {
+          const int hb = hb0 + hi;
           float v[32];
           acc_load32(c, hb * 32, v);
 #pragma unroll
@@ -386,19 +448,21 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       }
       // ---- colour output: sigmoid ------------------------------------------------------------------------------------
       {
-        float v[16];
         epi_wait_acc(c);
-        acc_load16(c, 0, v);
-        if (pc.valid) {
+        if (owner) {
+          float v[16];
+          acc_load16(c, 0, v);
+          if (pc.valid) {
 #pragma unroll
-          for (int i = 0; i < 3; ++i) a.rgb[pc.p * 3 + i] = sigmoidf_(v[i] + __ldg(a.bc4 + i));
+            for (int i = 0; i < 3; ++i) a.rgb[pc.p * 3 + i] = sigmoidf_(v[i] + __ldg(a.bc4 + i));
+          }
         }
         tc_fence_before();
       }
     }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ISSUER_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -407,7 +471,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 // =====================================================================================================
 // backward
 // =====================================================================================================
-__global__ void __launch_bounds__(CH_THREADS, 1)
+__global__ void FINE_BOUNDS
 fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
                 const __grid_constant__ FineArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -422,19 +486,26 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) chain_init_barriers(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
+  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
-  if (warp == 0) {
-    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
-  } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+  if (warp >= CTRL_WARP0) {
+    FINE_CTRL_REGS();
+    if (warp == PRODUCER_WARP) {
+      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+    } else if (warp == ISSUER_WARP) {
+      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+    }
   } else {
+    FINE_EPI_REGS();
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
+    const int hb0 = c.wg * HPW;
+    const int ck0 = c.wg * NCK;
+    const bool owner = c.wg == CH_WGS - 1;
     const float gscale = grad_scale_from_amax(__ldg(a.amax));
     const float ginv = 1.0f / gscale;
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
@@ -449,13 +520,16 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           const float r = a.rgb[pc.p * 3 + i];
           zc4[i] = a.d_rgb[pc.p * 3 + i] * gscale * r * (1.f - r);     // sigmoid backward (loss-scaled)
         }
+        if (owner) {
 #pragma unroll
-        for (int i = 0; i < 3; ++i) a.zc4[pc.p * 4 + i] = zc4[i];
-        a.zc4[pc.p * 4 + 3] = 0.f;
+          for (int i = 0; i < 3; ++i) a.zc4[pc.p * 4 + i] = zc4[i];
+          a.zc4[pc.p * 4 + 3] = 0.f;
+        }
       }
       // ---- colour lin4 backward on CUDA cores (3 x 256) + ReLU mask of C4 -> zbar_c3 ---------------------
 #pragma unroll 2
-      for (int hb = 0; hb < 8; ++hb) {
+      for (int hi = 0; hi < HPW; ++hi) {
+        const int hb = hb0 + hi;
         float v[32], h[32];
         uint4 q[4];
         get_chunk_raw(c, ptrs, ST_C1 + 3, tile, hb, q);
@@ -476,14 +550,16 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint8_t* zp = tile_base(ptrs, ST_ZC0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
         uint4 sb[2][4];
-        ld_half(cp, 0, sb[0]);
+        ld_half(cp, hb0, sb[0]);
+        if (kStashPrefetch) tile_prefetch_l2(cp, ck0 + 2, NCK - 2);
         epi_wait_acc(c);
 #pragma unroll
-        for (int hb = 0; hb < 8; ++hb) {
+        for (int hi = 0; hi < HPW; ++hi) {
+          const int hb = hb0 + hi;
           float v[32], h[32];
-          if (hb < 7) ld_half(cp, hb + 1, sb[(hb + 1) & 1]);
+          if (hi < HPW - 1) ld_half(cp, hb + 1, sb[(hi + 1) & 1]);
           acc_load32(c, hb * 32, v);
-          unpack4(sb[hb & 1], false, h);
+          unpack4(sb[hi & 1], false, h);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
           uint4 q[4];
@@ -494,9 +570,9 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         epi_signal_act(c);
       }
       // ---- colour lin0 backward, extras part: pts-bar, PE4(dirs)-bar, normals-bar -------------------------
-      {
+      epi_wait_acc(c);
+      if (owner) {
         float v[48];
-        epi_wait_acc(c);
         acc_load32(c, 0, v);
         acc_load16(c, 32, v + 32);
         xbar[0] = v[0]; xbar[1] = v[1]; xbar[2] = v[2];
@@ -507,18 +583,19 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
           for (int i = 0; i < 3; ++i) a.d_dirs[pc.p * 3 + i] = dd[i] * ginv;
         }
-        epi_signal_act(c);                 // ACT (zbar_c0) untouched: next step re-uses it
       }
+      epi_signal_act(c);                 // ACT (zbar_c0) untouched: next step re-uses it
       // ---- colour lin0 backward, feature part -> fbar (bf16) -> stash only -----------------------------------
       epi_wait_acc(c);
 #pragma unroll 2
-      for (int hb = 0; hb < 8; ++hb) {
+      for (int hi = 0; hi < HPW; ++hi) {
+        const int hb = hb0 + hi;
         float v[32];
         acc_load32(c, hb * 32, v);
         put_chunk_grad(c, ptrs, false, ST_FB, tile, hb, v);
       }
       // ---- adjoint of n = J_e^T g_e: gbar_e = J_e nbar -> AUX ; PE-Hessian term into xbar -------------------
-      {
+      if (owner) {
         float e[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -545,9 +622,10 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           row_half_store(c.aux + c.row * 16, h, q);
           row_half_store(stash_row(ptrs, ST_GE, tile, 0, c.row), h, q);
         }
-        epi_signal_act(c);
       }
+      epi_signal_act(c);
       // ---- adjoint pass l = 0..7:  dbar_l = W_l vbar_l ; vbar_{l+1} = dbar_l*sigma_l ; q_l -------------------
+      // 16-column chunks, H/delta chunks prefetched one chunk ahead (register budget: see FINE_EPI_REGS)
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int n_mma = (l == 3) ? 224 : 256;
@@ -556,44 +634,58 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint8_t* vp = tile_base(ptrs, ST_V1 + l, tile, c.row);
         uint8_t* qp = tile_base(ptrs, ST_Q0 + l, tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
-        uint4 sb[2][4], db[2][4];
-        ld_half(hp, 0, sb[0]);
-        ld_half(dp, 0, db[0]);
+        uint4 sb[PFD + 1][2], db[PFD + 1][2];
+#pragma unroll
+        for (int i = 0; i < PFD; ++i) {
+          chunk_load(hp, ck0 + i, sb[i]);
+          chunk_load(dp, ck0 + i, db[i]);
+        }
+        if (kStashPrefetch && (!kPrefetchNext || l == 0)) {
+          tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
+          tile_prefetch_l2(dp, ck0 + PFD, NCK - PFD);
+        }
         epi_wait_acc(c);
 #pragma unroll
-        for (int hb = 0; hb < 8; ++hb) {
-          float v[32], h[32], dl[32];
-          if (hb < 7) {
-            ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
-            ld_half(dp, hb + 1, db[(hb + 1) & 1]);
+        for (int i = 0; i < NCK; ++i) {
+          const int ck = ck0 + i;
+          if (i + PFD < NCK) {
+            chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+            chunk_load(dp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
           }
-          if (hb * 32 < n_mma) {
-            acc_load32(c, hb * 32, v);
+          if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l < 7) {     // next step's tiles, half a step + MMA ahead
+            tile_prefetch_l2(tile_base(ptrs, ST_H1 + l + 1, tile, c.row), ck0 + PFD, NCK - PFD);
+            tile_prefetch_l2(tile_base(ptrs, ST_D0 + l + 1, tile, c.row), ck0 + PFD, NCK - PFD);
+          }
+          float v[16], qv[16];
+          if (ck * 16 < n_mma) {
+            acc_load16(c, ck * 16, v);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
           }
-          unpack4(sb[hb & 1], false, h);
-          unpack4(db[hb & 1], false, dl);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sg = sigma_from_h(h[j]);
-            const float dbar = v[j];
-            v[j] = dbar * sg;                                       // vbar_{l+1}
-            dl[j] = SP_BETA * dbar * dl[j] * (1.f - sg);            // q_l
+          for (int jp = 0; jp < 8; ++jp) {
+            const float2 hh = chunk_pair(sb[i % (PFD + 1)], jp, false);
+            const float2 dd = chunk_pair(db[i % (PFD + 1)], jp, false);
+            const float s0 = sigma_from_h(hh.x), s1 = sigma_from_h(hh.y);
+            qv[2 * jp] = SP_BETA * v[2 * jp] * dd.x * (1.f - s0);             // q_l
+            qv[2 * jp + 1] = SP_BETA * v[2 * jp + 1] * dd.y * (1.f - s1);
+            v[2 * jp] *= s0;                                                    // vbar_{l+1}
+            v[2 * jp + 1] *= s1;
           }
-          uint4 q[4];
-          pack4_grad(v, q);
-          st_half(ap, hb, q);
-          st_half(vp, hb, q);
-          pack4_grad(dl, q);
-          st_half(qp, hb, q);
+          uint4 q2[2];
+          pack2_grad(v, q2);
+          chunk_store(ap, ck, q2);
+          chunk_store(vp, ck, q2);
+          pack2_grad(qv, q2);
+          chunk_store(qp, ck, q2);
         }
         if (l < 7) epi_signal_act(c);
       }
       // ---- fbar back into ACT (own rows) -----------------------------------------------------------------------
 #pragma unroll
-      for (int hb = 0; hb < 8; ++hb) {
+      for (int hi = 0; hi < HPW; ++hi) {
+        const int hb = hb0 + hi;
         uint4 q[4];
         get_chunk_raw(c, ptrs, ST_FB, tile, hb, q);
         row_half_store(c.act + (hb >> 1) * BLK_BYTES + c.row * 16, hb & 1, q);
@@ -603,49 +695,67 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll 1
       for (int l = 8; l >= 1; --l) {
         const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);    // H_l -> sigma_{l-1}
-        const uint8_t* qp = tile_base(ptrs, ST_Q0 + (l - 1), tile, c.row);    // q_{l-1} (own rows, written above)
+        const uint8_t* qp = tile_base(ptrs, ST_Q0 + (l - 1), tile, c.row);    // q_{l-1} (own chunks, written above)
         uint8_t* zp = tile_base(ptrs, ST_Z0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
-        uint4 sb[2][4], db[2][4];
-        ld_half(hp, 0, sb[0]);
-        ld_half(qp, 0, db[0]);
+        uint4 sb[PFD + 1][2], db[PFD + 1][2];
+#pragma unroll
+        for (int i = 0; i < PFD; ++i) {
+          chunk_load(hp, ck0 + i, sb[i]);
+          chunk_load(qp, ck0 + i, db[i]);
+        }
+        if (kStashPrefetch && (!kPrefetchNext || l == 8)) {
+          tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
+          tile_prefetch_l2(qp, ck0 + PFD, NCK - PFD);
+        }
         epi_wait_acc(c);
 #pragma unroll
-        for (int hb = 0; hb < 8; ++hb) {
-          float v[32], h[32], q[32];
-          if (hb < 7) {
-            ld_half(hp, hb + 1, sb[(hb + 1) & 1]);
-            ld_half(qp, hb + 1, db[(hb + 1) & 1]);
+        for (int i = 0; i < NCK; ++i) {
+          const int ck = ck0 + i;
+          if (i + PFD < NCK) {
+            chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+            chunk_load(qp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
           }
-          acc_load32(c, hb * 32, v);
-          unpack4(sb[hb & 1], false, h);
-          unpack4(db[hb & 1], kGradBf16, q);
+          if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l > 1) {
+            tile_prefetch_l2(tile_base(ptrs, ST_H1 + (l - 2), tile, c.row), ck0 + PFD, NCK - PFD);
+            tile_prefetch_l2(tile_base(ptrs, ST_Q0 + (l - 2), tile, c.row), ck0 + PFD, NCK - PFD);
+          }
+          float v[16];
+          acc_load16(c, ck * 16, v);
           if (l == 8) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(sbar, __ldg(a.w8row + hb * 32 + j), v[j]);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + ck * 16) + j4);
+              v[j4 * 4 + 0] = fmaf(sbar, w4.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(sbar, w4.y, v[j4 * 4 + 1]);
+              v[j4 * 4 + 2] = fmaf(sbar, w4.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(sbar, w4.w, v[j4 * 4 + 3]);
+            }
           }
-          if (l == 4 && hb == 6 && pc.valid) {                     // PE part of the skip input -> scratch row
+          if (l == 4 && ck >= 13 && pc.valid) {        // columns 217..255: PE part of the skip input -> scratch row
 #pragma unroll
-            for (int j = 25; j < 32; ++j) a.eb[pc.p * 40 + (j - 25)] = v[j];
+            for (int jj = 0; jj < 16; ++jj) {
+              const int col = ck * 16 + jj;
+              if (col >= 217) a.eb[pc.p * 40 + (col - 217)] = v[jj];
+            }
           }
-          if (l == 4 && hb == 7 && pc.valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a.eb[pc.p * 40 + 7 + j] = v[j];
+          for (int jp = 0; jp < 8; ++jp) {
+            const float2 hh = chunk_pair(sb[i % (PFD + 1)], jp, false);
+            const float2 qq = chunk_pair(db[i % (PFD + 1)], jp, kGradBf16);
+            v[2 * jp] = fmaf(v[2 * jp], sigma_from_h(hh.x), qq.x);
+            v[2 * jp + 1] = fmaf(v[2 * jp + 1], sigma_from_h(hh.y), qq.y);
           }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sigma_from_h(h[j]), q[j]);
-          uint4 qq[4];
-          pack4_grad(v, qq);
-          st_half(ap, hb, qq);
-          st_half(zp, hb, qq);
+          uint4 q2[2];
+          pack2_grad(v, q2);
+          chunk_store(ap, ck, q2);
+          chunk_store(zp, ck, q2);
         }
         epi_signal_act(c);
       }
       // ---- e-bar += W_0^T zbar_0 ; xbar += J_e^T e-bar -----------------------------------------------------------
-      {
+      epi_wait_acc(c);
+      if (owner) {
         float v[48];
         float eb[40];
-        epi_wait_acc(c);
         acc_load32(c, 0, v);
         acc_load16(c, 32, v + 32);
         eb[39] = 0.f;
@@ -657,12 +767,12 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
           for (int i = 0; i < 3; ++i) a.d_pts[pc.p * 3 + i] = (xbar[i] + xe[i]) * ginv;
         }
-        tc_fence_before();
       }
+      tc_fence_before();
     }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ISSUER_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -878,6 +988,21 @@ extern "C" int fmov_pack_all(const float* const* srcs, void* blob, float* side, 
   FMOV_LAUNCH_CHECK("pack_all_kernel");
   return OK;
 }
+
+#ifdef FMOV_TRACE
+/* debug builds only: copies the CTA-0 timeline of the last fine kernels to the host and resets it */
+extern "C" int fmov_debug_trace(long long* host, int max_events) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
+  if ((int)n > max_events) n = max_events;
+  if (n > 32768u) n = 32768u;
+  cudaMemcpyFromSymbol(host, g_trace, (size_t)n * 2 * sizeof(long long));
+  unsigned int zero = 0;
+  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
+  return (int)n;
+}
+#endif
 
 // ---- C ABI -----------------------------------------------------------------------------------------------
 extern "C" int fmov_fine_image_count(void) { return IMG_COUNT; }

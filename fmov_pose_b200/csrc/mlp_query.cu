@@ -131,16 +131,18 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) chain_init_barriers(s);
-  if (warp == 1) tmem_alloc(&s->tmem_base, 512);
+  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
-  if (warp == 0) {
-    if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
-  } else if (warp == 1) {
-    if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+  if (warp >= CTRL_WARP0) {
+    if (warp == PRODUCER_WARP) {
+      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+    } else if (warp == ISSUER_WARP) {
+      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+    }
   } else {
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
@@ -203,7 +205,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
     }
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ISSUER_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
