@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
+    ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also for N > 1 (NCCL inside the graph)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,7 +288,9 @@ def main():
     from fmov_pose_b200 import _lib as L
     from fmov_pose_b200 import synthetic
     from fmov_pose_b200.train import GraphedTrainStep, TrainStep
-    use_graph = not args.no_graph
+    # N > 1 runs launch eagerly: capturing the step with its NCCL all-reduces inside the graph timed out on the 2-GPU
+    # box in round 1 (tests/multi_gpu_graph_check.py; not yet root-caused), the eager sharded step is parity-checked
+    use_graph = (not args.no_graph) and (world == 1 or args.graph)
     scene = synthetic.build_scene(device=dev, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
     ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, group=group, capturable=use_graph)
     B = args.rays

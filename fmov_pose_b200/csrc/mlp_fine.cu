@@ -44,6 +44,9 @@ constexpr bool kPrefetchNext = true;
 constexpr bool kPrefetchNext = false;
 #endif
 constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks) in the backward hot loops
+// A/B-measured and NOT kept (profiles/ab.sh, same box, alternating builds): double-buffered TMEM loads in the reverse
+// sweep / colour / backward loops and separate loop bodies for the l == 8 / l == 4 specials (fine_fwd 5.23 -> 5.28 ms,
+// fine_bwd 7.71 -> 7.94 ms at 8192 rays: more code and registers, no latency won); PFD = 2 (spills at 96 registers).
 #define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)
 // Register budget: 640 threads put 5 warps on every SM sub-partition (16 K registers each), so ptxas caps the kernels
 // at 96 registers/thread.  setmaxnreg re-balancing (control warpgroup -> 24..56, epilogue -> 104..120) was tried at
