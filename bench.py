@@ -196,6 +196,22 @@ def measure_extras(scene, dev, use_graph=True):
     out["c5_grid_query"] = {"points": count, "ms": ms, "sdf_queries_per_s": count / ms * 1e3,
                             "tflops_algorithmic": count * F_S / ms / 1e9,
                             "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing"}
+    # whole-frame forward-only render (validate_image shape: 640x480 = 307,200 rays, 64+64 samples)
+    ds = scene["dataset"]
+    with torch.no_grad():
+        pose = scene["pose_network"](0)[:3]
+        rays_o, rays_d = ds.gen_rays_at(0, pose=pose)
+        rend.render_image(rays_o, rays_d, chunk_rays=16384)
+        torch.cuda.synchronize()
+        e0.record()
+        rend.render_image(rays_o, rays_d, chunk_rays=16384)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    n_rays = rays_o.shape[0] * rays_o.shape[1]
+    out["frame_render_640x480"] = {"ms_per_frame": ms, "rays_per_s": n_rays / ms * 1e3,
+                                   "note": "NeuSRenderer.render_image: forward-only, 16384-ray launches, 64+64 samples "
+                                           "(the reference issues 600 sequential 512-ray render() calls per frame)"}
     tg = {}
     for rays_t in (512, 4096):      # the reference's own batch size, and a large batch that amortises its launches
         try:

@@ -144,6 +144,43 @@ class NeuSRenderer:
         }
 
     # ------------------------------------------------------------------------------------------------
+    def render_image(self, rays_o, rays_d, near_far_fn=None, chunk_rays=8192, cos_anneal_ratio=1.0,
+                     background_rgb=None):
+        """Forward-only render of a whole frame: what validate_image / render_novel_image /
+        render_poses do with 600 sequential 512-ray render() calls under autograd (exp_runner.py:1444-1562,
+        1874-1926), as a few large no-grad launches.  rays_o, rays_d: [..., 3] (e.g. [H,W,3] from gen_rays_at).
+        Returns device tensors shaped like the input: color_fine [...,3], normals [...,3] = sum_j w_j * grad_j *
+        inside_j (exp_runner.py:1494-1501, world frame), depth_fine [...,1], weight_sum [...,1]."""
+        self._check()
+        shape = rays_o.shape[:-1]
+        ro = rays_o.reshape(-1, 3).float().contiguous()
+        rd = rays_d.reshape(-1, 3).float().contiguous()
+        N = ro.shape[0]
+        dev = ro.device
+        color = torch.empty(N, 3, device=dev)
+        normals = torch.empty(N, 3, device=dev)
+        depth = torch.empty(N, 1, device=dev)
+        wsum = torch.empty(N, 1, device=dev)
+        if near_far_fn is None:
+            def near_far_fn(o, d):          # Dataset.near_far_from_sphere (models/dataset.py:835-842)
+                a = torch.sum(d ** 2, dim=-1, keepdim=True)
+                b = 2.0 * torch.sum(o * d, dim=-1, keepdim=True)
+                mid = 0.5 * (-b) / a
+                return mid - 1.0, mid + 1.0
+        with torch.no_grad():
+            for i in range(0, N, chunk_rays):
+                o, d = ro[i:i + chunk_rays], rd[i:i + chunk_rays]
+                near, far = near_far_fn(o, d)
+                out = self.render(o, d, near, far, perturb_overwrite=0, background_rgb=background_rgb,
+                                  cos_anneal_ratio=cos_anneal_ratio, eval=True)
+                color[i:i + chunk_rays] = out["color_fine"]
+                normals[i:i + chunk_rays] = (out["gradients"] * (out["weights"] * out["inside_sphere"])[..., None]).sum(1)
+                depth[i:i + chunk_rays] = out["depth_fine"]
+                wsum[i:i + chunk_rays] = out["weight_sum"]
+        return {"color_fine": color.reshape(*shape, 3), "normals": normals.reshape(*shape, 3),
+                "depth_fine": depth.reshape(*shape, 1), "weight_sum": wsum.reshape(*shape, 1)}
+
+    # ------------------------------------------------------------------------------------------------
     def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None):
         """u = -sdf on the res^3 grid (models/renderer.py:9-37 with query_func of :506) in one launch.
         `first`/`count` select a contiguous x-major range (grid partitioning across ranks)."""

@@ -141,6 +141,12 @@ class GraphedTrainStep:
         self.launches_per_step = 0
         self._keep = []
 
+    def set_cos_anneal_ratio(self, ratio):
+        """cos_anneal_ratio is a launch constant of the compositing kernels, so it is part of the graph key: constant
+        for the shipped confs (anneal_end = 0 -> 1.0, exp_runner.py:1043-1047); while it ramps, every new value costs one
+        capture (quantise it on the caller side if anneal_end > 0)."""
+        self.car = float(ratio)
+
     def _body(self, img_id):
         return self.ts.step(img_id, self.B, pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car,
                             img_t=self.img)
@@ -177,7 +183,7 @@ class GraphedTrainStep:
         self.py.copy_(py, non_blocking=True)
         self.tr.copy_(t_rand.reshape(self.B, 1), non_blocking=True)
         self.img.fill_(int(img_id))
-        key = self.ts.graph_key(img_id)
+        key = (self.ts.graph_key(img_id), self.car)
         if key not in self.graphs:
             self._capture(key, img_id)
         g, ls, out = self.graphs[key]

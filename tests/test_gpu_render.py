@@ -135,3 +135,31 @@ def test_direct_field_calls_and_grid():
     a = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, first=0, count=half)
     b = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, first=half, count=res ** 3 - half)
     assert torch.equal(torch.cat([a, b]).cpu(), u.reshape(-1))
+
+
+def test_render_image_equals_chunked_render_calls():
+    """NeuSRenderer.render_image (whole-frame forward-only render in large launches) == the
+    reference's validate_image loop of 512-ray render() calls (exp_runner.py:1468-1501)."""
+    from fmov_pose_b200 import synthetic
+    sc = synthetic.build_scene(device=DEV, n_images=2, n_samples=32, n_importance=32, up_sample_steps=2, H=48, W=64)
+    ds, rend = sc["dataset"], sc["renderer"]
+    K = torch.tensor([[60.0, 0, 32.0], [0, 60.0, 24.0], [0, 0, 1.0]])
+    ds.intrinsics_all_inv = torch.linalg.inv(K)[None].repeat(2, 1, 1).contiguous().to(DEV)
+    with torch.no_grad():
+        pose = sc["pose_network"](1)[:3]
+        rays_o, rays_d = ds.gen_rays_at(1, pose=pose)
+        assert rays_o.shape == (48, 64, 3)
+        img = rend.render_image(rays_o, rays_d, chunk_rays=1000)          # ragged last chunk
+        ro, rd = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+        cols, nrms = [], []
+        for o, d in zip(ro.split(512), rd.split(512)):
+            near, far = ds.near_far_from_sphere(o, d)
+            out = rend.render(o.contiguous(), d.contiguous(), near, far, perturb_overwrite=0, cos_anneal_ratio=1.0, eval=True)
+            cols.append(out["color_fine"])
+            nrms.append((out["gradients"] * out["weights"][..., None] * out["inside_sphere"][..., None]).sum(1))
+    col = torch.cat(cols).reshape(48, 64, 3)
+    nrm = torch.cat(nrms).reshape(48, 64, 3)
+    assert float((img["color_fine"] - col).abs().max()) <= 1e-5
+    assert float((img["normals"] - nrm).abs().max()) <= 1e-4
+    assert img["depth_fine"].shape == (48, 64, 1) and bool(torch.isfinite(img["depth_fine"]).all())
+    assert float(img["weight_sum"].max()) > 0.5        # the sphere is in view
