@@ -265,7 +265,6 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
-    ap.add_argument("--graph", action="store_true", help="force CUDA-graph replay also for N > 1 (NCCL inside the graph)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -304,9 +303,8 @@ def main():
     from fmov_pose_b200 import _lib as L
     from fmov_pose_b200 import synthetic
     from fmov_pose_b200.train import GraphedTrainStep, TrainStep
-    # N > 1 runs launch eagerly: capturing the step with its NCCL all-reduces inside the graph timed out on the 2-GPU
-    # box in round 1 (tests/multi_gpu_graph_check.py; not yet root-caused), the eager sharded step is parity-checked
-    use_graph = (not args.no_graph) and (world == 1 or args.graph)
+    # the captured step contains its NCCL all-reduces (tests/multi_gpu_graph_check.py: graphed == eager on 2 GPUs)
+    use_graph = not args.no_graph
     scene = synthetic.build_scene(device=dev, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
     ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, group=group, capturable=use_graph)
     B = args.rays
@@ -438,8 +436,20 @@ def main():
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "extras": extras,
                 "tensor_frac_whole_step": flops_per_ray(n, m) * value / world / 1e12 / peak_tf}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if group is not None:
+        # teardown: graphs that hold NCCL kernels must be gone before the communicator is destroyed; measured in round 1:
+        # destroy_process_group() with live captured graphs never returns (the run had already printed its line), so
+        # the ranks leave through a barrier + hard exit instead
+        if gts is not None:
+            gts.graphs.clear()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if use_graph:
+            os._exit(0)
         torch.distributed.destroy_process_group()
     return 0
 

@@ -169,7 +169,8 @@ class GraphedTrainStep:
         self._keep = [b for lst in Stash._pool.values() for b in lst]      # keep the stash buffer alive with the graph
         g = torch.cuda.CUDAGraph()
         n0 = L.n_calls
-        with torch.cuda.graph(g, pool=self.pool):
+        # thread_local: other threads (NCCL watchdog, autograd workers) may keep calling the CUDA runtime during capture
+        with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
             ls, out = self._body(img_id)
         self.launches_per_step = L.n_calls - n0
         if self.pool is None:
