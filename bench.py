@@ -168,8 +168,8 @@ def time_cpu(B, n, m, steps_up, warm, iters):
 
 
 # DRAM traffic of the MLP kernels per sample point, from `ncu --set full` (dram__bytes_read + dram__bytes_write,
-# profiles/r1_final_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 3.94 GB, fine_bwd 8.94 GB, dw 5.91 GB
-NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 3.924e9 / 262144, "fine_bwd": 8.890e9 / 262144, "dw": 5.893e9 / 262144}
+# profiles/r1_final_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 4.02 GB, fine_bwd 9.85 GB, dw 5.90 GB
+NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 4.023e9 / 262144, "fine_bwd": 9.846e9 / 262144, "dw": 5.898e9 / 262144}
 
 
 def measure_extras(scene, dev, use_graph=True):
