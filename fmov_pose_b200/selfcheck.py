@@ -4,22 +4,25 @@ import numpy as np
 import torch
 
 
-def smoke(B=256, verbose=True):
+def smoke(B=256, verbose=True, n_samples=64, n_importance=64, up_sample_steps=4, white_bkgd=False,
+          cos_anneal_ratio=1.0, mask_weight=5.0):
     from fmov_pose_b200 import synthetic
     from fmov_pose_b200.train import TrainStep
     from oracle import neus_oracle as O
     dev = torch.device("cuda:0")
-    scene = synthetic.build_scene(device=dev, n_images=4, n_samples=64, n_importance=64, pose_type="seg", H=120, W=160)
+    scene = synthetic.build_scene(device=dev, n_images=4, n_samples=n_samples, n_importance=n_importance,
+                                 up_sample_steps=up_sample_steps, pose_type="seg", H=120, W=160)
     # frames are 160x120 here: scale the intrinsics accordingly
     ds = scene["dataset"]
     K = torch.tensor([[150.0, 0, 80.0], [0, 150.0, 60.0], [0, 0, 1.0]])
     ds.intrinsics_all_inv = torch.linalg.inv(K)[None].repeat(4, 1, 1).contiguous().to(dev)
-    ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, optimizer=False)
+    ts = TrainStep(scene, igr_weight=0.1, mask_weight=mask_weight, optimizer=False)
+    ts.background_rgb = torch.ones(1, 3, device=dev) if white_bkgd else None
     g = torch.Generator().manual_seed(0)
     px = torch.randint(30, 130, [B], generator=g).to(dev)
     py = torch.randint(10, 110, [B], generator=g).to(dev)
     t_rand = torch.rand(B, 1, generator=g).to(dev)
-    ls, out = ts.forward_backward(1, B, pixels=(px, py), t_rand=t_rand)
+    ls, out = ts.forward_backward(1, B, pixels=(px, py), t_rand=t_rand, cos_anneal_ratio=cos_anneal_ratio)
     torch.cuda.synchronize()
     # oracle on the same z samples
     cpu = lambda x: x.detach().cpu()
@@ -29,11 +32,12 @@ def smoke(B=256, verbose=True):
     pose = cpu(ts.pose_of(1))
     ro, rd = O.gen_rays(pose, cpu(ds.intrinsics_all_inv[1]), cpu(px), cpu(py))
     nr, fr = O.near_far_from_sphere(ro, rd)
-    ref = O.render(sdf_p, col_p, var, ro, rd, nr, fr, n_samples=64, n_importance=64, up_sample_steps=4,
-                   cos_anneal_ratio=1.0, z_vals=cpu(out["z_vals"]))
+    ref = O.render(sdf_p, col_p, var, ro, rd, nr, fr, n_samples=n_samples, n_importance=n_importance,
+                   up_sample_steps=up_sample_steps, cos_anneal_ratio=cos_anneal_ratio, z_vals=cpu(out["z_vals"]),
+                   background_rgb=torch.ones(1, 3) if white_bkgd else None)
     data_rgb = cpu(ds.images[1][(py, px)])
     mask = cpu(ds.masks[1][(py, px)])[:, :1]
-    rl = O.loss_block(ref, data_rgb, mask, 0.1, 5.0)
+    rl = O.loss_block(ref, data_rgb, mask, 0.1, mask_weight)
     rl["loss"].backward()
     col_err = (cpu(out["color_fine"]) - ref["color_fine"].detach()).abs().max().item()
     sdf_err = (cpu(out["sdf"]) - ref["sdf"].detach()).abs().max().item()

@@ -14,6 +14,7 @@ class TrainStep:
         self.s = scene
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
         self.group = group
+        self.background_rgb = None       # torch.ones([1,3]) when use_white_bkgd (exp_runner.py:556)
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
         scene["renderer"].process_group = group
         nets = [scene["sdf_network"], scene["deviation_network"], scene["color_network"]]
@@ -93,7 +94,8 @@ class TrainStep:
         data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         near, far = ds.near_far_from_sphere(rays_o, rays_d)
-        out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand)
+        out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
+                          background_rgb=self.background_rgb)
         ls = self.losses(out, true_rgb, mask)
         for p in self.all_params:
             p.grad = None

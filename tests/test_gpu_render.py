@@ -163,3 +163,47 @@ def test_render_image_equals_chunked_render_calls():
     assert float((img["normals"] - nrm).abs().max()) <= 1e-4
     assert img["depth_fine"].shape == (48, 64, 1) and bool(torch.isfinite(img["depth_fine"]).all())
     assert float(img["weight_sum"].max()) > 0.5        # the sphere is in view
+
+
+def test_full_size_batch_split_invariance():
+    """Size-independent properties at the benchmark's full size (8192 rays x 64+64 samples, 1.05 M points per launch):
+    rays are independent, so (i) the forward outputs of one 8192-ray call equal those of two 4096-ray calls bit for
+    bit, and (ii) for an additive loss the parameter / ray gradients of the whole batch equal the sum over the halves."""
+    from fmov_pose_b200 import synthetic
+    sc = synthetic.build_scene(device=DEV, n_images=2, H=120, W=160)
+    rend = sc["renderer"]
+    B = 8192
+    g = torch.Generator().manual_seed(5)
+    o = (torch.tensor([0.0, 0.0, -3.0]) + 0.02 * torch.randn(B, 3, generator=g)).to(DEV)
+    d = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 1.0]) + 0.15 * torch.randn(B, 3, generator=g), dim=-1).to(DEV)
+    tr = torch.rand(B, 1, generator=g).to(DEV)
+    params = [p for n in (sc["sdf_network"], sc["color_network"], sc["deviation_network"]) for p in n.parameters()
+              if p.requires_grad]
+
+    def run(sl):
+        ro, rd = o[sl].clone().requires_grad_(True), d[sl].clone().requires_grad_(True)
+        near, far = sc["dataset"].near_far_from_sphere(ro, rd)
+        out = rend.render(ro, rd, near.detach(), far.detach(), cos_anneal_ratio=1.0, t_rand=tr[sl])
+        loss = out["color_fine"].sum() + out["weight_sum"].sum() + out["depth_fine"].sum()
+        for p in params:
+            p.grad = None
+        loss.backward()
+        return out, [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params], ro.grad, rd.grad
+
+    out_w, g_w, go_w, gd_w = run(slice(0, B))
+    out_a, g_a, go_a, gd_a = run(slice(0, B // 2))
+    out_b, g_b, go_b, gd_b = run(slice(B // 2, B))
+    for k in ("color_fine", "weight_sum", "depth_fine", "z_vals", "sdf", "weights"):
+        whole = out_w[k].reshape(B, -1)
+        assert torch.equal(whole[: B // 2], out_a[k].reshape(B // 2, -1)), k
+        assert torch.equal(whole[B // 2:], out_b[k].reshape(B // 2, -1)), k
+    assert float(out_w["weight_sum"].max()) > 0.9 and float(out_w["weight_sum"].min()) < 0.1      # hits and misses
+    # ray gradients are per ray: equal up to the per-launch fp16 loss scale (amax differs between the launches)
+    assert rel(torch.cat([go_a, go_b]).cpu().numpy(), go_w.cpu().numpy()) <= 2e-3
+    assert rel(torch.cat([gd_a, gd_b]).cpu().numpy(), gd_w.cpu().numpy()) <= 2e-3
+    worst = 0.0
+    for w, a, b in zip(g_w, g_a, g_b):
+        if float(w.norm()) == 0.0:
+            continue
+        worst = max(worst, rel((a + b).cpu().numpy(), w.cpu().numpy()))
+    assert worst <= 3e-3, worst

@@ -106,3 +106,18 @@ def test_graphed_step_equals_eager_step(pose_type):
         assert float((a - b).abs().mean()) <= 1e-4, float((a - b).abs().mean())
         moved = max(moved, float(a.abs().max()))
     assert moved > 0
+
+
+@pytest.mark.parametrize("kw", [
+    dict(B=77, n_samples=16, n_importance=32, up_sample_steps=2, white_bkgd=True, cos_anneal_ratio=0.3, mask_weight=0.0),
+    dict(B=1, n_samples=64, n_importance=64, up_sample_steps=4),
+    dict(B=129, n_samples=48, n_importance=16, up_sample_steps=1, white_bkgd=True, mask_weight=1.0),
+    dict(B=200, n_samples=32, n_importance=64, up_sample_steps=4, cos_anneal_ratio=0.0),
+])
+def test_train_iteration_vs_oracle_ragged_and_variants(kw):
+    """Edge cases of the hot path against the oracle on the same z samples (north_star tolerances, asserted inside
+    selfcheck.smoke): ragged ray counts (1, 77, 129: partial 128-point tiles), sample counts other than 64+64, one
+    up-sample round, white background (exp_runner.py:556), cos-anneal ratios 0 / 0.3 (renderer.py:300-305),
+    mask_weight 0 (mask -> ones, exp_runner.py:564-566)."""
+    from fmov_pose_b200 import selfcheck
+    assert selfcheck.smoke(verbose=False, **kw)
