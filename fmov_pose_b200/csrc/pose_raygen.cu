@@ -255,6 +255,7 @@ struct RayArgs {
   const float* intr_inv;     // [3,3] (row stride given)
   int intr_stride;
   const long long* px; const long long* py;
+  const float* pxf; const float* pyf;      // sub-pixel coordinates (flow matches); used when px == nullptr
   long long B;
   float* rays_o; float* rays_d; float* near; float* far; float* c2w_out;
 };
@@ -274,7 +275,7 @@ __global__ void raygen_fwd_kernel(RayArgs a) {
   __syncthreads();
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= a.B) return;
-  const float x = (float)a.px[r], y = (float)a.py[r];
+  const float x = a.px ? (float)a.px[r] : a.pxf[r], y = a.px ? (float)a.py[r] : a.pyf[r];
   float p[3], v[3], d[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) p[i] = sK[i * 3] * x + sK[i * 3 + 1] * y + sK[i * 3 + 2];
@@ -307,7 +308,7 @@ __global__ void raygen_bwd_kernel(RayArgs a, const float* __restrict__ g_o, cons
 #pragma unroll
   for (int i = 0; i < 12; ++i) G[i] = 0.f;
   if (r < a.B) {
-    const float x = (float)a.px[r], y = (float)a.py[r];
+    const float x = a.px ? (float)a.px[r] : a.pxf[r], y = a.px ? (float)a.py[r] : a.pyf[r];
     float p[3], v[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) p[i] = sK[i * 3] * x + sK[i * 3 + 1] * y + sK[i * 3 + 2];
@@ -413,6 +414,42 @@ extern "C" int fmov_raygen_bwd(const float* intr_inv, int intr_stride, const lon
   if (B == 0) return OK;
   FMOV_REQUIRE(intr_inv && px && py && rays_o && rays_d, "fmov_raygen_bwd: null argument");
   a.intr_inv = intr_inv; a.intr_stride = intr_stride; a.px = px; a.py = py; a.B = B;
+  a.rays_o = const_cast<float*>(rays_o); a.rays_d = const_cast<float*>(rays_d);
+  raygen_bwd_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, g_o, g_d, g_near, g_far, g_c2w34);
+  FMOV_LAUNCH_CHECK("raygen_bwd_kernel");
+  return OK;
+}
+
+/* float-pixel variants (LoFTR flow matches are sub-pixel: models/dataset.py:712-715, 745-760) */
+extern "C" int fmov_raygen_xy_fwd(int mode, const float* c2w34, const float* rot, const float* trans, const float* scale,
+                                  const float* init34, const float* se3, const float* intr_inv, int intr_stride,
+                                  const float* px, const float* py, long long B, float* rays_o, float* rays_d,
+                                  float* near, float* far, float* c2w_out, void* stream) {
+  RayArgs a;
+  memset(&a, 0, sizeof(a));
+  int st = make_pose(a.pp, mode, c2w34, rot, trans, scale, init34, se3);
+  if (st) return st;
+  FMOV_REQUIRE(B >= 0 && intr_stride >= 3, "fmov_raygen_xy_fwd: bad sizes");
+  if (B == 0) return OK;
+  FMOV_REQUIRE(intr_inv && px && py && rays_o && rays_d, "fmov_raygen_xy_fwd: null argument");
+  a.intr_inv = intr_inv; a.intr_stride = intr_stride; a.pxf = px; a.pyf = py; a.B = B;
+  a.rays_o = rays_o; a.rays_d = rays_d; a.near = near; a.far = far; a.c2w_out = c2w_out;
+  raygen_fwd_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+  FMOV_LAUNCH_CHECK("raygen_fwd_kernel");
+  return OK;
+}
+
+extern "C" int fmov_raygen_xy_bwd(const float* intr_inv, int intr_stride, const float* px, const float* py, long long B,
+                                  const float* rays_o, const float* rays_d, const float* g_o, const float* g_d,
+                                  const float* g_near, const float* g_far, float* g_c2w34, void* stream) {
+  RayArgs a;
+  memset(&a, 0, sizeof(a));
+  FMOV_REQUIRE(B >= 0 && intr_stride >= 3, "fmov_raygen_xy_bwd: bad sizes");
+  FMOV_REQUIRE(g_c2w34, "fmov_raygen_xy_bwd: null output");
+  FMOV_CUDA(cudaMemsetAsync(g_c2w34, 0, 12 * sizeof(float), (cudaStream_t)stream));
+  if (B == 0) return OK;
+  FMOV_REQUIRE(intr_inv && px && py && rays_o && rays_d, "fmov_raygen_xy_bwd: null argument");
+  a.intr_inv = intr_inv; a.intr_stride = intr_stride; a.pxf = px; a.pyf = py; a.B = B;
   a.rays_o = const_cast<float*>(rays_o); a.rays_d = const_cast<float*>(rays_d);
   raygen_bwd_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, g_o, g_d, g_near, g_far, g_c2w34);
   FMOV_LAUNCH_CHECK("raygen_bwd_kernel");

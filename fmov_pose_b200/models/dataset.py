@@ -42,6 +42,58 @@ class RayDataset:
         self.intrinsics_all = intr.to(self.device)
         self.intrinsics_all_inv = torch.linalg.inv(intr).contiguous().to(self.device)
         self.use_mono_depth = False
+        # flow matches (dataset.py:324-415 builds these from LoFTR files on disk; here they are set from memory)
+        self.index_to_frame = {i: "%04d" % i for i in range(self.n_images)}
+        self.frame_to_index = {v: k for k, v in self.index_to_frame.items()}
+        self.flow_pairs = {}
+        self.loftr_interval_flows = {}
+
+    def set_flows(self, matches):
+        """matches: {(idx_a, idx_b): (xs_a, ys_a, xs_b, ys_b)} numpy float arrays of matched pixels.  Fills
+        `flow_pairs` / `loftr_interval_flows` with both directions, keyed as the reference (dataset.py:395-415)."""
+        for (a, b), (xa, ya, xb, yb) in matches.items():
+            fa, fb = self.index_to_frame[int(a)], self.index_to_frame[int(b)]
+            arr = [np.asarray(v, dtype=np.float32) for v in (xa, ya, xb, yb)]
+            self.loftr_interval_flows[fa + "_" + fb] = (arr[0], arr[1], arr[2], arr[3])
+            self.loftr_interval_flows[fb + "_" + fa] = (arr[2], arr[3], arr[0], arr[1])
+            self.flow_pairs.setdefault(fa, set()).add(fb)
+            self.flow_pairs.setdefault(fb, set()).add(fa)
+
+    def gen_random_ray_pairs_at(self, img_id_corr, batch_size, pose_network, current_img_num, interval=1, img_id=None,
+                                indexs=None):
+        """Dataset.gen_random_ray_pairs_at (models/dataset.py:683-792): `batch_size` matched pixel pairs between
+        frame img_id_corr and a random matched frame img_id -> (data [2*batch_size,10] = [rays of img_id_corr | rays of
+        img_id], pixels_xy, pixels_xy_corr, img_id, depth) or five Nones when there is no usable pair.  Matches are
+        sub-pixel floats: colours are read at the truncated pixel, ray directions use the float coordinates.
+        `img_id` / `indexs` inject the two host RNG draws (np.random.choice) for reproducible runs."""
+        img_id_corr = int(img_id_corr)
+        name_corr = self.index_to_frame[img_id_corr]
+        if name_corr not in self.flow_pairs:
+            return None, None, None, None, None
+        pairs_idx = sorted(self.frame_to_index[n] for n in self.flow_pairs[name_corr])
+        pairs_idx = [i for i in pairs_idx if i < current_img_num and abs(i - img_id_corr) <= interval]
+        if len(pairs_idx) == 0:
+            return None, None, None, None, None
+        if img_id is None:
+            img_id = int(np.random.choice(pairs_idx))
+        img_id = int(img_id)
+        xs1, ys1, xs2, ys2 = self.loftr_interval_flows[name_corr + "_" + self.index_to_frame[img_id]]
+        if indexs is None:
+            indexs = np.random.choice(len(xs1), batch_size, replace=True)
+        dev = self.device
+        px_c = torch.from_numpy(xs1[indexs]).to(dev)
+        py_c = torch.from_numpy(ys1[indexs]).to(dev)
+        px = torch.from_numpy(xs2[indexs]).to(dev)
+        py = torch.from_numpy(ys2[indexs]).to(dev)
+        color_c = self.images[img_id_corr][(py_c.long(), px_c.long())]
+        color = self.images[img_id][(py.long(), px.long())]
+        o_c, v_c = _RayGenFn.apply(pose_network(img_id_corr)[:3, :4], self.intrinsics_all_inv[img_id_corr], px_c, py_c)
+        o, v = _RayGenFn.apply(pose_network(img_id)[:3, :4], self.intrinsics_all_inv[img_id], px, py)
+        mask = torch.ones(2 * len(indexs), 1, device=dev)     # matches were filtered to the masks (dataset.py:770-772)
+        data = torch.cat([torch.cat([o_c, o], 0), torch.cat([v_c, v], 0), torch.cat([color_c, color], 0), mask], dim=-1)
+        depth = torch.zeros(2 * len(indexs), device=dev)
+        return (data, torch.stack([px, py], dim=-1), torch.stack([px_c, py_c], dim=-1),
+                torch.tensor(img_id, device=dev).long(), depth)
 
     def _bbox(self, img_idx, patch_size):
         if self.masks_np is None:

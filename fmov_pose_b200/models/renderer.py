@@ -4,7 +4,7 @@ Same constructor, attributes, `render()` signature and output dict (keys and sha
 models/renderer.py:486-498), differentiable where the reference's outputs are: `color_fine`,
 `weight_sum`, `depth_fine`, `weights`, `gradients`, `gradient_error`, `s_val` carry gradients to the SDF /
 colour / variance parameters and to `rays_o`, `rays_d` (→ pose parameters); with `n_importance == 0`
-also through `near` / `far` (models/renderer.py:390).  Not supported (explicit errors, no fallback):
+also through `near` / `far` (models/renderer.py:390).  `pts` carries its gradient to `rays_o`, `rays_d` (and z).  Not supported (explicit errors, no fallback):
 `n_outside > 0`, network shapes other than the shipped confs'.
 
 The jitter draw `torch.rand([B,1])` (renderer.py:404) stays in host PyTorch so RNG parity with the
@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from .. import fine as _fine
+from .. import flow as _flow
 from .. import ops as _ops
 from .. import packing as _packing
 
@@ -126,6 +127,8 @@ class NeuSRenderer:
         else:
             outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)
         (color, weight_sum, weight_max, depth, weights, cdf, inside, mid_z, pts, sdf, gradients, grad_err) = outs
+        if need_bwd:      # autograd link pts = o + d*mid_z (renderer.py:269-272); costs nothing unless pts is differentiated
+            pts = _flow.PtsFunction.apply(rays_o, rays_d, z_vals, pts, sample_dist)
         s_val = (1.0 / inv_s).reshape(1, 1).expand(batch_size, 1)     # mean over samples of a constant
         return {
             "color_fine": color,

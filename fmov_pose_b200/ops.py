@@ -105,13 +105,14 @@ def hierarchical_sample(qw, rays_o, rays_d, near, far, t_rand, n_samples, n_impo
 def raygen_fwd(mode, intr_inv, px, py, c2w34=None, rot=None, trans=None, scale=None, init34=None, se3=None):
     B = px.shape[0]
     dev = px.device
-    assert px.dtype == torch.int64 and py.dtype == torch.int64
+    assert px.dtype == py.dtype and px.dtype in (torch.int64, torch.float32), "pixels: int64 or float32 (sub-pixel)"
+    fn = L.lib().fmov_raygen_fwd if px.dtype == torch.int64 else L.lib().fmov_raygen_xy_fwd
     rays_o = torch.empty(B, 3, dtype=torch.float32, device=dev)
     rays_d = torch.empty(B, 3, dtype=torch.float32, device=dev)
     near = torch.empty(B, 1, dtype=torch.float32, device=dev)
     far = torch.empty(B, 1, dtype=torch.float32, device=dev)
     c2w_out = torch.empty(3, 4, dtype=torch.float32, device=dev)
-    L.check(L.lib().fmov_raygen_fwd(mode, L.ptr(c2w34), L.ptr(rot), L.ptr(trans), L.ptr(scale), L.ptr(init34), L.ptr(se3),
+    L.check(fn(mode, L.ptr(c2w34), L.ptr(rot), L.ptr(trans), L.ptr(scale), L.ptr(init34), L.ptr(se3),
                                     L.ptr(intr_inv), intr_inv.stride(0), L.ptr(px), L.ptr(py), L.c_ll(B), L.ptr(rays_o),
                                     L.ptr(rays_d), L.ptr(near), L.ptr(far), L.ptr(c2w_out), L.stream()), "fmov_raygen_fwd")
     return rays_o, rays_d, near, far, c2w_out
@@ -120,7 +121,8 @@ def raygen_fwd(mode, intr_inv, px, py, c2w34=None, rot=None, trans=None, scale=N
 def raygen_bwd(intr_inv, px, py, rays_o, rays_d, g_o, g_d, g_near, g_far):
     B = px.shape[0]
     g34 = torch.empty(3, 4, dtype=torch.float32, device=px.device)
-    L.check(L.lib().fmov_raygen_bwd(L.ptr(intr_inv), intr_inv.stride(0), L.ptr(px), L.ptr(py), L.c_ll(B), L.ptr(rays_o),
+    fn = L.lib().fmov_raygen_bwd if px.dtype == torch.int64 else L.lib().fmov_raygen_xy_bwd
+    L.check(fn(L.ptr(intr_inv), intr_inv.stride(0), L.ptr(px), L.ptr(py), L.c_ll(B), L.ptr(rays_o),
                                     L.ptr(rays_d), L.ptr(g_o), L.ptr(g_d), L.ptr(g_near), L.ptr(g_far), L.ptr(g34),
                                     L.stream()), "fmov_raygen_bwd")
     return g34

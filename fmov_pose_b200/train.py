@@ -5,14 +5,19 @@ parameter gradients are all-reduced so that N-GPU results equal the single-GPU s
 import torch
 import torch.nn.functional as F
 
+from . import flow as _flow
 from .models import camera as _camera
 
 
 class TrainStep:
     def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True,
-                 capturable=False):
+                 capturable=False, flow_weight=0.0, unit_sphere_weight=0.0, maintain_shape=False,
+                 detach_flow_on_sdf=False, detach_ref=False):
         self.s = scene
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
+        # exp_runner.py:150-160, 327-336 (train.flow_weight, unit_sphere_weight, maintain_shape, detach_*)
+        self.flow_weight, self.unit_sphere_weight = float(flow_weight), float(unit_sphere_weight)
+        self.maintain_shape, self.detach_flow_on_sdf, self.detach_ref = maintain_shape, detach_flow_on_sdf, detach_ref
         self.group = group
         self.background_rgb = None       # torch.ones([1,3]) when use_white_bkgd (exp_runner.py:556)
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
@@ -97,12 +102,66 @@ class TrainStep:
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
                           background_rgb=self.background_rgb)
         ls = self.losses(out, true_rgb, mask)
+        if self.unit_sphere_weight > 0 and self.group is None:      # exp_runner.py:714-724
+            ls["unit_sphere_loss"] = _flow.unit_sphere_loss(out, rays_o, rays_d, 2.0 / rend.n_samples,
+                                                            self.unit_sphere_weight)
+            ls["loss"] = ls["loss"] + ls["unit_sphere_loss"]
         for p in self.all_params:
             p.grad = None
         ls["loss"].backward()
         if self.group is not None:
             self.allreduce_grads()
         return ls, out
+
+    def flow_forward_backward(self, img_id_corr, batch_size, current_img_num, interval=1, additional_img_id=None,
+                              img_id=None, indexs=None, add_pixels=None, t_rand=None, cos_anneal_ratio=1.0):
+        """A `use_flow` iteration (exp_runner.py:441-456, 512-548, 562-599, 605-688, 714-724): batch_size//2 matched
+        pixel pairs between frame img_id_corr and a matched frame (+ batch_size rays of `additional_img_id` with
+        maintain_shape), one render of the concatenated rays, colour/eikonal/mask losses plus the reprojection loss
+        of every sample point into the other frame of the pair.  Returns (losses, render dict, img_id) or None when the
+        frame has no usable match (the reference then falls back to an ordinary iteration)."""
+        s = self.s
+        ds, rend, pn = s["dataset"], s["renderer"], s["pose_network"]
+        if pn is None:
+            raise NotImplementedError("flow iterations need a pose network (pose_type gf / seg), as the reference's "
+                                      "gen_random_ray_pairs_at (models/dataset.py:728, 749)")
+        data, pixels_xy, pixels_xy_corr, img_id, _ = ds.gen_random_ray_pairs_at(
+            img_id_corr, batch_size // 2, pn, current_img_num, interval, img_id=img_id, indexs=indexs)
+        if data is None:
+            return None
+        if self.maintain_shape:
+            add_pose = pn(additional_img_id)[:3]
+            add_data, _ = ds.gen_random_rays_at(additional_img_id, batch_size, add_pose, pixels=add_pixels)
+            data = torch.cat([data, add_data], dim=0)
+        rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
+        near, far = ds.near_far_from_sphere(rays_o, rays_d)
+        out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
+                          background_rgb=self.background_rgb)
+        ls = self.losses(out, true_rgb, mask)
+        sd = 2.0 / rend.n_samples
+        n_terms = None if self.group is None else 2 * (data.shape[0] // (4 if self.maintain_shape else 2)) * self.world
+        # the pose modules are evaluated again for the projection, as exp_runner.py:628-631, 660-663
+        fl = _flow.flow_loss(out, rays_o, rays_d, pn(int(img_id))[:3], pn(int(img_id_corr))[:3],
+                             ds.intrinsics_all[int(img_id)], ds.intrinsics_all[int(img_id_corr)], pixels_xy,
+                             pixels_xy_corr, sd, self.flow_weight, maintain_shape=self.maintain_shape,
+                             detach_flow_on_sdf=self.detach_flow_on_sdf, detach_ref=self.detach_ref, n_terms=n_terms)
+        ls["flow_loss"] = fl
+        ls["loss"] = ls["loss"] + fl
+        if self.unit_sphere_weight > 0:
+            ls["unit_sphere_loss"] = _flow.unit_sphere_loss(out, rays_o, rays_d, sd, self.unit_sphere_weight)
+            ls["loss"] = ls["loss"] + ls["unit_sphere_loss"]
+        for p in self.all_params:
+            p.grad = None
+        ls["loss"].backward()
+        if self.group is not None:
+            self.allreduce_grads()
+        return ls, out, img_id
+
+    def step_flow(self, *a, **kw):
+        r = self.flow_forward_backward(*a, **kw)
+        if r is not None and self.optimizer is not None:
+            self.optimizer.step()
+        return r
 
     def allreduce_grads(self):
         """one SUM all-reduce of all MLP + pose gradients (~3.2 MB fp32) over NCCL/NVLink"""

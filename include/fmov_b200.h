@@ -73,6 +73,16 @@ int fmov_raygen_bwd(const float* intr_inv, int intr_stride, const long long* px,
                     const float* rays_o, const float* rays_d, const float* g_o, const float* g_d, const float* g_near,
                     const float* g_far, float* g_c2w34, void* stream);
 
+/* same with float (sub-pixel) pixel coordinates: the LoFTR flow matches of Dataset.gen_random_ray_pairs_at
+ * (models/dataset.py:712-715, 728-760)                                                              */
+int fmov_raygen_xy_fwd(int mode, const float* c2w34, const float* rot, const float* trans, const float* scale,
+                       const float* init34, const float* se3, const float* intr_inv, int intr_stride, const float* px,
+                       const float* py, long long B, float* rays_o, float* rays_d, float* near, float* far,
+                       float* c2w_out, void* stream);
+int fmov_raygen_xy_bwd(const float* intr_inv, int intr_stride, const float* px, const float* py, long long B,
+                       const float* rays_o, const float* rays_d, const float* g_o, const float* g_d, const float* g_near,
+                       const float* g_far, float* g_c2w34, void* stream);
+
 /* ---- hierarchical sampling --------------------------------------------------------------- */
 /* coarse z + per-ray jitter (models/renderer.py:385-405); t_rand = the raw U[0,1) draw or NULL  */
 int fmov_sample_coarse(const float* near, const float* far, const float* t_rand, long long B, int n_samples,
@@ -106,6 +116,24 @@ int fmov_loss_fwd_bwd(const float* color, const float* weight_sum, const float* 
 int fmov_ray_reduce_bwd(const float* d_pts, const float* d_dirs, const float* d_dir_tc, const float* d_dist,
                         const float* d_mid, const float* rays_d, const float* z, long long B, int S, float sample_dist,
                         float* d_o, float* d_d, float* d_z, void* stream);
+
+/* ---- flow / reprojection and unit-sphere losses ------------------------------------ */
+/* exp_runner.py:605-688: err[r] = sum_j weights[r,j] * (pi(K (R_w p_rj + t_w)) - xy[r]),  p_rj = o_r + d_r*mid_z_rj
+ * (mid_z from z and sample_dist as models/renderer.py:261-267).  w2c34 [3,4] = rows 0..2 of inverse(c2w) of the matched
+ * frame (device), K33 = its intrinsics (device, row stride k_stride), xy [B,2] the matched pixels.  The caller applies
+ * F.l1_loss(err, 0) * flow_weight.  backward: d_weights [B,S] (NULL: detach_flow_on_sdf), d_o/d_d [B,3], d_z [B,S]
+ * (NULL unless z carries gradient, i.e. n_importance == 0), d_w2c34 [12] (zeroed by the call, summed over rays).  */
+int fmov_flow_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
+                  const float* weights, const float* w2c34, const float* K33, int k_stride, const float* xy, float* err,
+                  void* stream);
+int fmov_flow_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
+                  const float* weights, const float* w2c34, const float* K33, int k_stride, const float* xy,
+                  const float* g_err, float* d_weights, float* d_o, float* d_d, float* d_z, float* d_w2c34, void* stream);
+/* exp_runner.py:714-724: partial2 = (sum |w| over samples with |pts| > 1, their count) (zeroed by the call; NULL to
+ * skip); d_weights = g_scale[0] * sign(w) on those samples, 0 elsewhere (NULL to skip; g_scale device scalar).    */
+int fmov_unit_sphere_fwd_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z,
+                             float sample_dist, const float* weights, const float* g_scale, float* partial2,
+                             float* d_weights, void* stream);
 
 /* ---- fine stage: SDF value + feature + analytic normal + colour MLP, forward and backward -------- */
 /* forward: replaces sdf_network(pts), sdf_network.gradient(pts), color_network(...) of render_core

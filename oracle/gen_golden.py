@@ -286,6 +286,86 @@ def grid_case():
     print("grid40.npz written", u.min(), u.max())
 
 
+def _reference_block(start_marker, end_marker):
+    """Source text of a block of Runner.train (exp_runner.py cannot be imported: pyhocon/open3d/... are missing), cut
+    between two marker lines and dedented, so that the fixture below EXECUTES the reference's own lines."""
+    import textwrap
+    lines = open(os.path.join(REF, "exp_runner.py")).read().split("\n")
+    i0 = next(i for i, l in enumerate(lines) if l.strip() == start_marker)
+    i1 = next(i for i in range(i0 + 1, len(lines)) if lines[i].strip() == end_marker)
+    return textwrap.dedent("\n".join(lines[i0:i1])), (i0 + 1, i1)
+
+
+def flow_case(name, *, B, S, maintain_shape, detach_flow_on_sdf=False, seed=0):
+    """Flow / reprojection loss (exp_runner.py:604-688) and unit-sphere loss (:714-724): the reference's source lines
+    are exec'd on synthetic render outputs; pts = o + d*mid_z is built as render_core does (renderer.py:261-272)."""
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(seed)
+    src_flow, span_flow = _reference_block("if self.flow_weight > 0.0 and use_flow:", "if self.depth_weight > 0.0:")
+    src_unit, span_unit = _reference_block("if self.unit_sphere_weight > 0:", "if self.gradient_analysis:")
+    n_samples = S
+    sample_dist = 2.0 / n_samples
+
+    def rand_pose(t):
+        r = torch.randn(3, generator=g) * 0.2
+        K_ = torch.zeros(3, 3)
+        K_[0, 1], K_[0, 2], K_[1, 2] = -r[2], r[1], -r[0]
+        K_ = K_ - K_.T
+        R = torch.linalg.matrix_exp(K_)
+        return torch.cat([R, torch.tensor(t)[:, None] + 0.05 * torch.randn(3, 1, generator=g)], dim=1)
+
+    c2w = {0: rand_pose([0.1, 0.0, -3.0]).requires_grad_(True), 1: rand_pose([-0.2, 0.1, -2.8]).requires_grad_(True)}
+    intr = torch.eye(4)[None].repeat(2, 1, 1)
+    intr[:, :3, :3] = torch.tensor(INTR)
+    intr[1, 0, 0], intr[1, 1, 1] = 590.0, 605.0
+    # rays: origins at the camera centres of the two frames, directions towards the unit sphere
+    n = B // 4 if maintain_shape else B // 2
+    owner = torch.zeros(B, dtype=torch.long)
+    owner[n:2 * n if maintain_shape else B] = 1
+    px = torch.rand(B, generator=g) * 300 + 170
+    py = torch.rand(B, generator=g) * 300 + 90
+    rays_o = torch.stack([c2w[int(o)][:, 3].detach() for o in owner]).clone().requires_grad_(True)
+    dirs = []
+    for b in range(B):
+        p_ = torch.linalg.inv(intr[int(owner[b]), :3, :3]) @ torch.tensor([px[b], py[b], 1.0])
+        dirs.append(c2w[int(owner[b])][:, :3].detach() @ (p_ / p_.norm()))
+    rays_d = torch.stack(dirs).clone().requires_grad_(True)
+    near, far = near_far_ref(rays_o.detach(), rays_d.detach())
+    z = (near + (far - near) * torch.sort(torch.rand(B, S, generator=g), dim=-1)[0]).requires_grad_(True)
+    weights = (torch.rand(B, S, generator=g) ** 4 * 0.2 * (torch.rand(B, S, generator=g) > 0.1) - 0.002).requires_grad_(True)
+    # models/renderer.py:261-272
+    dists = z[..., 1:] - z[..., :-1]
+    dists = torch.cat([dists, torch.Tensor([sample_dist]).expand(dists[..., :1].shape)], -1)
+    mid_z_vals = z + dists * 0.5
+    pts = (rays_o[:, None, :] + rays_d[:, None, :] * mid_z_vals[..., :, None]).reshape(-1, 3)
+    render_out = {"pts": pts, "weights": weights}
+    pixels_xy = torch.stack([px[:n] + 3.0 * torch.randn(n, generator=g), py[:n] + 3.0 * torch.randn(n, generator=g)], -1)
+    pixels_xy_corr = torch.stack([px[n:2 * n] + 3.0 * torch.randn(n, generator=g),
+                                  py[n:2 * n] + 3.0 * torch.randn(n, generator=g)], -1)
+    self_ = SimpleNamespace(flow_weight=0.1, detach_flow_on_sdf=detach_flow_on_sdf, maintain_shape=maintain_shape,
+                            pose_type="gf", pose_network=lambda i: c2w[int(i)], detach_ref=False,
+                            dataset=SimpleNamespace(intrinsics_all=intr), unit_sphere_weight=0.05)
+    ns = dict(self=self_, use_flow=True, render_out=render_out, torch=torch, F=F, to_hom=camera.to_hom,
+              img_id=torch.tensor(1), img_id_corr=torch.tensor(0), pose_all=None, pixels_xy=pixels_xy,
+              pixels_xy_corr=pixels_xy_corr)
+    exec(compile(src_flow, "exp_runner.py[%d:%d]" % span_flow, "exec"), ns)
+    exec(compile(src_unit, "exp_runner.py[%d:%d]" % span_unit, "exec"), ns)
+    flow_loss, unit_loss = ns["flow_loss"], ns["unit_sphere_loss"]
+    leaves = dict(rays_o=rays_o, rays_d=rays_d, z=z, weights=weights, c2w_0=c2w[0], c2w_1=c2w[1])
+    gf = torch.autograd.grad(flow_loss, list(leaves.values()), retain_graph=True, allow_unused=True)
+    gu = torch.autograd.grad(unit_loss, [weights], allow_unused=True)
+    d = {k: v.detach().numpy() for k, v in leaves.items()}
+    d.update({"gflow_" + k: (torch.zeros_like(v) if g_ is None else g_).numpy() for (k, v), g_ in zip(leaves.items(), gf)})
+    d.update(gunit_weights=gu[0].numpy(), flow_loss=flow_loss.detach().numpy(), unit_sphere_loss=unit_loss.detach().numpy(),
+             pts=pts.detach().numpy(), intrinsics=intr.numpy(), pixels_xy=pixels_xy.numpy(),
+             pixels_xy_corr=pixels_xy_corr.numpy(), maintain_shape=np.array(maintain_shape),
+             detach_flow_on_sdf=np.array(detach_flow_on_sdf), flow_weight=np.array(0.1), unit_sphere_weight=np.array(0.05),
+             sample_dist=np.array(sample_dist), ref_lines_flow=np.array(span_flow), ref_lines_unit=np.array(span_unit))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print(f"{name}: flow_loss={flow_loss.item():.6f} unit_sphere_loss={unit_loss.item():.6f} "
+          f"(exp_runner.py lines {span_flow}, {span_unit})")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -306,3 +386,5 @@ if __name__ == "__main__":
     render_case("full_3200_seg", B=64, n_samples=32, n_importance=0, up_steps=4, pose_kind="seg",
                 mask_weight=5.0, seed=202, barf=True, perturb_std=0.05)
     grid_case()
+    flow_case("flow_half", B=32, S=48, maintain_shape=False, seed=5)
+    flow_case("flow_quarter_detach", B=64, S=32, maintain_shape=True, detach_flow_on_sdf=True, seed=6)

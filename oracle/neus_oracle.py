@@ -501,3 +501,49 @@ def train_step(sdf_p: Params, col_p: Params, variance, pose34, intr_inv, px, py,
                  background_rgb=background_rgb, cos_anneal_ratio=cos_anneal_ratio)
     losses = loss_block(out, true_rgb, mask, igr_weight, mask_weight)
     return losses, out
+
+
+# ----------------------------------------------------------------------------------------
+# Flow / reprojection loss and unit-sphere loss  (exp_runner.py:605-688, 714-724)
+# pinned by tests/golden/flow_*.npz, which oracle/gen_golden.py produces by exec'ing those very
+# source lines of the reference
+# ----------------------------------------------------------------------------------------
+def sample_points(rays_o, rays_d, z_vals, sample_dist: float):
+    """pts [B,S,3] = o + d * mid_z with mid_z = z + dists/2, last dist = sample_dist (models/renderer.py:261-272)."""
+    dists = torch.cat([z_vals[:, 1:] - z_vals[:, :-1], torch.full_like(z_vals[:, :1], sample_dist)], dim=-1)
+    mid = z_vals + 0.5 * dists
+    return rays_o[:, None, :] + rays_d[:, None, :] * mid[:, :, None]
+
+
+def reprojection_error(pts, weights, c2w34, K33, xy):
+    """err [n,2] = sum_j w_j * (project(pts_j into the frame with pose c2w, intrinsics K) - xy)
+    (exp_runner.py:634-654): w2c = inverse of the 4x4 pose, pixel = (K cam)[:2] / (K cam)[2]."""
+    c2w = torch.cat([c2w34[:3, :4], torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=c2w34.dtype)], dim=0)
+    w2c = torch.linalg.inv(c2w)[:3]
+    cam = pts @ w2c[:, :3].T + w2c[:, 3]
+    pix = cam @ K33[:3, :3].T
+    uv = pix[..., :2] / pix[..., 2:3]
+    return ((uv - xy[:, None, :]) * weights[..., None]).sum(dim=1)
+
+
+def flow_loss(rays_o, rays_d, z_vals, weights, c2w_1, c2w_0, K_1, K_0, pixels_xy, pixels_xy_corr, sample_dist: float,
+              flow_weight: float, maintain_shape: bool = False, detach_flow_on_sdf: bool = False):
+    """exp_runner.py:605-688.  Batch layout [frame-0 rays | frame-1 rays | (additional rays)]; frame-0 points go
+    into frame 1 against pixels_xy, frame-1 points into frame 0 against pixels_xy_corr; each term is
+    mean(|err|) * flow_weight (F.l1_loss against zeros)."""
+    B = z_vals.shape[0]
+    pts = sample_points(rays_o, rays_d, z_vals, sample_dist)
+    if detach_flow_on_sdf:
+        weights = weights.detach()
+    n = B // 4 if maintain_shape else B // 2
+    second = slice(n, 2 * n) if maintain_shape else slice(n, B)
+    e0 = reprojection_error(pts[:n], weights[:n], c2w_1, K_1, pixels_xy)
+    e1 = reprojection_error(pts[second], weights[second], c2w_0, K_0, pixels_xy_corr)
+    return (e0.abs().mean() + e1.abs().mean()) * flow_weight
+
+
+def unit_sphere_loss(rays_o, rays_d, z_vals, weights, sample_dist: float, unit_sphere_weight: float):
+    """exp_runner.py:714-724: mean |w| over the samples whose point lies outside the unit sphere (mask detached)."""
+    pts = sample_points(rays_o, rays_d, z_vals, sample_dist)
+    outside = (pts.norm(dim=-1) > 1.0).detach()
+    return weights[outside].abs().mean() * unit_sphere_weight

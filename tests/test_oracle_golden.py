@@ -127,3 +127,27 @@ def test_grid_query_matches_reference():
     res = int(d["res"])
     u = O.extract_fields(sdf_p, [-1.01] * 3, [1.01] * 3, res)
     np.testing.assert_allclose(u.numpy(), d["u"], rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["flow_half", "flow_quarter_detach"])
+def test_flow_and_unit_sphere_losses_match_the_reference_lines(name):
+    """fixtures = the reference's own exp_runner.py lines 605-688 / 714-724 exec'd by oracle/gen_golden.py"""
+    d = load_golden(name)
+    lv = {k: t(d, k).requires_grad_(True) for k in ("rays_o", "rays_d", "z", "weights", "c2w_0", "c2w_1")}
+    K = t(d, "intrinsics")
+    sd = float(d["sample_dist"])
+    np.testing.assert_allclose(O.sample_points(lv["rays_o"], lv["rays_d"], lv["z"], sd).reshape(-1, 3).detach().numpy(),
+                               d["pts"], atol=1e-6)
+    fl = O.flow_loss(lv["rays_o"], lv["rays_d"], lv["z"], lv["weights"], lv["c2w_1"], lv["c2w_0"], K[1], K[0],
+                     t(d, "pixels_xy"), t(d, "pixels_xy_corr"), sd, float(d["flow_weight"]),
+                     maintain_shape=bool(d["maintain_shape"]), detach_flow_on_sdf=bool(d["detach_flow_on_sdf"]))
+    np.testing.assert_allclose(fl.item(), float(d["flow_loss"]), rtol=2e-5)
+    g = torch.autograd.grad(fl, list(lv.values()), allow_unused=True)
+    for (k, v), gi in zip(lv.items(), g):
+        ref = d["gflow_" + k]
+        got = np.zeros_like(ref) if gi is None else gi.numpy()
+        np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-4 * np.abs(ref).max() + 1e-9, err_msg=k)
+    ul = O.unit_sphere_loss(lv["rays_o"], lv["rays_d"], lv["z"], lv["weights"], sd, float(d["unit_sphere_weight"]))
+    np.testing.assert_allclose(ul.item(), float(d["unit_sphere_loss"]), rtol=1e-5)
+    gu, = torch.autograd.grad(ul, [lv["weights"]])
+    np.testing.assert_allclose(gu.numpy(), d["gunit_weights"], rtol=1e-5, atol=1e-9)
