@@ -207,7 +207,9 @@ class RenderCoreFunction(torch.autograd.Function):
         f = ops.composite_fwd(rays_o, rays_d, z, sdf, nrm, rgb, inv_s_d, sd, car, bg=bg, full=True)
         eik = f["eik"].sum(0)
         group = cfg.get("group")
-        if group is not None:
+        if cfg.get("eik_den") is not None:      # micro-batch of a larger step: partial numerator / whole-batch normaliser
+            eik = torch.stack([eik[0], cfg["eik_den"].reshape(()).to(eik.dtype)])
+        elif group is not None:
             torch.distributed.all_reduce(eik, group=group)      # global eikonal normaliser
         gradient_error = eik[0] / (eik[1] + 1e-5)
         ctx.fw, ctx.stash, ctx.cfg = fw, stash, cfg

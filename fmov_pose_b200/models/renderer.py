@@ -97,7 +97,10 @@ class NeuSRenderer:
         return z
 
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
-               eval=False, t_rand=None):
+               eval=False, t_rand=None, z_vals=None, eik_den=None):
+        """models/renderer.py:374-498.  Extras for micro-batched steps (train.TrainStep, `micro_batch`): `z_vals`
+        injects samples drawn earlier by `sample_z`; `eik_den` (device scalar) is the whole-batch sum(relax) so that
+        `gradient_error` is this call's numerator over the global normaliser (the calls' values then add up)."""
         self._check()
         if not rays_o.is_cuda:
             raise RuntimeError("fmov_pose_b200 renders on CUDA tensors only (no CPU fallback)")
@@ -116,11 +119,12 @@ class NeuSRenderer:
         need_bwd = torch.is_grad_enabled() and not eval
         with torch.no_grad():      # one packing launch serves the sampling queries and the fine stage
             fw = _fine.FineWeights(W_s, b_s, W_c, b_c, need_backward=need_bwd)
-        z_vals = self.sample_z(rays_o, rays_d, near, far, t_rand, qw=fw.query)
+        if z_vals is None:
+            z_vals = self.sample_z(rays_o, rays_d, near, far, t_rand, qw=fw.query)
         n_samples = z_vals.shape[1]
         inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)   # fields.py:294, renderer.py:290
         cfg = dict(sample_dist=sample_dist, cos_anneal_ratio=cos_anneal_ratio, background_rgb=background_rgb,
-                   need_backward=need_bwd, group=self.process_group, fine_weights=fw)
+                   need_backward=need_bwd, group=self.process_group, fine_weights=fw, eik_den=eik_den)
         if not need_bwd:
             with torch.no_grad():
                 outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)

@@ -92,7 +92,10 @@ class TrainStep:
         loss = color_loss + eik * self.igr_weight + bce * self.mask_weight
         return dict(loss=loss, color_loss=color_loss, eikonal_loss=eik, mask_loss=bce)
 
-    def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None):
+    def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None,
+                         micro_batch=None):
+        if micro_batch is not None and batch_size > micro_batch:
+            return self.forward_backward_chunked(img_id, batch_size, micro_batch, pixels, t_rand, cos_anneal_ratio, img_t)
         s = self.s
         ds, rend = s["dataset"], s["renderer"]
         pose = self.pose_of(img_id, img_t)
@@ -112,6 +115,73 @@ class TrainStep:
         if self.group is not None:
             self.allreduce_grads()
         return ls, out
+
+    def forward_backward_chunked(self, img_id, batch_size, micro_batch, pixels=None, t_rand=None, cos_anneal_ratio=1.0,
+                                 img_t=None):
+        """The same iteration for ray batches whose activation stash does not fit HBM at once (27 GB per 8192 rays at
+        64+64: BASELINE config C3 puts 32 K / 16 K rays on a GPU at N = 2 / 4).  Rays and the no-grad hierarchical
+        samples are produced for the whole batch; the fine stage + losses + backward then run per micro-batch against
+        the WHOLE-batch normalisers (sum(mask), ray count, and sum(relax), which depends only on the sample positions
+        and is therefore known before the fine stage), gradients accumulate, and the pose / ray-generation graph is
+        back-propagated once at the end.  Result == the one-shot step up to fp32 summation order."""
+        s = self.s
+        ds, rend = s["dataset"], s["renderer"]
+        dev = self.params[0].device
+        pose = self.pose_of(img_id, img_t)
+        data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
+        rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
+        true_rgb, mask = true_rgb.detach(), mask.detach()      # slices of the same cat() as the rays
+        ro = rays_o.detach().contiguous().requires_grad_(rays_o.requires_grad)      # cut: per-chunk backward stops here
+        rd = rays_d.detach().contiguous().requires_grad_(rays_d.requires_grad)
+        if t_rand is None and rend.perturb > 0:
+            t_rand = torch.rand([batch_size, 1], device=dev)
+        sd = 2.0 / rend.n_samples
+        with torch.no_grad():
+            near, far = ds.near_far_from_sphere(ro, rd)
+            z_all = rend.sample_z(ro, rd, near, far, t_rand)
+            dists = torch.cat([z_all[:, 1:] - z_all[:, :-1], torch.full_like(z_all[:, :1], sd)], dim=-1)
+            pts = ro[:, None, :] + rd[:, None, :] * (z_all + 0.5 * dists)[:, :, None]
+            relax_sum = (torch.linalg.norm(pts, ord=2, dim=-1) < 1.2).sum().float()        # renderer.py:343-346
+            del pts, dists
+            m = (mask > 0.5).float() if self.mask_weight > 0.0 else torch.ones_like(mask)
+            pack = torch.stack([m.sum(), torch.full((), float(batch_size), device=dev), relax_sum])
+            if self.group is not None:
+                torch.distributed.all_reduce(pack, group=self.group)
+            mask_sum, n_rays, eik_den = pack[0] + 1e-5, pack[1], pack[2]
+        for p in self.all_params:
+            p.grad = None
+        tot = None
+        keep = {}
+        for i in range(0, batch_size, micro_batch):
+            sl = slice(i, min(i + micro_batch, batch_size))
+            o_c, d_c = ro[sl], rd[sl]
+            nf = ds.near_far_from_sphere(o_c, d_c)
+            tr_c = None if t_rand is None else t_rand[sl]
+            # n_importance == 0: z keeps its link to near/far (renderer.py:390), so it is rebuilt inside render()
+            out = rend.render(o_c, d_c, nf[0], nf[1], cos_anneal_ratio=cos_anneal_ratio, t_rand=tr_c,
+                              background_rgb=self.background_rgb, z_vals=z_all[sl] if rend.n_importance > 0 else None,
+                              eik_den=eik_den)
+            col = ((out["color_fine"] - true_rgb[sl]) * m[sl]).abs().sum() / mask_sum
+            bce = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), m[sl], reduction="sum") / n_rays
+            eik = out["gradient_error"]
+            loss = col + eik * self.igr_weight + bce * self.mask_weight
+            loss.backward()
+            part = torch.stack([loss.detach(), col.detach(), eik.detach(), bce.detach()])
+            tot = part if tot is None else tot + part
+            for k in ("color_fine", "weight_sum", "depth_fine", "weight_max"):
+                keep.setdefault(k, []).append(out[k].detach())
+            del out, loss
+        roots, grads = [], []
+        for t_, g_ in ((rays_o, ro.grad), (rays_d, rd.grad)):
+            if t_.requires_grad and g_ is not None:
+                roots.append(t_)
+                grads.append(g_)
+        if roots:
+            torch.autograd.backward(roots, grads)
+        if self.group is not None:
+            self.allreduce_grads()
+        ls = dict(loss=tot[0], color_loss=tot[1], eikonal_loss=tot[2], mask_loss=tot[3])
+        return ls, {k: torch.cat(v, 0) for k, v in keep.items()}
 
     def flow_forward_backward(self, img_id_corr, batch_size, current_img_num, interval=1, additional_img_id=None,
                               img_id=None, indexs=None, add_pixels=None, t_rand=None, cos_anneal_ratio=1.0):
@@ -171,8 +241,8 @@ class TrainStep:
         for p, g in zip(self.all_params, torch._utils._unflatten_dense_tensors(flat, grads)):
             p.grad = g
 
-    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None):
-        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t)
+    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None, micro_batch=None):
+        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t, micro_batch)
         if self.optimizer is not None:
             self.optimizer.step()
         return ls, out

@@ -28,14 +28,14 @@ def test_flow_and_unit_sphere_kernels_vs_reference_lines(name):
     fl = flow.flow_loss(out, lv["rays_o"], lv["rays_d"], lv["c2w_1"], lv["c2w_0"], K[1], K[0], t(d, "pixels_xy").to(DEV),
                         t(d, "pixels_xy_corr").to(DEV), sd, float(d["flow_weight"]),
                         maintain_shape=bool(d["maintain_shape"]), detach_flow_on_sdf=bool(d["detach_flow_on_sdf"]))
-    assert abs(float(fl) - float(d["flow_loss"])) <= 1e-4 * abs(float(d["flow_loss"]))      # fp32 sums
+    assert abs(float(fl.detach()) - float(d["flow_loss"])) <= 1e-4 * abs(float(d["flow_loss"]))      # fp32 sums
     g = torch.autograd.grad(fl, list(lv.values()), allow_unused=True)
     for (k, v), gi in zip(lv.items(), g):
         ref = d["gflow_" + k]
         got = np.zeros_like(ref) if gi is None else gi.cpu().numpy()
         assert rel(got, ref) <= 1e-3 if np.abs(ref).max() > 0 else np.abs(got).max() == 0, (k, rel(got, ref))
     ul = flow.unit_sphere_loss(out, lv["rays_o"], lv["rays_d"], sd, float(d["unit_sphere_weight"]))
-    np.testing.assert_allclose(float(ul), float(d["unit_sphere_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(float(ul.detach()), float(d["unit_sphere_loss"]), rtol=1e-5)
     gu, = torch.autograd.grad(ul, [lv["weights"]])
     np.testing.assert_allclose(gu.cpu().numpy(), d["gunit_weights"], rtol=1e-5, atol=1e-9)
 
@@ -107,8 +107,8 @@ def test_pair_sampler_contract():
     np.testing.assert_allclose(data[:8, 3:6].detach().cpu().numpy(), rd_ref.numpy(), atol=3e-6)
     np.testing.assert_allclose(data[:8, 0:3].detach().cpu().numpy(), ro_ref.numpy(), atol=1e-6)
     col = ds.images[3][torch.from_numpy(ys2[idx]).long(), torch.from_numpy(xs2[idx]).long()]
-    np.testing.assert_array_equal(data[8:, 6:9].cpu().numpy(), col.cpu().numpy())
-    assert float(data[:, 9].min()) == 1.0
+    np.testing.assert_array_equal(data[8:, 6:9].detach().cpu().numpy(), col.cpu().numpy())
+    assert float(data[:, 9].detach().min()) == 1.0
 
 
 @pytest.mark.parametrize("cfg", [dict(n_samples=16, n_importance=16, maintain_shape=True),
@@ -167,8 +167,8 @@ def test_flow_iteration_fused_kernels_equal_autograd_on_pts(cfg):
                     [n_ for n_, _ in list(sc["sdf_network"].named_parameters())]))
     (la, ga, _), (lb, gb, _) = res
     for k in ("loss", "flow_loss", "unit_sphere_loss", "color_loss"):
-        np.testing.assert_allclose(float(la[k]), float(lb[k]), rtol=2e-4, err_msg=k)
-    assert float(la["flow_loss"]) > 0 and float(la["unit_sphere_loss"]) > 0
+        np.testing.assert_allclose(float(la[k].detach()), float(lb[k].detach()), rtol=2e-4, err_msg=k)
+    assert float(la["flow_loss"].detach()) > 0 and float(la["unit_sphere_loss"].detach()) > 0
     n_checked = 0
     for a, b in zip(ga, gb):
         assert (a is None) == (b is None)
