@@ -252,6 +252,61 @@ def measure_extras(scene, dev, use_graph=True):
     return out
 
 
+def measure_grid_sharded(scene, dev, group, world):
+    """Config C5 as stated: the 512^3 validate_mesh grid partitioned into x-plane slabs across the ranks (one launch per
+    rank) + all-gather of the slabs over NCCL.  Collective: every rank calls it; device-timed, max over ranks."""
+    import torch
+    from fmov_pose_b200.grid import extract_fields_sharded
+    res = 512
+    bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
+    ms_all = []
+    for it in range(3):
+        if group is not None:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        u = extract_fields_sharded(scene["renderer"], bmin, bmax, res, group=group)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if group is not None:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        ms_all.append(ms.item())
+        del u
+    ms = min(ms_all[1:])
+    torch.cuda.empty_cache()
+    return {"grid": "512^3", "n_gpus": world, "ms": ms, "sdf_queries_per_s": res ** 3 / ms * 1e3,
+            "tflops_algorithmic": res ** 3 * F_S / ms / 1e9,
+            "note": "x-plane slabs, one fmov_sdf_query_grid launch per rank + NCCL all-gather of the slabs; max over ranks"}
+
+
+def measure_c3_micro(dev):
+    """Config C3's 65,536-ray batch on ONE GPU through TrainStep(micro_batch=8192): whole-batch sampling and normalisers,
+    fine stage + backward per 8192-ray micro-batch (the 27 GB stash is reused), one Adam step."""
+    import torch
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    sc = synthetic.build_scene(device=dev, n_samples=64, n_importance=64, up_sample_steps=4, pose_type="seg")
+    ts = TrainStep(sc, mask_weight=5.0)
+    B = 65536
+    g = torch.Generator().manual_seed(7)
+    px = torch.randint(140, 500, [B], generator=g).to(dev)
+    py = torch.randint(60, 420, [B], generator=g).to(dev)
+    tr = torch.rand(B, 1, generator=g).to(dev)
+    ts.step(2, B, pixels=(px, py), t_rand=tr, micro_batch=8192)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(2):
+        ts.step(3 + i, B, pixels=(px, py), t_rand=tr, micro_batch=8192)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 2
+    return {"ms_per_step": ms, "rays_per_s": B / ms * 1e3,
+            "note": "65,536 rays x (64+64) on one GPU, 8 micro-batches of 8192 rays, eager launches"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -416,6 +471,18 @@ def main():
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_extras(scene, dev, use_graph)
+        try:
+            extras["c3_65536rays_micro_batched"] = measure_c3_micro(dev)
+        except Exception as e:          # secondary number: report, do not fail the bench
+            extras["c3_65536rays_micro_batched"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    if not args.no_extras:              # collective (all ranks): config C5 across the N GPUs of this run
+        try:
+            grid = measure_grid_sharded(scene, dev, group, world)
+        except Exception as e:
+            grid = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        if rank == 0:
+            extras = extras or {}
+            extras["c5_grid_512_sharded"] = grid
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 1, 3)

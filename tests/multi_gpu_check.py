@@ -50,6 +50,25 @@ def main():
     print(f"rank {rank}: worst grad rel diff sharded-vs-single = {worst:.2e}; colour loss {loss_parts[0].item():.6f} vs "
           f"{ls1['color_loss'].item():.6f}; eikonal {ls['eikonal_loss'].item():.6f} vs {ls1['eikonal_loss'].item():.6f} -> "
           f"{'OK' if ok else 'MISMATCH'}")
+    # config C5: grid partitioned into x-plane slabs across the ranks == the single-GPU grid (ragged: 50 planes / world)
+    from fmov_pose_b200.grid import extract_fields_sharded
+    rend = scene["renderer"]
+    bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
+    for res in (48, 50):
+        u_sh = extract_fields_sharded(rend, bmin, bmax, res, group=dist.group.WORLD)
+        u_1 = rend.extract_fields(bmin, bmax, res).view(res, res, res)
+        same = torch.equal(u_sh, u_1)
+        print(f"rank {rank}: sharded {res}^3 grid == single-GPU grid: {same}")
+        ok = ok and same
+    # micro-batched + ray-sharded step == one-shot sharded step
+    scene["renderer"].process_group = dist.group.WORLD
+    ls_m, _ = ts.forward_backward(2, B // world, pixels=(px[sl], py[sl]), t_rand=tr[sl], micro_batch=B // world // 4)
+    worst_m = 0.0
+    for a, p in zip(sharded, ts.all_params):
+        if a.norm().item() > 0:
+            worst_m = max(worst_m, ((p.grad - a).norm() / a.norm()).item())
+    print(f"rank {rank}: micro-batched sharded step vs one-shot sharded step: worst grad rel diff {worst_m:.2e}")
+    ok = ok and worst_m < 5e-3
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -150,3 +150,42 @@ def test_ray_sharded_losses_and_grad_allreduce_gloo_world2():
     port = 29500 + (os.getpid() % 500)
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1), dict(ret)
+
+
+# ---- grid partitioning of the dense SDF query (config C5) ----------------------------------------------------
+def test_grid_slabs_cover_the_grid_exactly():
+    from fmov_pose_b200.grid import slab_of
+    for res in (1, 7, 64, 100, 512):
+        for world in (1, 2, 3, 4, 8):
+            nxt = 0
+            sizes = []
+            for r in range(world):
+                first, n = slab_of(res, world, r)
+                assert first == nxt and n >= 0
+                nxt += n
+                sizes.append(n)
+            assert nxt == res and max(sizes) - min(sizes) <= 1
+    assert slab_of(512, 8, 3) == (192, 64)
+
+
+def _grid_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fmov_pose_b200.grid import gather_slabs, slab_of
+    ok = True
+    for res in (6, 7):                      # even split and ragged split (7 planes over 2 ranks)
+        full = torch.arange(res ** 3, dtype=torch.float32)
+        first, n = slab_of(res, world, rank)
+        local = full[first * res * res: (first + n) * res * res].clone()
+        ok = ok and torch.equal(gather_slabs(local, res, dist.group.WORLD), full)
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_grid_slab_gather_gloo_world2():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 30100 + (os.getpid() % 500)
+    mp.spawn(_grid_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1), dict(ret)
