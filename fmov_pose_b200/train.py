@@ -2,11 +2,43 @@
 kernels, optionally ray-sharded across ranks: every rank renders its own ray shard with
 replicated weights; the three whole-batch normalisers (sum(mask), sum(relax), ray count) and the
 parameter gradients are all-reduced so that N-GPU results equal the single-GPU step on the union batch."""
+import math
+
 import torch
 import torch.nn.functional as F
 
 from . import flow as _flow
 from .models import camera as _camera
+
+
+class LRSchedule:
+    """Runner.update_learning_rate (exp_runner.py:1049-1087) as a pure host function: linear warm-up then cosine decay to
+    `learning_rate_alpha` for the networks; for pose_type "seg" each pose MLP follows its own cosine over its own
+    progress counter (`step / max_pro_iteration` with floor `pose_alpha`, or the global `step / end_iter` with floor
+    `learning_rate_alpha` for "_wo_global_conf" experiments)."""
+
+    def __init__(self, learning_rate=5e-4, learning_rate_alpha=0.05, warm_up_end=5000, end_iter=300000, pose_lr=5e-4,
+                 pose_alpha=0.5, max_pro_iteration=1000, wo_global_conf=False):
+        self.learning_rate, self.learning_rate_alpha = learning_rate, learning_rate_alpha
+        self.warm_up_end, self.end_iter = warm_up_end, end_iter
+        self.pose_lr, self.pose_alpha, self.max_pro_iteration = pose_lr, pose_alpha, max_pro_iteration
+        self.wo_global_conf = wo_global_conf
+
+    @staticmethod
+    def _cosine(progress, alpha):
+        return (math.cos(math.pi * progress) + 1.0) * 0.5 * (1 - alpha) + alpha
+
+    def net_lr(self, iter_step):
+        if iter_step < self.warm_up_end:
+            return self.learning_rate * (iter_step / self.warm_up_end)
+        return self.learning_rate * self._cosine((iter_step - self.warm_up_end) / (self.end_iter - self.warm_up_end),
+                                                 self.learning_rate_alpha)
+
+    def pose_mlp_lr(self, step):
+        """`step` = the pose MLP's own progress counter after this iteration's increment (SegLearnPose.step_progress)"""
+        if self.wo_global_conf:
+            return self.pose_lr * self._cosine(step / self.end_iter, self.learning_rate_alpha)
+        return self.pose_lr * self._cosine(step / self.max_pro_iteration, self.pose_alpha)
 
 
 class TrainStep:
@@ -35,8 +67,19 @@ class TrainStep:
             if capturable:        # learning rates live on the device so a captured step follows the LR schedule
                 lr = torch.tensor(float(lr), device=dev)
                 pose_lr = torch.tensor(float(pose_lr), device=dev)
+            # one Adam over [networks | pose MLP 0 | pose MLP 1 | ...]: the reference keeps one optimizer per pose MLP
+            # (exp_runner.py:258-262, 812-816); torch's Adam keeps its step count per parameter and skips parameters
+            # without a gradient, so param groups give the same updates with one fused launch set
             groups = [dict(params=self.params, lr=lr)]
-            if self.pose_params:
+            self.pose_group_of = {}
+            mlps = getattr(scene["pose_network"], "pose_mlps", None)
+            if mlps is not None:
+                for k, mlp in enumerate(mlps):
+                    ps = [p for p in mlp.parameters() if p.requires_grad]
+                    if ps:
+                        self.pose_group_of[k] = len(groups)
+                        groups.append(dict(params=ps, lr=pose_lr.clone() if torch.is_tensor(pose_lr) else pose_lr))
+            elif self.pose_params:
                 groups.append(dict(params=self.pose_params, lr=pose_lr))
             self.optimizer = torch.optim.Adam(groups, fused=True, capturable=capturable)
             if capturable:        # state is created up front: lazy creation inside a capture would be replayed
@@ -46,14 +89,38 @@ class TrainStep:
                                                        exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
         self.capturable = capturable
 
-    def set_lr(self, lr, pose_lr=None):
-        """exp_runner.py:1049-1087 writes param_group['lr'] every iteration; device-side when capturable."""
-        vals = [lr, lr if pose_lr is None else pose_lr]
-        for grp, v in zip(self.optimizer.param_groups, vals):
-            if torch.is_tensor(grp["lr"]):
-                grp["lr"].fill_(float(v))
-            else:
-                grp["lr"] = float(v)
+    @staticmethod
+    def _write_lr(grp, v):
+        if torch.is_tensor(grp["lr"]):
+            grp["lr"].fill_(float(v))
+        else:
+            grp["lr"] = float(v)
+
+    def set_lr(self, lr, pose_lr=None, pose_mlp_lrs=None):
+        """exp_runner.py:1049-1087 writes param_group['lr'] every iteration; device-side when capturable.
+        `pose_lr` applies to every pose group, `pose_mlp_lrs` = {pose MLP index: lr} to single pose MLPs."""
+        groups = self.optimizer.param_groups
+        self._write_lr(groups[0], lr)
+        for grp in groups[1:]:
+            self._write_lr(grp, lr if pose_lr is None else pose_lr)
+        for k, v in (pose_mlp_lrs or {}).items():
+            if k in getattr(self, "pose_group_of", {}):
+                self._write_lr(groups[self.pose_group_of[k]], v)
+
+    def update_learning_rate(self, schedule, iter_step, pose_mlp_index_set=None):
+        """Runner.update_learning_rate (exp_runner.py:1049-1087): networks from the global iteration; for SegLearnPose
+        every pose MLP in `pose_mlp_index_set` advances its progress counter and gets its own rate."""
+        groups = self.optimizer.param_groups
+        self._write_lr(groups[0], schedule.net_lr(iter_step))
+        pn = self.s["pose_network"]
+        if hasattr(pn, "pose_mlps"):
+            for k in (pose_mlp_index_set or ()):
+                step = float(pn.step_progress(k))
+                if k in self.pose_group_of:
+                    self._write_lr(groups[self.pose_group_of[k]], schedule.pose_mlp_lr(step))
+        else:        # pose_type gf / se3: the reference has no separate pose schedule (only self.optimizer's groups)
+            for grp in groups[1:]:
+                self._write_lr(grp, schedule.net_lr(iter_step))
 
     def pose_of(self, img_id, img_t=None):
         s = self.s

@@ -366,6 +366,41 @@ def flow_case(name, *, B, S, maintain_shape, detach_flow_on_sdf=False, seed=0):
           f"(exp_runner.py lines {span_flow}, {span_unit})")
 
 
+def lr_case():
+    """Runner.update_learning_rate (exp_runner.py:1049-1087), exec'd from the reference source on a fake Runner."""
+    from types import SimpleNamespace
+    src, span = _reference_block("def update_learning_rate(self, pose_mlp_index_set=None):", "def file_backup(self):")
+    ns = dict(np=np, torch=torch)
+    exec(compile(src, "exp_runner.py[%d:%d]" % span, "exec"), ns)
+    fn = ns["update_learning_rate"]
+    d = {}
+    for tag, base_dir in (("global", "exp/AP13/ours"), ("wo_global", "exp/AP13/ours_wo_global_conf")):
+        progress = torch.zeros(3)
+
+        def step_progress(i):
+            progress[i] += 1
+            return progress[i]
+        opt = SimpleNamespace(param_groups=[{"lr": 0.0}])
+        pose_opts = [SimpleNamespace(param_groups=[{"lr": 0.0}]) for _ in range(3)]
+        self_ = SimpleNamespace(iter_step=0, warm_up_end=50, learning_rate_alpha=0.05, end_iter=400, learning_rate=5e-4,
+                                optimizer=opt, pose_type="seg", pose_network=SimpleNamespace(step_progress=step_progress),
+                                base_exp_dir=base_dir, max_pro_iteration=120, pose_alpha=0.5, pose_optimizers=pose_opts,
+                                pose_lr=3e-4)
+        iters = list(range(0, 400, 7))
+        net, pose = [], []
+        for it in iters:
+            self_.iter_step = it
+            fn(self_, pose_mlp_index_set={it % 3})
+            net.append(opt.param_groups[0]["lr"])
+            pose.append([po.param_groups[0]["lr"] for po in pose_opts])
+        d[tag + ".iters"] = np.array(iters)
+        d[tag + ".net_lr"] = np.array(net, dtype=np.float64)
+        d[tag + ".pose_lr"] = np.array(pose, dtype=np.float64)
+    d["ref_lines"] = np.array(span)
+    np.savez_compressed(os.path.join(OUT, "lr_schedule.npz"), **d)
+    print("lr_schedule.npz written (exp_runner.py lines %d-%d)" % span)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
@@ -386,5 +421,6 @@ if __name__ == "__main__":
     render_case("full_3200_seg", B=64, n_samples=32, n_importance=0, up_steps=4, pose_kind="seg",
                 mask_weight=5.0, seed=202, barf=True, perturb_std=0.05)
     grid_case()
+    lr_case()
     flow_case("flow_half", B=32, S=48, maintain_shape=False, seed=5)
     flow_case("flow_quarter_detach", B=64, S=32, maintain_shape=True, detach_flow_on_sdf=True, seed=6)

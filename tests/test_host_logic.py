@@ -189,3 +189,37 @@ def test_grid_slab_gather_gloo_world2():
     port = 30100 + (os.getpid() % 500)
     mp.spawn(_grid_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1), dict(ret)
+
+
+# ---- learning-rate schedule + per-pose-MLP optimiser groups -----------------------------------
+@pytest.mark.parametrize("tag", ["global", "wo_global"])
+def test_lr_schedule_matches_the_reference_function(tag):
+    """fixture = Runner.update_learning_rate exec'd from the reference source (oracle/gen_golden.py::lr_case)"""
+    from fmov_pose_b200.train import LRSchedule, TrainStep
+    d = load_golden("lr_schedule")
+    sch = LRSchedule(learning_rate=5e-4, learning_rate_alpha=0.05, warm_up_end=50, end_iter=400, pose_lr=3e-4,
+                     pose_alpha=0.5, max_pro_iteration=120, wo_global_conf=(tag == "wo_global"))
+
+    class _Pose(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pose_mlps = torch.nn.ModuleList([torch.nn.Linear(2, 2) for _ in range(3)])
+            self.progress = torch.zeros(3)
+
+        def step_progress(self, i):
+            self.progress[i] += 1
+            return self.progress[i]
+
+    class _R:
+        process_group = None
+    scene = dict(renderer=_R(), sdf_network=torch.nn.Linear(3, 3), deviation_network=torch.nn.Module(),
+                 color_network=torch.nn.Module(), pose_network=_Pose())
+    ts = TrainStep(scene, lr=0.0, pose_lr=0.0)
+    assert len(ts.optimizer.param_groups) == 4 and ts.pose_group_of == {0: 1, 1: 2, 2: 3}
+    net, pose = [], []
+    for it in d[tag + ".iters"]:
+        ts.update_learning_rate(sch, int(it), {int(it) % 3})
+        net.append(ts.optimizer.param_groups[0]["lr"])
+        pose.append([ts.optimizer.param_groups[1 + k]["lr"] for k in range(3)])
+    np.testing.assert_allclose(net, d[tag + ".net_lr"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(pose, d[tag + ".pose_lr"], rtol=1e-12, atol=0)
