@@ -218,6 +218,7 @@ class RenderCoreFunction(torch.autograd.Function):
         ctx.save_for_backward(rays_o, rays_d, z, inv_s_d, sdf, nrm, rgb, ge)
         outs = (f["color"], f["weight_sum"], f["weight_max"], f["depth"], f["weights"], f["cdf"], f["inside"],
                 f["mid_z"], f["pts"], sdf.view(-1, 1), nrm.view(B, S, 3), gradient_error)
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None (NULL pointers), not as zero-filled tensors
         ctx.mark_non_differentiable(f["weight_max"], f["cdf"], f["inside"], f["mid_z"], f["pts"], outs[9])
         return outs
 

@@ -155,3 +155,50 @@ def test_micro_batched_step_equals_one_shot_step(cfg):
             assert rel(b.cpu().numpy(), a.cpu().numpy()) <= 5e-3, rel(b.cpu().numpy(), a.cpu().numpy())
             n += 1
     assert n > 40
+
+
+def test_training_trajectory_tracks_the_oracle_over_adam_steps():
+    """30 consecutive Adam iterations (render -> losses -> backward -> Adam) of this path and of the oracle (the
+    reference's PyTorch fp32 autograd formulation, run on the same GPU) from identical initial weights, with identical
+    pixels / jitter and the oracle fed this path's z samples: the loss trajectories must stay together (fp16 operand
+    rounding does not accumulate into drift) and the loss must go down."""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    B, n_steps, lr = 256, 30, 5e-4
+    sc = synthetic.build_scene(device=DEV, n_images=4, n_samples=32, n_importance=32, up_sample_steps=2, pose_type="seg")
+    for m in sc["pose_network"].pose_mlps:
+        m.disable_grad()                       # fixed poses: the trajectory below is the networks' (Adam over sdf+colour+variance)
+    ts = TrainStep(sc, mask_weight=5.0, lr=lr)
+    sdf_p = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in sc["sdf_network"].named_parameters()}
+    col_p = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in sc["color_network"].named_parameters()}
+    var = sc["deviation_network"].variance.detach().clone().requires_grad_(True)
+    leaves = [p for p in list(sdf_p.values()) + [var] + list(col_p.values()) if p.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=lr)
+    ds = sc["dataset"]
+    g = torch.Generator().manual_seed(21)
+    mine, ref = [], []
+    for it in range(n_steps):
+        img = it % 4
+        px = torch.randint(170, 470, [B], generator=g).to(DEV)
+        py = torch.randint(90, 390, [B], generator=g).to(DEV)
+        tr = torch.rand(B, 1, generator=g).to(DEV)
+        ls, out = ts.step(img, B, pixels=(px, py), t_rand=tr)
+        mine.append(float(ls["loss"].detach()))
+        with torch.device(DEV):                # the oracle's factory calls follow the default device
+            pose = ts.pose_of(img).detach()
+            ro, rd = O.gen_rays(pose, ds.intrinsics_all_inv[img], px, py)
+            nr, fr = O.near_far_from_sphere(ro, rd)
+            r = O.render(sdf_p, col_p, var, ro, rd, nr, fr, n_samples=32, n_importance=32, up_sample_steps=2,
+                         cos_anneal_ratio=1.0, z_vals=out["z_vals"].detach())
+            rl = O.loss_block(r, ds.images[img][(py, px)], ds.masks[img][(py, px)][:, :1], 0.1, 5.0)
+            opt.zero_grad()
+            rl["loss"].backward()
+            opt.step()
+        ref.append(float(rl["loss"].detach()))
+    mine, ref = np.array(mine), np.array(ref)
+    assert np.abs(mine - ref).max() <= 1e-2 * np.abs(ref).max(), (mine, ref)
+    assert mine[-5:].mean() < 0.8 * mine[:5].mean(), mine            # it trains
+    # the weights stayed together as well (relative to the distance travelled from the initial weights)
+    w_mine = sc["sdf_network"].lin4.weight_v.detach()
+    w_ref = sdf_p["lin4.weight_v"].detach()
+    assert float((w_mine - w_ref).abs().mean()) <= 0.1 * lr * n_steps
