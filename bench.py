@@ -321,6 +321,15 @@ def main():
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that printf to fd 1 (NCCL prints its version banner there when
+    # NCCL_DEBUG is set on the box) are sent to stderr, the line is written to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -343,7 +352,7 @@ def main():
                                            "/root/reference does not exist on the GPU box)"},
                 "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import torch
@@ -503,7 +512,7 @@ def main():
                 "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "extras": extras,
                 "tensor_frac_whole_step": flops_per_ray(n, m) * value / world / 1e12 / peak_tf}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if group is not None:
         # teardown: graphs that hold NCCL kernels must be gone before the communicator is destroyed; measured in round 1:
         # destroy_process_group() with live captured graphs never returns (the run had already printed its line), so
