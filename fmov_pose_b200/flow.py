@@ -34,6 +34,10 @@ class FlowReprojFunction(torch.autograd.Function):
         if K33.stride(1) != 1:
             K33 = K33.contiguous()
         B, S = z.shape
+        if not (rays_o.shape == (B, 3) and rays_d.shape == (B, 3) and weights.shape == (B, S) and xy.shape == (B, 2)
+                and w2c34.shape == (3, 4) and K33.shape == (3, 3)):
+            raise ValueError(f"flow reprojection: inconsistent shapes rays {tuple(rays_o.shape)} z {tuple(z.shape)} "
+                             f"weights {tuple(weights.shape)} xy {tuple(xy.shape)}")
         err = torch.empty(B, 2, dtype=torch.float32, device=z.device)
         L.check(L.lib().fmov_flow_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                       L.ptr(weights), L.ptr(w2c34), L.ptr(K33), K33.stride(0), L.ptr(xy), L.ptr(err),
