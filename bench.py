@@ -167,6 +167,8 @@ def time_cpu(B, n, m, steps_up, warm, iters):
     return B / med, med, threads
 
 
+# algorithmic HBM bytes per sample point of the MLP kernels (16 KiB blocks per 128-point tile x 128 B)
+KERNEL_BYTES_PER_POINT = {"fine_fwd": 15.3e3, "fine_bwd": 33.9e3, "dw": 22.5e3}
 # DRAM traffic of the MLP kernels per sample point, from `ncu --set full` (dram__bytes_read + dram__bytes_write,
 # profiles/r1_final_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 4.02 GB, fine_bwd 9.85 GB, dw 5.90 GB
 NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 4.023e9 / 262144, "fine_bwd": 9.846e9 / 262144, "dw": 5.898e9 / 262144}
@@ -477,6 +479,11 @@ def main():
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "share_of_step": (mlp[top]["ms"] / n_prof) / step_ms,
                 "kernel_ms_per_step": {k: v["ms"] / n_prof for k, v in prof.items()}}
+        # the same kernel against the HBM roofline: the stash design makes the fine-stage kernels HBM-bound
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        hbm_ach = KERNEL_BYTES_PER_POINT[top] * B * (n + m) / (avg_ms * 1e-3) / 1e9
+        roof["hbm_view"] = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                            "algorithmic_bytes_per_point": KERNEL_BYTES_PER_POINT[top]}
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         extras = measure_extras(scene, dev, use_graph)

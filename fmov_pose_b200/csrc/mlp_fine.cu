@@ -13,8 +13,9 @@
 //   reverse sweep delta_7 = W_8[0,:]*sigma_7;  v_l = W_l^T delta_l;  delta_{l-1} = v_l*sigma_{l-1};  n = J_e^T g_e
 //   adjoint pass dbar_l = W_l vbar_l;  vbar_{l+1} = dbar_l*sigma_l;  q_l = 100*dbar_l*delta_l*(1-sigma_l)
 //   backward     zbar_{l-1} = (W_l^T zbar_l)*sigma_{l-1} + q_{l-1}
-// fp16 operands in the forward (value pass, reverse sweep, colour net), bf16 for every gradient tile; fp32
-// accumulation in TMEM; fp32 epilogue math.
+// fp16 operands in the forward (value pass, reverse sweep, colour net); gradient tiles are fp16 with a per-step
+// power-of-two loss scale derived from max|upstream gradient| (fmov_grad_amax; bf16 tiles missed the 1e-2 gradient
+// bar on cancellation-heavy sums); fp32 accumulation in TMEM; fp32 epilogue math.
 // Epilogue warpgroups per tile slot (FMOV_FINE_WGS, default 2): with two, warpgroup w owns columns [128w, 128w+128) of
 // every 256-wide tile (32-column chunks hb = 4w..4w+3); warpgroup WGS-1 additionally owns the per-row state (normal,
 // x-bar, PE adjoints) and the narrow N=48 / N=16 steps.  A thread still only re-reads stash rows/chunks it wrote itself.

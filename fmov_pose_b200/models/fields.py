@@ -16,11 +16,6 @@ from .. import ops as _ops
 from .. import packing as _packing
 
 
-def _wn_linear(d_in, d_out, weight_norm):
-    lin = nn.Linear(d_in, d_out)
-    return lin
-
-
 class _WeightNormMLP(nn.Module):
     def _eff(self, l):
         lin = getattr(self, "lin" + str(l))
