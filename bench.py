@@ -227,17 +227,20 @@ def measure_extras(scene, dev, use_graph=True):
     sc2 = synthetic.build_scene(device=dev, n_samples=32, n_importance=0, up_sample_steps=4, pose_type="seg")
     ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph)
     g = torch.Generator().manual_seed(3)
-    B2 = 1024
+    B2, Bf = 1024, 512          # maintain_shape: 512 rays of the current frame + 512 rays of an earlier frame
     n_it = 24
     px = torch.randint(140, 500, [n_it, B2], generator=g).to(dev)
     py = torch.randint(60, 420, [n_it, B2], generator=g).to(dev)
     tr = torch.rand(n_it, B2, 1, generator=g).to(dev)
+    frames = [(1 + i % 3, i % 3) for i in range(n_it)]
     if use_graph:
         from fmov_pose_b200.train import GraphedTrainStep
-        g2 = GraphedTrainStep(ts2, B2)
-        step2 = lambda i: g2.step(i % 4, px[i], py[i], tr[i])
+        g2 = GraphedTrainStep(ts2, Bf, two_frames=True)
+        step2 = lambda i: g2.step(frames[i][0], px[i, :Bf], py[i, :Bf], tr[i], add_img_id=frames[i][1],
+                                  add_px=px[i, Bf:], add_py=py[i, Bf:])
     else:
-        step2 = lambda i: ts2.step(i % 4, B2, pixels=(px[i], py[i]), t_rand=tr[i])
+        step2 = lambda i: ts2.step(frames[i][0], Bf, pixels=(px[i, :Bf], py[i, :Bf]), t_rand=tr[i],
+                                   additional_img_id=frames[i][1], add_pixels=(px[i, Bf:], py[i, Bf:]))
     for i in range(8):
         step2(i)
     torch.cuda.synchronize()
@@ -249,7 +252,8 @@ def measure_extras(scene, dev, use_graph=True):
     ms = e0.elapsed_time(e1) / (n_it - 8)
     out["c2_literal_1024rays_32+0"] = {"ms_per_step": ms, "rays_per_s": B2 / ms * 1e3,
                                        "note": "confs/ho3d_virtual.conf as shipped (n_samples 32, n_importance 0, "
-                                               "maintain_shape 2x512 rays); " +
+                                               "maintain_shape: 512 rays of the current frame + 512 of an earlier "
+                                               "frame, two pose MLPs trained); " +
                                                ("CUDA-graph replay" if use_graph else "eager, host-launch bound")}
     return out
 

@@ -160,13 +160,22 @@ class TrainStep:
         return dict(loss=loss, color_loss=color_loss, eikonal_loss=eik, mask_loss=bce)
 
     def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None,
-                         micro_batch=None):
+                         micro_batch=None, additional_img_id=None, add_pixels=None, add_img_t=None):
+        """One ordinary iteration.  `additional_img_id` (with `maintain_shape`, exp_runner.py:512-548): `batch_size` more
+        rays of a second, already registered frame through ITS pose are appended, so the render sees 2*batch_size rays
+        (t_rand then has 2*batch_size rows) and two pose MLPs receive gradients."""
         if micro_batch is not None and batch_size > micro_batch:
+            assert additional_img_id is None, "micro-batching takes one frame per step"
             return self.forward_backward_chunked(img_id, batch_size, micro_batch, pixels, t_rand, cos_anneal_ratio, img_t)
         s = self.s
         ds, rend = s["dataset"], s["renderer"]
         pose = self.pose_of(img_id, img_t)
         data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
+        if additional_img_id is not None:
+            add_pose = self.pose_of(additional_img_id, add_img_t)
+            add_data, _ = ds.gen_random_rays_at(additional_img_id, batch_size, add_pose, pixels=add_pixels,
+                                                img_idx_t=add_img_t)
+            data = torch.cat([data, add_data], dim=0)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         near, far = ds.near_far_from_sphere(rays_o, rays_d)
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
@@ -308,8 +317,10 @@ class TrainStep:
         for p, g in zip(self.all_params, torch._utils._unflatten_dense_tensors(flat, grads)):
             p.grad = g
 
-    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None, micro_batch=None):
-        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t, micro_batch)
+    def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None, micro_batch=None,
+             additional_img_id=None, add_pixels=None, add_img_t=None):
+        ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t, micro_batch,
+                                        additional_img_id, add_pixels, add_img_t)
         if self.optimizer is not None:
             self.optimizer.step()
         return ls, out
@@ -325,15 +336,22 @@ class GraphedTrainStep:
     scalars (`TrainStep.set_lr`), the activation stash is the recycled Stash pool buffer.  Nothing in the step reads
     back to the host, so one replay == one reference iteration (exp_runner.py:497-599, 772-816)."""
 
-    def __init__(self, ts, batch_size, cos_anneal_ratio=1.0):
+    def __init__(self, ts, batch_size, cos_anneal_ratio=1.0, two_frames=False):
+        """`two_frames`: the maintain_shape iteration of the shipped confs (exp_runner.py:512-548): `batch_size` rays
+        of the current frame + `batch_size` rays of an earlier frame in one render; `step()` then also takes the second
+        frame's index and pixels, and t_rand has 2*batch_size rows."""
         assert ts.optimizer is None or ts.capturable, "build the TrainStep with capturable=True"
         self.ts, self.B, self.car = ts, int(batch_size), float(cos_anneal_ratio)
+        self.two = bool(two_frames)
         dev = ts.params[0].device
         self.dev = dev
         self.px = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.py = torch.zeros(self.B, dtype=torch.int64, device=dev)
-        self.tr = torch.zeros(self.B, 1, dtype=torch.float32, device=dev)
+        self.tr = torch.zeros(self.B * (2 if self.two else 1), 1, dtype=torch.float32, device=dev)
         self.img = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.px2 = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.py2 = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.img2 = torch.zeros(1, dtype=torch.int64, device=dev)
         self.graphs = {}
         self.pool = None
         self.launches_per_step = 0
@@ -345,11 +363,16 @@ class GraphedTrainStep:
         capture (quantise it on the caller side if anneal_end > 0)."""
         self.car = float(ratio)
 
-    def _body(self, img_id):
-        return self.ts.step(img_id, self.B, pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car,
-                            img_t=self.img)
+    def _kw(self, add_img_id):
+        kw = dict(pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car, img_t=self.img)
+        if self.two:
+            kw.update(additional_img_id=add_img_id, add_pixels=(self.px2, self.py2), add_img_t=self.img2)
+        return kw
 
-    def _capture(self, key, img_id):
+    def _body(self, img_id, add_img_id=None):
+        return self.ts.step(img_id, self.B, **self._kw(add_img_id))
+
+    def _capture(self, key, img_id, add_img_id=None):
         from . import _lib as L
         from .fine import Stash
         ts = self.ts
@@ -358,8 +381,7 @@ class GraphedTrainStep:
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             # eager pass without the optimizer: one-time library/cuBLAS initialisation and the stash allocation
-            ts.forward_backward(img_id, self.B, pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car,
-                                img_t=self.img)
+            ts.forward_backward(img_id, self.B, **self._kw(add_img_id))
         cur.wait_stream(side)
         torch.cuda.synchronize()
         for p in ts.all_params:
@@ -369,22 +391,27 @@ class GraphedTrainStep:
         n0 = L.n_calls
         # thread_local: other threads (NCCL watchdog, autograd workers) may keep calling the CUDA runtime during capture
         with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-            ls, out = self._body(img_id)
+            ls, out = self._body(img_id, add_img_id)
         self.launches_per_step = L.n_calls - n0
         if self.pool is None:
             self.pool = g.pool()
         self.graphs[key] = (g, ls, out)
 
-    def step(self, img_id, px, py, t_rand):
-        """px, py int64 [B], t_rand fp32 [B,1] (device or pinned host tensors) -> (losses, render dict): static
-        tensors that the next replay overwrites."""
+    def step(self, img_id, px, py, t_rand, add_img_id=None, add_px=None, add_py=None):
+        """px, py int64 [B], t_rand fp32 [B,1] ([2B,1] with two_frames) (device or pinned host tensors) -> (losses,
+        render dict): static tensors that the next replay overwrites."""
         self.px.copy_(px, non_blocking=True)
         self.py.copy_(py, non_blocking=True)
-        self.tr.copy_(t_rand.reshape(self.B, 1), non_blocking=True)
+        self.tr.copy_(t_rand.reshape(self.tr.shape), non_blocking=True)
         self.img.fill_(int(img_id))
         key = (self.ts.graph_key(img_id), self.car)
+        if self.two:
+            self.px2.copy_(add_px, non_blocking=True)
+            self.py2.copy_(add_py, non_blocking=True)
+            self.img2.fill_(int(add_img_id))
+            key = key + (self.ts.graph_key(add_img_id),)
         if key not in self.graphs:
-            self._capture(key, img_id)
+            self._capture(key, img_id, add_img_id)
         g, ls, out = self.graphs[key]
         g.replay()
         return ls, out

@@ -205,3 +205,52 @@ def test_training_trajectory_tracks_the_oracle_over_adam_steps():
     w_mine = sc["sdf_network"].lin4.weight_v.detach()
     w_ref = sdf_p["lin4.weight_v"].detach()
     assert float((w_mine - w_ref).abs().mean()) <= 0.1 * lr * n_steps
+
+
+def test_two_frame_maintain_shape_iteration_eager_and_graphed():
+    """The shipped confs' maintain_shape iteration (exp_runner.py:512-548): B rays of the current frame + B rays of an
+    earlier frame in one render.  (a) with the same frame twice it equals a single-frame step on the concatenated pixels;
+    (b) with two frames both pose MLPs (and only those) receive gradients; (c) graph replay == eager."""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import GraphedTrainStep, TrainStep
+    B = 128
+    g = torch.Generator().manual_seed(17)
+    px = torch.randint(200, 440, [2 * B], generator=g).to(DEV)
+    py = torch.randint(120, 360, [2 * B], generator=g).to(DEV)
+    tr = torch.rand(2 * B, 1, generator=g).to(DEV)
+    mk = lambda: synthetic.build_scene(device=DEV, n_images=6, n_samples=32, n_importance=0, pose_type="seg")
+    # (a)
+    ts1 = TrainStep(mk(), mask_weight=5.0, optimizer=False)
+    l1, _ = ts1.forward_backward(2, 2 * B, pixels=(px, py), t_rand=tr)
+    ts2 = TrainStep(mk(), mask_weight=5.0, optimizer=False)
+    l2, o2 = ts2.forward_backward(2, B, pixels=(px[:B], py[:B]), t_rand=tr, additional_img_id=2, add_pixels=(px[B:], py[B:]))
+    assert o2["color_fine"].shape[0] == 2 * B
+    np.testing.assert_allclose(float(l2["loss"].detach()), float(l1["loss"].detach()), rtol=1e-5)
+    for a, b in zip(ts1.all_params, ts2.all_params):
+        assert (a.grad is None) == (b.grad is None)
+        if a.grad is not None and float(a.grad.abs().max()) > 0:
+            assert rel(b.grad.cpu().numpy(), a.grad.cpu().numpy()) <= 2e-3
+    # (b)
+    sc = mk()
+    ts3 = TrainStep(sc, mask_weight=5.0, optimizer=False)
+    ts3.forward_backward(4, B, pixels=(px[:B], py[:B]), t_rand=tr, additional_img_id=1, add_pixels=(px[B:], py[B:]))
+    touched = [k for k, m in enumerate(sc["pose_network"].pose_mlps)
+               if any(p.grad is not None and float(p.grad.abs().max()) > 0 for p in m.parameters())]
+    assert touched == [1, 4], touched
+    # (c)
+    res = []
+    for graphed in (False, True):
+        sc = mk()
+        ts = TrainStep(sc, mask_weight=5.0, capturable=graphed)
+        gts = GraphedTrainStep(ts, B, two_frames=True) if graphed else None
+        losses = []
+        for it, (fa, fb) in enumerate([(4, 1), (3, 0), (4, 1)]):
+            if graphed:
+                ls, _ = gts.step(fa, px[:B], py[:B], tr, add_img_id=fb, add_px=px[B:], add_py=py[B:])
+            else:
+                ls, _ = ts.step(fa, B, pixels=(px[:B], py[:B]), t_rand=tr, additional_img_id=fb, add_pixels=(px[B:], py[B:]))
+            losses.append(float(ls["loss"].detach()))
+        res.append(losses)
+        if graphed:
+            assert len(gts.graphs) == 2
+    np.testing.assert_allclose(res[1], res[0], rtol=2e-3)
