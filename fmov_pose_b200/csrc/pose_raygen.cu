@@ -348,6 +348,172 @@ __global__ void raygen_bwd_kernel(RayArgs a, const float* __restrict__ g_o, cons
   if (threadIdx.x < 12) atomicAdd(&g34[threadIdx.x], acc[threadIdx.x]);
 }
 
+
+// =====================================================================================================
+// LearnPoseGF as ONE launch per direction (models/picture_pose.py:140-186): Gaussian-Fourier features of the frame
+// index -> Linear 256->64, GELU -> Linear 64->64, GELU -> heads (lin3 [6] | lin3_rot [3], lin3_trans [3], lin3_scale [1])
+// -> Rodrigues tail (mode 1 above).  21 k parameters: one block; the torch formulation is ~15 launches forward and ~30
+// backward per frame, which dominates the shipped 512-ray iterations.
+// =====================================================================================================
+struct PoseGfArgs {
+  const long long* cid;      // device int64 [1]: frame index
+  const float* b;            // [128] Fourier frequencies
+  const float* W1; const float* b1;      // [64,256], [64]
+  const float* W2; const float* b2;      // [64,64], [64]
+  const float* Wh[3]; const float* bh[3];   // heads, rows concatenated in order: rot(3) trans(3) [scale(1)]
+  int rows[3];
+  int n_heads;
+  float rot_k;               // pi or pi/6 (small_rot)
+  const float* init_all;     // [N,4,4] initial poses (or null: identity)
+  float* save;               // [256 ff | 64 z1 | 64 z2 | 8 out(rot*k, trans, scale)] = 392 floats
+};
+constexpr int GF_SAVE = 392;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * expf(-0.5f * x * x) * 0.39894228040143267794f;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) pose_gf_fwd_kernel(PoseGfArgs a, float* __restrict__ c2w34) {
+  __shared__ float ff[256], z1[64], h1[64], z2[64], h2[64], out[8], init[12];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const long long cid = a.cid[0];
+  if (t < 128) {
+    const float x = 6.283185307179586f * (float)cid;      // (2*pi*cid) in fp32, as the reference's tensor expression
+    const float ang = x * a.b[t];
+    ff[t] = sinf(ang) / 11.313708498984761f;              // / sqrt(embedding_size = 128)
+    ff[128 + t] = cosf(ang) / 11.313708498984761f;
+  }
+  if (t < 12) init[t] = a.init_all ? a.init_all[cid * 16 + t] : ((t % 5) == 0 ? 1.f : 0.f);
+  if (t < 8) out[t] = 0.f;
+  __syncthreads();
+  for (int j = warp * 8; j < warp * 8 + 8; ++j) {          // lin1: 8 output rows per warp
+    float s = 0.f;
+#pragma unroll
+    for (int i = lane; i < 256; i += 32) s = fmaf(a.W1[j * 256 + i], ff[i], s);
+    s = warp_sum(s);
+    if (lane == 0) { z1[j] = s + a.b1[j]; h1[j] = gelu_erf(z1[j]); }
+  }
+  __syncthreads();
+  for (int j = warp * 8; j < warp * 8 + 8; ++j) {          // lin2
+    float s = fmaf(a.W2[j * 64 + lane], h1[lane], a.W2[j * 64 + 32 + lane] * h1[32 + lane]);
+    s = warp_sum(s);
+    if (lane == 0) { z2[j] = s + a.b2[j]; h2[j] = gelu_erf(z2[j]); }
+  }
+  __syncthreads();
+  if (warp < 7) {                                          // heads: one output row per warp
+    int r = warp, hd = 0, base = 0;
+    while (hd < a.n_heads && r >= a.rows[hd]) { r -= a.rows[hd]; base += a.rows[hd]; ++hd; }
+    if (hd < a.n_heads) {
+      float s = fmaf(a.Wh[hd][r * 64 + lane], h2[lane], a.Wh[hd][r * 64 + 32 + lane] * h2[32 + lane]);
+      s = warp_sum(s);
+      if (lane == 0) out[base + r] = (s + a.bh[hd][r]) * (base + r < 3 ? a.rot_k : 1.f);
+    }
+  }
+  __syncthreads();
+  if (t < 256) a.save[t] = ff[t];
+  if (t < 64) { a.save[256 + t] = z1[t]; a.save[320 + t] = z2[t]; }
+  if (t < 8) a.save[384 + t] = out[t];
+  if (t == 0) {
+    int total = 0;
+    for (int h = 0; h < a.n_heads; ++h) total += a.rows[h];
+    PoseParams pp;
+    pp.mode = 1; pp.c2w = nullptr; pp.rot = out; pp.trans = out + 3; pp.scale = total > 6 ? out + 6 : nullptr;
+    pp.init = init; pp.se3 = nullptr;
+    float R[9], tt[3];
+    pose_fwd(pp, R, tt);
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) c2w34[i * 4 + j] = R[i * 3 + j];
+      c2w34[i * 4 + 3] = tt[i];
+    }
+  }
+}
+
+struct PoseGfGrads {
+  float* dW1; float* db1; float* dW2; float* db2;      // any may be null (frozen parameters)
+  float* dWh[3]; float* dbh[3];
+};
+
+__global__ void __launch_bounds__(256)
+pose_gf_bwd_kernel(PoseGfArgs a, const float* __restrict__ g34, PoseGfGrads g) {
+  __shared__ float ff[256], z1[64], h1[64], z2[64], h2[64], gout[8], gz2[64], gz1[64], init[12], outv[8];
+  const int t = threadIdx.x;
+  const long long cid = a.cid[0];
+  ff[t] = a.save[t];
+  if (t < 64) {
+    z1[t] = a.save[256 + t]; z2[t] = a.save[320 + t];
+    h1[t] = gelu_erf(z1[t]); h2[t] = gelu_erf(z2[t]);
+  }
+  if (t < 8) { outv[t] = a.save[384 + t]; gout[t] = 0.f; }
+  if (t < 12) init[t] = a.init_all ? a.init_all[cid * 16 + t] : ((t % 5) == 0 ? 1.f : 0.f);
+  __syncthreads();
+  int total = 0;
+  for (int h = 0; h < a.n_heads; ++h) total += a.rows[h];
+  if (t == 0) {      // tail backward (same maths as pose_bwd_kernel mode 1)
+    float GR[9], gt[3], Re[9], R0[9], t0[3], Gre[9], rb[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) { GR[i * 3 + j] = g34[i * 4 + j]; R0[i * 3 + j] = init[i * 4 + j]; }
+      gt[i] = g34[i * 4 + 3];
+      t0[i] = init[i * 4 + 3];
+    }
+    const float r[3] = {outv[0], outv[1], outv[2]};
+    rodrigues_fwd(r, Re);
+    const float sc = total > 6 ? outv[6] : 1.f;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float v = 0.f;
+        for (int m = 0; m < 3; ++m) v += GR[i * 3 + m] * R0[j * 3 + m];
+        Gre[i * 3 + j] = v + gt[i] * sc * t0[j];
+      }
+    rodrigues_bwd(r, Gre, rb);
+    for (int i = 0; i < 3; ++i) { gout[i] = rb[i] * a.rot_k; gout[3 + i] = gt[i]; }
+    if (total > 6) {
+      float v = 0.f;
+      for (int j = 0; j < 3; ++j) v += (Re[j] * gt[0] + Re[3 + j] * gt[1] + Re[6 + j] * gt[2]) * t0[j];
+      gout[6] = v;
+    }
+  }
+  __syncthreads();
+  // heads: dWh[r][i] = gout[r] * h2[i], dbh[r] = gout[r];  g_h2[i] = sum_r Wh[r][i] gout[r]
+  {
+    int base = 0;
+    for (int hd = 0; hd < a.n_heads; ++hd) {
+      const int n = a.rows[hd] * 64;
+      if (g.dWh[hd] && t < n) g.dWh[hd][t] = gout[base + t / 64] * h2[t % 64];
+      if (n > 256 && g.dWh[hd] && t + 256 < n) g.dWh[hd][t + 256] = gout[base + (t + 256) / 64] * h2[(t + 256) % 64];
+      if (g.dbh[hd] && t < a.rows[hd]) g.dbh[hd][t] = gout[base + t];
+      base += a.rows[hd];
+    }
+  }
+  if (t < 64) {
+    float s = 0.f;
+    int base = 0;
+    for (int hd = 0; hd < a.n_heads; ++hd) {
+      for (int r = 0; r < a.rows[hd]; ++r) s = fmaf(a.Wh[hd][r * 64 + t], gout[base + r], s);
+      base += a.rows[hd];
+    }
+    gz2[t] = s * gelu_erf_grad(z2[t]);
+    if (g.db2) g.db2[t] = gz2[t];
+  }
+  __syncthreads();
+  if (g.dW2)
+    for (int e = t; e < 64 * 64; e += 256) g.dW2[e] = gz2[e >> 6] * h1[e & 63];
+  if (t < 64) {
+    float s = 0.f;
+    for (int j = 0; j < 64; ++j) s = fmaf(a.W2[j * 64 + t], gz2[j], s);
+    gz1[t] = s * gelu_erf_grad(z1[t]);
+    if (g.db1) g.db1[t] = gz1[t];
+  }
+  __syncthreads();
+  if (g.dW1)
+    for (int e = t; e < 64 * 256; e += 256) g.dW1[e] = gz1[e >> 8] * ff[e & 255];
+}
+
 }  // namespace fmov
 using namespace fmov;
 
@@ -453,5 +619,57 @@ extern "C" int fmov_raygen_xy_bwd(const float* intr_inv, int intr_stride, const 
   a.rays_o = const_cast<float*>(rays_o); a.rays_d = const_cast<float*>(rays_d);
   raygen_bwd_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a, g_o, g_d, g_near, g_far, g_c2w34);
   FMOV_LAUNCH_CHECK("raygen_bwd_kernel");
+  return OK;
+}
+
+/* ---- LearnPoseGF in one launch per direction ---------------------------------------------------------- */
+static int fill_gf(PoseGfArgs& a, const long long* cid, const float* b, const float* W1, const float* b1, const float* W2,
+                   const float* b2, int n_heads, const float* const* Wh, const float* const* bh, const int* rows,
+                   float rot_k, const float* init_all, float* save) {
+  FMOV_REQUIRE(cid && b && W1 && b1 && W2 && b2 && Wh && bh && rows && save, "pose_gf: null argument");
+  FMOV_REQUIRE(n_heads >= 1 && n_heads <= 3, "pose_gf: 1..3 heads (got %d)", n_heads);
+  memset(&a, 0, sizeof(a));
+  int total = 0;
+  for (int h = 0; h < n_heads; ++h) {
+    FMOV_REQUIRE(Wh[h] && bh[h] && rows[h] >= 1 && rows[h] <= 6, "pose_gf: bad head %d", h);
+    a.Wh[h] = Wh[h]; a.bh[h] = bh[h]; a.rows[h] = rows[h];
+    total += rows[h];
+  }
+  FMOV_REQUIRE(total == 6 || total == 7, "pose_gf: heads must give rot(3)+trans(3)[+scale(1)] rows (got %d)", total);
+  a.cid = cid; a.b = b; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.n_heads = n_heads; a.rot_k = rot_k;
+  a.init_all = init_all; a.save = save;
+  return OK;
+}
+
+extern "C" int fmov_pose_gf_save_floats(void) { return GF_SAVE; }
+
+extern "C" int fmov_pose_gf_fwd(const long long* cid, const float* b, const float* W1, const float* b1, const float* W2,
+                                const float* b2, int n_heads, const float* const* Wh, const float* const* bh,
+                                const int* rows, float rot_k, const float* init_all, float* save, float* c2w34,
+                                void* stream) {
+  PoseGfArgs a;
+  int st = fill_gf(a, cid, b, W1, b1, W2, b2, n_heads, Wh, bh, rows, rot_k, init_all, save);
+  if (st) return st;
+  FMOV_REQUIRE(c2w34, "fmov_pose_gf_fwd: null output");
+  pose_gf_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, c2w34);
+  FMOV_LAUNCH_CHECK("pose_gf_fwd_kernel");
+  return OK;
+}
+
+extern "C" int fmov_pose_gf_bwd(const long long* cid, const float* b, const float* W1, const float* b1, const float* W2,
+                                const float* b2, int n_heads, const float* const* Wh, const float* const* bh,
+                                const int* rows, float rot_k, const float* init_all, const float* save,
+                                const float* g_c2w34, float* dW1, float* db1, float* dW2, float* db2, float* const* dWh,
+                                float* const* dbh, void* stream) {
+  PoseGfArgs a;
+  int st = fill_gf(a, cid, b, W1, b1, W2, b2, n_heads, Wh, bh, rows, rot_k, init_all, const_cast<float*>(save));
+  if (st) return st;
+  FMOV_REQUIRE(g_c2w34 && dWh && dbh, "fmov_pose_gf_bwd: null argument");
+  PoseGfGrads g;
+  memset(&g, 0, sizeof(g));
+  g.dW1 = dW1; g.db1 = db1; g.dW2 = dW2; g.db2 = db2;
+  for (int h = 0; h < n_heads; ++h) { g.dWh[h] = dWh[h]; g.dbh[h] = dbh[h]; }
+  pose_gf_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a, g_c2w34, g);
+  FMOV_LAUNCH_CHECK("pose_gf_bwd_kernel");
   return OK;
 }

@@ -2,9 +2,10 @@
 
 Same parameters (lin1, lin2, lin3 | lin3_rot / lin3_trans(frozen) / lin3_scale, init_c2w), same
 Gaussian-Fourier features (b ~ N(0, embedding_scale^2) drawn from np.random exactly like the reference,
-picture_pose.py:74-78), same control methods.  The 21 k-parameter MLP head stays in torch; its tail —
-Rodrigues exponential + composition with the (optionally scaled) initial pose, picture_pose.py:176-186 —
-runs in fmov_pose_fwd/_bwd (csrc/pose_raygen.cu)."""
+picture_pose.py:74-78), same control methods.  The whole forward — Fourier features, the 21 k-parameter GELU MLP, its
+heads and the tail (Rodrigues exponential + composition with the optionally scaled initial pose, picture_pose.py:140-186)
+— is ONE launch per direction, fmov_pose_gf_fwd/_bwd (csrc/pose_raygen.cu): the torch formulation costs ~45 launches per
+frame, a quarter of the shipped 512-ray iteration."""
 import numpy as np
 import torch
 import torch.nn as nn
@@ -12,26 +13,32 @@ import torch.nn as nn
 from .. import ops as _ops
 
 
-class _GfTailFn(torch.autograd.Function):
-    """c2w[3,4] = [Exp(rot) | trans] @ [R0 | scale * t0]"""
+class _PoseGfFn(torch.autograd.Function):
+    """Whole LearnPoseGF.forward (picture_pose.py:140-186) as one launch per direction (fmov_pose_gf_fwd/_bwd):
+    (cid int64 [1], b, init_c2w [N,4,4] | None, rot_k, W1, b1, W2, b2, head W/b ...) -> c2w [3,4]"""
 
     @staticmethod
-    def forward(ctx, rot, trans, scale, init44):
-        rot_c, trans_c = rot.detach().float().contiguous(), trans.detach().float().contiguous()
-        scale_c = None if scale is None else scale.detach().float().contiguous()
-        init_c = init44.detach().float().contiguous()
-        ctx.has_scale = scale is not None
-        ctx.save_for_backward(rot_c, trans_c, init_c, *(() if scale_c is None else (scale_c,)))
-        return _ops.pose_fwd(1, rot=rot_c, trans=trans_c, scale=scale_c, init34=init_c)
+    def forward(ctx, cid_t, b, init_all, rot_k, *params):
+        ps = [p.detach().float().contiguous() for p in params]
+        heads = [(ps[4 + 2 * i], ps[5 + 2 * i]) for i in range((len(ps) - 4) // 2)]
+        b_c = b.detach().float().contiguous().reshape(-1)
+        init_c = None if init_all is None else init_all.detach().float().contiguous()
+        c2w, save = _ops.pose_gf_fwd(cid_t, b_c, ps[0], ps[1], ps[2], ps[3], heads, float(rot_k), init_c)
+        ctx.save_for_backward(cid_t, b_c, save, *ps, *(() if init_c is None else (init_c,)))
+        ctx.n_params, ctx.rot_k, ctx.has_init = len(ps), float(rot_k), init_c is not None
+        return c2w
 
     @staticmethod
     def backward(ctx, g):
-        saved = ctx.saved_tensors
-        rot_c, trans_c, init_c = saved[:3]
-        scale_c = saved[3] if ctx.has_scale else None
-        g_rot, g_trans, g_scale, _ = _ops.pose_bwd(1, g.float().contiguous(), rot=rot_c, trans=trans_c, scale=scale_c,
-                                                   init34=init_c)
-        return g_rot, g_trans, (g_scale if ctx.has_scale else None), None
+        sv = ctx.saved_tensors
+        cid_t, b_c, save = sv[0], sv[1], sv[2]
+        ps = list(sv[3:3 + ctx.n_params])
+        init_c = sv[3 + ctx.n_params] if ctx.has_init else None
+        heads = [(ps[4 + 2 * i], ps[5 + 2 * i]) for i in range((len(ps) - 4) // 2)]
+        need = list(ctx.needs_input_grad[4:])
+        grads = _ops.pose_gf_bwd(cid_t, b_c, ps[0], ps[1], ps[2], ps[3], heads, ctx.rot_k, init_c, save,
+                                 g.float().contiguous(), need)
+        return (None, None, None, None) + tuple(grads)
 
 
 class LearnPoseGF(nn.Module):
@@ -107,23 +114,18 @@ class LearnPoseGF(nn.Module):
         device only (Fourier features and the init_c2w row), which keeps the call CUDA-graph capturable with the
         frame as a replay-time input (train.GraphedTrainStep)."""
         if cam_id_t is not None:
-            cid = cam_id_t.reshape(1).float()
+            cid_t = cam_id_t.reshape(1)
         else:
-            cid = torch.as_tensor(cam_id, device=self.b.device).reshape(1).float()
-        ang = (2.0 * np.pi * cid) @ self.b.T                   # [128]
-        ff = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1) / float(np.sqrt(self.embedding_size))
-        h = self.gelu2(self.lin2(self.gelu1(self.lin1(ff))))
-        k = np.pi / 6 if self.small_rot else np.pi
+            cid_t = torch.as_tensor(int(cam_id), dtype=torch.int64, device=self.b.device).reshape(1)
         if not self.emphasize_rot:
-            o = self.lin3(h)
-            rot, trans, scale = o[:3] * k, o[3:], None
+            heads = [self.lin3]
         else:
-            rot, trans, scale = self.lin3_rot(h) * k, self.lin3_trans(h), self.lin3_scale(h)
-        if self.init_c2w is not None:
-            init = self.init_c2w.index_select(0, cam_id_t.reshape(1))[0] if cam_id_t is not None else self.init_c2w[int(cam_id)]
-        else:
-            init = torch.eye(4, device=self.b.device)
-        c2w34 = _GfTailFn.apply(rot, trans, scale, init)
+            heads = [self.lin3_rot, self.lin3_trans, self.lin3_scale]
+        params = [self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias]
+        for h in heads:
+            params += [h.weight, h.bias]
+        k = np.pi / 6 if self.small_rot else np.pi
+        c2w34 = _PoseGfFn.apply(cid_t, self.b, self.init_c2w, float(k), *params)
         if self._bottom is None or self._bottom.device != c2w34.device:
             self._bottom = torch.cat([torch.zeros(1, 3, device=c2w34.device), torch.ones(1, 1, device=c2w34.device)], 1)
         return torch.cat([c2w34, self._bottom], dim=0)          # (4,4) like the reference

@@ -205,3 +205,40 @@ def ray_reduce_bwd(d_pts, d_dirs, d_dir_tc, d_dist, d_mid, rays_d, z, sample_dis
                                         L.ptr(rays_d), L.ptr(z), L.c_ll(B), S, L.c_float(sample_dist), L.ptr(d_o),
                                         L.ptr(d_d), L.ptr(d_z), L.stream()), "fmov_ray_reduce_bwd")
     return d_o, d_d, d_z
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[(t.data_ptr() if t is not None else 0) for t in tensors])
+
+
+def pose_gf_fwd(cid_t, b, W1, b1, W2, b2, heads, rot_k, init_all):
+    """LearnPoseGF.forward in one launch -> (c2w34 [3,4], save).  heads: [(W [r,64], bias [r]), ...]"""
+    dev = W1.device
+    assert cid_t.dtype == torch.int64 and cid_t.is_cuda and cid_t.numel() == 1
+    save = torch.empty(int(L.lib().fmov_pose_gf_save_floats()), dtype=torch.float32, device=dev)
+    c2w = torch.empty(3, 4, dtype=torch.float32, device=dev)
+    rows = (ctypes.c_int * len(heads))(*[int(w.shape[0]) for w, _ in heads])
+    L.check(L.lib().fmov_pose_gf_fwd(L.ptr(cid_t), L.ptr(b), L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), len(heads),
+                                     _ptr_array([w for w, _ in heads]), _ptr_array([x for _, x in heads]), rows,
+                                     L.c_float(rot_k), L.ptr(init_all), L.ptr(save), L.ptr(c2w), L.stream()),
+            "fmov_pose_gf_fwd")
+    return c2w, save
+
+
+def pose_gf_bwd(cid_t, b, W1, b1, W2, b2, heads, rot_k, init_all, save, g34, need):
+    """need: booleans per (W1, b1, W2, b2, then W/b of every head) -> gradients in the same order (None where not needed)"""
+    dev = W1.device
+    mk = lambda t, n: torch.empty_like(t) if n else None
+    dW1, db1, dW2, db2 = mk(W1, need[0]), mk(b1, need[1]), mk(W2, need[2]), mk(b2, need[3])
+    dWh = [mk(w, need[4 + 2 * i]) for i, (w, _) in enumerate(heads)]
+    dbh = [mk(x, need[5 + 2 * i]) for i, (_, x) in enumerate(heads)]
+    rows = (ctypes.c_int * len(heads))(*[int(w.shape[0]) for w, _ in heads])
+    L.check(L.lib().fmov_pose_gf_bwd(L.ptr(cid_t), L.ptr(b), L.ptr(W1), L.ptr(b1), L.ptr(W2), L.ptr(b2), len(heads),
+                                     _ptr_array([w for w, _ in heads]), _ptr_array([x for _, x in heads]), rows,
+                                     L.c_float(rot_k), L.ptr(init_all), L.ptr(save), L.ptr(g34), L.ptr(dW1), L.ptr(db1),
+                                     L.ptr(dW2), L.ptr(db2), _ptr_array(dWh), _ptr_array(dbh), L.stream()),
+            "fmov_pose_gf_bwd")
+    out = [dW1, db1, dW2, db2]
+    for w_, b_ in zip(dWh, dbh):
+        out += [w_, b_]
+    return out

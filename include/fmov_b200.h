@@ -63,6 +63,20 @@ int fmov_pose_fwd(int mode, const float* rot, const float* trans, const float* s
 int fmov_pose_bwd(int mode, const float* rot, const float* trans, const float* scale, const float* init34,
                   const float* se3, const float* g_c2w34, float* g_rot, float* g_trans, float* g_scale, float* g_se3,
                   void* stream);
+/* LearnPoseGF.forward (models/picture_pose.py:140-186) in ONE launch per direction: Gaussian-Fourier features of the frame
+ * index cid[0] (device int64) -> lin1 (256->64) GELU -> lin2 (64->64) GELU -> heads -> Rodrigues tail (mode 1 above) with
+ * init_all[cid] ([N,4,4]; NULL = identity).  Heads (HOST arrays of n_heads device pointers + row counts), rows concatenated
+ * as rot(3) trans(3) [scale(1)]: {lin3 (6)} or {lin3_rot (3), lin3_trans (3), lin3_scale (1)}; rot rows are multiplied by
+ * rot_k (pi, or pi/6 with small_rot).  save: fmov_pose_gf_save_floats() floats written by fwd, read by bwd.  Gradient
+ * pointers may be NULL (frozen parameters); dWh/dbh are HOST arrays of device pointers (entries may be NULL).       */
+int fmov_pose_gf_save_floats(void);
+int fmov_pose_gf_fwd(const long long* cid, const float* b, const float* W1, const float* b1, const float* W2,
+                     const float* b2, int n_heads, const float* const* Wh, const float* const* bh, const int* rows,
+                     float rot_k, const float* init_all, float* save, float* c2w34, void* stream);
+int fmov_pose_gf_bwd(const long long* cid, const float* b, const float* W1, const float* b1, const float* W2,
+                     const float* b2, int n_heads, const float* const* Wh, const float* const* bh, const int* rows,
+                     float rot_k, const float* init_all, const float* save, const float* g_c2w34, float* dW1, float* db1,
+                     float* dW2, float* db2, float* const* dWh, float* const* dbh, void* stream);
 /* Dataset.gen_random_rays_at ray math (models/dataset.py:656-671) + near_far_from_sphere (:835-842), with the
  * pose evaluated in-kernel (mode 0: c2w34 given). px/py are int64 pixel coordinates.                 */
 int fmov_raygen_fwd(int mode, const float* c2w34, const float* rot, const float* trans, const float* scale,
