@@ -16,6 +16,7 @@ from .. import fine as _fine
 from .. import flow as _flow
 from .. import ops as _ops
 from .. import packing as _packing
+from .. import weight_norm as _wn
 
 
 def extract_fields(bound_min, bound_max, resolution, query_func):
@@ -114,8 +115,7 @@ class NeuSRenderer:
                 t_rand = torch.rand([batch_size, 1], device=rays_o.device)
         else:
             t_rand = None
-        W_s, b_s = self.sdf_network.effective_weights()
-        W_c, b_c = self.color_network.effective_weights()
+        (W_s, b_s), (W_c, b_c) = _wn.effective_weights_fused([self.sdf_network, self.color_network])
         need_bwd = torch.is_grad_enabled() and not eval
         with torch.no_grad():      # one packing launch serves the sampling queries and the fine stage
             fw = _fine.FineWeights(W_s, b_s, W_c, b_c, need_backward=need_bwd)

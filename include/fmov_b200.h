@@ -36,6 +36,16 @@ int fmov_ti_to_rowmajor(const void* src, long long P, int cols, int ld, int kblo
 int fmov_selftest_gemm(const void* a_img, const void* b_img, int n, int kblocks, int a_bf16, int b_bf16, int mode,
                        float* out, void* stream);
 
+/* ---- weight normalisation of all layers in one launch ------------------------------------------------- */
+/* nn.utils.weight_norm(dim=0) of every linear layer (models/fields.py:81-82, 160-161): W = g * v / ||v|| per output row,
+ * and its backward dL/dW -> (dL/dv, dL/dg).  Every pointer argument is a HOST array of n_layers (<= 16) device pointers;
+ * layer i: v [rows[i], cols[i]], g [rows[i]] (weight_g), W / dW / dv like v, norm / dg [rows[i]].                     */
+int fmov_weight_norm_fwd(int n_layers, const float* const* v, const float* const* g, const int* rows, const int* cols,
+                         float* const* W, float* const* norm, void* stream);
+int fmov_weight_norm_bwd(int n_layers, const float* const* v, const float* const* g, const int* rows, const int* cols,
+                         const float* const* norm, const float* const* dW, float* const* dv, float* const* dg,
+                         void* stream);
+
 /* ---- SDF value query: SDFNetwork.sdf under no_grad ------------------------------------- */
 /* replaces models/fields.py:88-107 at the call sites models/renderer.py:424-428 (coarse),
  * :230-232 (up-sample rounds) and :506 via extract_fields :9-37 (dense grid).

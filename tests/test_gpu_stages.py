@@ -254,3 +254,35 @@ def test_fused_pose_module_vs_oracle(emphasize_rot, small_rot, cam):
     # device-side frame index (CUDA-graph path) gives the same pose
     pose_t = m(cam, torch.tensor([cam], device=DEV))
     np.testing.assert_array_equal(pose_t.detach().cpu().numpy(), pose.detach().cpu().numpy())
+
+
+def test_fused_weight_norm_vs_torch():
+    """fmov_weight_norm_fwd/_bwd (all layers of both MLPs in one launch) == torch._weight_norm per layer, values and the
+    gradients on weight_g / weight_v, including the 217-row and 3-row layers."""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.models.fields import RenderingNetwork, SDFNetwork
+    from fmov_pose_b200.weight_norm import effective_weights_fused
+    torch.manual_seed(3)
+    sdf = SDFNetwork(**synthetic.SDF_KW).to(DEV)
+    col = RenderingNetwork(**synthetic.COL_KW).to(DEV)
+    with torch.no_grad():
+        for net in (sdf, col):
+            for n_, p_ in net.named_parameters():
+                if n_.endswith("weight_g"):
+                    p_.mul_(1.0 + 0.3 * torch.rand_like(p_))
+    (Ws, bs), (Wc, bc) = effective_weights_fused([sdf, col])
+    Ws_ref, _ = sdf.effective_weights()
+    Wc_ref, _ = col.effective_weights()
+    assert len(Ws) == 9 and len(Wc) == 5 and bs[3].shape == (217,)
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    Gs = [torch.randn(w.shape, device=DEV, generator=gen) for w in list(Ws) + list(Wc)]
+    for a, b in zip(list(Ws) + list(Wc), list(Ws_ref) + list(Wc_ref)):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-6, atol=1e-8)
+    params = [p for net in (sdf, col) for n_, p in net.named_parameters() if "weight_" in n_]
+    loss = sum((w * g_).sum() for w, g_ in zip(list(Ws) + list(Wc), Gs))
+    got = torch.autograd.grad(loss, params)
+    loss_ref = sum((w * g_).sum() for w, g_ in zip(list(Ws_ref) + list(Wc_ref), Gs))
+    ref = torch.autograd.grad(loss_ref, params)
+    for a, b in zip(got, ref):
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-12))
+        assert err <= 1e-5, err
