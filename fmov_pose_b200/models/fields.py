@@ -24,7 +24,13 @@ class _WeightNormMLP(nn.Module):
         return lin.weight, lin.bias
 
     def effective_weights(self):
-        """([W_l], [b_l]) with W_l = g * v / |v| (nn.utils.weight_norm, dim=0) — differentiable."""
+        """([W_l], [b_l]) with W_l = g * v / |v| (nn.utils.weight_norm, dim=0) — differentiable.  On the GPU every layer
+        comes from the one fused launch (`weight_norm.effective_weights_fused`, which `NeuSRenderer.render` uses for both
+        networks at once), so all call sites see bit-identical weights; the per-layer torch expression below only serves
+        parameter inspection on the CPU (shape checks in the host-logic tests)."""
+        if next(self.parameters()).is_cuda:
+            from ..weight_norm import effective_weights_fused
+            return effective_weights_fused([self])[0]
         Ws, bs = [], []
         for l in range(self.num_layers - 1):
             W, b = self._eff(l)

@@ -271,8 +271,9 @@ def test_fused_weight_norm_vs_torch():
                 if n_.endswith("weight_g"):
                     p_.mul_(1.0 + 0.3 * torch.rand_like(p_))
     (Ws, bs), (Wc, bc) = effective_weights_fused([sdf, col])
-    Ws_ref, _ = sdf.effective_weights()
-    Wc_ref, _ = col.effective_weights()
+    tw = lambda net, l: torch._weight_norm(getattr(net, f"lin{l}").weight_v, getattr(net, f"lin{l}").weight_g, 0)
+    Ws_ref = [tw(sdf, l) for l in range(9)]
+    Wc_ref = [tw(col, l) for l in range(5)]
     assert len(Ws) == 9 and len(Wc) == 5 and bs[3].shape == (217,)
     gen = torch.Generator(device=DEV).manual_seed(1)
     Gs = [torch.randn(w.shape, device=DEV, generator=gen) for w in list(Ws) + list(Wc)]
