@@ -11,8 +11,12 @@ LIB = os.path.join(HERE, "libfmov_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math_off_placeholder"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.endswith("placeholder")]
-NVCC_FLAGS += os.environ.get("FMOV_NVCC_EXTRA", "").split()      # experiment switches (-DFMOV_...), A/B builds
+_EXTRA = os.environ.get("FMOV_NVCC_EXTRA", "").split()           # experiment switches (-DFMOV_...), A/B builds
+NVCC_FLAGS += _EXTRA
 LIB = os.environ.get("FMOV_LIB_OUT", LIB)
+if _EXTRA:       # variant builds keep their own objects (staleness is judged by mtime, not by flags)
+    import hashlib
+    OBJ = os.path.join(HERE, "_build", "variant_" + hashlib.sha1(" ".join(_EXTRA).encode()).hexdigest()[:10])
 
 
 def _nvcc():
@@ -58,7 +62,7 @@ def build(force=False, verbose=False):
     if verbose:
         for o in outs:
             sys.stderr.write(o)
-    if jobs or not os.path.exists(LIB):
+    if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         run([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 

@@ -44,6 +44,9 @@ constexpr bool kPrefetchNext = true;
 #else
 constexpr bool kPrefetchNext = false;
 #endif
+#ifndef FMOV_RQ_PH
+#define FMOV_RQ_PH 2
+#endif
 constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks) in the backward hot loops
 // A/B-measured and NOT kept (profiles/ab.sh, same box, alternating builds): double-buffered TMEM loads in the reverse
 // sweep / colour / backward loops and separate loop bodies for the l == 8 / l == 4 specials (fine_fwd 5.23 -> 5.28 ms,
@@ -100,9 +103,26 @@ static long long img_offset(int id) {
 enum StashId {
   ST_PE = 0, ST_H1 = 1 /*..H8=8*/, ST_F = 9, ST_D0 = 10 /*..D7=17*/, ST_X = 18, ST_C1 = 19 /*..C4=22*/,
   ST_ZC0 = 23 /*..ZC3=26*/, ST_FB = 27, ST_GE = 28, ST_V1 = 29 /*..V8=36*/, ST_Q0 = 37 /*..Q7=44*/,
-  ST_Z0 = 45 /*..Z7=52*/, ST_COUNT = 53
+  ST_Z0 = 45 /*..Z7=52*/,
+#ifdef FMOV_RELU_BITS
+  ST_CM = 53, ST_COUNT = 54     // experiment: ReLU sign bits of C1..C4, [layer][32-column chunk][row] uint32 = one block per tile
+#else
+  ST_COUNT = 53
+#endif
 };
-__host__ __device__ inline int stash_kb(int id) { return (id == ST_PE || id == ST_X || id == ST_GE) ? 1 : 4; }
+__host__ __device__ inline int stash_kb(int id) {
+#ifdef FMOV_RELU_BITS
+  if (id == ST_CM) return 1;
+#endif
+  return (id == ST_PE || id == ST_X || id == ST_GE) ? 1 : 4;
+}
+// written by fmov_fine_fwd (a forward-only stash holds exactly these)
+__host__ __device__ inline bool stash_is_forward(int id) {
+#ifdef FMOV_RELU_BITS
+  if (id == ST_CM) return true;
+#endif
+  return id <= ST_C1 + 3;
+}
 
 struct FineArgs {
   long long B;
@@ -447,6 +467,12 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b4.w, 0.f);
           }
           put_chunk(c, ptrs, true, ST_C1 + l, tile, hb, false, v);
+#ifdef FMOV_RELU_BITS
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+          reinterpret_cast<uint32_t*>(stash_tile(ptrs, ST_CM, tile))[(l * 8 + hb) * TILE_M + c.row] = m;
+#endif
         }
         epi_signal_act(c);
       }
@@ -534,15 +560,26 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll 2
       for (int hi = 0; hi < HPW; ++hi) {
         const int hb = hb0 + hi;
-        float v[32], h[32];
+        float v[32];
+#ifdef FMOV_RELU_BITS
+        // experiment (off by default): the backward pass reads the ReLU signs as one word per 32 columns instead of the
+        // fp16 C tiles (16 blocks -> 1 block per tile; DESIGN.md §3 "HBM budget")
+        const uint32_t m = reinterpret_cast<const uint32_t*>(stash_tile(ptrs, ST_CM, tile))[(3 * 8 + hb) * TILE_M + c.row];
+#else
+        float h[32];
         uint4 q[4];
         get_chunk_raw(c, ptrs, ST_C1 + 3, tile, hb, q);
         unpack4(q, false, h);
+#endif
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = hb * 32 + j;
           const float ab = zc4[0] * __ldg(a.wc4 + col) + zc4[1] * __ldg(a.wc4 + 256 + col) + zc4[2] * __ldg(a.wc4 + 512 + col);
+#ifdef FMOV_RELU_BITS
+          v[j] = ((m >> j) & 1u) ? ab : 0.f;
+#else
           v[j] = h[j] > 0.f ? ab : 0.f;
+#endif
         }
         put_chunk_grad(c, ptrs, true, ST_ZC0 + 3, tile, hb, v);
       }
@@ -553,6 +590,22 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const uint8_t* cp = tile_base(ptrs, ST_C1 + (l - 1), tile, c.row);
         uint8_t* zp = tile_base(ptrs, ST_ZC0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
+#ifdef FMOV_RELU_BITS
+        (void)cp;
+        uint32_t mw[HPW];
+#pragma unroll
+        for (int hi = 0; hi < HPW; ++hi)
+          mw[hi] = reinterpret_cast<const uint32_t*>(stash_tile(ptrs, ST_CM, tile))[((l - 1) * 8 + hb0 + hi) * TILE_M + c.row];
+        epi_wait_acc(c);
+#pragma unroll
+        for (int hi = 0; hi < HPW; ++hi) {
+          const int hb = hb0 + hi;
+          float v[32];
+          acc_load32(c, hb * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((mw[hi] >> j) & 1u) ? v[j] : 0.f;
+          uint4 q[4];
+#else
         uint4 sb[2][4];
         ld_half(cp, hb0, sb[0]);
         if (kStashPrefetch) tile_prefetch_l2(cp, ck0 + 2, NCK - 2);
@@ -567,6 +620,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
           uint4 q[4];
+#endif
           pack4_grad(v, q);
           st_half(ap, hb, q);
           st_half(zp, hb, q);
@@ -636,8 +690,40 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const uint8_t* hp = tile_base(ptrs, ST_H1 + l, tile, c.row);      // H_{l+1} -> sigma_l
         const uint8_t* dp = tile_base(ptrs, ST_D0 + l, tile, c.row);      // delta_l
         uint8_t* vp = tile_base(ptrs, ST_V1 + l, tile, c.row);
-        uint8_t* qp = tile_base(ptrs, ST_Q0 + l, tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
+#ifdef FMOV_RECOMPUTE_Q
+        // experiment (off by default): q_l is not spilled; the backward pass rebuilds it from V-bar, delta and sigma, which
+        // removes the Q write here and the delta read ("HBM budget")
+        uint4 sb[PFD + 1][2];
+#pragma unroll
+        for (int i = 0; i < PFD; ++i) chunk_load(hp, ck0 + i, sb[i]);
+        if (kStashPrefetch) tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
+        (void)dp;
+        epi_wait_acc(c);
+#pragma unroll
+        for (int i = 0; i < NCK; ++i) {
+          const int ck = ck0 + i;
+          if (i + PFD < NCK) chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+          float v[16];
+          if (ck * 16 < n_mma) {
+            acc_load16(c, ck * 16, v);
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+          }
+#pragma unroll
+          for (int jp = 0; jp < 8; ++jp) {
+            const float2 hh = chunk_pair(sb[i % (PFD + 1)], jp, false);
+            v[2 * jp] *= sigma_from_h(hh.x);                                    // vbar_{l+1}
+            v[2 * jp + 1] *= sigma_from_h(hh.y);
+          }
+          uint4 q2[2];
+          pack2_grad(v, q2);
+          chunk_store(ap, ck, q2);
+          chunk_store(vp, ck, q2);
+        }
+#else
+        uint8_t* qp = tile_base(ptrs, ST_Q0 + l, tile, c.row);
         uint4 sb[PFD + 1][2], db[PFD + 1][2];
 #pragma unroll
         for (int i = 0; i < PFD; ++i) {
@@ -684,6 +770,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           pack2_grad(qv, q2);
           chunk_store(qp, ck, q2);
         }
+#endif
         if (l < 7) epi_signal_act(c);
       }
       // ---- fbar back into ACT (own rows) -----------------------------------------------------------------------
@@ -696,6 +783,89 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       }
       epi_signal_act(c);
       // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------
+#ifdef FMOV_RECOMPUTE_Q
+      // q_{l-1} = 100 * dbar_{l-1} * delta_{l-1} * (1 - sigma_{l-1}) with dbar_{l-1} = vbar_l / sigma_{l-1}: rebuilt from the
+      // V-bar tile the adjoint pass wrote (own chunks) and the forward's delta tile.  sigma = 0 only where h = 0 (padding
+      // columns, fp16 underflow): vbar and delta are 0 there as well and so is q.  Three operand streams: the loads are
+      // pipelined in 8-column pieces (one uint4 per stream and stage) to stay inside the 96-register budget.
+#pragma unroll 1
+      for (int l = 8; l >= 1; --l) {
+        const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);    // H_l -> sigma_{l-1}
+        const uint8_t* vp = tile_base(ptrs, ST_V1 + (l - 1), tile, c.row);    // vbar_l (gradient format)
+        const uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);    // delta_{l-1} (fp16)
+        uint8_t* zp = tile_base(ptrs, ST_Z0 + (l - 1), tile, c.row);
+        uint8_t* ap = c.act + c.row * 16;
+        constexpr int PH = FMOV_RQ_PH;          // prefetch distance in 8-column pieces
+        constexpr int NP = 2 * NCK;             // pieces per warpgroup
+        const int pc0 = 2 * ck0;                // first piece (= 16-byte chunk column of the 256-wide tile)
+        auto piece = [](const uint8_t* tp, int pi) {
+          return *reinterpret_cast<const uint4*>(tp + (pi >> 3) * BLK_BYTES + (pi & 7) * TI_CHUNK_STRIDE);
+        };
+        uint4 sb[PH + 1], vb[PH + 1], db[PH + 1];
+#pragma unroll
+        for (int i = 0; i < PH; ++i) {
+          sb[i] = piece(hp, pc0 + i);
+          vb[i] = piece(vp, pc0 + i);
+          db[i] = piece(dp, pc0 + i);
+        }
+        if (kStashPrefetch) {
+          tile_prefetch_l2(hp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
+          tile_prefetch_l2(vp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
+          tile_prefetch_l2(dp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
+        }
+        epi_wait_acc(c);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+          const int ck = ck0 + (i >> 1);
+          if (i + PH < NP) {
+            sb[(i + PH) % (PH + 1)] = piece(hp, pc0 + i + PH);
+            vb[(i + PH) % (PH + 1)] = piece(vp, pc0 + i + PH);
+            db[(i + PH) % (PH + 1)] = piece(dp, pc0 + i + PH);
+          }
+          if ((i & 1) == 0) {
+            acc_load16(c, ck * 16, v);
+            if (l == 8) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + ck * 16) + j4);
+                v[j4 * 4 + 0] = fmaf(sbar, w4.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(sbar, w4.y, v[j4 * 4 + 1]);
+                v[j4 * 4 + 2] = fmaf(sbar, w4.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(sbar, w4.w, v[j4 * 4 + 3]);
+              }
+            }
+            if (l == 4 && ck >= 13 && pc.valid) {        // columns 217..255: PE part of the skip input -> scratch row
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                const int col = ck * 16 + jj;
+                if (col >= 217) a.eb[pc.p * 40 + (col - 217)] = v[jj];
+              }
+            }
+          }
+          const uint4 hq = sb[i % (PH + 1)], vq = vb[i % (PH + 1)], dq = db[i % (PH + 1)];
+#pragma unroll
+          for (int jp = 0; jp < 4; ++jp) {
+            const float2 hh = chunk_pair(&hq, jp, false);
+            const float2 vv = chunk_pair(&vq, jp, kGradBf16);
+            const float2 dd = chunk_pair(&dq, jp, false);
+            const float e0 = ex2_approx(hh.x * (-SP_BETA * 1.4426950408889634f));      // 1 - sigma
+            const float e1 = ex2_approx(hh.y * (-SP_BETA * 1.4426950408889634f));
+            const float s0 = 1.0f - e0, s1 = 1.0f - e1;
+            const float r0 = s0 > 0.f ? __fdividef(SP_BETA * e0, s0) : 0.f;
+            const float r1 = s1 > 0.f ? __fdividef(SP_BETA * e1, s1) : 0.f;
+            const int j = (i & 1) * 8 + 2 * jp;
+            v[j] = fmaf(v[j], s0, vv.x * dd.x * r0);
+            v[j + 1] = fmaf(v[j + 1], s1, vv.y * dd.y * r1);
+          }
+          if (i & 1) {
+            uint4 q2[2];
+            pack2_grad(v, q2);
+            chunk_store(ap, ck, q2);
+            chunk_store(zp, ck, q2);
+          }
+        }
+        epi_signal_act(c);
+      }
+#else
 #pragma unroll 1
       for (int l = 8; l >= 1; --l) {
         const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);    // H_l -> sigma_{l-1}
@@ -755,6 +925,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         }
         epi_signal_act(c);
       }
+#endif
       // ---- e-bar += W_0^T zbar_0 ; xbar += J_e^T e-bar -----------------------------------------------------------
       epi_wait_acc(c);
       if (owner) {
@@ -1022,6 +1193,7 @@ extern "C" long long fmov_fine_blob_bytes(void) { return img_offset(IMG_COUNT); 
 extern "C" int fmov_grad_is_bf16(void) { return kGradBf16 ? 1 : 0; }
 extern "C" int fmov_fine_stash_count(void) { return ST_COUNT; }
 extern "C" int fmov_fine_stash_blocks(int id) { return (id >= 0 && id < ST_COUNT) ? stash_kb(id) : -1; }
+extern "C" int fmov_fine_stash_is_forward(int id) { return (id >= 0 && id < ST_COUNT) ? (stash_is_forward(id) ? 1 : 0) : -1; }
 
 static int fill_args(FineArgs& a, ChainPtrs& ptrs, long long B, int S, const float* rays_o, const float* rays_d,
                      const float* z, float sample_dist, const void* wblob, void* const* stash, const float* bias_sdf,
@@ -1063,7 +1235,8 @@ extern "C" int fmov_fine_fwd(long long B, int S, const float* rays_o, const floa
   int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, nullptr);
   if (st) return st;
   FMOV_REQUIRE(sdf && nrm && rgb && ge, "fmov_fine_fwd: null output");
-  for (int i = 0; i <= ST_C1 + 3; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_fwd: stash tensor %d is null", i);
+  for (int i = 0; i < ST_COUNT; ++i)
+    if (stash_is_forward(i)) FMOV_REQUIRE(stash[i], "fmov_fine_fwd: stash tensor %d is null", i);
   a.sdf = sdf; a.nrm = nrm; a.rgb = rgb; a.ge = ge;
   fine_fwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
   FMOV_LAUNCH_CHECK("fine_fwd_kernel");

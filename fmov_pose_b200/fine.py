@@ -15,7 +15,6 @@ SQ2 = math.sqrt(2.0)
 IMG_F0, IMG_T0, IMG_C0 = 0, 9, 17
 IMG_CT0A, IMG_CT0B, IMG_CT1, IMG_CT2, IMG_CT3 = 22, 23, 24, 25, 26
 IMG_FB0, IMG_TB0 = 27, 35
-ST_FWD_LAST = 22          # stash ids 0..22 are written by the forward kernel
 
 
 def _img_info(i):
@@ -75,7 +74,9 @@ class Stash:
         self.nt = (P + 127) // 128
         self.device = device
         self.blocks = [lib.fmov_fine_stash_blocks(i) for i in range(n)]
-        n_fwd = sum(self.blocks[: ST_FWD_LAST + 1])
+        # buffer order: the tensors the forward kernel writes first, so that a forward-only stash is a prefix
+        self.order = sorted(range(n), key=lambda i: (0 if lib.fmov_fine_stash_is_forward(i) else 1, i))
+        n_fwd = sum(self.blocks[i] for i in range(n) if lib.fmov_fine_stash_is_forward(i))
         n_all = sum(self.blocks)
         self.key = (str(device), self.nt)
         self.buf = None
@@ -91,12 +92,11 @@ class Stash:
 
     def _carve(self):
         have = self.buf.numel() // (self.nt * 16384)
-        self.tensors, off = [], 0
-        for nb in self.blocks:
+        self.tensors, off = [None] * len(self.blocks), 0
+        for i in self.order:
+            nb = self.blocks[i]
             if off + nb <= have:
-                self.tensors.append(self.buf[off * self.nt * 16384: (off + nb) * self.nt * 16384])
-            else:
-                self.tensors.append(None)
+                self.tensors[i] = self.buf[off * self.nt * 16384: (off + nb) * self.nt * 16384]
             off += nb
         self.ptrs = (ctypes.c_void_p * len(self.blocks))(*[(t.data_ptr() if t is not None else 0) for t in self.tensors])
 

@@ -177,6 +177,7 @@ int fmov_side_floats(void);
 int fmov_side_offset(int which);
 int fmov_fine_stash_count(void);
 int fmov_fine_stash_blocks(int id);
+int fmov_fine_stash_is_forward(int id);   /* 1: written by fmov_fine_fwd (a forward-only render needs only these) */
 int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
                   const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
                   const float* bias_col, const float* bc4, float* sdf, float* nrm, float* rgb, float* ge, void* stream);

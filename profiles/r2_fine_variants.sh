@@ -1,0 +1,39 @@
+#!/bin/bash
+# Round-2 A/B of the fine-stage HBM-traffic experiments that were written at the end of round 1 without GPU time left
+# (compiled and spill-checked only: profiles/spills_by_line.py).  Variants of libfmov_b200.so:
+#   base      default build
+#   relu      -DFMOV_RELU_BITS                       colour backward reads ReLU sign words (16 -> 1 block per tile)
+#   rq        -DFMOV_RECOMPUTE_Q                     q_l rebuilt in the backward pass from V-bar, delta, sigma (-32 blocks)
+#   relu_rq   both                                   fine_bwd 265 -> 218 blocks per 128-point tile (-18 %)
+#   relu_rq1 / relu_rq3   same with FMOV_RQ_PH=1 / 3 (prefetch distance of the three operand streams, in 8-column pieces)
+#
+#   bash profiles/r2_fine_variants.sh build        here (no GPU): builds fmov_pose_b200/libfmov_<name>.so (they travel with gpurun)
+#   gpurun --timeout 1500 -- 'bash profiles/r2_fine_variants.sh run'      parity subset per variant, then alternating benches
+set -u
+cd "$(dirname "$0")/.."
+declare -A FLAGS=( [base]="" [relu]="-DFMOV_RELU_BITS" [rq]="-DFMOV_RECOMPUTE_Q" [relu_rq]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q"
+                   [relu_rq1]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=1" [relu_rq3]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=3" )
+ORDER="base relu rq relu_rq relu_rq1 relu_rq3"
+case "${1:-}" in
+build)
+  for v in $ORDER; do
+    FMOV_NVCC_EXTRA="${FLAGS[$v]}" FMOV_LIB_OUT="$PWD/fmov_pose_b200/libfmov_$v.so" python -m fmov_pose_b200.build || exit 1
+    echo "built libfmov_$v.so  (${FLAGS[$v]})"
+  done ;;
+run)
+  mkdir -p gpurun_out
+  for v in $ORDER; do
+    # parity first: a variant that is not green is not timed
+    if FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 600 python -m pytest tests/test_gpu_render.py tests/test_gpu_train_step.py -x -q \
+         > "gpurun_out/r2_variant_$v.pytest.log" 2>&1; then echo "$v parity ok"; else echo "$v PARITY FAILED"; tail -15 "gpurun_out/r2_variant_$v.pytest.log"; FLAGS[$v]="FAILED"; fi
+  done
+  for rep in 1 2 3; do
+    for v in $ORDER; do
+      [ "${FLAGS[$v]}" = "FAILED" ] && continue
+      FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 300 python bench.py --steps 10 --warmup 3 --no_cpu_baseline --no_extras 2>/dev/null | tail -1 \
+        | python -c "import sys,json; d=json.loads(sys.stdin.read()); k=d['roofline']['kernel_ms_per_step']; print('$v', round(d['value']), round(d['ms_per_step'],2), {a:round(b,2) for a,b in k.items() if b>0.5})" \
+        | tee -a gpurun_out/r2_variants.txt
+    done
+  done ;;
+*) echo "usage: $0 build|run"; exit 2 ;;
+esac
