@@ -258,6 +258,50 @@ def measure_extras(scene, dev, use_graph=True):
     return out
 
 
+def measure_marching_cubes_child():
+    """`bench.py --mc_only` (a child process of the default run): validate_mesh's whole device path at config C5's size
+    — the 512^3 u = -sdf grid from the network, then marching cubes on it — prints one JSON object.  HBM roofline of the
+    three marching-cubes passes: each reads the grid once (4 B/point); the mesh itself is small against that."""
+    import torch
+    from fmov_pose_b200 import mcubes_gpu, synthetic
+    dev = torch.device("cuda:0")
+    scene = synthetic.build_scene(device=dev, n_images=2, H=48, W=64)
+    rend = scene["renderer"]
+    res = 512
+    bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
+    u = rend.extract_fields(bmin, bmax, res).reshape(res, res, res)
+    h = 2.02 / (res - 1)
+    for _ in range(2):
+        v, t = mcubes_gpu.marching_cubes(u, 0.0, scale=(h, h, h), offset=(-1.01,) * 3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        v, t = mcubes_gpu.marching_cubes(u, 0.0, scale=(h, h, h), offset=(-1.01,) * 3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    alg = 3 * 4 * res ** 3 + int(v.numel()) * 4 + int(t.numel()) * 4
+    r = torch.linalg.norm(v, dim=1)
+    print(json.dumps({"grid": "512^3", "ms": ms, "vertices": int(v.shape[0]), "triangles": int(t.shape[0]),
+                      "radius_min_max": [float(r.min()), float(r.max())],
+                      "algorithmic_gb_per_s": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / hbm,
+                      "note": "fmov_mc_count + cumsum + fmov_mc_vertices + fmov_mc_triangles incl. the host sync for the "
+                              "output sizes; the reference copies the grid to the host and runs PyMCubes on one core"}))
+
+
+def measure_marching_cubes():
+    """runs in a child process so that the (round-1-unverified) kernels cannot take the bench's CUDA context down"""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--mc_only"], capture_output=True, text=True, timeout=300)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    return json.loads(lines[-1])
+
+
 def measure_grid_sharded(scene, dev, group, world):
     """Config C5 as stated: the 512^3 validate_mesh grid partitioned into x-plane slabs across the ranks (one launch per
     rank) + all-gather of the slabs over NCCL.  Collective: every rank calls it; device-timed, max over ranks."""
@@ -326,7 +370,11 @@ def main():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
+    ap.add_argument("--mc_only", action="store_true", help="internal: marching-cubes extra, run as a child process")
     args = ap.parse_args()
+    if args.mc_only:
+        measure_marching_cubes_child()
+        return 0
     # stdout carries exactly ONE JSON line: libraries that printf to fd 1 (NCCL prints its version banner there when
     # NCCL_DEBUG is set on the box) are sent to stderr, the line is written to the saved descriptor
     sys.stdout.flush()
@@ -495,6 +543,10 @@ def main():
             extras["c3_65536rays_micro_batched"] = measure_c3_micro(dev)
         except Exception as e:          # secondary number: report, do not fail the bench
             extras["c3_65536rays_micro_batched"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        try:
+            extras["c5_marching_cubes_512"] = measure_marching_cubes()
+        except Exception as e:
+            extras["c5_marching_cubes_512"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if not args.no_extras:              # collective (all ranks): config C5 across the N GPUs of this run
         try:
             grid = measure_grid_sharded(scene, dev, group, world)

@@ -14,6 +14,7 @@ import torch
 
 from .. import fine as _fine
 from .. import flow as _flow
+from .. import mcubes_gpu as _mcubes
 from .. import ops as _ops
 from .. import packing as _packing
 from .. import weight_norm as _wn
@@ -40,20 +41,15 @@ def extract_fields(bound_min, bound_max, resolution, query_func):
 
 
 def extract_geometry(bound_min, bound_max, resolution, threshold, query_func=None, u=None):
-    """models/renderer.py:40-51. Marching cubes itself is third-party CPU code (PyMCubes) and out of
-    scope; it is imported lazily so that everything up to the `u` grid works without it."""
+    """models/renderer.py:40-51: grid -> marching cubes -> vertices in world coordinates.  The reference calls PyMCubes on
+    the host (`mcubes.marching_cubes`, :43); here the grid stays on the GPU and `mcubes_gpu` extracts the indexed mesh
+    there (same vertices; triangulation per mc_tables.py).  Returns numpy (vertices float64 [V,3], triangles int64 [T,3])."""
     if u is None:
         u = extract_fields(bound_min, bound_max, resolution, query_func)
-    try:
-        import mcubes
-    except ImportError as e:  # pragma: no cover
-        raise RuntimeError("PyMCubes is required for marching cubes (the SDF grid itself is available via "
-                           "NeuSRenderer.extract_fields)") from e
-    vertices, triangles = mcubes.marching_cubes(u, threshold)
-    b_max_np = bound_max.detach().cpu().numpy()
-    b_min_np = bound_min.detach().cpu().numpy()
-    vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
-    return vertices, triangles
+    if not torch.is_tensor(u):
+        dev = bound_min.device if torch.is_tensor(bound_min) and bound_min.is_cuda else torch.device("cuda")
+        u = torch.as_tensor(np.ascontiguousarray(u), dtype=torch.float32).to(dev)
+    return _mcubes.extract_geometry(u, threshold, [float(v) for v in bound_min], [float(v) for v in bound_max])
 
 
 class NeuSRenderer:
@@ -205,8 +201,10 @@ class NeuSRenderer:
         return out
 
     def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+        """models/renderer.py:500-507: the 512^3 grid query and the marching cubes both run on the device; only the
+        mesh crosses to the host (the reference copies 512 chunks of the grid to the host and runs PyMCubes there)."""
         u = self.extract_fields(bound_min, bound_max, resolution).reshape(resolution, resolution, resolution)
-        return extract_geometry(bound_min, bound_max, resolution, threshold, u=u.cpu().numpy())
+        return extract_geometry(bound_min, bound_max, resolution, threshold, u=u)
 
     def extract_color(self, vertices):
         """models/renderer.py:509-532: colour at mesh vertices with view dir = -normal."""

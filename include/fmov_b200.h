@@ -196,6 +196,24 @@ int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc
 int fmov_grad_amax(const float* d_sdf, const float* d_nrm, const float* d_rgb, long long P, float* amax, void* stream);
 int fmov_grad_is_bf16(void);
 
+/* ---- marching cubes on the dense u grid -------------------------------------------------------------------
+ * replaces `mcubes.marching_cubes(u, threshold)` (PyMCubes, CPU) at models/renderer.py:43 and the rescale of
+ * models/renderer.py:47-50.  u: [X,Y,Z] fp32, z fastest (the layout fmov_sdf_query_grid writes).  Indexed mesh: one vertex
+ * per crossed grid edge, ordered by (grid point x-major, axis); triangles ordered by (cell x-major, case-table order).
+ *   1. fmov_mc_set_tables (once): HOST case table [256][15] + triangle counts [256] (fmov_pose_b200/mc_tables.py)
+ *   2. fmov_mc_count: per 256-point chunk (fmov_mc_chunk_count of them) the number of vertices / triangles
+ *   3. caller: exclusive prefix sums (int64) over the chunks; totals size the outputs
+ *   4. fmov_mc_vertices: verts [V,3] = index coordinate * (sx,sy,sz) + (ox,oy,oz); vid3 [X*Y*Z,3] int32 scratch receives the
+ *      vertex id of every crossed edge (other entries stay unwritten and are never read)
+ *   5. fmov_mc_triangles: tris [T,3] int32 vertex ids                                                                    */
+int fmov_mc_set_tables(const signed char* tri_table, const unsigned char* n_tris);
+long long fmov_mc_chunk_count(int X, int Y, int Z);
+int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, void* stream);
+int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, float sx, float sy,
+                     float sz, float ox, float oy, float oz, float* verts, int* vid3, void* stream);
+int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* vid3,
+                      int* tris, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,79 @@
+// Host emulation of csrc/marching_cubes.cu: the per-point device functions of csrc/mc_core.cuh compiled by g++ and
+// driven chunk by chunk exactly as the three kernels drive them (sequential "threads", prefix sums on the host).
+// Used by tests/test_marching_cubes_host_emulation.py; test infrastructure, never shipped.
+//   mc_host_emul X Y Z iso u.bin tables.bin verts.bin tris.bin     (tables.bin = int8[256*15] + uint8[256])
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../fmov_pose_b200/csrc/mc_core.cuh"
+
+using namespace fmov;
+
+template <class T>
+static std::vector<T> slurp(const char* path, size_t n) {
+  std::vector<T> v(n);
+  FILE* f = fopen(path, "rb");
+  if (!f || fread(v.data(), sizeof(T), n, f) != n) { fprintf(stderr, "cannot read %s\n", path); exit(2); }
+  fclose(f);
+  return v;
+}
+template <class T>
+static void dump(const char* path, const std::vector<T>& v) {
+  FILE* f = fopen(path, "wb");
+  if (!f || (v.size() && fwrite(v.data(), sizeof(T), v.size(), f) != v.size())) { fprintf(stderr, "cannot write %s\n", path); exit(2); }
+  fclose(f);
+}
+
+int main(int argc, char** argv) {
+  if (argc != 9) return 2;
+  McGrid g;
+  g.X = atoi(argv[1]); g.Y = atoi(argv[2]); g.Z = atoi(argv[3]); g.iso = (float)atof(argv[4]);
+  g.n = (long long)g.X * g.Y * g.Z;
+  g.n_chunks = (g.n + MC_CHUNK - 1) / MC_CHUNK;
+  std::vector<float> u = slurp<float>(argv[5], (size_t)g.n);
+  std::vector<signed char> tab = slurp<signed char>(argv[6], 256 * 15 + 256);
+  g.u = u.data();
+  g.tri = tab.data();
+  g.ntri = reinterpret_cast<const unsigned char*>(tab.data() + 256 * 15);
+  // pass 1: per-chunk counts (mc_count_kernel)
+  std::vector<long long> voff(g.n_chunks + 1, 0), toff(g.n_chunks + 1, 0);
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    long long nv = 0, nt = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const McPoint q = mc_point(g, ch * MC_CHUNK + tid, true);
+      nv += mc_vertex_count(q);
+      nt += q.ntri;
+    }
+    voff[ch + 1] = voff[ch] + nv;
+    toff[ch + 1] = toff[ch] + nt;
+  }
+  std::vector<float> verts((size_t)voff[g.n_chunks] * 3);
+  std::vector<int> tris((size_t)toff[g.n_chunks] * 3, -7);
+  std::vector<int> vid3((size_t)g.n * 3, -1);          // -1: an entry the triangle pass must never read
+  McXform xf;
+  for (int a = 0; a < 3; ++a) { xf.s[a] = 1.f; xf.o[a] = 0.f; }
+  // pass 2: vertices (mc_vertices_kernel)
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    int local = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const long long p = ch * MC_CHUNK + tid;
+      const McPoint q = mc_point(g, p, false);
+      const int nv = mc_vertex_count(q);
+      if (nv) mc_emit_vertices(g, xf, p, q, voff[ch] + local, verts.data(), vid3.data());
+      local += nv;
+    }
+  }
+  // pass 3: triangles (mc_triangles_kernel)
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    int local = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const long long p = ch * MC_CHUNK + tid;
+      const McPoint q = mc_point(g, p, true);
+      if (q.ntri) mc_emit_triangles(g, p, q, toff[ch] + local, vid3.data(), tris.data());
+      local += q.ntri;
+    }
+  }
+  dump(argv[7], verts);
+  dump(argv[8], tris);
+  return 0;
+}

@@ -1,0 +1,55 @@
+"""The per-point device code of the marching-cubes kernels (csrc/mc_core.cuh: case build-up, vertex interpolation,
+edge -> vertex-id mapping) compiled by g++ and driven like the kernels drive it, against the numpy oracle.  This is the
+CPU-side check of the CUDA path's logic; the kernels themselves are checked on the GPU by test_gpu_zz_marching_cubes.py."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from fmov_pose_b200 import mc_tables as T
+from oracle import marching_cubes as MC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emul(tmp_path_factory):
+    d = tmp_path_factory.mktemp("mc_emul")
+    exe = str(d / "mc_host_emul")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-x", "c++", os.path.join(ROOT, "tests", "host", "mc_host_emul.cpp"),
+                    "-o", exe], check=True)
+    tab = str(d / "tables.bin")
+    with open(tab, "wb") as f:
+        f.write(np.ascontiguousarray(T.TRI_TABLE, dtype=np.int8).tobytes())
+        f.write(np.ascontiguousarray(T.N_TRIS, dtype=np.uint8).tobytes())
+
+    def run(u, iso):
+        up, vp, tp = str(d / "u.bin"), str(d / "v.bin"), str(d / "t.bin")
+        np.ascontiguousarray(u, dtype=np.float32).tofile(up)
+        X, Y, Z = u.shape
+        subprocess.run([exe, str(X), str(Y), str(Z), repr(float(iso)), up, tab, vp, tp], check=True)
+        return np.fromfile(vp, dtype=np.float32).reshape(-1, 3), np.fromfile(tp, dtype=np.int32).reshape(-1, 3)
+    return run
+
+
+def _field(kind, shape, seed=0):
+    ax = [np.linspace(-1.0, 1.0, n) for n in shape]
+    xx, yy, zz = np.meshgrid(*ax, indexing="ij")
+    if kind == "sphere":
+        return (0.55 - np.sqrt(xx ** 2 + yy ** 2 + zz ** 2)).astype(np.float32)
+    if kind == "waves":
+        return (np.sin(5 * xx) * np.cos(4 * yy) + np.sin(3 * zz + 0.3) * 0.7 + 0.1).astype(np.float32)
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind,shape,iso", [("sphere", (33, 29, 31), 0.0), ("waves", (37, 18, 50), 0.05),
+                                            ("noise", (17, 16, 19), 0.0), ("noise", (2, 2, 2), 0.0),
+                                            ("noise", (3, 129, 2), 0.25), ("sphere", (9, 300, 7), 0.0)])
+def test_device_logic_equals_the_oracle(emul, kind, shape, iso):
+    u = _field(kind, shape)
+    v, t = emul(u, iso)
+    v_ref, t_ref = MC.marching_cubes(u, iso, T.TRI_TABLE, T.N_TRIS)
+    assert v.shape == v_ref.shape and t.shape == t_ref.shape
+    np.testing.assert_allclose(v, v_ref, rtol=0, atol=2e-5)
+    np.testing.assert_array_equal(t.astype(np.int64), t_ref)          # also proves no unwritten vid3 entry was read
