@@ -111,3 +111,8 @@ def barf_pose(se3_row, noise_pose):
 
 pose = Pose()
 lie = Lie()
+
+
+def to_hom(X):
+    """[..., 3] -> [..., 4] homogeneous coordinates (models/camera.py:266-270; used by exp_runner.py:638, 671)"""
+    return torch.cat([X, torch.ones_like(X[..., :1])], dim=-1)

@@ -1,0 +1,121 @@
+"""The loader adapter of the drop-in boundary (fmov_pose_b200/models/dataset.py::make_dataset_class): a stand-in for the
+reference's Dataset (same attribute names as models/dataset.py:146-545 fills) gets the kernel-backed ray functions; rays,
+colours and pose gradients against the oracle's restatement of models/dataset.py:547-576, 656-671, 728-760.  (Named to
+run after the train-step suites: written after round 1's GPU budget was spent.)"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import neus_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class _FakeReferenceDataset:
+    """what Dataset.__init__ leaves behind, from memory instead of disk"""
+
+    def __init__(self, n=3, H=48, W=64):
+        g = torch.Generator().manual_seed(5)
+        self.n_images, self.H, self.W = n, H, W
+        self.images = torch.rand(n, H, W, 3, generator=g)
+        self.masks = (torch.rand(n, H, W, 3, generator=g) > 0.4).float()
+        self.masks_np = self.masks.numpy()
+        K = torch.tensor([[60.0, 0, 32.0, 0], [0, 60.0, 24.0, 0], [0, 0, 1.0, 0], [0, 0, 0, 1.0]])
+        self.intrinsics_all = K[None].repeat(n, 1, 1).to(DEV)
+        self.intrinsics_all_inv = torch.inverse(self.intrinsics_all)
+        self.pose_all = torch.eye(4)[None].repeat(n, 1, 1).to(DEV)
+        self.use_mono_depth = False
+        self.index_to_frame = {i: "%04d" % i for i in range(n)}
+        self.frame_to_index = {v: k for k, v in self.index_to_frame.items()}
+        rng = np.random.default_rng(0)
+        m = [rng.uniform(1, W - 2, 40).astype(np.float32), rng.uniform(1, H - 2, 40).astype(np.float32),
+             rng.uniform(1, W - 2, 40).astype(np.float32), rng.uniform(1, H - 2, 40).astype(np.float32)]
+        self.flow_pairs = {"0000": {"0001"}, "0001": {"0000"}}
+        self.loftr_interval_flows = {"0000_0001": tuple(m), "0001_0000": (m[2], m[3], m[0], m[1])}
+
+
+def _pose(seed):
+    g = torch.Generator().manual_seed(seed)
+    r = torch.randn(3, generator=g) * 0.2
+    R = O.rodrigues_exp(r[None])[0]
+    p = torch.cat([R, torch.tensor([[0.1], [-0.2], [-3.0]])], dim=1)
+    return p.to(DEV).requires_grad_(True)
+
+
+def _make():
+    from fmov_pose_b200.models.dataset import make_dataset_class
+    return make_dataset_class(_FakeReferenceDataset)()
+
+
+def test_random_rays_match_the_reference_formula_and_carry_pose_gradients():
+    ds = _make()
+    pose = _pose(1)
+    torch.manual_seed(11)
+    np.random.seed(11)
+    data, depth = ds.gen_random_rays_at(1, 256, pose, mask_guided_sampling=True, patch_size=5)
+    assert depth is None and data.shape == (256, 10) and data.is_cuda
+    # recover the pixel draw from the colours is not possible: redo the same RNG calls
+    torch.manual_seed(11)
+    np.random.seed(11)
+    if np.random.rand() < 0.7:
+        ys, xs = np.where(ds.masks_np[1][:, :, 0] > 0.5)
+        y0, y1, x0, x1 = max(ys.min() - 5, 0), min(ys.max() + 5, ds.H), max(xs.min() - 5, 0), min(xs.max() + 5, ds.W)
+    else:
+        y0, y1, x0, x1 = 0, ds.H, 0, ds.W
+    px = torch.randint(low=x0, high=x1, size=[256])
+    py = torch.randint(low=y0, high=y1, size=[256])
+    p_cpu = pose.detach().cpu().double().requires_grad_(True)
+    o_ref, v_ref = O.gen_rays(p_cpu, ds.intrinsics_all_inv[1, :3, :3].cpu().double(), px, py)
+    np.testing.assert_allclose(data[:, 0:3].detach().cpu().numpy(), o_ref.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(data[:, 3:6].detach().cpu().numpy(), v_ref.detach().numpy(), atol=2e-6)
+    np.testing.assert_array_equal(data[:, 6:9].cpu().numpy(), ds.images[1][(py, px)].cpu().numpy())
+    np.testing.assert_array_equal(data[:, 9].cpu().numpy(), ds.masks[1][(py, px)][:, 0].cpu().numpy())
+    w = torch.randn(256, 6, generator=torch.Generator().manual_seed(2))
+    (data[:, :6] * w.to(DEV)).sum().backward()
+    (torch.cat([o_ref, v_ref], 1) * w.double()).sum().backward()
+    np.testing.assert_allclose(pose.grad.cpu().numpy(), p_cpu.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("level", [1, 4])
+def test_full_frame_rays_at_every_resolution_level(level):
+    ds = _make()
+    pose = _pose(2).detach()
+    o, v, m = ds.gen_rays_at(2, resolution_level=level, pose=pose, with_mask=True)
+    Hl, Wl = ds.H // level, ds.W // level
+    assert o.shape == (Hl, Wl, 3) and v.shape == (Hl, Wl, 3) and m.shape == (Hl, Wl)
+    # same op on the same device as inside the adapter: CPU and CUDA linspace may differ in the last bit, which flips
+    # the truncated pixel of points that sit on an integer (the reference has the same fragility)
+    tx = torch.linspace(0, ds.W - 1, Wl, device=DEV).cpu()
+    ty = torch.linspace(0, ds.H - 1, Hl, device=DEV).cpu()
+    gx, gy = torch.meshgrid(tx, ty, indexing="ij")
+    o_ref, v_ref = O.gen_rays(pose.cpu().double(), ds.intrinsics_all_inv[2, :3, :3].cpu().double(), gx.reshape(-1).double(),
+                              gy.reshape(-1).double())
+    np.testing.assert_allclose(v.transpose(0, 1).reshape(-1, 3).cpu().numpy(), v_ref.numpy(), atol=2e-6)
+    np.testing.assert_allclose(o.transpose(0, 1).reshape(-1, 3).cpu().numpy(), o_ref.numpy(), atol=1e-6)
+    want_mask = ds.masks[2].cpu()[(gy.long(), gx.long())][..., 0].transpose(0, 1)
+    np.testing.assert_array_equal(m.cpu().numpy(), want_mask.cpu().numpy())
+    o2, v2 = ds.gen_rays_at(2, resolution_level=level)                  # pose=None -> pose_all (GT pose)
+    assert torch.allclose(o2, torch.zeros_like(o2))
+
+
+def test_ray_pairs_follow_the_matches():
+    ds = _make()
+    poses = [_pose(3).detach(), _pose(4).detach(), _pose(5).detach()]
+    net = lambda i: torch.cat([poses[int(i)], torch.tensor([[0, 0, 0, 1.0]], device=DEV)], 0)
+    np.random.seed(3)
+    data, xy, xy_corr, img_id, depth = ds.gen_random_ray_pairs_at(torch.tensor(0), 32, net, current_img_num=3, interval=1)
+    assert int(img_id) == 1 and data.shape == (64, 10) and depth.shape == (64,)
+    np.random.seed(3)
+    np.random.choice([1])
+    idx = np.random.choice(40, 32, replace=True)
+    xs1, ys1, xs2, ys2 = ds.loftr_interval_flows["0000_0001"]
+    np.testing.assert_array_equal(xy_corr.cpu().numpy(), np.stack([xs1[idx], ys1[idx]], -1))
+    np.testing.assert_array_equal(xy.cpu().numpy(), np.stack([xs2[idx], ys2[idx]], -1))
+    o_ref, v_ref = O.gen_rays(poses[0].cpu().double(), ds.intrinsics_all_inv[0, :3, :3].cpu().double(),
+                              torch.from_numpy(xs1[idx]).double(), torch.from_numpy(ys1[idx]).double())
+    np.testing.assert_allclose(data[:32, 3:6].cpu().numpy(), v_ref.numpy(), atol=2e-6)
+    np.testing.assert_allclose(data[:32, 0:3].cpu().numpy(), o_ref.numpy(), atol=1e-6)
+    assert (data[:, 9] == 1).all()
+    # a frame without matches: five Nones, as the reference
+    assert ds.gen_random_ray_pairs_at(torch.tensor(2), 8, net, 3) == (None, None, None, None, None)
