@@ -8,9 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libfmov_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math_off_placeholder"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if not f.endswith("placeholder")]
+# no --use_fast_math: the epilogues pick their approximations explicitly (ex2.approx, __fdividef) where parity allows
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 _EXTRA = os.environ.get("FMOV_NVCC_EXTRA", "").split()           # experiment switches (-DFMOV_...), A/B builds
 NVCC_FLAGS += _EXTRA
 LIB = os.environ.get("FMOV_LIB_OUT", LIB)

@@ -141,3 +141,32 @@ def test_constructor_and_method_signatures_match_the_reference_classes():
         print("CTOR-OK")
     ''')
     assert "CTOR-OK" in out
+
+
+def test_launcher_runs_a_script_with_the_aliases_in_place(tmp_path):
+    """python -m fmov_pose_b200.dropin <script> [args]: the script sees `models.*` = the mirror, its own directory on
+    sys.path and its own argv (no reference checkout needed for this one)"""
+    script = tmp_path / "runner_like.py"
+    (tmp_path / "utils").mkdir()
+    (tmp_path / "utils" / "__init__.py").write_text("MARK = 'local utils'\n")
+    script.write_text(textwrap.dedent('''
+        import sys
+        from models.fields import SDFNetwork, NeRF
+        from models.renderer import NeuSRenderer
+        import models.camera as camera
+        from models.camera import to_hom
+        from models.picture_pose import LearnPoseGF, SegLearnPose
+        from models.pixel_pose import SegDeepPixelPose
+        from utils import MARK
+        assert __name__ == "__main__" and MARK == "local utils"
+        assert SDFNetwork.__module__ == "fmov_pose_b200.models.fields"
+        try:
+            SegDeepPixelPose(3)
+        except NotImplementedError:
+            print("ARGS", sys.argv[1:])
+    '''))
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "fmov_pose_b200.dropin", str(script), "--mode", "train"], env=env,
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "ARGS ['--mode', 'train']" in r.stdout
