@@ -114,6 +114,9 @@ __host__ __device__ inline int stash_kb(int id) {
 #ifdef FMOV_RELU_BITS
   if (id == ST_CM) return 1;
 #endif
+#ifdef FMOV_RECOMPUTE_Q
+  if (id >= ST_Q0 && id < ST_Q0 + 8) return 0;          // q is never materialised: 32 blocks per tile less stash memory
+#endif
   return (id == ST_PE || id == ST_X || id == ST_GE) ? 1 : 4;
 }
 // written by fmov_fine_fwd (a forward-only stash holds exactly these)
