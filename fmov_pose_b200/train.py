@@ -7,8 +7,33 @@ import math
 import torch
 import torch.nn.functional as F
 
+from . import _lib as _L
 from . import flow as _flow
+from . import ops as _ops
 from .models import camera as _camera
+
+
+class _FusedLossFn(torch.autograd.Function):
+    """colour + mask loss terms of exp_runner.py:562-599 in one launch (fmov_loss_fwd_bwd computes the per-ray terms and
+    their gradients together): (color [B,3], weight_sum [B,1]) -> (color_loss, mask_loss) scalars."""
+
+    @staticmethod
+    def forward(ctx, color, weight_sum, true_rgb, mask, mask_sum, n_rays_global, mask_weight):
+        partial, g_color, g_wsum = _ops.loss_fwd_bwd(_L.f32c(color.detach()), _L.f32c(weight_sum.detach()),
+                                                     _L.f32c(true_rgb), _L.f32c(mask), _L.f32c(mask_sum.reshape(1)),
+                                                     int(n_rays_global), float(mask_weight))
+        ctx.save_for_backward(g_color, g_wsum)
+        ctx.mask_weight = float(mask_weight)
+        sums = partial.sum(0)
+        return sums[0], sums[1]
+
+    @staticmethod
+    def backward(ctx, g_col, g_bce):
+        g_color, g_wsum = ctx.saved_tensors
+        gc = None if g_col is None else g_color * g_col
+        # the kernel's weight_sum gradient already carries mask_weight (loss = colour + mask_weight * bce)
+        gw = None if (g_bce is None or ctx.mask_weight == 0.0) else g_wsum * (g_bce / ctx.mask_weight)
+        return gc, gw, None, None, None, None, None
 
 
 class LRSchedule:
@@ -44,8 +69,9 @@ class LRSchedule:
 class TrainStep:
     def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True,
                  capturable=False, flow_weight=0.0, unit_sphere_weight=0.0, maintain_shape=False,
-                 detach_flow_on_sdf=False, detach_ref=False):
+                 detach_flow_on_sdf=False, detach_ref=False, fused_loss=False):
         self.s = scene
+        self.fused_loss = bool(fused_loss)       # colour + mask terms through fmov_loss_fwd_bwd (one launch instead of ~40)
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
         # exp_runner.py:150-160, 327-336 (train.flow_weight, unit_sphere_weight, maintain_shape, detach_*)
         self.flow_weight, self.unit_sphere_weight = float(flow_weight), float(unit_sphere_weight)
@@ -152,6 +178,13 @@ class TrainStep:
             torch.distributed.all_reduce(pack, group=self.group)
             msum, n_rays = pack[0], pack[1]
         mask_sum = msum + 1e-5
+        if self.fused_loss:
+            # the kernel thresholds the raw mask itself; every rank holds the same number of rays (fixed split)
+            color_loss, bce = _FusedLossFn.apply(out["color_fine"], out["weight_sum"], true_rgb, mask, mask_sum,
+                                                 mask.shape[0] * self.world, self.mask_weight)
+            eik = out["gradient_error"]
+            loss = color_loss + eik * self.igr_weight + bce * self.mask_weight
+            return dict(loss=loss, color_loss=color_loss, eikonal_loss=eik, mask_loss=bce)
         color_error = (out["color_fine"] - true_rgb) * mask
         color_loss = color_error.abs().sum() / mask_sum
         eik = out["gradient_error"]                       # already globally normalised by the renderer

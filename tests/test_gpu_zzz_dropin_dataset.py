@@ -119,3 +119,33 @@ def test_ray_pairs_follow_the_matches():
     assert (data[:, 9] == 1).all()
     # a frame without matches: five Nones, as the reference
     assert ds.gen_random_ray_pairs_at(torch.tensor(2), 8, net, 3) == (None, None, None, None, None)
+
+
+@pytest.mark.parametrize("mask_weight", [5.0, 0.0])
+def test_fused_loss_step_equals_the_torch_loss_step(mask_weight):
+    """TrainStep(fused_loss=True): colour + mask terms through fmov_loss_fwd_bwd (one launch) == the torch formulation
+    of exp_runner.py:562-599 — losses and every network / pose gradient of one iteration"""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    B = 300
+    g = torch.Generator().manual_seed(7)
+    px = torch.randint(150, 490, [B], generator=g).to(DEV)
+    py = torch.randint(70, 410, [B], generator=g).to(DEV)
+    tr = torch.rand(B, 1, generator=g).to(DEV)
+    res = []
+    for fused in (False, True):
+        sc = synthetic.build_scene(device=DEV, n_images=4, n_samples=16, n_importance=16, up_sample_steps=2, pose_type="seg")
+        ts = TrainStep(sc, mask_weight=mask_weight, optimizer=False, fused_loss=fused)
+        ls, out = ts.forward_backward(2, B, pixels=(px, py), t_rand=tr)
+        res.append((ls, [None if p.grad is None else p.grad.detach().clone() for p in ts.all_params]))
+    (la, ga), (lb, gb) = res
+    for k in ("loss", "color_loss", "eikonal_loss", "mask_loss"):
+        np.testing.assert_allclose(float(lb[k].detach()), float(la[k].detach()), rtol=2e-5, atol=1e-7, err_msg=k)
+    n = 0
+    for a, b in zip(ga, gb):
+        assert (a is None) == (b is None)
+        if a is not None and float(a.abs().max()) > 0:
+            e = float((a - b).norm() / a.norm())
+            assert e <= 1e-4, e
+            n += 1
+    assert n > 40
