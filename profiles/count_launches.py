@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 for name, kw, B, two in (("literal 2x512 rays 32+0", dict(n_samples=32, n_importance=0), 512, True),
                          ("8192 rays 64+64", dict(n_samples=64, n_importance=64), 8192, False)):
     sc = synthetic.build_scene(device=dev, pose_type="seg", **kw)
-    ts = TrainStep(sc, mask_weight=5.0)
+    ts = TrainStep(sc, mask_weight=5.0, fused_loss="--fused_loss" in sys.argv)
     g = torch.Generator().manual_seed(0)
     px = torch.randint(140, 500, [2 * B], generator=g).to(dev)
     py = torch.randint(60, 420, [2 * B], generator=g).to(dev)
@@ -28,9 +28,14 @@ for name, kw, B, two in (("literal 2x512 rays 32+0", dict(n_samples=32, n_import
         ts.step(2, B, pixels=(px[:B], py[:B]), t_rand=tr, **add)
         torch.cuda.synchronize()
     cnt = collections.Counter()
+    names = collections.Counter()
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA and "memcpy" not in ev.name.lower() and "memset" not in ev.name.lower():
             cnt["fmov" if "fmov::" in ev.name else "torch/other"] += 1
+            names[ev.name[:110]] += 1
     print(f"{name}: {sum(cnt.values())} kernel launches per iteration ({dict(cnt)})")
+    if "--names" in sys.argv:          # which torch glue is left to fuse
+        for k, v in names.most_common(40):
+            print(f"    {v:4d} x {k}")
     del ts, sc
     torch.cuda.empty_cache()
