@@ -65,10 +65,10 @@ def marching_cubes(u, isovalue, tri_table, n_tris):
 
 def extract_geometry(u, threshold, bound_min, bound_max, tri_table, n_tris):
     """models/renderer.py:40-51 on a given grid: marching cubes + rescale from index to world coordinates."""
-    res = u.shape[0]
+    res = np.asarray(u.shape, dtype=np.float64)          # the reference's grids are cubic (one `resolution`)
     v, t = marching_cubes(u, threshold, tri_table, n_tris)
     b_min, b_max = np.asarray(bound_min, dtype=np.float64), np.asarray(bound_max, dtype=np.float64)
-    return v / (res - 1.0) * (b_max - b_min)[None, :] + b_min[None, :], t
+    return v / (res - 1.0)[None, :] * (b_max - b_min)[None, :] + b_min[None, :], t
 
 
 # ---- mesh properties used by the tests -----------------------------------------------------------------------------

@@ -1,0 +1,82 @@
+// Host stand-in for the five marching-cubes entry points of libfmov_b200.so (same C signatures, host pointers): the
+// kernels' per-point code (csrc/mc_core.cuh) driven chunk by chunk.  Lets the Python glue of fmov_pose_b200/mcubes_gpu.py
+// (argument marshalling, prefix sums, output sizing) run on the CPU in tests/test_marching_cubes_host_emulation.py.
+// Test infrastructure, never shipped.
+#include <cstring>
+#include <vector>
+#include "../../fmov_pose_b200/csrc/mc_core.cuh"
+
+using namespace fmov;
+
+static signed char g_tri[256 * 15];
+static unsigned char g_ntri[256];
+static bool g_set = false;
+
+static bool grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
+  if (!u || X < 2 || Y < 2 || Z < 2 || !g_set) return false;
+  g.u = u; g.X = X; g.Y = Y; g.Z = Z; g.iso = iso;
+  g.n = (long long)X * Y * Z;
+  g.n_chunks = (g.n + MC_CHUNK - 1) / MC_CHUNK;
+  g.tri = g_tri; g.ntri = g_ntri;
+  return true;
+}
+
+extern "C" {
+int fmov_mc_set_tables(const signed char* tri, const unsigned char* ntri) {
+  if (!tri || !ntri) return -1;
+  memcpy(g_tri, tri, sizeof(g_tri));
+  memcpy(g_ntri, ntri, sizeof(g_ntri));
+  g_set = true;
+  return 0;
+}
+long long fmov_mc_chunk_count(int X, int Y, int Z) { return ((long long)X * Y * Z + MC_CHUNK - 1) / MC_CHUNK; }
+int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, void*) {
+  McGrid g;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt) return -1;
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    int nv = 0, nt = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const McPoint q = mc_point(g, ch * MC_CHUNK + tid, true);
+      nv += mc_vertex_count(q);
+      nt += q.ntri;
+    }
+    chunk_nv[ch] = nv;
+    chunk_nt[ch] = nt;
+  }
+  return 0;
+}
+int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, float sx, float sy, float sz,
+                     float ox, float oy, float oz, float* verts, int* vid3, void*) {
+  McGrid g;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_voff || !verts || !vid3) return -1;
+  McXform xf;
+  xf.s[0] = sx; xf.s[1] = sy; xf.s[2] = sz; xf.o[0] = ox; xf.o[1] = oy; xf.o[2] = oz;
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    int local = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const long long p = ch * MC_CHUNK + tid;
+      const McPoint q = mc_point(g, p, false);
+      const int nv = mc_vertex_count(q);
+      if (nv) mc_emit_vertices(g, xf, p, q, chunk_voff[ch] + local, verts, vid3);
+      local += nv;
+    }
+  }
+  return 0;
+}
+int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* vid3, int* tris,
+                      void*) {
+  McGrid g;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_toff || !vid3 || !tris) return -1;
+  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+    int local = 0;
+    for (int tid = 0; tid < MC_CHUNK; ++tid) {
+      const long long p = ch * MC_CHUNK + tid;
+      const McPoint q = mc_point(g, p, true);
+      if (q.ntri) mc_emit_triangles(g, p, q, chunk_toff[ch] + local, vid3, tris);
+      local += q.ntri;
+    }
+  }
+  return 0;
+}
+const char* fmov_last_error(void) { return "host stand-in"; }
+}

@@ -53,3 +53,47 @@ def test_device_logic_equals_the_oracle(emul, kind, shape, iso):
     assert v.shape == v_ref.shape and t.shape == t_ref.shape
     np.testing.assert_allclose(v, v_ref, rtol=0, atol=2e-5)
     np.testing.assert_array_equal(t.astype(np.int64), t_ref)          # also proves no unwritten vid3 entry was read
+
+
+def test_python_glue_end_to_end_on_a_host_stand_in(tmp_path, monkeypatch):
+    """fmov_pose_b200/mcubes_gpu.py (marshalling, chunk prefix sums, output sizing, world-coordinate transform) against the
+    oracle, with the five C entry points served by a host build of the same per-point code and CPU tensors standing in for
+    device memory (the product refuses CPU tensors; the test lifts exactly that check)."""
+    import contextlib
+    import ctypes
+
+    import torch
+
+    from fmov_pose_b200 import _lib as L
+    from fmov_pose_b200 import mcubes_gpu
+
+    so = str(tmp_path / "libmc_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                    os.path.join(ROOT, "tests", "host", "mc_host_lib.cpp"), "-o", so], check=True)
+    fake = ctypes.CDLL(so)
+    fake.fmov_mc_chunk_count.restype = ctypes.c_longlong
+    fake.fmov_last_error.restype = ctypes.c_char_p
+    monkeypatch.setattr(L, "lib", lambda: fake)
+    monkeypatch.setattr(L, "ptr", lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr()))
+    monkeypatch.setattr(L, "stream", lambda: ctypes.c_void_p(0))
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(mcubes_gpu, "_tables_on", set())
+
+    class _AsCuda(torch.Tensor):          # a CPU tensor that answers is_cuda like device memory would
+        is_cuda = True
+
+    for kind, shape, iso in (("sphere", (33, 29, 31), 0.0), ("noise", (17, 16, 19), 0.1), ("noise", (2, 2, 2), 0.0)):
+        u = _field(kind, shape)
+        ut = torch.from_numpy(u).as_subclass(_AsCuda)
+        v, t = mcubes_gpu.marching_cubes(ut, iso)
+        v_ref, t_ref = MC.marching_cubes(u, iso, T.TRI_TABLE, T.N_TRIS)
+        assert v.dtype == torch.float32 and t.dtype == torch.int32
+        np.testing.assert_allclose(v.numpy(), v_ref, atol=2e-5)
+        np.testing.assert_array_equal(t.numpy().astype(np.int64), t_ref)
+        vw, tw = mcubes_gpu.extract_geometry(ut, iso, [-1.0, -2.0, 0.0], [1.0, 2.0, 4.0])
+        vw_ref, _ = MC.extract_geometry(u, iso, [-1.0, -2.0, 0.0], [1.0, 2.0, 4.0], T.TRI_TABLE, T.N_TRIS)
+        assert vw.dtype == np.float64 and tw.dtype == np.int64
+        np.testing.assert_allclose(vw, vw_ref, atol=1e-5)
+    empty = torch.full((5, 5, 5), -1.0).as_subclass(_AsCuda)
+    v, t = mcubes_gpu.marching_cubes(empty, 0.0)
+    assert v.shape == (0, 3) and t.shape == (0, 3)
