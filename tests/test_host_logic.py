@@ -223,3 +223,47 @@ def test_lr_schedule_matches_the_reference_function(tag):
         pose.append([ts.optimizer.param_groups[1 + k]["lr"] for k in range(3)])
     np.testing.assert_allclose(net, d[tag + ".net_lr"], rtol=1e-12, atol=0)
     np.testing.assert_allclose(pose, d[tag + ".pose_lr"], rtol=1e-12, atol=0)
+
+
+def test_fused_loss_function_glue_matches_the_torch_loss_block(monkeypatch):
+    """train._FusedLossFn around fmov_loss_fwd_bwd: with the kernel replaced by a torch transcription of
+    csrc/composite.cu::loss_fwd_bwd_kernel the function must reproduce exp_runner.py:562-599 (values and gradients),
+    including the mask_weight scaling carried by the kernel's weight_sum gradient."""
+    import torch.nn.functional as F
+
+    from fmov_pose_b200 import _lib as L
+    from fmov_pose_b200 import ops, train
+
+    def kernel(color, wsum, true_rgb, mask, mask_sum, n_rays_global, mask_weight):
+        m = (mask > 0.5).float() if mask_weight > 0 else torch.ones_like(mask)
+        e = (color - true_rgb) * m
+        g_color = torch.sign(e) * m / mask_sum
+        x = wsum.clamp(1e-3, 1 - 1e-3)
+        bce = -(m * torch.log(x) + (1 - m) * torch.log(1 - x))
+        g_x = (-(m / x) + (1 - m) / (1 - x)) / n_rays_global * mask_weight
+        g_w = torch.where((wsum >= 1e-3) & (wsum <= 1 - 1e-3), g_x, torch.zeros_like(g_x))
+        partial = torch.cat([e.abs().sum(-1, keepdim=True) / mask_sum, bce / n_rays_global], dim=1)
+        return partial, g_color, g_w
+
+    monkeypatch.setattr(ops, "loss_fwd_bwd", kernel)
+    monkeypatch.setattr(L, "f32c", lambda t: t.float().contiguous())
+    g = torch.Generator().manual_seed(0)
+    B = 97
+    for mask_weight in (5.0, 0.0):
+        color = torch.rand(B, 3, generator=g).requires_grad_(True)
+        wsum = (torch.rand(B, 1, generator=g) * 1.2 - 0.1).requires_grad_(True)          # some outside the clip range
+        rgb = torch.rand(B, 3, generator=g)
+        raw_mask = torch.rand(B, 1, generator=g)
+        mask = (raw_mask > 0.5).float() if mask_weight > 0 else torch.ones_like(raw_mask)
+        mask_sum = mask.sum() + 1e-5
+        col, bce = train._FusedLossFn.apply(color, wsum, rgb, mask, mask_sum, B, mask_weight)
+        (col + bce * mask_weight).backward()
+        got = (col.item(), bce.item(), color.grad.clone(), wsum.grad.clone() if wsum.grad is not None else torch.zeros_like(wsum))
+        color.grad = None
+        wsum.grad = None
+        col_r = ((color - rgb) * mask).abs().sum() / mask_sum
+        bce_r = F.binary_cross_entropy(wsum.clip(1e-3, 1 - 1e-3), mask, reduction="sum") / B
+        (col_r + bce_r * mask_weight).backward()
+        assert abs(got[0] - col_r.item()) < 1e-6 and abs(got[1] - bce_r.item()) < 1e-5
+        np.testing.assert_allclose(got[2].numpy(), color.grad.numpy(), atol=1e-7)
+        np.testing.assert_allclose(got[3].numpy(), wsum.grad.numpy(), atol=1e-6)
