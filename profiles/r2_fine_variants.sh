@@ -9,6 +9,7 @@
 #
 #   bash profiles/r2_fine_variants.sh build        here (no GPU): builds fmov_pose_b200/libfmov_<name>.so (they travel with gpurun)
 #   gpurun --timeout 1500 -- 'bash profiles/r2_fine_variants.sh run'      parity subset per variant, then alternating benches
+#   gpurun --timeout 1500 -- 'bash profiles/r2_fine_variants.sh ncu relu_rq'   ncu --set full of the fine/dw kernels + marching cubes
 set -u
 cd "$(dirname "$0")/.."
 declare -A FLAGS=( [base]="" [relu]="-DFMOV_RELU_BITS" [rq]="-DFMOV_RECOMPUTE_Q" [relu_rq]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q"
@@ -35,5 +36,15 @@ run)
         | tee -a gpurun_out/r2_variants.txt
     done
   done ;;
-*) echo "usage: $0 build|run"; exit 2 ;;
+ncu)
+  # one --set full capture of the step's kernels with the chosen variant (default relu_rq) and of the marching-cubes passes;
+  # read back here with `python profiles/summarize.py full gpurun_out/<file>.ncu-rep`
+  v="${2:-relu_rq}"
+  mkdir -p gpurun_out
+  FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 900 ncu --set full --clock-control none --import-source on \
+    -k regex:'fine_|dw_kernel' -c 6 -o "gpurun_out/r2_step_$v" -f python profiles/run_kernels.py step 2048 > "gpurun_out/r2_ncu_$v.log" 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:'mc_' -c 9 -o gpurun_out/r2_mc -f \
+    python bench.py --mc_only > gpurun_out/r2_ncu_mc.log 2>&1
+  tail -3 "gpurun_out/r2_ncu_$v.log" gpurun_out/r2_ncu_mc.log ;;
+*) echo "usage: $0 build|run|ncu [variant]"; exit 2 ;;
 esac
