@@ -340,6 +340,49 @@ __device__ __forceinline__ void tile_prefetch_l2(const uint8_t* tilep, int ck_fi
   }
 }
 
+// ---- L2 eviction-priority hints (experiment, -DFMOV_L2_HINTS): a kernel that reads a stash tensor twice marks the first
+// read evict_last and everything it streams evict_first, so that the second read has a chance to hit the 126 MB L2.
+// Hints cannot change results, only where lines live.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ldg_pol(const void* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void stg_pol(void* p, const uint4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void chunk_load_pol(const uint8_t* tilep, int ck, uint4* q, uint64_t pol) {
+  const uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+  q[0] = ldg_pol(p, pol);
+  q[1] = ldg_pol(p + TI_CHUNK_STRIDE, pol);
+}
+__device__ __forceinline__ void chunk_store_pol(uint8_t* tilep, int ck, const uint4* q, uint64_t pol) {
+  uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+  stg_pol(p, q[0], pol);
+  stg_pol(p + TI_CHUNK_STRIDE, q[1], pol);
+}
+__device__ __forceinline__ void tile_prefetch_l2_keep(const uint8_t* tilep, int ck_first, int n_ck) {
+  if ((threadIdx.x & 7) == 0) {
+    for (int ck = ck_first; ck < ck_first + n_ck; ++ck) {
+      const uint8_t* p = tilep + (ck >> 2) * BLK_BYTES + (2 * (ck & 3)) * TI_CHUNK_STRIDE;
+      asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+      asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p + TI_CHUNK_STRIDE));
+    }
+  }
+}
+
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------
 // chunk ch (0..7) of row r sits at blk + ch*2048 + r*16: the 32 lanes of a warp touch 512 contiguous bytes.
 __device__ __forceinline__ void pack4_grad(const float* v, uint4* q) {   // gradient tile format

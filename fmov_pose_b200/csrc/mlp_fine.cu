@@ -52,6 +52,19 @@ constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks
 // sweep / colour / backward loops and separate loop bodies for the l == 8 / l == 4 specials (fine_fwd 5.23 -> 5.28 ms,
 // fine_bwd 7.71 -> 7.94 ms at 8192 rays: more code and registers, no latency won); PFD = 2 (spills at 96 registers).
 #define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)
+// -DFMOV_L2_HINTS (experiment, fine_bwd only): H is read twice (adjoint pass, then ordinary backward) — first read
+// evict_last, everything that is used once evict_first.  KEEP / STREAM name the intent at each site.
+#ifdef FMOV_L2_HINTS
+#define LD_KEEP(tp, ck, q) chunk_load_pol(tp, ck, q, pol_keep)
+#define LD_STREAM(tp, ck, q) chunk_load_pol(tp, ck, q, pol_stream)
+#define ST_STREAM(tp, ck, q) chunk_store_pol(tp, ck, q, pol_stream)
+#define PF_KEEP(tp, a, b) tile_prefetch_l2_keep(tp, a, b)
+#else
+#define LD_KEEP(tp, ck, q) chunk_load(tp, ck, q)
+#define LD_STREAM(tp, ck, q) chunk_load(tp, ck, q)
+#define ST_STREAM(tp, ck, q) chunk_store(tp, ck, q)
+#define PF_KEEP(tp, a, b) tile_prefetch_l2(tp, a, b)
+#endif
 // Register budget: 640 threads put 5 warps on every SM sub-partition (16 K registers each), so ptxas caps the kernels
 // at 96 registers/thread.  setmaxnreg re-balancing (control warpgroup -> 24..56, epilogue -> 104..120) was tried at
 // compile time and dropped: ptxas 12.9 either fails (C7600, control <= 32) or compiles the epilogue region against
@@ -541,6 +554,9 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
     const bool owner = c.wg == CH_WGS - 1;
     const float gscale = grad_scale_from_amax(__ldg(a.amax));
     const float ginv = 1.0f / gscale;
+#ifdef FMOV_L2_HINTS
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+#endif
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
@@ -699,14 +715,14 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         // removes the Q write here and the delta read ("HBM budget")
         uint4 sb[PFD + 1][2];
 #pragma unroll
-        for (int i = 0; i < PFD; ++i) chunk_load(hp, ck0 + i, sb[i]);
-        if (kStashPrefetch) tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
+        for (int i = 0; i < PFD; ++i) LD_KEEP(hp, ck0 + i, sb[i]);
+        if (kStashPrefetch) PF_KEEP(hp, ck0 + PFD, NCK - PFD);
         (void)dp;
         epi_wait_acc(c);
 #pragma unroll
         for (int i = 0; i < NCK; ++i) {
           const int ck = ck0 + i;
-          if (i + PFD < NCK) chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+          if (i + PFD < NCK) LD_KEEP(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
           float v[16];
           if (ck * 16 < n_mma) {
             acc_load16(c, ck * 16, v);
@@ -730,11 +746,11 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint4 sb[PFD + 1][2], db[PFD + 1][2];
 #pragma unroll
         for (int i = 0; i < PFD; ++i) {
-          chunk_load(hp, ck0 + i, sb[i]);
-          chunk_load(dp, ck0 + i, db[i]);
+          LD_KEEP(hp, ck0 + i, sb[i]);
+          LD_STREAM(dp, ck0 + i, db[i]);
         }
         if (kStashPrefetch && (!kPrefetchNext || l == 0)) {
-          tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
+          PF_KEEP(hp, ck0 + PFD, NCK - PFD);
           tile_prefetch_l2(dp, ck0 + PFD, NCK - PFD);
         }
         epi_wait_acc(c);
@@ -742,8 +758,8 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int i = 0; i < NCK; ++i) {
           const int ck = ck0 + i;
           if (i + PFD < NCK) {
-            chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
-            chunk_load(dp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
+            LD_KEEP(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+            LD_STREAM(dp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
           }
           if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l < 7) {     // next step's tiles, half a step + MMA ahead
             tile_prefetch_l2(tile_base(ptrs, ST_H1 + l + 1, tile, c.row), ck0 + PFD, NCK - PFD);
@@ -769,9 +785,9 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q2[2];
           pack2_grad(v, q2);
           chunk_store(ap, ck, q2);
-          chunk_store(vp, ck, q2);
+          ST_STREAM(vp, ck, q2);              // V-bar is only read again by the dW kernel
           pack2_grad(qv, q2);
-          chunk_store(qp, ck, q2);
+          chunk_store(qp, ck, q2);            // q comes back in the ordinary backward pass: default policy
         }
 #endif
         if (l < 7) epi_signal_act(c);
@@ -801,9 +817,15 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         constexpr int PH = FMOV_RQ_PH;          // prefetch distance in 8-column pieces
         constexpr int NP = 2 * NCK;             // pieces per warpgroup
         const int pc0 = 2 * ck0;                // first piece (= 16-byte chunk column of the 256-wide tile)
+#ifdef FMOV_L2_HINTS
+        auto piece = [pol_stream](const uint8_t* tp, int pi) {          // last use of all three streams
+          return ldg_pol(tp + (pi >> 3) * BLK_BYTES + (pi & 7) * TI_CHUNK_STRIDE, pol_stream);
+        };
+#else
         auto piece = [](const uint8_t* tp, int pi) {
           return *reinterpret_cast<const uint4*>(tp + (pi >> 3) * BLK_BYTES + (pi & 7) * TI_CHUNK_STRIDE);
         };
+#endif
         uint4 sb[PH + 1], vb[PH + 1], db[PH + 1];
 #pragma unroll
         for (int i = 0; i < PH; ++i) {
@@ -863,7 +885,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             uint4 q2[2];
             pack2_grad(v, q2);
             chunk_store(ap, ck, q2);
-            chunk_store(zp, ck, q2);
+            ST_STREAM(zp, ck, q2);
           }
         }
         epi_signal_act(c);
@@ -878,8 +900,8 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint4 sb[PFD + 1][2], db[PFD + 1][2];
 #pragma unroll
         for (int i = 0; i < PFD; ++i) {
-          chunk_load(hp, ck0 + i, sb[i]);
-          chunk_load(qp, ck0 + i, db[i]);
+          LD_STREAM(hp, ck0 + i, sb[i]);          // last use of H and q
+          LD_STREAM(qp, ck0 + i, db[i]);
         }
         if (kStashPrefetch && (!kPrefetchNext || l == 8)) {
           tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
@@ -890,8 +912,8 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         for (int i = 0; i < NCK; ++i) {
           const int ck = ck0 + i;
           if (i + PFD < NCK) {
-            chunk_load(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
-            chunk_load(qp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
+            LD_STREAM(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
+            LD_STREAM(qp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
           }
           if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l > 1) {
             tile_prefetch_l2(tile_base(ptrs, ST_H1 + (l - 2), tile, c.row), ck0 + PFD, NCK - PFD);
@@ -924,7 +946,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q2[2];
           pack2_grad(v, q2);
           chunk_store(ap, ck, q2);
-          chunk_store(zp, ck, q2);
+          ST_STREAM(zp, ck, q2);
         }
         epi_signal_act(c);
       }

@@ -6,6 +6,7 @@
 #   rq        -DFMOV_RECOMPUTE_Q                     q_l rebuilt in the backward pass from V-bar, delta, sigma (-32 blocks)
 #   relu_rq   both                                   fine_bwd 265 -> 218 blocks per 128-point tile (-18 %)
 #   relu_rq1 / relu_rq3   same with FMOV_RQ_PH=1 / 3 (prefetch distance of the three operand streams, in 8-column pieces)
+#   l2 / relu_rq_l2       -DFMOV_L2_HINTS: fine_bwd reads H twice; first read evict_last, single-use traffic evict_first
 #
 #   bash profiles/r2_fine_variants.sh build        here (no GPU): builds fmov_pose_b200/libfmov_<name>.so (they travel with gpurun)
 #   gpurun --timeout 1500 -- 'bash profiles/r2_fine_variants.sh run'      parity subset per variant, then alternating benches
@@ -13,8 +14,9 @@
 set -u
 cd "$(dirname "$0")/.."
 declare -A FLAGS=( [base]="" [relu]="-DFMOV_RELU_BITS" [rq]="-DFMOV_RECOMPUTE_Q" [relu_rq]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q"
-                   [relu_rq1]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=1" [relu_rq3]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=3" )
-ORDER="base relu rq relu_rq relu_rq1 relu_rq3"
+                   [relu_rq1]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=1" [relu_rq3]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=3"
+                   [l2]="-DFMOV_L2_HINTS" [relu_rq_l2]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS" )
+ORDER="base relu rq relu_rq relu_rq1 relu_rq3 l2 relu_rq_l2"
 case "${1:-}" in
 build)
   for v in $ORDER; do
