@@ -69,8 +69,8 @@ def test_random_rays_match_the_reference_formula_and_carry_pose_gradients():
     o_ref, v_ref = O.gen_rays(p_cpu, ds.intrinsics_all_inv[1, :3, :3].cpu().double(), px, py)
     np.testing.assert_allclose(data[:, 0:3].detach().cpu().numpy(), o_ref.detach().numpy(), atol=1e-6)
     np.testing.assert_allclose(data[:, 3:6].detach().cpu().numpy(), v_ref.detach().numpy(), atol=2e-6)
-    np.testing.assert_array_equal(data[:, 6:9].cpu().numpy(), ds.images[1][(py, px)].cpu().numpy())
-    np.testing.assert_array_equal(data[:, 9].cpu().numpy(), ds.masks[1][(py, px)][:, 0].cpu().numpy())
+    np.testing.assert_array_equal(data[:, 6:9].detach().cpu().numpy(), ds.images[1][(py, px)].cpu().numpy())
+    np.testing.assert_array_equal(data[:, 9].detach().cpu().numpy(), ds.masks[1][(py, px)][:, 0].cpu().numpy())
     w = torch.randn(256, 6, generator=torch.Generator().manual_seed(2))
     (data[:, :6] * w.to(DEV)).sum().backward()
     (torch.cat([o_ref, v_ref], 1) * w.double()).sum().backward()
