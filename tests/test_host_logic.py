@@ -267,3 +267,52 @@ def test_fused_loss_function_glue_matches_the_torch_loss_block(monkeypatch):
         assert abs(got[0] - col_r.item()) < 1e-6 and abs(got[1] - bce_r.item()) < 1e-5
         np.testing.assert_allclose(got[2].numpy(), color.grad.numpy(), atol=1e-7)
         np.testing.assert_allclose(got[3].numpy(), wsum.grad.numpy(), atol=1e-6)
+
+
+def test_stash_layout_follows_the_library_directory(monkeypatch):
+    """fine.Stash carves ONE buffer by the library's stash directory: the tensors the forward kernel writes come first (a
+    forward-only stash is a prefix of the full one), also when an experiment build appends a forward tensor at the end of
+    the id range (-DFMOV_RELU_BITS) or gives tensors zero blocks (-DFMOV_RECOMPUTE_Q)."""
+    from fmov_pose_b200 import _lib as L
+    from fmov_pose_b200 import fine
+
+    class FakeLib:
+        def __init__(self, blocks, fwd):
+            self.blocks, self.fwd = blocks, fwd
+
+        def fmov_fine_stash_count(self):
+            return len(self.blocks)
+
+        def fmov_fine_stash_blocks(self, i):
+            return self.blocks[i]
+
+        def fmov_fine_stash_is_forward(self, i):
+            return 1 if i in self.fwd else 0
+
+    default = FakeLib([1] + [4] * 8 + [4] + [4] * 8 + [1] + [4] * 4 + [4] * 4 + [4, 1] + [4] * 8 + [4] * 8 + [4] * 8, set(range(23)))
+    variant = FakeLib(default.blocks[:37] + [0] * 8 + default.blocks[45:] + [1], set(range(23)) | {53})
+    for lib in (default, variant):
+        monkeypatch.setattr(L, "lib", lambda lib=lib: lib)
+        fine.Stash._pool.clear()
+        P = 128 * 5 + 3                                     # 6 tiles
+        full = fine.Stash(P, torch.device("cpu"), with_backward=True)
+        n = len(lib.blocks)
+        assert full.nt == 6 and len(full.tensors) == n
+        spans = []
+        for i, t in enumerate(full.tensors):
+            assert t is not None and t.numel() == lib.blocks[i] * 6 * 16384, i
+            off = t.data_ptr() - full.buf.data_ptr()
+            spans.append((off, off + t.numel(), i))
+        used = sorted(s for s in spans if s[1] > s[0])
+        assert all(a[1] == b[0] for a, b in zip(used, used[1:])) and used[0][0] == 0          # contiguous, no overlap
+        assert used[-1][1] == sum(lib.blocks) * 6 * 16384 == full.buf.numel()
+        n_fwd_bytes = sum(lib.blocks[i] for i in lib.fwd) * 6 * 16384
+        assert all((s[1] <= n_fwd_bytes) == (s[2] in lib.fwd) for s in used)                  # forward tensors = prefix
+        full.buf = None                                      # do not recycle: the next stash must size itself
+        fwd_only = fine.Stash(P, torch.device("cpu"), with_backward=False)
+        assert fwd_only.buf.numel() == n_fwd_bytes
+        assert all((t is not None) == (i in lib.fwd) for i, t in enumerate(fwd_only.tensors) if lib.blocks[i] > 0)
+        fwd_only.ensure_backward(P, torch.device("cpu"))
+        assert all(t is not None for t in fwd_only.tensors) and fwd_only.buf.numel() == sum(lib.blocks) * 6 * 16384
+        fwd_only.buf = None
+    fine.Stash._pool.clear()
