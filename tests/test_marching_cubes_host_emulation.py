@@ -97,3 +97,26 @@ def test_python_glue_end_to_end_on_a_host_stand_in(tmp_path, monkeypatch):
     empty = torch.full((5, 5, 5), -1.0).as_subclass(_AsCuda)
     v, t = mcubes_gpu.marching_cubes(empty, 0.0)
     assert v.shape == (0, 3) and t.shape == (0, 3)
+
+
+def test_values_exactly_on_the_isovalue(emul):
+    """integer-valued fields: many corners sit exactly on the iso-value (counted as "not below", PyMCubes' `<`), vertices
+    then coincide with grid corners (t = 0 or 1) and triangles may degenerate, but ids, counts and topology must still agree
+    with the oracle and the surface must stay closed inside the grid"""
+    rng = np.random.default_rng(4)
+    for shape, iso in (((9, 8, 7), 0.0), ((6, 11, 5), 1.0), ((12, 12, 12), -1.0)):
+        u = rng.integers(-2, 3, size=shape).astype(np.float32)
+        v, t = emul(u, iso)
+        v_ref, t_ref = MC.marching_cubes(u, iso, T.TRI_TABLE, T.N_TRIS)
+        np.testing.assert_allclose(v, v_ref, atol=1e-6)
+        np.testing.assert_array_equal(t.astype(np.int64), t_ref)
+        assert np.isfinite(v).all()
+        d = np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]).astype(np.int64)
+        key = np.minimum(d[:, 0], d[:, 1]) * len(v) + np.maximum(d[:, 0], d[:, 1])
+        uniq, cnt = np.unique(key, return_counts=True)
+        assert cnt.max() <= 2
+        open_edges = uniq[cnt == 1]
+        a, b = v[open_edges // len(v)], v[open_edges % len(v)]
+        hi = np.asarray(shape, dtype=np.float32) - 1
+        on_border = lambda p: ((p == 0) | (p == hi)).any(axis=1)
+        assert on_border(a).all() and on_border(b).all()
