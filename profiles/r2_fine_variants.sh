@@ -44,7 +44,7 @@ ncu)
   v="${2:-relu_rq}"
   mkdir -p gpurun_out
   FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'fine_|dw_kernel' -c 6 -o "gpurun_out/r2_step_$v" -f python profiles/run_kernels.py step 2048 > "gpurun_out/r2_ncu_$v.log" 2>&1
+    -k regex:'fine_|dw_kernel|composite_|sample_round' -c 14 -o "gpurun_out/r2_step_$v" -f python profiles/run_kernels.py step 2048 > "gpurun_out/r2_ncu_$v.log" 2>&1
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:'mc_' -c 9 -o gpurun_out/r2_mc -f \
     python bench.py --mc_only > gpurun_out/r2_ncu_mc.log 2>&1
   tail -3 "gpurun_out/r2_ncu_$v.log" gpurun_out/r2_ncu_mc.log ;;
