@@ -557,9 +557,10 @@ def main():
             extras["c5_grid_512_sharded"] = grid
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 1, 3)
+        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 2, 8)          # ~10-15 s of host work on the box's cores
         cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"3 steps of {args.cpu_rays} rays ({n}+{m}), oracle port of the reference PyTorch CPU path"}
+               "sample": f"median of 8 steps (2 warm-up) of {args.cpu_rays} rays ({n}+{m}), oracle port of the reference "
+                         "PyTorch CPU path, all host threads"}
     if rank == 0:
         line = {"metric": "train rays/s (fwd+bwd+Adam)", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
