@@ -383,6 +383,15 @@ __device__ __forceinline__ void tile_prefetch_l2_keep(const uint8_t* tilep, int 
   }
 }
 
+__device__ __forceinline__ void row_half_store_pol(uint8_t* rowp, int h, const uint4* q, uint64_t pol) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) stg_pol(rowp + (4 * h + i) * TI_CHUNK_STRIDE, q[i], pol);
+}
+__device__ __forceinline__ void row_half_load_pol(const uint8_t* rowp, int h, uint4* q, uint64_t pol) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) q[i] = ldg_pol(rowp + (4 * h + i) * TI_CHUNK_STRIDE, pol);
+}
+
 // ---- rows of tile images: a half block = 32 columns = 4 x 16-byte chunks --------------------------------
 // chunk ch (0..7) of row r sits at blk + ch*2048 + r*16: the 32 lanes of a warp touch 512 contiguous bytes.
 __device__ __forceinline__ void pack4_grad(const float* v, uint4* q) {   // gradient tile format

@@ -52,6 +52,17 @@ constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks
 // sweep / colour / backward loops and separate loop bodies for the l == 8 / l == 4 specials (fine_fwd 5.23 -> 5.28 ms,
 // fine_bwd 7.71 -> 7.94 ms at 8192 rays: more code and registers, no latency won); PFD = 2 (spills at 96 registers).
 #define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)
+// -DFMOV_L2_HINTS_FWD (experiment, fine_fwd only): H1..H7 are written by the value pass and read back by the reverse sweep
+// (132 MB in flight against 126 MB of L2): H stores evict_last, every other stash store and the last-use H loads evict_first.
+#ifdef FMOV_L2_HINTS_FWD
+#define FWD_ST_CHUNK(tp, ck, q, keep) chunk_store_pol(tp, ck, q, (keep) ? fpol_keep : fpol_stream)
+#define FWD_LD_HALF_STREAM(tp, hb, q) row_half_load_pol((tp) + ((hb) >> 1) * BLK_BYTES, (hb) & 1, q, fpol_stream)
+#define FWD_ST_HALF_STREAM(tp, hb, q) row_half_store_pol((tp) + ((hb) >> 1) * BLK_BYTES, (hb) & 1, q, fpol_stream)
+#else
+#define FWD_ST_CHUNK(tp, ck, q, keep) chunk_store(tp, ck, q)
+#define FWD_LD_HALF_STREAM(tp, hb, q) ld_half(tp, hb, q)
+#define FWD_ST_HALF_STREAM(tp, hb, q) st_half(tp, hb, q)
+#endif
 // -DFMOV_L2_HINTS (experiment, fine_bwd only): H is read twice (adjoint pass, then ordinary backward) — first read
 // evict_last, everything that is used once evict_first.  KEEP / STREAM name the intent at each site.
 #ifdef FMOV_L2_HINTS
@@ -289,6 +300,9 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
     const int hb0 = c.wg * HPW;
     const int ck0 = c.wg * NCK;
     const bool owner = c.wg == CH_WGS - 1;      // warpgroup that owns the per-row state and the narrow steps
+#ifdef FMOV_L2_HINTS_FWD
+    const uint64_t fpol_keep = l2_policy_evict_last(), fpol_stream = l2_policy_evict_first();
+#endif
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
@@ -355,7 +369,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q2[2];
           pack2(v, false, q2);
           chunk_store(actp, ck, q2);
-          chunk_store(hsp, ck, q2);
+          FWD_ST_CHUNK(hsp, ck, q2, l < 7);          // H1..H7 come back in the reverse sweep, H8 does not
         }
         epi_signal_act(c);
       }
@@ -392,14 +406,14 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
         uint4 sb[2][4];
-        ld_half(hp, hb0, sb[0]);
+        FWD_LD_HALF_STREAM(hp, hb0, sb[0]);
         if (kStashPrefetch) tile_prefetch_l2(hp, ck0 + 2, NCK - 2);
         epi_wait_acc(c);
 #pragma unroll
         for (int hi = 0; hi < HPW; ++hi) {
           const int hb = hb0 + hi;
           float v[32], h[32];
-          if (hi < HPW - 1) ld_half(hp, hb + 1, sb[(hi + 1) & 1]);
+          if (hi < HPW - 1) FWD_LD_HALF_STREAM(hp, hb + 1, sb[(hi + 1) & 1]);
           acc_load32(c, hb * 32, v);
           unpack4(sb[hi & 1], false, h);
           if (l == 4 && hb == 6 && pc.valid) {
@@ -417,7 +431,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q[4];
           pack4(v, false, q);
           st_half(ap, hb, q);
-          st_half(dp, hb, q);
+          FWD_ST_HALF_STREAM(dp, hb, q);
         }
         epi_signal_act(c);
       }

@@ -7,6 +7,8 @@
 #   relu_rq   both                                   fine_bwd 265 -> 218 blocks per 128-point tile (-18 %)
 #   relu_rq1 / relu_rq3   same with FMOV_RQ_PH=1 / 3 (prefetch distance of the three operand streams, in 8-column pieces)
 #   l2 / relu_rq_l2       -DFMOV_L2_HINTS: fine_bwd reads H twice; first read evict_last, single-use traffic evict_first
+#   l2fwd / all           -DFMOV_L2_HINTS_FWD: fine_fwd writes H1..H7 evict_last (read back by its reverse sweep), delta stores
+#                         and the last-use H loads evict_first
 #
 #   bash profiles/r2_fine_variants.sh build        here (no GPU): builds fmov_pose_b200/libfmov_<name>.so (they travel with gpurun)
 #   gpurun --timeout 1500 -- 'bash profiles/r2_fine_variants.sh run'      parity subset per variant, then alternating benches
@@ -15,8 +17,9 @@ set -u
 cd "$(dirname "$0")/.."
 declare -A FLAGS=( [base]="" [relu]="-DFMOV_RELU_BITS" [rq]="-DFMOV_RECOMPUTE_Q" [relu_rq]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q"
                    [relu_rq1]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=1" [relu_rq3]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=3"
-                   [l2]="-DFMOV_L2_HINTS" [relu_rq_l2]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS" )
-ORDER="base relu rq relu_rq relu_rq1 relu_rq3 l2 relu_rq_l2"
+                   [l2]="-DFMOV_L2_HINTS" [relu_rq_l2]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS"
+                   [l2fwd]="-DFMOV_L2_HINTS_FWD" [all]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS -DFMOV_L2_HINTS_FWD" )
+ORDER="base relu rq relu_rq relu_rq1 relu_rq3 l2 relu_rq_l2 l2fwd all"
 case "${1:-}" in
 build)
   for v in $ORDER; do
