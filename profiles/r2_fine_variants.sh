@@ -19,7 +19,7 @@ declare -A FLAGS=( [base]="" [relu]="-DFMOV_RELU_BITS" [rq]="-DFMOV_RECOMPUTE_Q"
                    [relu_rq1]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=1" [relu_rq3]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_RQ_PH=3"
                    [l2]="-DFMOV_L2_HINTS" [relu_rq_l2]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS"
                    [l2fwd]="-DFMOV_L2_HINTS_FWD" [all]="-DFMOV_RELU_BITS -DFMOV_RECOMPUTE_Q -DFMOV_L2_HINTS -DFMOV_L2_HINTS_FWD" )
-ORDER="base relu rq relu_rq relu_rq1 relu_rq3 l2 relu_rq_l2 l2fwd all"
+ORDER="${VARIANTS:-base relu rq relu_rq relu_rq1 relu_rq3 l2 relu_rq_l2 l2fwd all}"        # VARIANTS="base relu_rq all" trims the run (~2.5 GPU-min per variant)
 case "${1:-}" in
 build)
   for v in $ORDER; do
@@ -33,7 +33,7 @@ run)
     if FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 600 python -m pytest tests/test_gpu_render.py tests/test_gpu_train_step.py -x -q \
          > "gpurun_out/r2_variant_$v.pytest.log" 2>&1; then echo "$v parity ok"; else echo "$v PARITY FAILED"; tail -15 "gpurun_out/r2_variant_$v.pytest.log"; FLAGS[$v]="FAILED"; fi
   done
-  for rep in 1 2 3; do
+  for rep in 1 2; do
     for v in $ORDER; do
       [ "${FLAGS[$v]}" = "FAILED" ] && continue
       FMOV_LIB="$PWD/fmov_pose_b200/libfmov_$v.so" timeout 300 python bench.py --steps 10 --warmup 3 --no_cpu_baseline --no_extras 2>/dev/null | tail -1 \
