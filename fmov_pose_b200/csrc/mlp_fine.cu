@@ -1300,7 +1300,8 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
   int st = fill_args(a, ptrs, B, S, rays_o, rays_d, z, sample_dist, wblob, stash, bias_sdf, b8, w8row, bias_col, bc4, wc4);
   if (st) return st;
   FMOV_REQUIRE(wc4 && rgb && ge && d_sdf && d_nrm && d_rgb && amax && d_pts && d_dirs && zc4 && eb_scratch, "fmov_fine_bwd: null argument");
-  for (int i = 0; i < ST_COUNT; ++i) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);
+  for (int i = 0; i < ST_COUNT; ++i)
+    if (stash_kb(i) > 0) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);      // 0 blocks: never touched
   a.rgb = const_cast<float*>(rgb); a.ge = const_cast<float*>(ge);
   a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4; a.eb = eb_scratch; a.amax = amax;
   fine_bwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
