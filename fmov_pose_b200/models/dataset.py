@@ -30,6 +30,25 @@ class _RayGenFn(torch.autograd.Function):
         return g34, None, None, None
 
 
+class _RayGenNearFarFn(torch.autograd.Function):
+    """as _RayGenFn, plus near / far of Dataset.near_far_from_sphere (models/dataset.py:835-842), which the kernel
+    computes anyway: (pose[3,4], K^-1, px, py) -> rays_o, rays_d [B,3], near, far [B,1]; backward -> d pose[3,4]"""
+
+    @staticmethod
+    def forward(ctx, pose34, intr_inv, px, py):
+        p = pose34.detach().float().contiguous()
+        rays_o, rays_d, near, far, _ = _ops.raygen_fwd(0, intr_inv, px, py, c2w34=p)
+        ctx.save_for_backward(intr_inv, px, py, rays_o, rays_d)
+        return rays_o, rays_d, near, far
+
+    @staticmethod
+    def backward(ctx, g_o, g_d, g_near, g_far):
+        intr_inv, px, py, rays_o, rays_d = ctx.saved_tensors
+        c = lambda g: None if g is None else g.float().contiguous()
+        g34 = _ops.raygen_bwd(intr_inv, px, py, rays_o, rays_d, c(g_o), c(g_d), c(g_near), c(g_far))
+        return g34, None, None, None
+
+
 class RayDataset:
     def __init__(self, images, masks, intrinsics, device="cuda"):
         """images [N,H,W,3] fp32 in [0,1], masks [N,H,W,3] fp32, intrinsics [N,3,3] or [3,3]."""
@@ -105,10 +124,12 @@ class RayDataset:
                 max(xs.min() - patch_size, 0), min(xs.max() + patch_size, self.W))
 
     def gen_random_rays_at(self, img_idx, batch_size, pose, mask_guided_sampling=False, patch_size=30, pixels=None,
-                           img_idx_t=None):
+                           img_idx_t=None, with_near_far=False):
         """-> (data [B,10] = rays_o, rays_v, rgb, mask ; depth=None).  `pixels=(px,py)` injects the int64 pixel
         draw (for RNG parity / pinned-host pipelines); otherwise torch.randint on the device as the reference.
-        `img_idx_t` (int64 device tensor [1]) makes the frame a device-side input (CUDA-graph replay)."""
+        `img_idx_t` (int64 device tensor [1]) makes the frame a device-side input (CUDA-graph replay).
+        `with_near_far`: also return the kernel's near / far (-> data, None, near, far), saving the torch
+        near_far_from_sphere call and its backward."""
         img_idx = int(img_idx)
         if pixels is None:
             if mask_guided_sampling and np.random.rand() < 0.7:
@@ -128,6 +149,9 @@ class RayDataset:
             color = self.images[img_idx][(py, px)]
             mask = self.masks[img_idx][(py, px)]
             intr_inv = self.intrinsics_all_inv[img_idx]
+        if with_near_far:
+            rays_o, rays_v, near, far = _RayGenNearFarFn.apply(pose[:3, :4], intr_inv, px, py)
+            return torch.cat([rays_o, rays_v, color, mask[:, :1]], dim=-1), None, near, far
         rays_o, rays_v = _RayGenFn.apply(pose[:3, :4], intr_inv, px, py)
         return torch.cat([rays_o, rays_v, color, mask[:, :1]], dim=-1), None
 

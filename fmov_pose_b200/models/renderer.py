@@ -52,6 +52,25 @@ def extract_geometry(bound_min, bound_max, resolution, threshold, query_func=Non
     return _mcubes.extract_geometry(u, threshold, [float(v) for v in bound_min], [float(v) for v in bound_max])
 
 
+class _CoarseZFn(torch.autograd.Function):
+    """z = near + (far - near) * linspace(0, 1, n) + jitter (models/renderer.py:389-390, 403-405) through fmov_sample_coarse,
+    keeping the autograd link to near / far that the reference has when n_importance == 0:
+    dz_j/dnear = 1 - t_j, dz_j/dfar = t_j."""
+
+    @staticmethod
+    def forward(ctx, near, far, t_rand, n_samples):
+        z = _ops.sample_coarse(near.detach(), far.detach(), t_rand, n_samples, n_samples)
+        ctx.n = n_samples
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        lin = torch.linspace(0.0, 1.0, ctx.n, device=g_z.device, dtype=g_z.dtype)
+        g_far = g_z @ lin[:, None]
+        g_near = g_z.sum(dim=1, keepdim=True) - g_far
+        return g_near, g_far, None, None
+
+
 class NeuSRenderer:
     def __init__(self, nerf, sdf_network, deviation_network, color_network, n_samples, n_importance, n_outside,
                  up_sample_steps, perturb):
@@ -87,6 +106,8 @@ class NeuSRenderer:
                                                 rays_d.detach().float().contiguous(), near.detach(), far.detach(),
                                                 t_rand, self.n_samples, self.n_importance, self.up_sample_steps)
         # n_importance == 0: z keeps its autograd link to near/far (renderer.py:389-390, 403-405)
+        if getattr(self, "fused_coarse", False):          # opt-in (train.TrainStep(fused_rays=True)): one launch + 3 in backward
+            return _CoarseZFn.apply(near, far, t_rand, self.n_samples)
         lin = torch.linspace(0.0, 1.0, self.n_samples, device=near.device)
         z = near + (far - near) * lin[None, :]
         if t_rand is not None:

@@ -69,9 +69,14 @@ class LRSchedule:
 class TrainStep:
     def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True,
                  capturable=False, flow_weight=0.0, unit_sphere_weight=0.0, maintain_shape=False,
-                 detach_flow_on_sdf=False, detach_ref=False, fused_loss=False):
+                 detach_flow_on_sdf=False, detach_ref=False, fused_loss=False, fused_rays=False):
         self.s = scene
         self.fused_loss = bool(fused_loss)       # colour + mask terms through fmov_loss_fwd_bwd (one launch instead of ~40)
+        # near / far straight from the ray-generation kernel (it computes them and their pose gradients anyway) and, for
+        # n_importance == 0, the coarse z through fmov_sample_coarse with a closed-form backward: ~40 torch launches less
+        self.fused_rays = bool(fused_rays)
+        if self.fused_rays:
+            scene["renderer"].fused_coarse = True
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
         # exp_runner.py:150-160, 327-336 (train.flow_weight, unit_sphere_weight, maintain_shape, detach_*)
         self.flow_weight, self.unit_sphere_weight = float(flow_weight), float(unit_sphere_weight)
@@ -203,14 +208,19 @@ class TrainStep:
         s = self.s
         ds, rend = s["dataset"], s["renderer"]
         pose = self.pose_of(img_id, img_t)
-        data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
+        nf = self.fused_rays
+        r = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t, with_near_far=nf)
+        data, near, far = r[0], (r[2] if nf else None), (r[3] if nf else None)
         if additional_img_id is not None:
             add_pose = self.pose_of(additional_img_id, add_img_t)
-            add_data, _ = ds.gen_random_rays_at(additional_img_id, batch_size, add_pose, pixels=add_pixels,
-                                                img_idx_t=add_img_t)
-            data = torch.cat([data, add_data], dim=0)
+            r = ds.gen_random_rays_at(additional_img_id, batch_size, add_pose, pixels=add_pixels, img_idx_t=add_img_t,
+                                      with_near_far=nf)
+            data = torch.cat([data, r[0]], dim=0)
+            if nf:
+                near, far = torch.cat([near, r[2]], dim=0), torch.cat([far, r[3]], dim=0)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
-        near, far = ds.near_far_from_sphere(rays_o, rays_d)
+        if not nf:
+            near, far = ds.near_far_from_sphere(rays_o, rays_d)
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
                           background_rgb=self.background_rgb)
         ls = self.losses(out, true_rgb, mask)

@@ -149,3 +149,41 @@ def test_fused_loss_step_equals_the_torch_loss_step(mask_weight):
             assert e <= 1e-4, e
             n += 1
     assert n > 40
+
+
+@pytest.mark.parametrize("cfg", [dict(n_samples=32, n_importance=0, two=True), dict(n_samples=16, n_importance=16, two=False)])
+def test_fused_ray_path_step_equals_the_default_step(cfg):
+    """TrainStep(fused_rays=True): near / far from the ray-generation kernel and (n_importance == 0) the coarse z through
+    fmov_sample_coarse with its closed-form backward == the torch formulation — losses, network and pose gradients of the
+    shipped two-frame 32+0 iteration (z carries the pose gradient there) and of a 16+16 iteration"""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    B = 256
+    g = torch.Generator().manual_seed(9)
+    px = torch.randint(150, 490, [2 * B], generator=g).to(DEV)
+    py = torch.randint(70, 410, [2 * B], generator=g).to(DEV)
+    tr = torch.rand(2 * B if cfg["two"] else B, 1, generator=g).to(DEV)
+    add = dict(additional_img_id=1, add_pixels=(px[B:], py[B:])) if cfg["two"] else {}
+    res = []
+    for fused in (False, True):
+        sc = synthetic.build_scene(device=DEV, n_images=4, n_samples=cfg["n_samples"], n_importance=cfg["n_importance"],
+                                   up_sample_steps=2, pose_type="seg")
+        ts = TrainStep(sc, mask_weight=5.0, optimizer=False, fused_rays=fused)
+        ls, out = ts.forward_backward(2, B, pixels=(px[:B], py[:B]), t_rand=tr, **add)
+        res.append((ls, out["color_fine"].detach().clone(),
+                    [None if p.grad is None else p.grad.detach().clone() for p in ts.all_params], len(ts.params)))
+    (la, ca, ga, n_net), (lb, cb, gb, _) = res
+    for k in ("loss", "color_loss", "eikonal_loss", "mask_loss"):
+        np.testing.assert_allclose(float(lb[k].detach()), float(la[k].detach()), rtol=1e-4, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(cb.cpu().numpy(), ca.cpu().numpy(), atol=2e-5)
+    n_net_checked = n_pose_checked = 0
+    for i, (a, b) in enumerate(zip(ga, gb)):
+        assert (a is None) == (b is None), i
+        if a is not None and float(a.abs().max()) > 0:
+            e = float((a - b).norm() / a.norm())
+            assert e <= 5e-3, (i, e)
+            if i < n_net:
+                n_net_checked += 1
+            else:
+                n_pose_checked += 1
+    assert n_net_checked > 40 and n_pose_checked > 0

@@ -316,3 +316,73 @@ def test_stash_layout_follows_the_library_directory(monkeypatch):
         assert all(t is not None for t in fwd_only.tensors) and fwd_only.buf.numel() == sum(lib.blocks) * 6 * 16384
         fwd_only.buf = None
     fine.Stash._pool.clear()
+
+
+def test_fused_ray_path_autograd_glue(monkeypatch):
+    """TrainStep(fused_rays=True): _RayGenNearFarFn (near / far from the ray-generation kernel) and _CoarseZFn (coarse z through
+    fmov_sample_coarse with a closed-form backward).  With the kernels replaced by torch transcriptions of what they
+    compute, values and gradients must equal the reference formulas (models/dataset.py:656-671, 835-842;
+    models/renderer.py:389-390, 403-405)."""
+    from fmov_pose_b200 import ops
+    from fmov_pose_b200.models import dataset as D
+    from fmov_pose_b200.models import renderer as R
+    from oracle import neus_oracle as O
+
+    def raygen_fwd(mode, intr_inv, px, py, c2w34=None, **kw):
+        o, d = O.gen_rays(c2w34, intr_inv, px, py)
+        near, far = O.near_far_from_sphere(o, d)
+        return o.contiguous(), d, near, far, c2w34
+
+    def raygen_bwd(intr_inv, px, py, rays_o, rays_d, g_o, g_d, g_near, g_far):
+        # what fmov_raygen_bwd returns: d(loss)/d(pose) given the four upstream gradients (None = zero)
+        with torch.enable_grad():
+            q = saved["pose"].clone().requires_grad_(True)
+            o, d = O.gen_rays(q, intr_inv, px, py)
+            near, far = O.near_far_from_sphere(o, d)
+            tot = 0
+            for t_, g_ in ((o, g_o), (d, g_d), (near, g_near), (far, g_far)):
+                if g_ is not None:
+                    tot = tot + (t_ * g_).sum()
+            return torch.autograd.grad(tot, q)[0]
+
+    saved = {}
+    monkeypatch.setattr(ops, "raygen_fwd", raygen_fwd)
+    monkeypatch.setattr(ops, "raygen_bwd", raygen_bwd)
+    g = torch.Generator().manual_seed(1)
+    pose = torch.cat([O.rodrigues_exp(torch.randn(1, 3, generator=g) * 0.2)[0], torch.tensor([[0.1], [0.2], [-3.0]])], 1)
+    pose = pose.requires_grad_(True)
+    saved["pose"] = pose
+    Kinv = torch.inverse(torch.tensor([[60.0, 0, 32.0], [0, 60.0, 24.0], [0, 0, 1.0]]))
+    px, py = torch.randint(0, 64, [50], generator=g), torch.randint(0, 48, [50], generator=g)
+    w = [torch.randn(50, 3, generator=g), torch.randn(50, 3, generator=g), torch.randn(50, 1, generator=g),
+         torch.randn(50, 1, generator=g)]
+    o, d, near, far = D._RayGenNearFarFn.apply(pose, Kinv, px, py)
+    ((o * w[0]).sum() + (d * w[1]).sum() + (near * w[2]).sum() + (far * w[3]).sum()).backward()
+    got = pose.grad.clone()
+    pose.grad = None
+    o2, d2 = O.gen_rays(pose, Kinv, px, py)
+    n2, f2 = O.near_far_from_sphere(o2, d2)
+    ((o2 * w[0]).sum() + (d2 * w[1]).sum() + (n2 * w[2]).sum() + (f2 * w[3]).sum()).backward()
+    np.testing.assert_allclose(near.detach().numpy(), n2.detach().numpy(), atol=1e-6)
+    np.testing.assert_allclose(got.numpy(), pose.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+    # coarse z
+    def sample_coarse(near, far, t_rand, n_samples, z_stride):
+        lin = torch.linspace(0.0, 1.0, n_samples)
+        z = near + (far - near) * lin[None, :]
+        return z if t_rand is None else z + (t_rand - 0.5) * 2.0 / n_samples
+
+    monkeypatch.setattr(ops, "sample_coarse", sample_coarse)
+    for t_rand in (None, torch.rand(50, 1, generator=g)):
+        nr = (torch.rand(50, 1, generator=g) + 1.5).requires_grad_(True)
+        fr = (nr.detach() + 2.0).requires_grad_(True)
+        gz = torch.randn(50, 32, generator=g)
+        z = R._CoarseZFn.apply(nr, fr, t_rand, 32)
+        (z * gz).sum().backward()
+        got = (nr.grad.clone(), fr.grad.clone())
+        nr.grad = fr.grad = None
+        z2 = sample_coarse(nr, fr, t_rand, 32, 32)
+        (z2 * gz).sum().backward()
+        np.testing.assert_allclose(z.detach().numpy(), z2.detach().numpy(), atol=1e-7)
+        np.testing.assert_allclose(got[0].numpy(), nr.grad.numpy(), rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(got[1].numpy(), fr.grad.numpy(), rtol=1e-5, atol=1e-5)
