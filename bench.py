@@ -224,8 +224,19 @@ def measure_extras(scene, dev, use_graph=True):
         torch.cuda.empty_cache()
     out["torch_fp32_port_on_this_gpu"] = dict(tg, note="oracle port of the reference (PyTorch fp32 eager autograd, 64+64, "
                                               "fwd+bwd+Adam) on the same B200: baseline for north_star's 50x target")
+    out["c2_literal_1024rays_32+0"] = measure_literal(dev, use_graph, fused=False)
+    return out
+
+
+def measure_literal(dev, use_graph=True, fused=False):
+    """the shipped confs/ho3d_virtual.conf iteration: 2 x 512 rays of two frames, 32+0 samples, both pose MLPs trained.
+    `fused`: TrainStep(fused_loss=True, fused_rays=True) — the opt-in glue fusions (fewer torch launches)."""
+    import torch
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sc2 = synthetic.build_scene(device=dev, n_samples=32, n_importance=0, up_sample_steps=4, pose_type="seg")
-    ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph)
+    ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph, fused_loss=fused, fused_rays=fused)
     g = torch.Generator().manual_seed(3)
     B2, Bf = 1024, 512          # maintain_shape: 512 rays of the current frame + 512 rays of an earlier frame
     n_it = 24
@@ -250,12 +261,12 @@ def measure_extras(scene, dev, use_graph=True):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (n_it - 8)
-    out["c2_literal_1024rays_32+0"] = {"ms_per_step": ms, "rays_per_s": B2 / ms * 1e3,
-                                       "note": "confs/ho3d_virtual.conf as shipped (n_samples 32, n_importance 0, "
-                                               "maintain_shape: 512 rays of the current frame + 512 of an earlier "
-                                               "frame, two pose MLPs trained); " +
-                                               ("CUDA-graph replay" if use_graph else "eager, host-launch bound")}
-    return out
+    return {"ms_per_step": ms, "rays_per_s": B2 / ms * 1e3,
+            "library_calls_per_step": getattr(g2, "launches_per_step", None) if use_graph else None,
+            "note": "confs/ho3d_virtual.conf as shipped (n_samples 32, n_importance 0, maintain_shape: 512 rays of the "
+                    "current frame + 512 of an earlier frame, two pose MLPs trained); " +
+                    ("CUDA-graph replay" if use_graph else "eager, host-launch bound") +
+                    ("; TrainStep(fused_loss=True, fused_rays=True)" if fused else "")}
 
 
 def measure_marching_cubes_child():
@@ -292,10 +303,10 @@ def measure_marching_cubes_child():
                               "output sizes; the reference copies the grid to the host and runs PyMCubes on one core"}))
 
 
-def measure_marching_cubes():
-    """runs in a child process so that the (round-1-unverified) kernels cannot take the bench's CUDA context down"""
+def measure_in_child(flag):
+    """runs in a child process so that code paths that have not run on hardware yet cannot take the bench's CUDA context down"""
     import subprocess
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--mc_only"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), flag], capture_output=True, text=True, timeout=300)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     if r.returncode != 0 or not lines:
         return {"error": (r.stderr or r.stdout)[-300:]}
@@ -371,9 +382,14 @@ def main():
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     ap.add_argument("--mc_only", action="store_true", help="internal: marching-cubes extra, run as a child process")
+    ap.add_argument("--literal_fused_only", action="store_true", help="internal: literal step with the opt-in glue fusions")
     args = ap.parse_args()
     if args.mc_only:
         measure_marching_cubes_child()
+        return 0
+    if args.literal_fused_only:
+        import torch
+        print(json.dumps(measure_literal(torch.device("cuda:0"), use_graph=not args.no_graph, fused=True)))
         return 0
     # stdout carries exactly ONE JSON line: libraries that printf to fd 1 (NCCL prints its version banner there when
     # NCCL_DEBUG is set on the box) are sent to stderr, the line is written to the saved descriptor
@@ -544,9 +560,13 @@ def main():
         except Exception as e:          # secondary number: report, do not fail the bench
             extras["c3_65536rays_micro_batched"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
         try:
-            extras["c5_marching_cubes_512"] = measure_marching_cubes()
+            extras["c5_marching_cubes_512"] = measure_in_child("--mc_only")
         except Exception as e:
             extras["c5_marching_cubes_512"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        try:
+            extras["c2_literal_1024rays_32+0_fused_glue"] = measure_in_child("--literal_fused_only")
+        except Exception as e:
+            extras["c2_literal_1024rays_32+0_fused_glue"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if not args.no_extras:              # collective (all ranks): config C5 across the N GPUs of this run
         try:
             grid = measure_grid_sharded(scene, dev, group, world)
