@@ -554,7 +554,10 @@ def main():
                             "algorithmic_bytes_per_point": KERNEL_BYTES_PER_POINT[top]}
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
-        extras = measure_extras(scene, dev, use_graph)
+        try:
+            extras = measure_extras(scene, dev, use_graph)
+        except Exception as e:          # secondary numbers must never cost the headline line
+            extras = {"error": f"measure_extras: {type(e).__name__}: {str(e)[:300]}"}
         try:
             extras["c3_65536rays_micro_batched"] = measure_c3_micro(dev)
         except Exception as e:          # secondary number: report, do not fail the bench
