@@ -209,12 +209,13 @@ class TrainStep:
         ds, rend = s["dataset"], s["renderer"]
         pose = self.pose_of(img_id, img_t)
         nf = self.fused_rays
-        r = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t, with_near_far=nf)
+        nf_kw = dict(with_near_far=True) if nf else {}          # default call unchanged (any dataset with the reference's API)
+        r = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t, **nf_kw)
         data, near, far = r[0], (r[2] if nf else None), (r[3] if nf else None)
         if additional_img_id is not None:
             add_pose = self.pose_of(additional_img_id, add_img_t)
             r = ds.gen_random_rays_at(additional_img_id, batch_size, add_pose, pixels=add_pixels, img_idx_t=add_img_t,
-                                      with_near_far=nf)
+                                      **nf_kw)
             data = torch.cat([data, r[0]], dim=0)
             if nf:
                 near, far = torch.cat([near, r[2]], dim=0), torch.cat([far, r[3]], dim=0)
