@@ -386,3 +386,34 @@ def test_fused_ray_path_autograd_glue(monkeypatch):
         np.testing.assert_allclose(z.detach().numpy(), z2.detach().numpy(), atol=1e-7)
         np.testing.assert_allclose(got[0].numpy(), nr.grad.numpy(), rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(got[1].numpy(), fr.grad.numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("level", [1, 2, 4])
+def test_ray_dataset_full_frame_grid_at_every_resolution_level(monkeypatch, level):
+    """RayDataset.gen_rays_at (models/dataset.py:547-576): pixel grid linspace(0, W-1, W//l) — integer centres at l = 1,
+    sub-pixel otherwise — ray layout [H/l, W/l, 3] and the mask lookup at the truncated pixel; the kernel is replaced by the
+    oracle's formula so that the host logic runs on the CPU."""
+    from fmov_pose_b200.models import dataset as D
+    from oracle import neus_oracle as O
+
+    class _Fn:
+        @staticmethod
+        def apply(pose34, intr_inv, px, py):
+            assert px.dtype == (torch.int64 if level == 1 else torch.float32) and px.is_contiguous()
+            return O.gen_rays(pose34, intr_inv, px, py)
+
+    monkeypatch.setattr(D, "_RayGenFn", _Fn)
+    g = torch.Generator().manual_seed(0)
+    H, W = 24, 32
+    ds = D.RayDataset(torch.rand(2, H, W, 3, generator=g), (torch.rand(2, H, W, 3, generator=g) > 0.5).float(),
+                      [[30.0, 0, 16.0], [0, 30.0, 12.0], [0, 0, 1.0]], device="cpu")
+    pose = torch.cat([O.rodrigues_exp(torch.tensor([[0.1, -0.2, 0.05]]))[0], torch.tensor([[0.0], [0.1], [-3.0]])], 1)
+    o, v, m = ds.gen_rays_at(1, resolution_level=level, pose=pose, with_mask=True)
+    Hl, Wl = H // level, W // level
+    assert o.shape == (Hl, Wl, 3) and v.shape == (Hl, Wl, 3) and m.shape == (Hl, Wl)
+    tx, ty = torch.linspace(0, W - 1, Wl), torch.linspace(0, H - 1, Hl)
+    gx, gy = torch.meshgrid(tx, ty, indexing="ij")
+    o_ref, v_ref = O.gen_rays(pose, ds.intrinsics_all_inv[1], gx.reshape(-1), gy.reshape(-1))
+    np.testing.assert_allclose(v.transpose(0, 1).reshape(-1, 3).numpy(), v_ref.numpy(), atol=1e-6)
+    np.testing.assert_allclose(o.transpose(0, 1).reshape(-1, 3).numpy(), o_ref.numpy(), atol=1e-6)
+    np.testing.assert_array_equal(m.numpy(), ds.masks[1][(gy.long(), gx.long())][..., 0].transpose(0, 1).numpy())
