@@ -65,7 +65,11 @@ __global__ void pack_image_kernel(PackArgs a) {
       v[j] = x;
     }
     uint4 q;
-    if (a.bf16) {
+    if (a.bf16 == 2) {      // residual image: what the fp16 image of the same matrix drops
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] -= __half2float(__float2half_rn(v[j]));
+    }
+    if (a.bf16 == 1) {
       q.x = pack_bf2(v[0], v[1]); q.y = pack_bf2(v[2], v[3]); q.z = pack_bf2(v[4], v[5]); q.w = pack_bf2(v[6], v[7]);
     } else {
       q.x = pack_h2(v[0], v[1]); q.y = pack_h2(v[2], v[3]); q.z = pack_h2(v[4], v[5]); q.w = pack_h2(v[6], v[7]);

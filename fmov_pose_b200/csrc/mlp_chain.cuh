@@ -81,15 +81,22 @@ struct ChainStep {
   uint8_t no_mma;       // epilogue-only step (no weights / MMA / accumulator)
   uint8_t pf[2];        // stash tensors (4-block tiles) this step's epilogue reads from HBM; 0xFF = none.
                         // The producer warp bulk-prefetches them into L2 one step ahead.
-  uint8_t pad[3];
+  uint8_t flags;        // CHF_* bits (0 for an ordinary step)
+  uint8_t pad[2];
 };
+// Step flags: let several GEMM passes share one accumulator (split-precision chains: hi*W_hi + lo*W_hi + hi*W_lo).
+constexpr uint8_t CHF_A_OTHER = 1;     // A operand = the OTHER tile slot's ACT / AUX region (holds the fp16 residuals)
+constexpr uint8_t CHF_ACCUM = 2;       // continue on the previous step's accumulator: no operand wait, never zero-initialise
+constexpr uint8_t CHF_NO_COMMIT = 4;   // more passes follow: do not signal the epilogue after this step
+constexpr uint8_t CHF_W2 = 8;          // weights come from ChainPtrs::weights2 (residual images)
 struct ChainTable {
   int n_steps;
-  int pad_;
+  int slots;            // tiles in flight per CTA: 0 -> CH_SLOTS; 1 for chains that use slot 1's buffers for residuals
   ChainStep step[MAX_STEPS];
 };
 struct ChainPtrs {
   const uint8_t* weights;        // packed weight images
+  const uint8_t* weights2;       // second blob (CHF_W2 steps), may be null
   uint8_t* stash[MAX_STASH];     // tile-image tensors in HBM
 };
 
@@ -141,37 +148,18 @@ template <int N>
 __device__ __forceinline__ void chain_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- producer warp -------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
-}
-// (measured on B200: the bulk L2 prefetch of the next step's stash tiles did NOT help — fine_bwd 12.3 -> 14.1 ms at
-//  8192 rays — the epilogues are occupancy/latency bound rather than DRAM-latency bound; kept behind a macro)
-__device__ __forceinline__ void chain_prefetch_step(const ChainTable& tb, const ChainPtrs& ptrs, int si, long long tile) {
-#ifndef FMOV_L2_PREFETCH
-  return;
-#endif
-  const ChainStep& st = tb.step[si];
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-    if (st.pf[j] != 0xFF) bulk_prefetch_l2(ptrs.stash[st.pf[j]] + (size_t)tile * 4 * BLK_BYTES, 4 * BLK_BYTES);
-}
+// (measured on B200 and removed: a bulk L2 prefetch of the next step's stash tiles from this warp — fine_bwd 12.3 -> 14.1 ms
+//  at 8192 rays; the stash reads are prefetched by the epilogue threads instead, see tile_prefetch_l2)
 __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, const ChainPtrs& ptrs, ChainSmem* s,
                                                       uint8_t* wst, int n_my_tiles, long long tile0, long long tile_stride) {
-  const uint8_t* __restrict__ wblob = ptrs.weights;
+  const int SL = tb.slots > 0 ? tb.slots : CH_SLOTS;
   uint32_t it = 0;
-  for (int k0 = 0; k0 < n_my_tiles; k0 += CH_SLOTS) {
-    const int nslot = (n_my_tiles - k0 < CH_SLOTS) ? (n_my_tiles - k0) : CH_SLOTS;
-    if (k0 == 0)
-      for (int slot = 0; slot < nslot; ++slot) chain_prefetch_step(tb, ptrs, 0, tile0 + (long long)slot * tile_stride);
+  for (int k0 = 0; k0 < n_my_tiles; k0 += SL) {
+    const int nslot = (n_my_tiles - k0 < SL) ? (n_my_tiles - k0) : SL;
     for (int si = 0; si < tb.n_steps; ++si) {
       const ChainStep st = tb.step[si];
-      // L2 prefetch of what the NEXT step's epilogue will read (one step of lead hides the HBM latency)
-      for (int slot = 0; slot < nslot; ++slot) {
-        if (si + 1 < tb.n_steps) chain_prefetch_step(tb, ptrs, si + 1, tile0 + (long long)(k0 + slot) * tile_stride);
-        else if (k0 + CH_SLOTS + slot < n_my_tiles)
-          chain_prefetch_step(tb, ptrs, 0, tile0 + (long long)(k0 + CH_SLOTS + slot) * tile_stride);
-      }
       if (st.no_mma) continue;
+      const uint8_t* __restrict__ wblob = (st.flags & CHF_W2) ? ptrs.weights2 : ptrs.weights;
       const uint32_t bytes = (uint32_t)st.n * (128u / CH_WSPLIT);
       const int nsl = (st.nkb_a + st.nkb_aux) * CH_WSPLIT;      // consecutive slices of this step's weight image
       for (int slot = 0; slot < nslot; ++slot)
@@ -190,21 +178,26 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
                                                  uint8_t* wst, uint32_t tmem, int n_my_tiles) {
   uint32_t it = 0;
   uint32_t nstep[CH_SLOTS] = {0, 0};
-  for (int k0 = 0; k0 < n_my_tiles; k0 += CH_SLOTS) {
-    const int nslot = (n_my_tiles - k0 < CH_SLOTS) ? (n_my_tiles - k0) : CH_SLOTS;
+  const int SL = tb.slots > 0 ? tb.slots : CH_SLOTS;
+  for (int k0 = 0; k0 < n_my_tiles; k0 += SL) {
+    const int nslot = (n_my_tiles - k0 < SL) ? (n_my_tiles - k0) : SL;
     for (int si = 0; si < tb.n_steps; ++si) {
       const ChainStep st = tb.step[si];
       if (st.no_mma) continue;
       const uint32_t idesc = umma_idesc(128, st.n, st.a_fmt, st.b_fmt, 0, 0);
       const int nkb = st.nkb_a + st.nkb_aux;
       for (int slot = 0; slot < nslot; ++slot) {
-        uint8_t* act = act0 + slot * 4 * BLK_BYTES;
-        uint8_t* aux = aux0 + slot * BLK_BYTES;
-        FMOV_TR(1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
-        mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
-        FMOV_TR(2, slot, nstep[slot]);            // operand ready seen
-        ++nstep[slot];
-        tc_fence_after();
+        const int aslot = slot ^ (st.flags & CHF_A_OTHER);
+        uint8_t* act = act0 + aslot * 4 * BLK_BYTES;
+        uint8_t* aux = aux0 + aslot * BLK_BYTES;
+        const uint32_t accum = (st.flags & CHF_ACCUM) ? 1u : 0u;
+        if (!accum) {
+          FMOV_TR(1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
+          mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
+          FMOV_TR(2, slot, nstep[slot]);            // operand ready seen
+          ++nstep[slot];
+          tc_fence_after();
+        }
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t a_base = smem_u32(kb < st.nkb_a ? act + kb * BLK_BYTES : aux + (kb - st.nkb_a) * BLK_BYTES);
 #pragma unroll
@@ -218,12 +211,12 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
               const int ks = part * (4 / CH_WSPLIT) + kk;            // K = 16 slice of the k-block
               umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
                        umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
-                       (kb | ks) != 0 ? 1u : 0u);
+                       ((kb | ks) != 0 ? 1u : 0u) | accum);
             }
             umma_commit(&s->w_empty[stage]);   // slot reusable once these MMAs have read it
           }
         }
-        umma_commit(&s->acc_ready[slot]);
+        if (!(st.flags & CHF_NO_COMMIT)) umma_commit(&s->acc_ready[slot]);
         FMOV_TR(3, slot, nstep[slot] - 1);        // all MMAs of the step issued
       }
     }
@@ -340,7 +333,7 @@ __device__ __forceinline__ void tile_prefetch_l2(const uint8_t* tilep, int ck_fi
   }
 }
 
-// ---- L2 eviction-priority hints (experiment, -DFMOV_L2_HINTS): a kernel that reads a stash tensor twice marks the first
+// ---- L2 eviction-priority hints: a kernel that reads a stash tensor twice marks the first
 // read evict_last and everything it streams evict_first, so that the second read has a chance to hit the 126 MB L2.
 // Hints cannot change results, only where lines live.
 __device__ __forceinline__ uint64_t l2_policy_evict_last() {

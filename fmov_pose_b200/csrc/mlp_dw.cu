@@ -403,8 +403,8 @@ extern "C" int fmov_dw(long long P, void* const* stash, const float* d_sdf, cons
   }
   DwPtrs ptrs;
   for (int i = 0; i < S_COUNT; ++i) {
-    const bool is_q = i >= S_Q0 && i < S_Q0 + 8;          // q tiles feed no weight gradient (and do not exist in
-    if (!is_q) FMOV_REQUIRE(stash[i], "fmov_dw: stash tensor %d is null", i);      // -DFMOV_RECOMPUTE_Q builds)
+    const bool is_q = i >= S_Q0 && i < S_Q0 + 8;          // q tiles feed no weight gradient (and are not stored:
+    if (!is_q) FMOV_REQUIRE(stash[i], "fmov_dw: stash tensor %d is null", i);      // the backward rebuilds q)
     ptrs.stash[i] = reinterpret_cast<const uint8_t*>(stash[i]);
   }
   const long long n_tiles = (P + 127) / 128;

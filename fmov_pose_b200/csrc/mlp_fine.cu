@@ -31,59 +31,27 @@ namespace fmov {
 using FL = ChainLayout;
 constexpr int HPW = 8 / CH_WGS;          // 32-column chunks per warpgroup
 constexpr int NCK = CH_CHUNKS;           // 16-column chunks per warpgroup
-#ifndef FMOV_FINE_PFD
-#define FMOV_FINE_PFD 1
-#endif
-#ifdef FMOV_NO_STASH_PREFETCH
-constexpr bool kStashPrefetch = false;
-#else
-constexpr bool kStashPrefetch = true;
-#endif
-#ifdef FMOV_PREFETCH_NEXT
-constexpr bool kPrefetchNext = true;
-#else
-constexpr bool kPrefetchNext = false;
-#endif
-#ifndef FMOV_RQ_PH
-#define FMOV_RQ_PH 2
-#endif
-constexpr int PFD = FMOV_FINE_PFD;       // stash-read prefetch distance (chunks) in the backward hot loops
-// A/B-measured and NOT kept (profiles/ab.sh, same box, alternating builds): double-buffered TMEM loads in the reverse
-// sweep / colour / backward loops and separate loop bodies for the l == 8 / l == 4 specials (fine_fwd 5.23 -> 5.28 ms,
-// fine_bwd 7.71 -> 7.94 ms at 8192 rays: more code and registers, no latency won); PFD = 2 (spills at 96 registers).
+constexpr int PFD = 1;                   // stash-read prefetch distance (chunks) in the backward hot loops
+constexpr int RQ_PH = 2;                 // prefetch distance (8-column pieces) of the three operand streams that rebuild q
+// Measured on B200 and decided (round 2, profiles/r2_fine_variants.txt; alternating builds on one box, 8192 rays x 128):
+//   kept     ReLU signs of C1..C4 as one 32-bit word per row and 32 columns (16 -> 1 block per tile read by the colour
+//            backward); q_l rebuilt in the ordinary backward from V-bar, delta and sigma instead of stored (-32 blocks);
+//            L2 eviction hints in fine_bwd (first read of H evict_last, single-use traffic evict_first):
+//            fine_bwd 7.72 -> 7.16 ms, stash 203 -> 172 blocks per tile (27 -> 23 GB per 8192 rays)
+//   dropped  eviction hints in fine_fwd (5.17 -> 5.4 ms), bulk L2 prefetch from the producer warp, thread-issued prefetch
+//            one step ahead, PFD = 2 (spills at 96 registers), double-buffered TMEM loads and peeled special-case layers,
+//            setmaxnreg re-balancing (ptxas 12.9 compiles the epilogue region against the smaller budget)
+// -18 % fine_bwd traffic bought -7 % time: the epilogues are latency bound (16 warps, long-scoreboard 9.9 cycles per
+// issue), not bandwidth bound — see DESIGN.md §3.
 #define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)
-// -DFMOV_L2_HINTS_FWD (experiment, fine_fwd only): H1..H7 are written by the value pass and read back by the reverse sweep
-// (132 MB in flight against 126 MB of L2): H stores evict_last, every other stash store and the last-use H loads evict_first.
-#ifdef FMOV_L2_HINTS_FWD
-#define FWD_ST_CHUNK(tp, ck, q, keep) chunk_store_pol(tp, ck, q, (keep) ? fpol_keep : fpol_stream)
-#define FWD_LD_HALF_STREAM(tp, hb, q) row_half_load_pol((tp) + ((hb) >> 1) * BLK_BYTES, (hb) & 1, q, fpol_stream)
-#define FWD_ST_HALF_STREAM(tp, hb, q) row_half_store_pol((tp) + ((hb) >> 1) * BLK_BYTES, (hb) & 1, q, fpol_stream)
-#else
-#define FWD_ST_CHUNK(tp, ck, q, keep) chunk_store(tp, ck, q)
-#define FWD_LD_HALF_STREAM(tp, hb, q) ld_half(tp, hb, q)
-#define FWD_ST_HALF_STREAM(tp, hb, q) st_half(tp, hb, q)
-#endif
-// -DFMOV_L2_HINTS (experiment, fine_bwd only): H is read twice (adjoint pass, then ordinary backward) — first read
-// evict_last, everything that is used once evict_first.  KEEP / STREAM name the intent at each site.
-#ifdef FMOV_L2_HINTS
+// fine_bwd reads H twice (adjoint pass, then ordinary backward): KEEP / STREAM name the L2 eviction intent at each site
 #define LD_KEEP(tp, ck, q) chunk_load_pol(tp, ck, q, pol_keep)
 #define LD_STREAM(tp, ck, q) chunk_load_pol(tp, ck, q, pol_stream)
 #define ST_STREAM(tp, ck, q) chunk_store_pol(tp, ck, q, pol_stream)
 #define PF_KEEP(tp, a, b) tile_prefetch_l2_keep(tp, a, b)
-#else
-#define LD_KEEP(tp, ck, q) chunk_load(tp, ck, q)
-#define LD_STREAM(tp, ck, q) chunk_load(tp, ck, q)
-#define ST_STREAM(tp, ck, q) chunk_store(tp, ck, q)
-#define PF_KEEP(tp, a, b) tile_prefetch_l2(tp, a, b)
-#endif
 // Register budget: 640 threads put 5 warps on every SM sub-partition (16 K registers each), so ptxas caps the kernels
-// at 96 registers/thread.  setmaxnreg re-balancing (control warpgroup -> 24..56, epilogue -> 104..120) was tried at
-// compile time and dropped: ptxas 12.9 either fails (C7600, control <= 32) or compiles the epilogue region against
-// the SMALLER budget (spill bytes tracked the control value: 5.6 KB at 40, 1.5 KB at 56 against 0.4 KB for the plain
-// 96-register build), so it never reached the GPU.  The hot loops are written in 16-column chunks so that they fit 96
-// registers without spills; the remaining spills (ptxas -v) sit in the once-per-tile positional-encoding steps.
-#define FINE_CTRL_REGS()
-#define FINE_EPI_REGS()
+// at 96 registers/thread.  The hot loops are written in 16-column chunks so that they fit 96 registers without spills;
+// the remaining spills (ptxas -v) sit in the once-per-tile positional-encoding steps.
 
 // ---- weight image directory ---------------------------------------------------------------------
 enum ImgId {
@@ -128,26 +96,16 @@ enum StashId {
   ST_PE = 0, ST_H1 = 1 /*..H8=8*/, ST_F = 9, ST_D0 = 10 /*..D7=17*/, ST_X = 18, ST_C1 = 19 /*..C4=22*/,
   ST_ZC0 = 23 /*..ZC3=26*/, ST_FB = 27, ST_GE = 28, ST_V1 = 29 /*..V8=36*/, ST_Q0 = 37 /*..Q7=44*/,
   ST_Z0 = 45 /*..Z7=52*/,
-#ifdef FMOV_RELU_BITS
   ST_CM = 53, ST_COUNT = 54     // experiment: ReLU sign bits of C1..C4, [layer][32-column chunk][row] uint32 = one block per tile
-#else
-  ST_COUNT = 53
-#endif
 };
 __host__ __device__ inline int stash_kb(int id) {
-#ifdef FMOV_RELU_BITS
   if (id == ST_CM) return 1;
-#endif
-#ifdef FMOV_RECOMPUTE_Q
   if (id >= ST_Q0 && id < ST_Q0 + 8) return 0;          // q is never materialised: 32 blocks per tile less stash memory
-#endif
   return (id == ST_PE || id == ST_X || id == ST_GE) ? 1 : 4;
 }
 // written by fmov_fine_fwd (a forward-only stash holds exactly these)
 __host__ __device__ inline bool stash_is_forward(int id) {
-#ifdef FMOV_RELU_BITS
   if (id == ST_CM) return true;
-#endif
   return id <= ST_C1 + 3;
 }
 
@@ -287,22 +245,17 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const uint32_t tmem = s->tmem_base;
 
   if (warp >= CTRL_WARP0) {
-    FINE_CTRL_REGS();
     if (warp == PRODUCER_WARP) {
       if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
     } else if (warp == ISSUER_WARP) {
       if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
     }
   } else {
-    FINE_EPI_REGS();
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
     const int hb0 = c.wg * HPW;
     const int ck0 = c.wg * NCK;
     const bool owner = c.wg == CH_WGS - 1;      // warpgroup that owns the per-row state and the narrow steps
-#ifdef FMOV_L2_HINTS_FWD
-    const uint64_t fpol_keep = l2_policy_evict_last(), fpol_stream = l2_policy_evict_first();
-#endif
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
@@ -369,7 +322,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q2[2];
           pack2(v, false, q2);
           chunk_store(actp, ck, q2);
-          FWD_ST_CHUNK(hsp, ck, q2, l < 7);          // H1..H7 come back in the reverse sweep, H8 does not
+          chunk_store(hsp, ck, q2);
         }
         epi_signal_act(c);
       }
@@ -406,14 +359,14 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
         uint4 sb[2][4];
-        FWD_LD_HALF_STREAM(hp, hb0, sb[0]);
-        if (kStashPrefetch) tile_prefetch_l2(hp, ck0 + 2, NCK - 2);
+        ld_half(hp, hb0, sb[0]);
+        tile_prefetch_l2(hp, ck0 + 2, NCK - 2);
         epi_wait_acc(c);
 #pragma unroll
         for (int hi = 0; hi < HPW; ++hi) {
           const int hb = hb0 + hi;
           float v[32], h[32];
-          if (hi < HPW - 1) FWD_LD_HALF_STREAM(hp, hb + 1, sb[(hi + 1) & 1]);
+          if (hi < HPW - 1) ld_half(hp, hb + 1, sb[(hi + 1) & 1]);
           acc_load32(c, hb * 32, v);
           unpack4(sb[hi & 1], false, h);
           if (l == 4 && hb == 6 && pc.valid) {
@@ -431,7 +384,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           uint4 q[4];
           pack4(v, false, q);
           st_half(ap, hb, q);
-          FWD_ST_HALF_STREAM(dp, hb, q);
+          st_half(dp, hb, q);
         }
         epi_signal_act(c);
       }
@@ -497,12 +450,10 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             v[j4 * 4 + 3] = fmaxf(v[j4 * 4 + 3] + b4.w, 0.f);
           }
           put_chunk(c, ptrs, true, ST_C1 + l, tile, hb, false, v);
-#ifdef FMOV_RELU_BITS
           uint32_t m = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
           reinterpret_cast<uint32_t*>(stash_tile(ptrs, ST_CM, tile))[(l * 8 + hb) * TILE_M + c.row] = m;
-#endif
         }
         epi_signal_act(c);
       }
@@ -553,14 +504,12 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const uint32_t tmem = s->tmem_base;
 
   if (warp >= CTRL_WARP0) {
-    FINE_CTRL_REGS();
     if (warp == PRODUCER_WARP) {
       if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
     } else if (warp == ISSUER_WARP) {
       if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
     }
   } else {
-    FINE_EPI_REGS();
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
     const int hb0 = c.wg * HPW;
@@ -568,9 +517,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
     const bool owner = c.wg == CH_WGS - 1;
     const float gscale = grad_scale_from_amax(__ldg(a.amax));
     const float ginv = 1.0f / gscale;
-#ifdef FMOV_L2_HINTS
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-#endif
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const PointCtx pc = load_sample(a, tile, c.row);
@@ -594,25 +541,14 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       for (int hi = 0; hi < HPW; ++hi) {
         const int hb = hb0 + hi;
         float v[32];
-#ifdef FMOV_RELU_BITS
         // experiment (off by default): the backward pass reads the ReLU signs as one word per 32 columns instead of the
         // fp16 C tiles (16 blocks -> 1 block per tile; DESIGN.md §3 "HBM budget")
         const uint32_t m = reinterpret_cast<const uint32_t*>(stash_tile(ptrs, ST_CM, tile))[(3 * 8 + hb) * TILE_M + c.row];
-#else
-        float h[32];
-        uint4 q[4];
-        get_chunk_raw(c, ptrs, ST_C1 + 3, tile, hb, q);
-        unpack4(q, false, h);
-#endif
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = hb * 32 + j;
           const float ab = zc4[0] * __ldg(a.wc4 + col) + zc4[1] * __ldg(a.wc4 + 256 + col) + zc4[2] * __ldg(a.wc4 + 512 + col);
-#ifdef FMOV_RELU_BITS
           v[j] = ((m >> j) & 1u) ? ab : 0.f;
-#else
-          v[j] = h[j] > 0.f ? ab : 0.f;
-#endif
         }
         put_chunk_grad(c, ptrs, true, ST_ZC0 + 3, tile, hb, v);
       }
@@ -623,7 +559,6 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const uint8_t* cp = tile_base(ptrs, ST_C1 + (l - 1), tile, c.row);
         uint8_t* zp = tile_base(ptrs, ST_ZC0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
-#ifdef FMOV_RELU_BITS
         (void)cp;
         uint32_t mw[HPW];
 #pragma unroll
@@ -638,22 +573,6 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((mw[hi] >> j) & 1u) ? v[j] : 0.f;
           uint4 q[4];
-#else
-        uint4 sb[2][4];
-        ld_half(cp, hb0, sb[0]);
-        if (kStashPrefetch) tile_prefetch_l2(cp, ck0 + 2, NCK - 2);
-        epi_wait_acc(c);
-#pragma unroll
-        for (int hi = 0; hi < HPW; ++hi) {
-          const int hb = hb0 + hi;
-          float v[32], h[32];
-          if (hi < HPW - 1) ld_half(cp, hb + 1, sb[(hi + 1) & 1]);
-          acc_load32(c, hb * 32, v);
-          unpack4(sb[hi & 1], false, h);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
-          uint4 q[4];
-#endif
           pack4_grad(v, q);
           st_half(ap, hb, q);
           st_half(zp, hb, q);
@@ -716,7 +635,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       }
       epi_signal_act(c);
       // ---- adjoint pass l = 0..7:  dbar_l = W_l vbar_l ; vbar_{l+1} = dbar_l*sigma_l ; q_l -------------------
-      // 16-column chunks, H/delta chunks prefetched one chunk ahead (register budget: see FINE_EPI_REGS)
+      // 16-column chunks, H/delta chunks prefetched one chunk ahead (register budget: 96, see above)
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
         const int n_mma = (l == 3) ? 224 : 256;
@@ -724,13 +643,12 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const uint8_t* dp = tile_base(ptrs, ST_D0 + l, tile, c.row);      // delta_l
         uint8_t* vp = tile_base(ptrs, ST_V1 + l, tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
-#ifdef FMOV_RECOMPUTE_Q
         // experiment (off by default): q_l is not spilled; the backward pass rebuilds it from V-bar, delta and sigma, which
         // removes the Q write here and the delta read ("HBM budget")
         uint4 sb[PFD + 1][2];
 #pragma unroll
         for (int i = 0; i < PFD; ++i) LD_KEEP(hp, ck0 + i, sb[i]);
-        if (kStashPrefetch) PF_KEEP(hp, ck0 + PFD, NCK - PFD);
+        PF_KEEP(hp, ck0 + PFD, NCK - PFD);
         (void)dp;
         epi_wait_acc(c);
 #pragma unroll
@@ -755,55 +673,6 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           chunk_store(ap, ck, q2);
           chunk_store(vp, ck, q2);
         }
-#else
-        uint8_t* qp = tile_base(ptrs, ST_Q0 + l, tile, c.row);
-        uint4 sb[PFD + 1][2], db[PFD + 1][2];
-#pragma unroll
-        for (int i = 0; i < PFD; ++i) {
-          LD_KEEP(hp, ck0 + i, sb[i]);
-          LD_STREAM(dp, ck0 + i, db[i]);
-        }
-        if (kStashPrefetch && (!kPrefetchNext || l == 0)) {
-          PF_KEEP(hp, ck0 + PFD, NCK - PFD);
-          tile_prefetch_l2(dp, ck0 + PFD, NCK - PFD);
-        }
-        epi_wait_acc(c);
-#pragma unroll
-        for (int i = 0; i < NCK; ++i) {
-          const int ck = ck0 + i;
-          if (i + PFD < NCK) {
-            LD_KEEP(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
-            LD_STREAM(dp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
-          }
-          if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l < 7) {     // next step's tiles, half a step + MMA ahead
-            tile_prefetch_l2(tile_base(ptrs, ST_H1 + l + 1, tile, c.row), ck0 + PFD, NCK - PFD);
-            tile_prefetch_l2(tile_base(ptrs, ST_D0 + l + 1, tile, c.row), ck0 + PFD, NCK - PFD);
-          }
-          float v[16], qv[16];
-          if (ck * 16 < n_mma) {
-            acc_load16(c, ck * 16, v);
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
-          }
-#pragma unroll
-          for (int jp = 0; jp < 8; ++jp) {
-            const float2 hh = chunk_pair(sb[i % (PFD + 1)], jp, false);
-            const float2 dd = chunk_pair(db[i % (PFD + 1)], jp, false);
-            const float s0 = sigma_from_h(hh.x), s1 = sigma_from_h(hh.y);
-            qv[2 * jp] = SP_BETA * v[2 * jp] * dd.x * (1.f - s0);             // q_l
-            qv[2 * jp + 1] = SP_BETA * v[2 * jp + 1] * dd.y * (1.f - s1);
-            v[2 * jp] *= s0;                                                    // vbar_{l+1}
-            v[2 * jp + 1] *= s1;
-          }
-          uint4 q2[2];
-          pack2_grad(v, q2);
-          chunk_store(ap, ck, q2);
-          ST_STREAM(vp, ck, q2);              // V-bar is only read again by the dW kernel
-          pack2_grad(qv, q2);
-          chunk_store(qp, ck, q2);            // q comes back in the ordinary backward pass: default policy
-        }
-#endif
         if (l < 7) epi_signal_act(c);
       }
       // ---- fbar back into ACT (own rows) -----------------------------------------------------------------------
@@ -816,7 +685,6 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       }
       epi_signal_act(c);
       // ---- ordinary backward l = 8..1: zbar_{l-1} = (zbar_l W_l)*sigma_{l-1} + q_{l-1} ------------------------
-#ifdef FMOV_RECOMPUTE_Q
       // q_{l-1} = 100 * dbar_{l-1} * delta_{l-1} * (1 - sigma_{l-1}) with dbar_{l-1} = vbar_l / sigma_{l-1}: rebuilt from the
       // V-bar tile the adjoint pass wrote (own chunks) and the forward's delta tile.  sigma = 0 only where h = 0 (padding
       // columns, fp16 underflow): vbar and delta are 0 there as well and so is q.  Three operand streams: the loads are
@@ -828,18 +696,12 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const uint8_t* dp = tile_base(ptrs, ST_D0 + (l - 1), tile, c.row);    // delta_{l-1} (fp16)
         uint8_t* zp = tile_base(ptrs, ST_Z0 + (l - 1), tile, c.row);
         uint8_t* ap = c.act + c.row * 16;
-        constexpr int PH = FMOV_RQ_PH;          // prefetch distance in 8-column pieces
+        constexpr int PH = RQ_PH;          // prefetch distance in 8-column pieces
         constexpr int NP = 2 * NCK;             // pieces per warpgroup
         const int pc0 = 2 * ck0;                // first piece (= 16-byte chunk column of the 256-wide tile)
-#ifdef FMOV_L2_HINTS
         auto piece = [pol_stream](const uint8_t* tp, int pi) {          // last use of all three streams
           return ldg_pol(tp + (pi >> 3) * BLK_BYTES + (pi & 7) * TI_CHUNK_STRIDE, pol_stream);
         };
-#else
-        auto piece = [](const uint8_t* tp, int pi) {
-          return *reinterpret_cast<const uint4*>(tp + (pi >> 3) * BLK_BYTES + (pi & 7) * TI_CHUNK_STRIDE);
-        };
-#endif
         uint4 sb[PH + 1], vb[PH + 1], db[PH + 1];
 #pragma unroll
         for (int i = 0; i < PH; ++i) {
@@ -847,11 +709,9 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           vb[i] = piece(vp, pc0 + i);
           db[i] = piece(dp, pc0 + i);
         }
-        if (kStashPrefetch) {
-          tile_prefetch_l2(hp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
-          tile_prefetch_l2(vp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
-          tile_prefetch_l2(dp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
-        }
+        tile_prefetch_l2(hp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
+        tile_prefetch_l2(vp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
+        tile_prefetch_l2(dp, ck0 + (PH + 1) / 2, NCK - (PH + 1) / 2);
         epi_wait_acc(c);
         float v[16];
 #pragma unroll
@@ -904,67 +764,6 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         }
         epi_signal_act(c);
       }
-#else
-#pragma unroll 1
-      for (int l = 8; l >= 1; --l) {
-        const uint8_t* hp = tile_base(ptrs, ST_H1 + (l - 1), tile, c.row);    // H_l -> sigma_{l-1}
-        const uint8_t* qp = tile_base(ptrs, ST_Q0 + (l - 1), tile, c.row);    // q_{l-1} (own chunks, written above)
-        uint8_t* zp = tile_base(ptrs, ST_Z0 + (l - 1), tile, c.row);
-        uint8_t* ap = c.act + c.row * 16;
-        uint4 sb[PFD + 1][2], db[PFD + 1][2];
-#pragma unroll
-        for (int i = 0; i < PFD; ++i) {
-          LD_STREAM(hp, ck0 + i, sb[i]);          // last use of H and q
-          LD_STREAM(qp, ck0 + i, db[i]);
-        }
-        if (kStashPrefetch && (!kPrefetchNext || l == 8)) {
-          tile_prefetch_l2(hp, ck0 + PFD, NCK - PFD);
-          tile_prefetch_l2(qp, ck0 + PFD, NCK - PFD);
-        }
-        epi_wait_acc(c);
-#pragma unroll
-        for (int i = 0; i < NCK; ++i) {
-          const int ck = ck0 + i;
-          if (i + PFD < NCK) {
-            LD_STREAM(hp, ck + PFD, sb[(i + PFD) % (PFD + 1)]);
-            LD_STREAM(qp, ck + PFD, db[(i + PFD) % (PFD + 1)]);
-          }
-          if (kStashPrefetch && kPrefetchNext && i == NCK / 2 && l > 1) {
-            tile_prefetch_l2(tile_base(ptrs, ST_H1 + (l - 2), tile, c.row), ck0 + PFD, NCK - PFD);
-            tile_prefetch_l2(tile_base(ptrs, ST_Q0 + (l - 2), tile, c.row), ck0 + PFD, NCK - PFD);
-          }
-          float v[16];
-          acc_load16(c, ck * 16, v);
-          if (l == 8) {
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8row + ck * 16) + j4);
-              v[j4 * 4 + 0] = fmaf(sbar, w4.x, v[j4 * 4 + 0]); v[j4 * 4 + 1] = fmaf(sbar, w4.y, v[j4 * 4 + 1]);
-              v[j4 * 4 + 2] = fmaf(sbar, w4.z, v[j4 * 4 + 2]); v[j4 * 4 + 3] = fmaf(sbar, w4.w, v[j4 * 4 + 3]);
-            }
-          }
-          if (l == 4 && ck >= 13 && pc.valid) {        // columns 217..255: PE part of the skip input -> scratch row
-#pragma unroll
-            for (int jj = 0; jj < 16; ++jj) {
-              const int col = ck * 16 + jj;
-              if (col >= 217) a.eb[pc.p * 40 + (col - 217)] = v[jj];
-            }
-          }
-#pragma unroll
-          for (int jp = 0; jp < 8; ++jp) {
-            const float2 hh = chunk_pair(sb[i % (PFD + 1)], jp, false);
-            const float2 qq = chunk_pair(db[i % (PFD + 1)], jp, kGradBf16);
-            v[2 * jp] = fmaf(v[2 * jp], sigma_from_h(hh.x), qq.x);
-            v[2 * jp + 1] = fmaf(v[2 * jp + 1], sigma_from_h(hh.y), qq.y);
-          }
-          uint4 q2[2];
-          pack2_grad(v, q2);
-          chunk_store(ap, ck, q2);
-          ST_STREAM(zp, ck, q2);
-        }
-        epi_signal_act(c);
-      }
-#endif
       // ---- e-bar += W_0^T zbar_0 ; xbar += J_e^T e-bar -----------------------------------------------------------
       epi_wait_acc(c);
       if (owner) {

@@ -116,6 +116,45 @@ __device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const f
   row_half_store(blk + row * 16, h, q);
 }
 
+// split-precision variants: value = hi + lo with hi = fp16(v), lo = fp16(v - hi) (relative error 2^-22)
+__device__ __forceinline__ void split16(const float* v, float* lo) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) lo[i] = v[i] - __half2float(__float2half_rn(v[i]));
+}
+__device__ __forceinline__ void pe6_half_to_block_hilo(uint8_t* blk_hi, uint8_t* blk_lo, int row, const float x[3], int h) {
+  float e[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) e[i] = 0.f;
+  e[0] = x[0]; e[1] = x[1]; e[2] = x[2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float f = (float)(1 << k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      // the residual image carries what fp16 drops, so the encoding itself must be accurate: libm sincosf
+      float s, co;
+      sincosf(x[c] * f, &s, &co);
+      e[3 + 6 * k + c] = s;
+      e[6 + 6 * k + c] = co;
+    }
+  }
+  const float* eh = e + 32 * h;
+  uint4 q[4];
+  pack4(eh, false, q);
+  row_half_store(blk_hi + row * 16, h, q);
+  float lo[32];
+  split16(eh, lo);
+  split16(eh + 16, lo + 16);
+  pack4(lo, false, q);
+  row_half_store(blk_lo + row * 16, h, q);
+}
+// softplus(beta = 100) to fp32 accuracy (the fast polynomial's 4e-7 is fine for fp16 tiles, not for hi/lo pairs)
+__device__ __forceinline__ float softplus100_precise(float z) {
+  const float t = z * SP_BETA;
+  return t > 20.f ? z : log1pf(expf(t)) * (1.0f / SP_BETA);
+}
+
+template <bool PRECISE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
                  const __grid_constant__ QueryArgs a) {
@@ -147,14 +186,19 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
     const float b8 = __ldg(a.b8);
-    for (int k = c.slot; k < n_my; k += CH_SLOTS) {
+    // PRECISE: one tile in flight (slot 0); slot 1's ACT / AUX hold the fp16 residuals of slot 0's operands
+    uint8_t* const act_lo = act0 + 4 * BLK_BYTES;
+    uint8_t* const aux_lo = aux0 + BLK_BYTES;
+    if (PRECISE && c.slot != 0) goto epilogue_done;
+    for (int k = c.slot; k < n_my; k += (PRECISE ? 1 : CH_SLOTS)) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const long long p = tile * TILE_M + c.row;
       const bool valid = p < a.P;
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) load_point(a, p, x);
       x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
-      if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
+      if (PRECISE) pe6_half_to_block_hilo(c.aux, aux_lo, c.row, x, c.wg);
+      else if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
       else pe6_to_block(c.aux, c.row, x);
       epi_signal_act(c);
       float sdf = 0.f;
@@ -173,10 +217,17 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
-            v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
-            v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
-            v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
-            v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
+            if (PRECISE) {
+              v[j4 * 4 + 0] = softplus100_precise(v[j4 * 4 + 0] + b4.x);
+              v[j4 * 4 + 1] = softplus100_precise(v[j4 * 4 + 1] + b4.y);
+              v[j4 * 4 + 2] = softplus100_precise(v[j4 * 4 + 2] + b4.z);
+              v[j4 * 4 + 3] = softplus100_precise(v[j4 * 4 + 3] + b4.w);
+            } else {
+              v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
+              v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
+              v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
+              v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
+            }
           }
           if (l == 7) {
 #pragma unroll
@@ -189,6 +240,12 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
             uint4 q2[2];
             pack2(v, false, q2);
             chunk_store(actp, ck, q2);
+            if (PRECISE) {
+              float lo[16];
+              split16(v, lo);
+              pack2(lo, false, q2);
+              chunk_store(act_lo + c.row * 16, ck, q2);
+            }
           }
         }
         if (l < 7) epi_signal_act(c);
@@ -203,6 +260,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
       }
       if (c.wg == CH_WGS - 1 && valid) a.out[p] = (sdf + b8) * a.out_scale;
     }
+  epilogue_done:;
   }
   __syncthreads();
   if (warp == ISSUER_WARP) {
@@ -234,6 +292,24 @@ static void build_query_table(ChainTable& tb) {
   }
 }
 
+// Split-precision chain: per layer three passes into one accumulator, hi*W_hi + lo*W_hi + hi*W_lo (the residual images
+// have the layout of the forward blob), one tile in flight.  Result error ~1e-6 instead of the fp16 chain's ~1e-3.
+static void build_query_table_precise(ChainTable& tb) {
+  ChainTable f;
+  build_query_table(f);
+  memset(&tb, 0, sizeof(tb));
+  tb.n_steps = 24;
+  tb.slots = 1;
+  for (int l = 0; l < 8; ++l) {
+    for (int pass = 0; pass < 3; ++pass) {
+      ChainStep st = f.step[l];
+      st.flags = (pass == 0 ? 0 : CHF_ACCUM) | (pass == 2 ? 0 : CHF_NO_COMMIT) | (pass == 1 ? CHF_A_OTHER : 0) |
+                 (pass == 2 ? CHF_W2 : 0);
+      tb.step[l * 3 + pass] = st;
+    }
+  }
+}
+
 extern "C" long long fmov_sdf_fwd_blob_bytes(void) {
   ChainTable tb;
   build_query_table(tb);
@@ -248,26 +324,29 @@ extern "C" long long fmov_sdf_fwd_blob_offset(int layer) {
   return tb.step[layer].w_off;
 }
 
-static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cudaStream_t stream) {
-  static ChainTable tb;
+static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cudaStream_t stream, const void* wblob_lo = nullptr) {
+  static ChainTable tb, tbp;
   static bool init = false;
-  if (!init) { build_query_table(tb); init = true; }
+  if (!init) { build_query_table(tb); build_query_table_precise(tbp); init = true; }
   ChainPtrs ptrs;
   memset(&ptrs, 0, sizeof(ptrs));
   ptrs.weights = reinterpret_cast<const uint8_t*>(wblob);
+  ptrs.weights2 = reinterpret_cast<const uint8_t*>(wblob_lo);
   int dev = 0, sms = 0;
   FMOV_CUDA(cudaGetDevice(&dev));
   FMOV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static bool attr_set = false;
   if (!attr_set) {
-    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
     attr_set = true;
   }
   long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
   if (n_tiles == 0) return OK;
   int grid = (int)(n_tiles < sms ? n_tiles : sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  sdf_query_kernel<<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tb, ptrs, a);
+  if (wblob_lo) sdf_query_kernel<true><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tbp, ptrs, a);
+  else sdf_query_kernel<false><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tb, ptrs, a);
   FMOV_LAUNCH_CHECK("sdf_query_kernel");
   return OK;
 }
@@ -309,4 +388,35 @@ extern "C" int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int r
   for (int i = 0; i < 3; ++i) { a.bmin[i] = bmin3[i]; a.bmax[i] = bmax3[i]; }
   a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
   return launch_query(a, wblob, 0, (cudaStream_t)stream);
+}
+
+// ---- split-precision ("precise") entry points: SDF to ~1e-5 of the fp32 network everywhere (north_star: SDF <= 1e-3), for
+// SDFNetwork.sdf and extract_fields (models/fields.py:106-107, models/renderer.py:9-37, :506).  `wblob_lo` = the images of
+// the fp16 residuals W - fp16(W), same layout as `wblob` (fmov_pack_image with fmt = 2).
+extern "C" int fmov_sdf_query_points_precise(const float* pts, long long P, const void* wblob, const void* wblob_lo,
+                                             const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
+                                             float out_scale, float* out, void* stream) {
+  FMOV_REQUIRE(P >= 0 && (P == 0 || (pts && out && wblob && wblob_lo && bias8x256 && w8_row0)),
+               "fmov_sdf_query_points_precise: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 0; a.P = P; a.pts = pts; a.in_scale = in_scale; a.out_scale = out_scale;
+  a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob, 0, (cudaStream_t)stream, wblob_lo);
+}
+
+extern "C" int fmov_sdf_query_grid_precise(const float* bmin3, const float* bmax3, int res, long long first, long long count,
+                                           const void* wblob, const void* wblob_lo, const float* bias8x256,
+                                           const float* w8_row0, const float* b8, float in_scale, float out_scale, float* out,
+                                           void* stream) {
+  FMOV_REQUIRE(res > 0 && first >= 0 && count >= 0 && first + count <= (long long)res * res * res,
+               "fmov_sdf_query_grid_precise: bad range first=%lld count=%lld res=%d", first, count, res);
+  FMOV_REQUIRE(bmin3 && bmax3 && (count == 0 || (out && wblob && wblob_lo && bias8x256 && w8_row0)),
+               "fmov_sdf_query_grid_precise: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 2; a.P = count; a.res = res; a.grid_off = first;
+  for (int i = 0; i < 3; ++i) { a.bmin[i] = bmin3[i]; a.bmax[i] = bmax3[i]; }
+  a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob, 0, (cudaStream_t)stream, wblob_lo);
 }

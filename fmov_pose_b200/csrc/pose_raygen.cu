@@ -286,9 +286,12 @@ __global__ void raygen_fwd_kernel(RayArgs a) {
   for (int i = 0; i < 3; ++i) d[i] = sR[i * 3] * v[0] + sR[i * 3 + 1] * v[1] + sR[i * 3 + 2] * v[2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) { a.rays_o[r * 3 + i] = st[i]; a.rays_d[r * 3 + i] = d[i]; }
-  const float aa = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-  const float bb = 2.f * (st[0] * d[0] + st[1] * d[1] + st[2] * d[2]);
-  const float mid = 0.5f * (-bb) / aa;
+  // Dataset.near_far_from_sphere (models/dataset.py:835-842) in torch's own operation order and rounding: a = sum(d**2),
+  // b = 2 * sum(o*d), mid = 0.5 * (-b) / a with every product and sum rounded separately (no FMA contraction), so that the
+  // fused path draws bit-identical samples to the torch expression evaluated on the same rays
+  const float aa = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
+  const float bb = __fmul_rn(2.f, __fadd_rn(__fadd_rn(__fmul_rn(st[0], d[0]), __fmul_rn(st[1], d[1])), __fmul_rn(st[2], d[2])));
+  const float mid = __fdiv_rn(__fmul_rn(0.5f, -bb), aa);
   if (a.near) a.near[r] = mid - 1.f;
   if (a.far) a.far[r] = mid + 1.f;
 }

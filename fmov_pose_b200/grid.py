@@ -35,7 +35,7 @@ def gather_slabs(local, resolution, group=None):
     return torch.cat(parts)
 
 
-def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=None, to_host=False):
+def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=None, to_host=False, precise=True):
     """u = -sdf on the res^3 grid with the x-planes partitioned across the ranks of `group`.
     -> [res,res,res] tensor on every rank (device; pinned host memory when to_host: what validate_mesh hands to
     marching cubes, exp_runner.py:1630-1640)."""
@@ -44,7 +44,7 @@ def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=Non
     rank = dist.get_rank(group) if group is not None else 0
     first, n = slab_of(resolution, world, rank)
     plane = resolution * resolution
-    local = renderer.extract_fields(bound_min, bound_max, resolution, first=first * plane, count=n * plane)
+    local = renderer.extract_fields(bound_min, bound_max, resolution, first=first * plane, count=n * plane, precise=precise)
     u = gather_slabs(local, resolution, group).view(resolution, resolution, resolution)
     if to_host:
         host = torch.empty(u.shape, dtype=u.dtype, pin_memory=True)

@@ -205,12 +205,14 @@ class NeuSRenderer:
                 "depth_fine": depth.reshape(*shape, 1), "weight_sum": wsum.reshape(*shape, 1)}
 
     # ------------------------------------------------------------------------------------------------
-    def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None):
+    def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None, precise=True):
         """u = -sdf on the res^3 grid (models/renderer.py:9-37 with query_func of :506) in one launch.
-        `first`/`count` select a contiguous x-major range (grid partitioning across ranks)."""
+        `first`/`count` select a contiguous x-major range (grid partitioning across ranks).
+        `precise` (default): split-precision chain, within ~1e-5 of the fp32 network on the whole +-1.01 box (the plain
+        fp16 chain is 1.3e-3 off at the box corners, above north_star's 1e-3)."""
         with torch.no_grad():
             W, b = self.sdf_network.effective_weights()
-            qw = _packing.SdfQueryWeights(W, b)
+            qw = _packing.SdfQueryWeights(W, b, precise=precise)
             total = resolution ** 3
             if count is None:
                 count = total - first
@@ -218,13 +220,13 @@ class NeuSRenderer:
                 out = torch.empty(count, dtype=torch.float32, device=W[0].device)
             sc = float(self.sdf_network.scale)
             _ops.sdf_query_grid(qw, [float(v) for v in bound_min], [float(v) for v in bound_max], resolution, first,
-                                count, out, in_scale=sc, out_scale=-1.0 / sc)
+                                count, out, in_scale=sc, out_scale=-1.0 / sc, precise=precise)
         return out
 
-    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0):
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0, precise=True):
         """models/renderer.py:500-507: the 512^3 grid query and the marching cubes both run on the device; only the
         mesh crosses to the host (the reference copies 512 chunks of the grid to the host and runs PyMCubes there)."""
-        u = self.extract_fields(bound_min, bound_max, resolution).reshape(resolution, resolution, resolution)
+        u = self.extract_fields(bound_min, bound_max, resolution, precise=precise).reshape(resolution, resolution, resolution)
         return extract_geometry(bound_min, bound_max, resolution, threshold, u=u)
 
     def extract_color(self, vertices):

@@ -6,12 +6,19 @@ import torch
 from . import _lib as L
 
 
-def sdf_query_points(qw, pts, in_scale=1.0, out_scale=1.0):
-    """SDFNetwork.sdf(pts) under no_grad (models/fields.py:106-107) -> [P,1]"""
+def sdf_query_points(qw, pts, in_scale=1.0, out_scale=1.0, precise=False):
+    """SDFNetwork.sdf(pts) under no_grad (models/fields.py:106-107) -> [P,1].  `precise`: split-precision chain
+    (qw built with precise=True), ~1e-5 of the fp32 network instead of ~1e-3."""
     pts = L.f32c(pts)
     P = pts.shape[0]
     out = torch.empty(P, 1, dtype=torch.float32, device=pts.device)
-    if P:
+    if P and precise:
+        assert qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the split-precision chain"
+        L.check(L.lib().fmov_sdf_query_points_precise(L.ptr(pts), L.c_ll(P), L.ptr(qw.blob), L.ptr(qw.blob_lo),
+                                                      L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(in_scale),
+                                                      L.c_float(out_scale), L.ptr(out), L.stream()),
+                "fmov_sdf_query_points_precise")
+    elif P:
         L.check(L.lib().fmov_sdf_query_points(L.ptr(pts), L.c_ll(P), L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8),
                                               L.ptr(qw.b8), L.c_float(in_scale), L.c_float(out_scale), L.ptr(out),
                                               L.stream()), "fmov_sdf_query_points")
@@ -31,10 +38,18 @@ def sdf_query_rays(qw, rays_o, rays_d, z, S, z_off=0, in_scale=1.0, out_scale=1.
     return out
 
 
-def sdf_query_grid(qw, bmin, bmax, res, first, count, out, in_scale=1.0, out_scale=-1.0):
+def sdf_query_grid(qw, bmin, bmax, res, first, count, out, in_scale=1.0, out_scale=-1.0, precise=False):
     """-sdf on points [first, first+count) of the x-major res^3 grid (models/renderer.py:9-37, :506)."""
     bm = (ctypes.c_float * 3)(*[float(v) for v in bmin])
     bx = (ctypes.c_float * 3)(*[float(v) for v in bmax])
+    if precise:
+        assert qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the split-precision chain"
+        with L.timed("sdf_query_grid_precise"):
+            L.check(L.lib().fmov_sdf_query_grid_precise(bm, bx, int(res), L.c_ll(first), L.c_ll(count), L.ptr(qw.blob),
+                                                        L.ptr(qw.blob_lo), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
+                                                        L.c_float(in_scale), L.c_float(out_scale), L.ptr(out),
+                                                        L.stream()), "fmov_sdf_query_grid_precise")
+        return out
     L.check(L.lib().fmov_sdf_query_grid(bm, bx, int(res), L.c_ll(first), L.c_ll(count), L.ptr(qw.blob), L.ptr(qw.bias),
                                         L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(in_scale), L.c_float(out_scale),
                                         L.ptr(out), L.stream()), "fmov_sdf_query_grid")

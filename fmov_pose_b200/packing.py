@@ -64,26 +64,32 @@ class SdfQueryWeights:
     def from_views(cls, blob, bias, w8, b8):
         self = cls.__new__(cls)
         self.blob, self.bias, self.w8, self.b8 = blob, bias, w8, b8
+        self.blob_lo = None
         return self
 
-    def __init__(self, W, b):
-        """W, b: lists of the 9 effective fp32 weights / biases of the SDF net (CUDA)."""
+    def __init__(self, W, b, precise=False):
+        """W, b: lists of the 9 effective fp32 weights / biases of the SDF net (CUDA).  `precise`: also pack the fp16
+        residual images (`blob_lo`) that the split-precision chain (fmov_sdf_query_*_precise) adds in."""
         dev = W[0].device
         lib = L.lib()
         assert len(W) == 9 and W[0].shape == (256, 39) and W[3].shape == (217, 256) and W[8].shape[1] == 256, \
             "kernels are built for the 8x256, multires=6, skip_in=(4,) SDF network of the shipped confs"
         self.blob = torch.zeros(int(lib.fmov_sdf_fwd_blob_bytes()), dtype=torch.uint8, device=dev)
-        for l in range(8):
-            off = int(lib.fmov_sdf_fwd_blob_offset(l))
-            Wl = W[l].detach().float()
-            if l == 0:
-                pack_image(Wl, self.blob, off, 256, 1, [(0, 0, 39)])
-            elif l == 3:
-                pack_image(Wl, self.blob, off, 224, 4, [(0, 0, 256)])
-            elif l == 4:
-                pack_image(Wl, self.blob, off, 256, 5, [(0, 0, 217), (256, 217, 39)], scale=1.0 / SQ2)
-            else:
-                pack_image(Wl, self.blob, off, 256, 4, [(0, 0, 256)])
+        self.blob_lo = torch.zeros_like(self.blob) if precise else None
+        for fmt, blob in ((0, self.blob), (2, self.blob_lo)):
+            if blob is None:
+                continue
+            for l in range(8):
+                off = int(lib.fmov_sdf_fwd_blob_offset(l))
+                Wl = W[l].detach().float()
+                if l == 0:
+                    pack_image(Wl, blob, off, 256, 1, [(0, 0, 39)], bf16=fmt)
+                elif l == 3:
+                    pack_image(Wl, blob, off, 224, 4, [(0, 0, 256)], bf16=fmt)
+                elif l == 4:
+                    pack_image(Wl, blob, off, 256, 5, [(0, 0, 217), (256, 217, 39)], scale=1.0 / SQ2, bf16=fmt)
+                else:
+                    pack_image(Wl, blob, off, 256, 4, [(0, 0, 256)], bf16=fmt)
         self.bias = torch.zeros(8, 256, dtype=torch.float32, device=dev)
         for l in range(8):
             self.bias[l, : b[l].numel()] = b[l].detach().float()

@@ -26,7 +26,8 @@ const char* fmov_last_error(void);
 int fmov_version(void);
 
 /* ---- weight / tile images (host glue for the MLP kernels) ----------------------------- */
-/* fp32 matrix -> SW128 operand image [npad x 64*kblocks]; see api.cu. seg_* are HOST arrays. */
+/* fp32 matrix -> no-swizzle operand image [npad x 64*kblocks]; see api.cu. seg_* are HOST arrays.
+ * bf16: 0 = fp16 image, 1 = bf16 image, 2 = fp16 image of the residual x - fp16(x) (split-precision chains). */
 int fmov_pack_image(const float* src, long long stride_n, long long stride_k, int n_valid, int row_off, int nseg,
                     const int* seg_dst, const int* seg_src, const int* seg_len, float scale, int bf16, void* dst,
                     int npad, int kblocks, void* stream);
@@ -62,6 +63,18 @@ int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z
 int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
                         const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
                         float out_scale, float* out, void* stream);
+
+/* split-precision ("precise") value chain for SDFNetwork.sdf / extract_fields (models/fields.py:106-107,
+ * models/renderer.py:9-37, :506): every layer accumulates hi*W_hi + lo*W_hi + hi*W_lo with hi = fp16(v), lo = fp16(v - hi),
+ * so the result is within ~1e-5 of the fp32 network everywhere in the +-1.01 box (north_star: SDF <= 1e-3; the plain
+ * fp16 chain reaches 1.3e-3 at |x| ~ 1.75).  wblob_lo: residual images W - fp16(W) in wblob's layout
+ * (fmov_pack_image with bf16 = 2).  About 3x the cost of the plain chain. */
+int fmov_sdf_query_points_precise(const float* pts, long long P, const void* wblob, const void* wblob_lo,
+                                  const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
+                                  float out_scale, float* out, void* stream);
+int fmov_sdf_query_grid_precise(const float* bmin3, const float* bmax3, int res, long long first, long long count,
+                                const void* wblob, const void* wblob_lo, const float* bias8x256, const float* w8_row0,
+                                const float* b8, float in_scale, float out_scale, float* out, void* stream);
 
 /* ---- pose + ray generation ------------------------------------------------------------ */
 /* mode 1: LearnPoseGF tail  c2w = [Exp(rot)|trans] @ [R0 | scale*t0]  (models/picture_pose.py:176-186,

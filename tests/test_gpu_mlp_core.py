@@ -97,9 +97,26 @@ def test_sdf_query_rays_and_grid_vs_oracle():
     out = torch.empty(res ** 3, device=_dev())
     ops.sdf_query_grid(qw, [-1.01] * 3, [1.01] * 3, res, 0, res ** 3, out)
     torch.cuda.synchronize()
-    err = (out.cpu().reshape(res, res, res).numpy() - d["u"])
-    # corners of the +-1.01 box are at |x| = 1.75: fp16-operand far-field error (DESIGN.md "precision")
-    assert np.abs(err).max() <= 2e-3, np.abs(err).max()
+    err = np.abs(out.cpu().reshape(res, res, res).numpy() - d["u"])
+    # the plain fp16 chain: inside the unit ball <= 1e-3; the corners of the +-1.01 box are at |x| = 1.75, where the fp16
+    # rounding of x itself is 5e-4 — that is what the split-precision chain below is for
+    ax = np.linspace(-1.01, 1.01, res, dtype=np.float32)
+    rr = np.sqrt(ax[:, None, None] ** 2 + ax[None, :, None] ** 2 + ax[None, None, :] ** 2)
+    assert err[rr < 1.0].max() <= 1e-3 and err.max() <= 2e-3, (err[rr < 1.0].max(), err.max())
+    # config C5 as the reference runs it (models/renderer.py:9-37, :506): split-precision chain, north_star's SDF <= 1e-3
+    # against the REFERENCE's own grid on the whole box, with an order of magnitude to spare
+    qwp = packing.SdfQueryWeights(W, b, precise=True)
+    outp = torch.empty(res ** 3, device=_dev())
+    ops.sdf_query_grid(qwp, [-1.01] * 3, [1.01] * 3, res, 0, res ** 3, outp, precise=True)
+    torch.cuda.synchronize()
+    errp = np.abs(outp.cpu().reshape(res, res, res).numpy() - d["u"])
+    assert errp.max() <= 1e-4, errp.max()
+    # points mode of the same chain, far field included (|x| up to 2)
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(5000, 3, generator=g) * 2 - 1) * 1.2
+    gotp = ops.sdf_query_points(qwp, pts.to(_dev()), precise=True)
+    refp = O.sdf_value(p, pts)
+    assert (gotp.cpu() - refp).abs().max().item() <= 1e-4
     # rays mode
     B, S = 37, 64
     g = torch.Generator().manual_seed(3)

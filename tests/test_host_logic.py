@@ -271,8 +271,8 @@ def test_fused_loss_function_glue_matches_the_torch_loss_block(monkeypatch):
 
 def test_stash_layout_follows_the_library_directory(monkeypatch):
     """fine.Stash carves ONE buffer by the library's stash directory: the tensors the forward kernel writes come first (a
-    forward-only stash is a prefix of the full one), also when an experiment build appends a forward tensor at the end of
-    the id range (-DFMOV_RELU_BITS) or gives tensors zero blocks (-DFMOV_RECOMPUTE_Q)."""
+    forward-only stash is a prefix of the full one), also when a forward tensor sits at the end of the id range
+    (the ReLU sign words) or tensors have zero blocks (the q tiles, which the backward rebuilds instead of storing)."""
     from fmov_pose_b200 import _lib as L
     from fmov_pose_b200 import fine
 
