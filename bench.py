@@ -153,7 +153,13 @@ def time_torch_gpu(B, n, m, steps_up, dev, warm=2, iters=5):
 
 
 def time_cpu(B, n, m, steps_up, warm, iters):
+    """-> (rays/s, s/step, threads, kind): the reference's own sources (oracle/_ref, `kind: "reference"`) when the build
+    container installed them (oracle/build_ref.py), else the oracle port."""
     threads = os.cpu_count() or 1
+    from oracle import ref_arm
+    if ref_arm.available():
+        rps, med, threads = ref_arm.time_cpu(B, n, m, steps_up, warm, iters, threads)
+        return rps, med, threads, "reference"
     fn = cpu_reference_step_fn(B, n, m, steps_up, threads)
     for _ in range(warm):
         fn()
@@ -164,14 +170,40 @@ def time_cpu(B, n, m, steps_up, warm, iters):
         ts.append(time.perf_counter() - t0)
     ts.sort()
     med = ts[len(ts) // 2]
-    return B / med, med, threads
+    return B / med, med, threads, "port"
 
 
-# algorithmic HBM bytes per sample point of the MLP kernels (16 KiB blocks per 128-point tile x 128 B)
-KERNEL_BYTES_PER_POINT = {"fine_fwd": 15.3e3, "fine_bwd": 33.9e3, "dw": 22.5e3}
-# DRAM traffic of the MLP kernels per sample point, from `ncu --set full` (dram__bytes_read + dram__bytes_write,
-# profiles/r1_final_ncu_full.txt: 2048 rays x 128 samples): fine_fwd 4.02 GB, fine_bwd 9.85 GB, dw 5.90 GB
-NCU_DRAM_BYTES_PER_POINT = {"fine_fwd": 4.023e9 / 262144, "fine_bwd": 9.846e9 / 262144, "dw": 5.898e9 / 262144}
+def reference_gpu_arm(rays, n, m, two=False, timeout=600):
+    """reference-PyTorch on THIS GPU — the unmodified reference sources (oracle/_ref) under
+    torch.set_default_tensor_type("torch.cuda.FloatTensor") as exp_runner.py:2030 runs them — in a child process (the
+    reference claims the module name `models` and changes the default tensor type).  north_star's 50x denominator."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_arm.py"), "gpu", str(rays), str(n), str(m)] +
+                       (["two"] if two else []), capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    return json.loads(lines[-1])
+
+
+# algorithmic HBM bytes per sample point of the MLP kernels (DESIGN.md §3: 16 KiB blocks per 128-point tile x 128 B;
+# fine_fwd 119, fine_bwd 218, dw 176 blocks)
+KERNEL_BYTES_PER_POINT = {"fine_fwd": 119 * 128.0, "fine_bwd": 218 * 128.0, "dw": 176 * 128.0}
+# algorithmic HBM bytes per RAY of the HBM-class kernels (fp32 row-major I/O, S samples per ray; SURVEY.md §8d)
+HBM_KERNEL_BYTES_PER_RAY = {
+    "composite_fwd": lambda S: 4.0 * (S * (1 + 3 + 3 + 1) + S * (1 + 1 + 1 + 1 + 3) + 6 + 8),      # in: sdf, n, rgb, z; out: w, cdf, inside, mid_z, pts, per-ray
+    "composite_bwd": lambda S: 4.0 * (S * (1 + 3 + 3 + 1) + S * (1 + 3 + 3 + 1 + 1) + 6 + 12),     # in: same; out: d_sdf, d_n, d_rgb, d_dist, d_mid, per-ray
+    "sample_round": lambda S: 4.0 * (2 * S + 2 * S + 16 + 6),                                       # z, sdf read + written back, new samples
+}
+
+
+def measured_traffic(kernel, rays):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` summary of
+    this very configuration (profiles/r2_ncu_traffic.json, keyed by rays per launch); None when not captured"""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        return float(tab[str(rays)][kernel])
+    except Exception:
+        return None
 
 
 def measure_extras(scene, dev, use_graph=True):
@@ -185,19 +217,23 @@ def measure_extras(scene, dev, use_graph=True):
     res, count = 512, 512 ** 3 // 8
     buf = torch.empty(count, dtype=torch.float32, device=dev)
     bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
-    for _ in range(2):
-        rend.extract_fields(bmin, bmax, res, first=0, count=count, out=buf)
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        rend.extract_fields(bmin, bmax, res, first=0, count=count, out=buf)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
-    out["c5_grid_query"] = {"points": count, "ms": ms, "sdf_queries_per_s": count / ms * 1e3,
-                            "tflops_algorithmic": count * F_S / ms / 1e9,
-                            "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing"}
+    for tag, precise in (("c5_grid_query", True), ("c5_grid_query_fast_fp16_chain", False)):
+        for _ in range(2):
+            rend.extract_fields(bmin, bmax, res, first=0, count=count, out=buf, precise=precise)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            rend.extract_fields(bmin, bmax, res, first=0, count=count, out=buf, precise=precise)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[tag] = {"points": count, "ms": ms, "sdf_queries_per_s": count / ms * 1e3,
+                    "tflops_algorithmic": count * F_S / ms / 1e9,
+                    "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing; " +
+                            ("split-precision chain (default of extract_fields: SDF within 1e-4 of fp32 on the whole box; "
+                             "3 MMA passes per layer, one tile in flight)" if precise else
+                             "plain fp16 chain (1.3e-3 at the box corners)")}
     # whole-frame forward-only render (validate_image shape: 640x480 = 307,200 rays, 64+64 samples)
     ds = scene["dataset"]
     with torch.no_grad():
@@ -214,29 +250,41 @@ def measure_extras(scene, dev, use_graph=True):
     out["frame_render_640x480"] = {"ms_per_frame": ms, "rays_per_s": n_rays / ms * 1e3,
                                    "note": "NeuSRenderer.render_image: forward-only, 16384-ray launches, 64+64 samples "
                                            "(the reference issues 600 sequential 512-ray render() calls per frame)"}
+    torch.cuda.empty_cache()
     tg = {}
-    for rays_t in (512, 4096):      # the reference's own batch size, and a large batch that amortises its launches
-        try:
-            rps, ms_t = time_torch_gpu(rays_t, 64, 64, 4, dev)
-            tg[f"{rays_t}_rays"] = {"rays_per_s": rps, "ms_per_step": ms_t}
-        except Exception as e:      # e.g. out of memory at the large batch: report, do not fail the bench
-            tg[f"{rays_t}_rays"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
-        torch.cuda.empty_cache()
-    out["torch_fp32_port_on_this_gpu"] = dict(tg, note="oracle port of the reference (PyTorch fp32 eager autograd, 64+64, "
-                                              "fwd+bwd+Adam) on the same B200: baseline for north_star's 50x target")
-    out["c2_literal_1024rays_32+0"] = measure_literal(dev, use_graph, fused=False)
+    from oracle import ref_arm
+    if ref_arm.available():
+        for tag, (rays_t, nn_, mm_, two) in {"512_rays_64+64": (512, 64, 64, False), "4096_rays_64+64": (4096, 64, 64, False),
+                                             "1024_rays_32+0_two_frames": (1024, 32, 0, True)}.items():
+            try:
+                tg[tag] = reference_gpu_arm(rays_t, nn_, mm_, two)
+            except Exception as e:
+                tg[tag] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        note = ("the UNMODIFIED reference sources (oracle/_ref: NeuSRenderer.render, fields, SegLearnPose, "
+                "Dataset.gen_random_rays_at) + loss block + backward + Adam under torch.set_default_tensor_type(cuda), as "
+                "exp_runner.py:2030 runs them, on the same B200: north_star's 50x denominator")
+    else:
+        for rays_t in (512, 4096):      # the reference's own batch size, and a large batch that amortises its launches
+            try:
+                rps, ms_t = time_torch_gpu(rays_t, 64, 64, 4, dev)
+                tg[f"{rays_t}_rays_64+64"] = {"rays_per_s": rps, "ms_per_step": ms_t}
+            except Exception as e:      # e.g. out of memory at the large batch: report, do not fail the bench
+                tg[f"{rays_t}_rays_64+64"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            torch.cuda.empty_cache()
+        note = "oracle port of the reference (oracle/_ref absent) on the same B200"
+    out["reference_pytorch_on_this_gpu"] = dict(tg, note=note)
+    out["c2_literal_1024rays_32+0"] = measure_literal(dev, use_graph)
     return out
 
 
-def measure_literal(dev, use_graph=True, fused=False):
-    """the shipped confs/ho3d_virtual.conf iteration: 2 x 512 rays of two frames, 32+0 samples, both pose MLPs trained.
-    `fused`: TrainStep(fused_loss=True, fused_rays=True) — the opt-in glue fusions (fewer torch launches)."""
+def measure_literal(dev, use_graph=True):
+    """the shipped confs/ho3d_virtual.conf iteration: 2 x 512 rays of two frames, 32+0 samples, both pose MLPs trained"""
     import torch
     from fmov_pose_b200 import synthetic
     from fmov_pose_b200.train import TrainStep
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sc2 = synthetic.build_scene(device=dev, n_samples=32, n_importance=0, up_sample_steps=4, pose_type="seg")
-    ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph, fused_loss=fused, fused_rays=fused)
+    ts2 = TrainStep(sc2, mask_weight=5.0, capturable=use_graph)
     g = torch.Generator().manual_seed(3)
     B2, Bf = 1024, 512          # maintain_shape: 512 rays of the current frame + 512 rays of an earlier frame
     n_it = 24
@@ -265,8 +313,7 @@ def measure_literal(dev, use_graph=True, fused=False):
             "library_calls_per_step": getattr(g2, "launches_per_step", None) if use_graph else None,
             "note": "confs/ho3d_virtual.conf as shipped (n_samples 32, n_importance 0, maintain_shape: 512 rays of the "
                     "current frame + 512 of an earlier frame, two pose MLPs trained); " +
-                    ("CUDA-graph replay" if use_graph else "eager, host-launch bound") +
-                    ("; TrainStep(fused_loss=True, fused_rays=True)" if fused else "")}
+                    ("CUDA-graph replay" if use_graph else "eager, host-launch bound")}
 
 
 def measure_marching_cubes_child():
@@ -382,14 +429,9 @@ def main():
     ap.add_argument("--no_extras", action="store_true")
     ap.add_argument("--no_graph", action="store_true", help="eager launches instead of CUDA-graph replay of the step")
     ap.add_argument("--mc_only", action="store_true", help="internal: marching-cubes extra, run as a child process")
-    ap.add_argument("--literal_fused_only", action="store_true", help="internal: literal step with the opt-in glue fusions")
     args = ap.parse_args()
     if args.mc_only:
         measure_marching_cubes_child()
-        return 0
-    if args.literal_fused_only:
-        import torch
-        print(json.dumps(measure_literal(torch.device("cuda:0"), use_graph=not args.no_graph, fused=True)))
         return 0
     # stdout carries exactly ONE JSON line: libraries that printf to fd 1 (NCCL prints its version banner there when
     # NCCL_DEBUG is set on the box) are sent to stderr, the line is written to the saved descriptor
@@ -410,16 +452,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        warm, iters = max(1, min(args.warmup, 2)), max(1, min(args.steps, 5))
-        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, warm, iters)
+        # CPU arm: the reference's models/picture_pose.py:6-8 switches the default tensor type to CUDA whenever a GPU is
+        # visible, so the GPUs are hidden from this process before torch is imported
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""
+        warm, iters = max(1, min(args.warmup, 2)), max(1, min(args.steps, 8))
+        rps, sec, threads, kind = time_cpu(args.cpu_rays, n, m, up, warm, iters)
+        what = ("the UNMODIFIED reference sources (oracle/_ref: NeuSRenderer.render, SDF / colour / variance networks, "
+                "SegLearnPose pose MLP) + the loss block and Adam calls of exp_runner.py:562-599, 772-816" if kind == "reference"
+                else "oracle port of the reference PyTorch path (oracle/_ref was not built: /root/reference only exists "
+                     "in the build container)")
         line = {"impl": "reference", "metric": "train rays/s (fwd+bwd+Adam)", "value": rps, "unit": "rays/s",
                 "n_gpus": args.gpus, "steps": iters, "warmup": warm, "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload, "rays_per_step": args.cpu_rays, "n_samples": n, "n_importance": m},
-                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-                                 "sample": f"{iters} steps of {args.cpu_rays} rays ({n}+{m}); oracle port of the "
-                                           "reference PyTorch path (the reference itself is not pip-installable and "
-                                           "/root/reference does not exist on the GPU box)"},
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": kind,
+                                 "sample": f"median of {iters} steps ({warm} warm-up) of {args.cpu_rays} rays ({n}+{m}), "
+                                           f"all host threads, GPUs hidden; {what}"},
                 "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -538,20 +586,46 @@ def main():
         fl = KERNEL_FLOPS_PER_POINT[top] * B * (n + m)
         ach = fl / (avg_ms * 1e-3) / 1e12
         step_ms = ms_dev / args.steps
+        traffic = measured_traffic(top, B)
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "traffic": NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B * (n + m) or None,
-                "traffic_note": "dram bytes per launch from ncu --set full at 2048 rays, scaled by points "
-                                "(profiles/r1_final_ncu_full.txt); HBM view: %.0f GB/s of %.1f measured" % (
-                                    NCU_DRAM_BYTES_PER_POINT.get(top, 0.0) * B * (n + m) / (avg_ms * 1e-3) / 1e9,
-                                    peaks.get("hbm_gbs", 6650.0)),
+                "traffic": traffic,
+                "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at this batch size, ncu --set full "
+                                 "(profiles/r2_ncu_traffic.json)" if traffic else
+                                 "no ncu --set full capture committed for this batch size (profiles/r2_ncu_traffic.json)"),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
+                "timing_note": "per-kernel times: CUDA events around each launch in an eager pass of the same step, outside "
+                               "the timed graph replay (events cannot be recorded inside a replay)",
                 "share_of_step": (mlp[top]["ms"] / n_prof) / step_ms,
                 "kernel_ms_per_step": {k: v["ms"] / n_prof for k, v in prof.items()}}
-        # the same kernel against the HBM roofline: the stash design makes the fine-stage kernels HBM-bound
+        # the same kernel against the HBM roofline (the fine-stage kernels stream their activation stash through HBM)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         hbm_ach = KERNEL_BYTES_PER_POINT[top] * B * (n + m) / (avg_ms * 1e-3) / 1e9
         roof["hbm_view"] = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                             "algorithmic_bytes_per_point": KERNEL_BYTES_PER_POINT[top]}
+        # every MLP kernel on both rooflines + the HBM-class kernels (north_star: "achieved HBM GB/s for sampling and
+        # compositing"), all from the same live CUDA-event pass
+        per = {}
+        for k, v in mlp.items():
+            t_ms = v["ms"] / v["count"]
+            per[k] = {"ms": t_ms, "tflops": KERNEL_FLOPS_PER_POINT[k] * B * (n + m) / (t_ms * 1e-3) / 1e12,
+                      "tensor_frac": KERNEL_FLOPS_PER_POINT[k] * B * (n + m) / (t_ms * 1e-3) / 1e12 / peak_tf,
+                      "hbm_gbs": KERNEL_BYTES_PER_POINT[k] * B * (n + m) / (t_ms * 1e-3) / 1e9,
+                      "hbm_frac": KERNEL_BYTES_PER_POINT[k] * B * (n + m) / (t_ms * 1e-3) / 1e9 / hbm_peak,
+                      "dram_bytes_ncu": measured_traffic(k, B)}
+        if "sdf_query" in prof:
+            v = prof["sdf_query"]
+            pts_q = B * (n + (m - m // up if m > 0 else 0))
+            t_ms = v["ms"] / n_prof
+            per["sdf_query (all sampling queries of a step)"] = {"ms": t_ms, "tflops": pts_q * F_S / (t_ms * 1e-3) / 1e12,
+                                                                 "tensor_frac": pts_q * F_S / (t_ms * 1e-3) / 1e12 / peak_tf}
+        for k, fn in HBM_KERNEL_BYTES_PER_RAY.items():
+            if k in prof:
+                v = prof[k]
+                t_ms = v["ms"] / v["count"]
+                by = fn(n + m) * B
+                per[k] = {"ms": t_ms, "hbm_gbs": by / (t_ms * 1e-3) / 1e9, "hbm_frac": by / (t_ms * 1e-3) / 1e9 / hbm_peak,
+                          "algorithmic_bytes": by, "dram_bytes_ncu": measured_traffic(k, B)}
+        roof["kernels"] = per
     extras = None
     if rank == 0 and world == 1 and not args.no_extras:
         try:
@@ -566,10 +640,6 @@ def main():
             extras["c5_marching_cubes_512"] = measure_in_child("--mc_only")
         except Exception as e:
             extras["c5_marching_cubes_512"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
-        try:
-            extras["c2_literal_1024rays_32+0_fused_glue"] = measure_in_child("--literal_fused_only")
-        except Exception as e:
-            extras["c2_literal_1024rays_32+0_fused_glue"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if not args.no_extras:              # collective (all ranks): config C5 across the N GPUs of this run
         try:
             grid = measure_grid_sharded(scene, dev, group, world)
@@ -580,10 +650,14 @@ def main():
             extras["c5_grid_512_sharded"] = grid
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, sec, threads = time_cpu(args.cpu_rays, n, m, up, 2, 8)          # ~10-15 s of host work on the box's cores
-        cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": f"median of 8 steps (2 warm-up) of {args.cpu_rays} rays ({n}+{m}), oracle port of the reference "
-                         "PyTorch CPU path, all host threads"}
+        # ~10-20 s of host work on the box's cores, in a child process with the GPUs hidden (see --impl reference)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "8", "--warmup", "2",
+                                "--cpu_rays", str(args.cpu_rays), "--n_samples", str(n), "--n_importance", str(m)],
+                               capture_output=True, text=True, timeout=900, cwd=ROOT)
+            cpu = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])["cpu_baseline"]
+        except Exception as e:
+            cpu = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
     if rank == 0:
         line = {"metric": "train rays/s (fwd+bwd+Adam)", "value": value, "unit": "rays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,

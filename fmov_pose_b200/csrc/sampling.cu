@@ -56,6 +56,65 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// sample_pdf(bins, weights, n_new, det=True) of models/renderer.py:54-86 for one ray, by one warp:
+// Z[0..n) = bins, Q[0..n-1) = weights + 1e-5 (renderer.py:57), C[0..n) = scratch that receives the cdf, out[0..n_new).
+__device__ __forceinline__ void warp_sample_pdf(const float* Z, const float* Q, float* C, int n, int n_new, int lane,
+                                                float* out) {
+  const int ns = n - 1;
+  const int per = (ns + 31) / 32;             // contiguous sections per lane
+  const int j0 = lane * per;
+  float lsum = 0.f;
+  for (int k = 0; k < per; ++k)
+    if (j0 + k < ns) lsum += Q[j0 + k];
+  const float total = warp_sum(lsum);
+  const float incl_s = warp_incl_scan_add(lsum, lane);
+  const float run = incl_s - lsum;             // exclusive prefix of this lane's chunk
+  // cdf[0] = 0, cdf[j+1] = cumsum(pdf)[j]   (renderer.py:58-60)
+  if (lane == 0) C[0] = 0.f;
+  float cum = run / total;
+  for (int k = 0; k < per; ++k) {
+    const int j = j0 + k;
+    if (j < ns) {
+      cum += Q[j] / total;
+      C[j + 1] = cum;
+    }
+  }
+  __syncwarp();
+  // ---- inverse CDF (renderer.py:62-84) ---------------------------------------------------
+  for (int k = lane; k < n_new; k += 32) {
+    // torch.linspace(0.5/m, 1-0.5/m, m)
+    const float a = 0.5f / (float)n_new, b = 1.0f - 0.5f / (float)n_new;
+    const float step = (b - a) / (float)(n_new - 1 > 0 ? n_new - 1 : 1);
+    const float u = (k < n_new / 2) ? a + step * (float)k : b - step * (float)(n_new - 1 - k);
+    int lo = 0, hi = n;                         // searchsorted(cdf, u, right=True) = #{cdf <= u}
+    while (lo < hi) { int m = (lo + hi) >> 1; if (C[m] <= u) lo = m + 1; else hi = m; }
+    const int below = max(lo - 1, 0), above = min(n - 1, lo);
+    const float cb = C[below], ca = C[above];
+    float denom = ca - cb;
+    if (denom < 1e-5f) denom = 1.0f;
+    const float t = (u - cb) / denom;
+    out[k] = Z[below] + t * (Z[above] - Z[below]);
+  }
+}
+
+// sample_pdf on given bins / weights (the inverse-CDF stage of the round kernel on its own): warp per ray
+__global__ void __launch_bounds__(SAMP_WARPS * 32)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, long long B, int n, int n_new,
+                  float* __restrict__ out) {
+  __shared__ float sz[SAMP_WARPS][SAMP_MAXS];
+  __shared__ float sc[SAMP_WARPS][SAMP_MAXS];
+  __shared__ float sq[SAMP_WARPS][SAMP_MAXS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ray = (long long)blockIdx.x * SAMP_WARPS + warp;
+  if (ray >= B) return;
+  for (int i = lane; i < n; i += 32) {
+    sz[warp][i] = bins[ray * n + i];
+    if (i < n - 1) sq[warp][i] = weights[ray * (n - 1) + i] + 1e-5f;
+  }
+  __syncwarp();
+  warp_sample_pdf(sz[warp], sq[warp], sc[warp], n, n_new, lane, out + ray * n_new);
+}
+
 // One warp per ray.
 //   merge:    z[:, :n_sorted] (sorted) and z[:, n_sorted:n_sorted+n_tail] (sorted) -> z[:, :n_cur] sorted,
 //             sdf permuted identically when with_sdf (not on the last round, renderer.py:229-240)
@@ -153,50 +212,17 @@ sample_round_kernel(const float* __restrict__ rays_o, const float* __restrict__ 
   const float incl = warp_incl_scan_mul(prod, lane);
   float T = __shfl_up_sync(0xffffffffu, incl, 1);
   if (lane == 0) T = 1.0f;
-  // pass 2: weights + 1e-5, local sums (renderer.py:57-58)
-  float lsum = 0.f;
+  // pass 2: weights + 1e-5 (renderer.py:57)
   for (int k = 0; k < per; ++k) {
     const int j = j0 + k;
     if (j < ns) {
       const float alpha = C[j];
-      const float w = alpha * T + 1e-5f;
+      Q[j] = alpha * T + 1e-5f;
       T *= (1.0f - alpha + 1e-7f);
-      Q[j] = w;
-      lsum += w;
     }
   }
-  const float total = warp_sum(lsum);
-  const float incl_s = warp_incl_scan_add(lsum, lane);
-  float run = incl_s - lsum;                   // exclusive prefix of this lane's chunk
-  __syncwarp();
-  // cdf[0] = 0, cdf[j+1] = cumsum(pdf)[j]   (renderer.py:59-60)
-  if (lane == 0) C[0] = 0.f;
-  __syncwarp();
-  float cum = run / total;
-  for (int k = 0; k < per; ++k) {
-    const int j = j0 + k;
-    if (j < ns) {
-      cum += Q[j] / total;
-      // store after everyone has finished reading alpha from C[] (done: pass 2 complete before the sync above)
-      C[j + 1] = cum;
-    }
-  }
-  __syncwarp();
-  // ---- inverse CDF (renderer.py:62-84) ---------------------------------------------------
-  for (int k = lane; k < n_new; k += 32) {
-    // torch.linspace(0.5/m, 1-0.5/m, m)
-    const float a = 0.5f / (float)n_new, b = 1.0f - 0.5f / (float)n_new;
-    const float step = (b - a) / (float)(n_new - 1 > 0 ? n_new - 1 : 1);
-    const float u = (k < n_new / 2) ? a + step * (float)k : b - step * (float)(n_new - 1 - k);
-    int lo = 0, hi = n;                         // searchsorted(cdf, u, right=True) = #{cdf <= u}
-    while (lo < hi) { int m = (lo + hi) >> 1; if (C[m] <= u) lo = m + 1; else hi = m; }
-    const int below = max(lo - 1, 0), above = min(n - 1, lo);
-    const float cb = C[below], ca = C[above];
-    float denom = ca - cb;
-    if (denom < 1e-5f) denom = 1.0f;
-    const float t = (u - cb) / denom;
-    zr[n + k] = Z[below] + t * (Z[above] - Z[below]);
-  }
+  __syncwarp();          // every lane has finished reading alpha from C[] before the cdf overwrites it
+  warp_sample_pdf(Z, Q, C, n, n_new, lane, zr + n);
 }
 
 }  // namespace fmov
@@ -227,5 +253,19 @@ extern "C" int fmov_sample_round(const float* rays_o, const float* rays_d, float
   sample_round_kernel<<<grid, SAMP_WARPS * 32, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, sdf, B, z_stride, n_sorted,
                                                                          n_tail, with_sdf, n_new, inv_s);
   FMOV_LAUNCH_CHECK("sample_round_kernel");
+  return OK;
+}
+
+// sample_pdf(bins [B,n], weights [B,n-1], n_new, det=True) -> out [B,n_new]  (models/renderer.py:54-86): the inverse-CDF
+// stage of fmov_sample_round on caller-given weights (known-answer tests; also usable as a stand-alone resampler)
+extern "C" int fmov_sample_pdf(const float* bins, const float* weights, long long B, int n, int n_new, float* out,
+                               void* stream) {
+  FMOV_REQUIRE(B >= 0 && n >= 2 && n <= SAMP_MAXS && n_new >= 1, "fmov_sample_pdf: bad shape (n=%d n_new=%d, max %d bins)", n,
+               n_new, SAMP_MAXS);
+  if (B == 0) return OK;
+  FMOV_REQUIRE(bins && weights && out, "fmov_sample_pdf: null argument");
+  const int grid = (int)((B + SAMP_WARPS - 1) / SAMP_WARPS);
+  sample_pdf_kernel<<<grid, SAMP_WARPS * 32, 0, (cudaStream_t)stream>>>(bins, weights, B, n, n_new, out);
+  FMOV_LAUNCH_CHECK("sample_pdf_kernel");
   return OK;
 }

@@ -210,7 +210,16 @@ class RenderCoreFunction(torch.autograd.Function):
         if cfg.get("eik_den") is not None:      # micro-batch of a larger step: partial numerator / whole-batch normaliser
             eik = torch.stack([eik[0], cfg["eik_den"].reshape(()).to(eik.dtype)])
         elif group is not None:
-            torch.distributed.all_reduce(eik, group=group)      # global eikonal normaliser
+            # global eikonal normaliser; the caller's other whole-batch sums (sum(mask), ray count) ride on
+            # the same collective: one all-reduce per forward instead of two
+            extra = cfg.get("reduce_extra")
+            if extra is not None:
+                pack = torch.cat([eik, extra.reshape(-1)])
+                torch.distributed.all_reduce(pack, group=group)
+                eik = pack[:2]
+                extra.copy_(pack[2:].view_as(extra))
+            else:
+                torch.distributed.all_reduce(eik, group=group)
         gradient_error = eik[0] / (eik[1] + 1e-5)
         ctx.fw, ctx.stash, ctx.cfg = fw, stash, cfg
         ctx.bg = bg

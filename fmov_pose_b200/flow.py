@@ -69,13 +69,15 @@ class UnitSphereFunction(torch.autograd.Function):
     (exp_runner.py:714-724; the mask is detached there, so only `weights` receives a gradient)."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, z, weights, sample_dist):
+    def forward(ctx, rays_o, rays_d, z, weights, sample_dist, group=None):
         rays_o, rays_d, z, weights = L.f32c(rays_o), L.f32c(rays_d), L.f32c(z), L.f32c(weights)
         B, S = z.shape
         part = torch.empty(2, dtype=torch.float32, device=z.device)
         L.check(L.lib().fmov_unit_sphere_fwd_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z),
                                                  L.c_float(sample_dist), L.ptr(weights), L.ptr(None), L.ptr(part),
                                                  L.ptr(None), L.stream()), "fmov_unit_sphere_fwd_bwd")
+        if group is not None:          # ray-sharded: the mean runs over the outside samples of ALL ranks
+            torch.distributed.all_reduce(part, group=group)
         ctx.save_for_backward(rays_o, rays_d, z, weights, part)
         ctx.sample_dist = float(sample_dist)
         return part[0] / part[1]          # F.l1_loss(weights[outside], 0): nan when nothing is outside, as the reference
@@ -89,7 +91,7 @@ class UnitSphereFunction(torch.autograd.Function):
         L.check(L.lib().fmov_unit_sphere_fwd_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z),
                                                  L.c_float(ctx.sample_dist), L.ptr(weights), L.ptr(g_scale), L.ptr(None),
                                                  L.ptr(d_w), L.stream()), "fmov_unit_sphere_fwd_bwd")
-        return None, None, None, d_w, None
+        return None, None, None, d_w, None, None
 
 
 class PtsFunction(torch.autograd.Function):
@@ -139,7 +141,8 @@ def flow_loss(render_out, rays_o, rays_d, c2w_1, c2w_0, K_1, K_0, pixels_xy, pix
     return total
 
 
-def unit_sphere_loss(render_out, rays_o, rays_d, sample_dist, unit_sphere_weight):
-    """exp_runner.py:714-724"""
+def unit_sphere_loss(render_out, rays_o, rays_d, sample_dist, unit_sphere_weight, group=None):
+    """exp_runner.py:714-724; `group`: ray-sharded step — (sum, count) are all-reduced so every rank optimises the
+    single-GPU objective (mean over the outside samples of the whole batch)"""
     return UnitSphereFunction.apply(rays_o, rays_d, render_out["z_vals"], render_out["weights"],
-                                    sample_dist) * unit_sphere_weight
+                                    sample_dist, group) * unit_sphere_weight

@@ -83,7 +83,6 @@ class NeuSRenderer:
         self.n_outside = n_outside
         self.up_sample_steps = up_sample_steps
         self.perturb = perturb
-        self.process_group = None      # set for ray-sharded data parallel runs (global eikonal normaliser)
 
     # ------------------------------------------------------------------------------------------------
     def _check(self):
@@ -115,10 +114,14 @@ class NeuSRenderer:
         return z
 
     def render(self, rays_o, rays_d, near, far, perturb_overwrite=-1, background_rgb=None, cos_anneal_ratio=0.0,
-               eval=False, t_rand=None, z_vals=None, eik_den=None):
+               eval=False, t_rand=None, z_vals=None, eik_den=None, group=None, reduce_extra=None):
         """models/renderer.py:374-498.  Extras for micro-batched steps (train.TrainStep, `micro_batch`): `z_vals`
         injects samples drawn earlier by `sample_z`; `eik_den` (device scalar) is the whole-batch sum(relax) so that
-        `gradient_error` is this call's numerator over the global normaliser (the calls' values then add up)."""
+        `gradient_error` is this call's numerator over the global normaliser (the calls' values then add up).
+        Ray-sharded train steps pass `group` (torch.distributed process group): the eikonal numerator / normaliser are
+        then summed over the ranks — a COLLECTIVE, issued only for calls that ask for it and run with autograd (never
+        for eval / no-grad renders such as validate_image on one rank) — and `reduce_extra` (a small fp32 device
+        tensor, e.g. [sum(mask), ray count]) is summed in place by the same all-reduce."""
         self._check()
         if not rays_o.is_cuda:
             raise RuntimeError("fmov_pose_b200 renders on CUDA tensors only (no CPU fallback)")
@@ -141,7 +144,8 @@ class NeuSRenderer:
         n_samples = z_vals.shape[1]
         inv_s = torch.exp(self.deviation_network.variance * 10.0).clip(1e-6, 1e6)   # fields.py:294, renderer.py:290
         cfg = dict(sample_dist=sample_dist, cos_anneal_ratio=cos_anneal_ratio, background_rgb=background_rgb,
-                   need_backward=need_bwd, group=self.process_group, fine_weights=fw, eik_den=eik_den)
+                   need_backward=need_bwd, group=group if need_bwd else None, fine_weights=fw, eik_den=eik_den,
+                   reduce_extra=reduce_extra if need_bwd else None)
         if not need_bwd:
             with torch.no_grad():
                 outs = _fine.RenderCoreFunction.apply(rays_o, rays_d, z_vals, inv_s, cfg, *W_s, *b_s, *W_c, *b_c)

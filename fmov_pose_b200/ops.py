@@ -78,6 +78,17 @@ def sample_round(rays_o, rays_d, z, sdf, n_sorted, n_tail, with_sdf, n_new, inv_
             "fmov_sample_round")
 
 
+def sample_pdf(bins, weights, n_new):
+    """sample_pdf(bins, weights, n_new, det=True) (models/renderer.py:54-86) -> [B, n_new]"""
+    bins, weights = L.f32c(bins), L.f32c(weights)
+    B, n = bins.shape
+    assert tuple(weights.shape) == (B, n - 1)
+    out = torch.empty(B, n_new, dtype=torch.float32, device=bins.device)
+    L.check(L.lib().fmov_sample_pdf(L.ptr(bins), L.ptr(weights), L.c_ll(B), n, int(n_new), L.ptr(out), L.stream()),
+            "fmov_sample_pdf")
+    return out
+
+
 def hierarchical_sample(qw, rays_o, rays_d, near, far, t_rand, n_samples, n_importance, up_sample_steps, scale=1.0):
     """z_vals [B, n_samples+n_importance] — renderer.py:385-446 (coarse z, no-grad SDF queries,
     up_sample rounds with inv_s = 64*2^i, cat_z_vals merges). All device work, no host sync."""

@@ -69,14 +69,20 @@ class LRSchedule:
 class TrainStep:
     def __init__(self, scene, igr_weight=0.1, mask_weight=5.0, lr=5e-4, pose_lr=5e-4, group=None, optimizer=True,
                  capturable=False, flow_weight=0.0, unit_sphere_weight=0.0, maintain_shape=False,
-                 detach_flow_on_sdf=False, detach_ref=False, fused_loss=False, fused_rays=False):
+                 detach_flow_on_sdf=False, detach_ref=False, fused_loss=True, fused_rays=None):
+        """`optimizer`: True = this library's FlatAdam (gradient gather + Adam in two launches, only the parameter groups
+        of the rendered frames are stepped — also across ranks), "torch" = torch.optim.Adam(fused=True) with one param
+        group per pose MLP, False = none (the caller steps).  `fused_loss`: colour + mask terms through
+        fmov_loss_fwd_bwd (one launch instead of ~40 torch ops).  `fused_rays`: near / far from the ray-generation kernel
+        and, for n_importance == 0, the coarse z through fmov_sample_coarse with its closed-form backward (~40 torch
+        launches less); None = on when the dataset is this package's RayDataset (the call needs its `with_near_far`)."""
+        from .models.dataset import RayDataset
         self.s = scene
-        self.fused_loss = bool(fused_loss)       # colour + mask terms through fmov_loss_fwd_bwd (one launch instead of ~40)
-        # near / far straight from the ray-generation kernel (it computes them and their pose gradients anyway) and, for
-        # n_importance == 0, the coarse z through fmov_sample_coarse with a closed-form backward: ~40 torch launches less
+        self.fused_loss = bool(fused_loss)
+        if fused_rays is None:
+            fused_rays = isinstance(scene.get("dataset"), RayDataset)
         self.fused_rays = bool(fused_rays)
-        if self.fused_rays:
-            scene["renderer"].fused_coarse = True
+        scene["renderer"].fused_coarse = self.fused_rays
         self.igr_weight, self.mask_weight = igr_weight, mask_weight
         # exp_runner.py:150-160, 327-336 (train.flow_weight, unit_sphere_weight, maintain_shape, detach_*)
         self.flow_weight, self.unit_sphere_weight = float(flow_weight), float(unit_sphere_weight)
@@ -84,7 +90,6 @@ class TrainStep:
         self.group = group
         self.background_rgb = None       # torch.ones([1,3]) when use_white_bkgd (exp_runner.py:556)
         self.world = torch.distributed.get_world_size(group) if group is not None else 1
-        scene["renderer"].process_group = group
         nets = [scene["sdf_network"], scene["deviation_network"], scene["color_network"]]
         self.params = [p for n in nets for p in n.parameters() if p.requires_grad]
         if scene["pose_network"] is not None:
@@ -93,16 +98,17 @@ class TrainStep:
             self.pose_params = []
         self.all_params = self.params + self.pose_params
         self.optimizer = None
+        self.own_optimizer = False
+        self.pose_group_of = {}
         if optimizer:       # exp_runner.py:264-269 (nets) and :258-262 (pose MLPs)
             dev = self.params[0].device
-            if capturable:        # learning rates live on the device so a captured step follows the LR schedule
+            own = optimizer != "torch"
+            if capturable and not own:        # learning rates live on the device so a captured step follows the LR schedule
                 lr = torch.tensor(float(lr), device=dev)
                 pose_lr = torch.tensor(float(pose_lr), device=dev)
-            # one Adam over [networks | pose MLP 0 | pose MLP 1 | ...]: the reference keeps one optimizer per pose MLP
-            # (exp_runner.py:258-262, 812-816); torch's Adam keeps its step count per parameter and skips parameters
-            # without a gradient, so param groups give the same updates with one fused launch set
+            # one optimiser over [networks | pose MLP 0 | pose MLP 1 | ...]: the reference keeps one Adam per pose MLP
+            # (exp_runner.py:258-262, 812-816) and steps only those of the rendered frames
             groups = [dict(params=self.params, lr=lr)]
-            self.pose_group_of = {}
             mlps = getattr(scene["pose_network"], "pose_mlps", None)
             if mlps is not None:
                 for k, mlp in enumerate(mlps):
@@ -112,13 +118,35 @@ class TrainStep:
                         groups.append(dict(params=ps, lr=pose_lr.clone() if torch.is_tensor(pose_lr) else pose_lr))
             elif self.pose_params:
                 groups.append(dict(params=self.pose_params, lr=pose_lr))
-            self.optimizer = torch.optim.Adam(groups, fused=True, capturable=capturable)
-            if capturable:        # state is created up front: lazy creation inside a capture would be replayed
-                for grp in self.optimizer.param_groups:
-                    for p in grp["params"]:
-                        self.optimizer.state[p] = dict(step=torch.zeros((), dtype=torch.float32, device=p.device),
-                                                       exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
+            if own:
+                from .optim import FlatAdam
+                self.optimizer = FlatAdam(groups, process_group=group)
+                self.own_optimizer = True
+                capturable = True
+            else:
+                # torch keeps its step count per parameter and skips parameters without a gradient, so param groups give
+                # the reference's per-pose-MLP updates on one GPU
+                self.optimizer = torch.optim.Adam(groups, fused=True, capturable=capturable)
+                if capturable:        # state is created up front: lazy creation inside a capture would be replayed
+                    for grp in self.optimizer.param_groups:
+                        for p in grp["params"]:
+                            self.optimizer.state[p] = dict(step=torch.zeros((), dtype=torch.float32, device=p.device),
+                                                           exp_avg=torch.zeros_like(p), exp_avg_sq=torch.zeros_like(p))
         self.capturable = capturable
+
+    def active_groups(self, *img_ids):
+        """optimiser groups a step over these frames updates: the networks + the pose MLP of every rendered frame
+        (pose_mlp_index_set, exp_runner.py:785-791); gf / se3 poses live in one always-active group"""
+        act = {0}
+        pn = self.s["pose_network"]
+        seg = getattr(pn, "segment_img_num", None)
+        if self.pose_group_of and seg:
+            for i in img_ids:
+                if i is not None and int(i) // seg in self.pose_group_of:
+                    act.add(self.pose_group_of[int(i) // seg])
+        elif self.pose_params:
+            act.add(1)
+        return sorted(act)
 
     @staticmethod
     def _write_lr(grp, v):
@@ -170,21 +198,27 @@ class TrainStep:
         seg = getattr(pn, "segment_img_num", None)
         return int(img_id) // seg if seg else 0
 
-    def losses(self, out, true_rgb, mask):
-        """exp_runner.py:562-599, 772-779 with global normalisers when ray-sharded."""
+    def mask_stats(self, mask):
+        """-> (mask in {0,1}, stats = [sum(mask), ray count] on this rank).  Under ray sharding `stats` rides on the
+        eikonal normaliser's all-reduce inside render() (one collective for all three whole-batch normalisers)."""
         if self.mask_weight > 0.0:
             mask = (mask > 0.5).float()
         else:
             mask = torch.ones_like(mask)
-        msum = mask.sum()
-        n_rays = torch.full((), float(mask.shape[0]), device=mask.device)
-        if self.group is not None:
-            pack = torch.stack([msum, n_rays])
-            torch.distributed.all_reduce(pack, group=self.group)
-            msum, n_rays = pack[0], pack[1]
+        stats = torch.stack([mask.sum(), torch.full((), float(mask.shape[0]), device=mask.device)])
+        return mask, stats
+
+    def losses(self, out, true_rgb, mask, stats=None):
+        """exp_runner.py:562-599, 772-779 with global normalisers when ray-sharded.  `stats`: what mask_stats returned,
+        already summed over the ranks by render(); None = compute (and all-reduce) here."""
+        if stats is None:
+            mask, stats = self.mask_stats(mask)
+            if self.group is not None:
+                torch.distributed.all_reduce(stats, group=self.group)
+        msum, n_rays = stats[0], stats[1]
         mask_sum = msum + 1e-5
         if self.fused_loss:
-            # the kernel thresholds the raw mask itself; every rank holds the same number of rays (fixed split)
+            # every rank holds the same number of rays (fixed split), so the global ray count is known on the host
             color_loss, bce = _FusedLossFn.apply(out["color_fine"], out["weight_sum"], true_rgb, mask, mask_sum,
                                                  mask.shape[0] * self.world, self.mask_weight)
             eik = out["gradient_error"]
@@ -198,13 +232,14 @@ class TrainStep:
         return dict(loss=loss, color_loss=color_loss, eikonal_loss=eik, mask_loss=bce)
 
     def forward_backward(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None,
-                         micro_batch=None, additional_img_id=None, add_pixels=None, add_img_t=None):
+                         micro_batch=None, additional_img_id=None, add_pixels=None, add_img_t=None, reduce=True):
         """One ordinary iteration.  `additional_img_id` (with `maintain_shape`, exp_runner.py:512-548): `batch_size` more
         rays of a second, already registered frame through ITS pose are appended, so the render sees 2*batch_size rays
         (t_rand then has 2*batch_size rows) and two pose MLPs receive gradients."""
         if micro_batch is not None and batch_size > micro_batch:
             assert additional_img_id is None, "micro-batching takes one frame per step"
-            return self.forward_backward_chunked(img_id, batch_size, micro_batch, pixels, t_rand, cos_anneal_ratio, img_t)
+            return self.forward_backward_chunked(img_id, batch_size, micro_batch, pixels, t_rand, cos_anneal_ratio, img_t,
+                                                 reduce=reduce)
         s = self.s
         ds, rend = s["dataset"], s["renderer"]
         pose = self.pose_of(img_id, img_t)
@@ -222,22 +257,23 @@ class TrainStep:
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         if not nf:
             near, far = ds.near_far_from_sphere(rays_o, rays_d)
+        mask, stats = self.mask_stats(mask)
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
-                          background_rgb=self.background_rgb)
-        ls = self.losses(out, true_rgb, mask)
-        if self.unit_sphere_weight > 0 and self.group is None:      # exp_runner.py:714-724
+                          background_rgb=self.background_rgb, group=self.group, reduce_extra=stats)
+        ls = self.losses(out, true_rgb, mask, stats)
+        if self.unit_sphere_weight > 0:      # exp_runner.py:714-724
             ls["unit_sphere_loss"] = _flow.unit_sphere_loss(out, rays_o, rays_d, 2.0 / rend.n_samples,
-                                                            self.unit_sphere_weight)
+                                                            self.unit_sphere_weight, group=self.group)
             ls["loss"] = ls["loss"] + ls["unit_sphere_loss"]
         for p in self.all_params:
             p.grad = None
         ls["loss"].backward()
-        if self.group is not None:
+        if self.group is not None and reduce:
             self.allreduce_grads()
         return ls, out
 
     def forward_backward_chunked(self, img_id, batch_size, micro_batch, pixels=None, t_rand=None, cos_anneal_ratio=1.0,
-                                 img_t=None):
+                                 img_t=None, reduce=True):
         """The same iteration for ray batches whose activation stash does not fit HBM at once (27 GB per 8192 rays at
         64+64: BASELINE config C3 puts 32 K / 16 K rays on a GPU at N = 2 / 4).  Rays and the no-grad hierarchical
         samples are produced for the whole batch; the fine stage + losses + backward then run per micro-batch against
@@ -298,13 +334,13 @@ class TrainStep:
                 grads.append(g_)
         if roots:
             torch.autograd.backward(roots, grads)
-        if self.group is not None:
+        if self.group is not None and reduce:
             self.allreduce_grads()
         ls = dict(loss=tot[0], color_loss=tot[1], eikonal_loss=tot[2], mask_loss=tot[3])
         return ls, {k: torch.cat(v, 0) for k, v in keep.items()}
 
     def flow_forward_backward(self, img_id_corr, batch_size, current_img_num, interval=1, additional_img_id=None,
-                              img_id=None, indexs=None, add_pixels=None, t_rand=None, cos_anneal_ratio=1.0):
+                              img_id=None, indexs=None, add_pixels=None, t_rand=None, cos_anneal_ratio=1.0, reduce=True):
         """A `use_flow` iteration (exp_runner.py:441-456, 512-548, 562-599, 605-688, 714-724): batch_size//2 matched
         pixel pairs between frame img_id_corr and a matched frame (+ batch_size rays of `additional_img_id` with
         maintain_shape), one render of the concatenated rays, colour/eikonal/mask losses plus the reprojection loss
@@ -325,9 +361,10 @@ class TrainStep:
             data = torch.cat([data, add_data], dim=0)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         near, far = ds.near_far_from_sphere(rays_o, rays_d)
+        mask, stats = self.mask_stats(mask)
         out = rend.render(rays_o, rays_d, near, far, cos_anneal_ratio=cos_anneal_ratio, t_rand=t_rand,
-                          background_rgb=self.background_rgb)
-        ls = self.losses(out, true_rgb, mask)
+                          background_rgb=self.background_rgb, group=self.group, reduce_extra=stats)
+        ls = self.losses(out, true_rgb, mask, stats)
         sd = 2.0 / rend.n_samples
         n_terms = None if self.group is None else 2 * (data.shape[0] // (4 if self.maintain_shape else 2)) * self.world
         # the pose modules are evaluated again for the projection, as exp_runner.py:628-631, 660-663
@@ -338,35 +375,51 @@ class TrainStep:
         ls["flow_loss"] = fl
         ls["loss"] = ls["loss"] + fl
         if self.unit_sphere_weight > 0:
-            ls["unit_sphere_loss"] = _flow.unit_sphere_loss(out, rays_o, rays_d, sd, self.unit_sphere_weight)
+            ls["unit_sphere_loss"] = _flow.unit_sphere_loss(out, rays_o, rays_d, sd, self.unit_sphere_weight,
+                                                            group=self.group)
             ls["loss"] = ls["loss"] + ls["unit_sphere_loss"]
         for p in self.all_params:
             p.grad = None
         ls["loss"].backward()
-        if self.group is not None:
+        if self.group is not None and reduce:
             self.allreduce_grads()
         return ls, out, img_id
 
-    def step_flow(self, *a, **kw):
-        r = self.flow_forward_backward(*a, **kw)
+    def step_flow(self, img_id_corr, batch_size, current_img_num, interval=1, additional_img_id=None, **kw):
+        r = self.flow_forward_backward(img_id_corr, batch_size, current_img_num, interval, additional_img_id,
+                                       reduce=not self.own_optimizer, **kw)
         if r is not None and self.optimizer is not None:
-            self.optimizer.step()
+            if self.own_optimizer:
+                self.optimizer.step(self.active_groups(img_id_corr, r[2], additional_img_id))
+            else:
+                self.optimizer.step()
         return r
 
     def allreduce_grads(self):
-        """one SUM all-reduce of all MLP + pose gradients (~3.2 MB fp32) over NCCL/NVLink"""
+        """one SUM all-reduce of all MLP + pose gradients (~3.2 MB fp32) over NCCL/NVLink, for callers that step the
+        parameters themselves (`optimizer=False` / "torch"; FlatAdam reduces its own flat buffer).  A per-parameter
+        has-gradient flag rides along: parameters that NO rank produced a gradient for (pose MLPs of frames nobody
+        rendered) keep `grad = None`, so an optimiser skips them exactly as on one GPU (exp_runner.py:785-816).  Reading
+        the flags is a host sync; inside a CUDA-graph capture it is skipped and such gradients stay zero tensors."""
         grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.all_params]
-        flat = torch._utils._flatten_dense_tensors(grads)
+        flags = torch.tensor([0.0 if p.grad is None else 1.0 for p in self.all_params], device=grads[0].device)
+        flat = torch._utils._flatten_dense_tensors(grads + [flags])
         torch.distributed.all_reduce(flat, group=self.group)
-        for p, g in zip(self.all_params, torch._utils._unflatten_dense_tensors(flat, grads)):
-            p.grad = g
+        parts = torch._utils._unflatten_dense_tensors(flat, grads + [flags])
+        capturing = grads[0].is_cuda and torch.cuda.is_current_stream_capturing()
+        have = None if capturing else (parts[-1] > 0).tolist()
+        for i, (p, g) in enumerate(zip(self.all_params, parts[:-1])):
+            p.grad = g if (have is None or have[i]) else None
 
     def step(self, img_id, batch_size, pixels=None, t_rand=None, cos_anneal_ratio=1.0, img_t=None, micro_batch=None,
              additional_img_id=None, add_pixels=None, add_img_t=None):
         ls, out = self.forward_backward(img_id, batch_size, pixels, t_rand, cos_anneal_ratio, img_t, micro_batch,
-                                        additional_img_id, add_pixels, add_img_t)
+                                        additional_img_id, add_pixels, add_img_t, reduce=not self.own_optimizer)
         if self.optimizer is not None:
-            self.optimizer.step()
+            if self.own_optimizer:      # gathers the local gradients, all-reduces them when sharded, steps the union
+                self.optimizer.step(self.active_groups(img_id, additional_img_id))
+            else:
+                self.optimizer.step()
         return ls, out
 
 
@@ -384,7 +437,7 @@ class GraphedTrainStep:
         """`two_frames`: the maintain_shape iteration of the shipped confs (exp_runner.py:512-548): `batch_size` rays
         of the current frame + `batch_size` rays of an earlier frame in one render; `step()` then also takes the second
         frame's index and pixels, and t_rand has 2*batch_size rows."""
-        assert ts.optimizer is None or ts.capturable, "build the TrainStep with capturable=True"
+        assert ts.optimizer is None or ts.capturable, "build the TrainStep with capturable=True (or the default FlatAdam)"
         self.ts, self.B, self.car = ts, int(batch_size), float(cos_anneal_ratio)
         self.two = bool(two_frames)
         dev = ts.params[0].device

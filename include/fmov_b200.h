@@ -129,6 +129,9 @@ int fmov_sample_coarse(const float* near, const float* far, const float* t_rand,
  * (:168-220, :54-86) writing n_new samples after the merged ones.                                  */
 int fmov_sample_round(const float* rays_o, const float* rays_d, float* z, float* sdf, long long B, int z_stride,
                       int n_sorted, int n_tail, int with_sdf, int n_new, float inv_s, void* stream);
+/* sample_pdf(bins [B,n], weights [B,n-1], n_new, det=True) -> out [B,n_new]: models/renderer.py:54-86 on caller-given
+ * weights (the inverse-CDF stage of fmov_sample_round, exposed for known-answer tests). */
+int fmov_sample_pdf(const float* bins, const float* weights, long long B, int n, int n_new, float* out, void* stream);
 
 /* ---- compositing + losses ------------------------------------------------------------------ */
 /* render_core tail (models/renderer.py:261-272, 290-358) + render() reductions (:477-498).
@@ -208,6 +211,19 @@ int fmov_dw(long long P, void* const* stash, const float* d_sdf, const float* zc
 /* device scalar amax = max|upstream per-sample gradient|: sets the power-of-two loss scale of the fp16 gradient tiles */
 int fmov_grad_amax(const float* d_sdf, const float* d_nrm, const float* d_rgb, long long P, float* amax, void* stream);
 int fmov_grad_is_bf16(void);
+
+/* ---- optimiser tail: gradient gather + Adam in two launches ------------------------------------------------
+ * replaces optimizer.step() / pose_optimizers[k].step() (torch.optim.Adam; exp_runner.py:258-269, 812-816) and the
+ * flatten / unflatten copies around the gradient all-reduce.  fmov_grad_gather: HOST arrays of n (<= 160) gradient tensors
+ * -> flat G (+ one flag per parameter group at G[n_total..]); fmov_adam_step: Adam over every tensor of every group whose
+ * flag is > 0, device tables built once by the caller (see csrc/optim.cu); lr / step [n_groups] are device floats.     */
+int fmov_adam_chunk(void);
+int fmov_grad_gather(int n, const float* const* src, const long long* dst_off, const int* numel, int n_groups,
+                     unsigned long long active_mask, const float* flags_in, float* G, long long n_total, void* stream);
+int fmov_adam_step(float* const* param, const long long* off, const int* numel, const int* group, const int* chunk_tensor,
+                   const int* chunk_e0, int n_chunks, int n_groups, const float* G, long long n_total, float* M, float* V,
+                   const float* lr, float* step, float beta1, float beta2, float eps, float grad_scale, unsigned int* done,
+                   void* stream);
 
 /* ---- marching cubes on the dense u grid -------------------------------------------------------------------
  * replaces `mcubes.marching_cubes(u, threshold)` (PyMCubes, CPU) at models/renderer.py:43 and the rescale of

@@ -36,7 +36,6 @@ def main():
     loss_parts = torch.stack([ls["color_loss"].detach(), ls["mask_loss"].detach()])
     dist.all_reduce(loss_parts)
     ts1 = TrainStep(scene, mask_weight=5.0, group=None, optimizer=False)
-    scene["renderer"].process_group = None
     ls1, _ = ts1.forward_backward(2, B, pixels=(px, py), t_rand=tr)
     worst = 0.0
     for a, p in zip(sharded, ts1.all_params):
@@ -61,7 +60,6 @@ def main():
         print(f"rank {rank}: sharded {res}^3 grid == single-GPU grid: {same}")
         ok = ok and same
     # micro-batched + ray-sharded step == one-shot sharded step
-    scene["renderer"].process_group = dist.group.WORLD
     ls_m, _ = ts.forward_backward(2, B // world, pixels=(px[sl], py[sl]), t_rand=tr[sl], micro_batch=B // world // 4)
     worst_m = 0.0
     for a, p in zip(sharded, ts.all_params):
@@ -69,6 +67,35 @@ def main():
             worst_m = max(worst_m, ((p.grad - a).norm() / a.norm()).item())
     print(f"rank {rank}: micro-batched sharded step vs one-shot sharded step: worst grad rel diff {worst_m:.2e}")
     ok = ok and worst_m < 5e-3
+    # Two optimiser steps with the ranks rendering frames of DIFFERENT pose MLPs (the advisor's case): FlatAdam all-reduces
+    # gradients + group flags, so the union {networks, pose MLP of rank 0's frame, pose MLP of rank 1's frame} is stepped and
+    # the pose MLPs of frames nobody rendered keep parameters, moments and step counters — equal to one process that renders
+    # both frames in one batch (maintain_shape-style two-frame step) on the union.
+    from fmov_pose_b200 import synthetic as syn
+    Bh = 256
+    frames = [(0, 1), (2, 1)]                     # (rank-0 frame, rank-1 frame) per step
+    def fresh():
+        sc = syn.build_scene(device=dev, n_images=4, n_samples=16, n_importance=16, up_sample_steps=2, pose_type="seg", H=120, W=160)
+        sc["dataset"].intrinsics_all_inv = torch.linalg.inv(K)[None].repeat(4, 1, 1).contiguous().to(dev)
+        return sc
+    sc_a, sc_b = fresh(), fresh()
+    ts_a = TrainStep(sc_a, mask_weight=5.0, group=dist.group.WORLD)
+    ts_b = TrainStep(sc_b, mask_weight=5.0, group=None)
+    for it, fr in enumerate(frames):
+        sl0, sl1 = slice(0, Bh), slice(Bh, 2 * Bh)
+        mine = sl0 if rank == 0 else sl1
+        if world == 2:
+            ts_a.step(fr[rank], Bh, pixels=(px[mine], py[mine]), t_rand=tr[mine])
+        ts_b.step(fr[0], Bh, pixels=(px[sl0], py[sl0]), t_rand=tr[:2 * Bh], additional_img_id=fr[1], add_pixels=(px[sl1], py[sl1]))
+    if world == 2:
+        worst_o = 0.0
+        for a, b in zip(ts_a.all_params, ts_b.all_params):
+            worst_o = max(worst_o, float((a - b).abs().max()))
+        steps_a = [float(v) for v in ts_a.optimizer.step_count]
+        steps_b = [float(v) for v in ts_b.optimizer.step_count]
+        print(f"rank {rank}: FlatAdam 2 steps, frames differ per rank: max |param diff| vs single process {worst_o:.2e}; "
+              f"group step counters {steps_a} vs {steps_b}")
+        ok = ok and worst_o < 2e-4 and steps_a == steps_b and steps_a[4] == 0.0      # pose MLP 3 was never rendered
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -168,6 +168,35 @@ def test_render_image_equals_chunked_render_calls():
     assert float(img["weight_sum"].max()) > 0.5        # the sphere is in view
 
 
+def test_render_image_vs_oracle():
+    """Whole-frame forward render (exp_runner.py:1444-1501) against the ORACLE: colour, the
+    weight-averaged inside-sphere normals validate_image writes (exp_runner.py:1494-1501), depth and weight_sum of
+    NeuSRenderer.render_image vs the fp32 oracle rendering the same deterministic z samples (perturb 0)."""
+    from fmov_pose_b200 import synthetic
+    sc = synthetic.build_scene(device=DEV, n_images=2, n_samples=32, n_importance=32, up_sample_steps=2, H=48, W=64)
+    ds, rend = sc["dataset"], sc["renderer"]
+    K = torch.tensor([[60.0, 0, 32.0], [0, 60.0, 24.0], [0, 0, 1.0]])
+    ds.intrinsics_all_inv = torch.linalg.inv(K)[None].repeat(2, 1, 1).contiguous().to(DEV)
+    with torch.no_grad():
+        pose = sc["pose_network"](1)[:3]
+        rays_o, rays_d = ds.gen_rays_at(1, pose=pose)
+        img = rend.render_image(rays_o, rays_d, chunk_rays=4096)
+        ro, rd = rays_o.reshape(-1, 3).contiguous(), rays_d.reshape(-1, 3).contiguous()
+        near, far = ds.near_far_from_sphere(ro, rd)
+        z = rend.sample_z(ro, rd, near, far, None)          # perturb 0: the samples render_image drew
+    sdf_p = {k: v.detach() for k, v in sc["sdf_network"].named_parameters()}
+    col_p = {k: v.detach() for k, v in sc["color_network"].named_parameters()}
+    with torch.device(DEV):
+        ref = O.render(sdf_p, col_p, sc["deviation_network"].variance.detach(), ro, rd, near, far, n_samples=32,
+                       n_importance=32, up_sample_steps=2, cos_anneal_ratio=1.0, z_vals=z, eval=True)
+    nrm_ref = (ref["gradients"] * (ref["weights"] * ref["inside_sphere"])[..., None]).sum(1).detach()
+    assert float((img["color_fine"].reshape(-1, 3) - ref["color_fine"].detach()).abs().max()) <= 2e-3
+    assert float((img["normals"].reshape(-1, 3) - nrm_ref).abs().max()) <= 5e-3
+    assert float((img["weight_sum"].reshape(-1, 1) - ref["weight_sum"].detach()).abs().max()) <= 5e-3
+    assert float((img["depth_fine"].reshape(-1, 1) - ref["depth_fine"].detach()).abs().max()) <= 1e-2
+    assert float(ref["weight_sum"].max()) > 0.5 and float(ref["weight_sum"].min()) < 0.1       # object and background
+
+
 def test_full_size_batch_split_invariance():
     """Size-independent properties at the benchmark's full size (8192 rays x 64+64 samples, 1.05 M points per launch):
     rays are independent, so (i) the forward outputs of one 8192-ray call equal those of two 4096-ray calls bit for

@@ -90,6 +90,24 @@ def test_sample_pdf_kat_through_round_kernel():
         np.testing.assert_allclose(zz[:, 64:80].cpu().numpy(), d[f"up.new{inv_s}"], atol=2e-5)
 
 
+def test_sample_pdf_edge_kats_through_the_kernel():
+    """The reference's own sample_pdf outputs (kat.npz 'pdf.*': all-zero weights, dead bins, a single spike, exact ties at
+    the u grid, saturated first / last bin; models/renderer.py:54-86) through the inverse-CDF device code of the round
+    kernel (fmov_sample_pdf = the same warp_sample_pdf function on caller-given weights)."""
+    from fmov_pose_b200 import ops
+    d = load_golden("kat")
+    bins, w = t(d, "pdf.bins").to(DEV), t(d, "pdf.w").to(DEV)
+    for n_new in (16, 5):
+        got = ops.sample_pdf(bins, w, n_new).cpu().numpy()
+        ref = d[f"pdf.out{n_new}"]
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, atol=2e-5, err_msg=f"n_new={n_new}")
+        assert np.all(np.diff(got, axis=1) >= -1e-6), "inverse CDF of increasing u must be monotone"
+    # the oracle restatement on the same inputs (pinned bit-exactly to the reference in test_oracle_golden.py)
+    got = ops.sample_pdf(bins, w, 16).cpu()
+    np.testing.assert_allclose(got.numpy(), O.sample_pdf_det(bins.cpu(), w.cpu(), 16).numpy(), atol=2e-5)
+
+
 @pytest.mark.parametrize("n,m,steps,perturb", [(64, 64, 4, True), (16, 32, 2, True), (32, 0, 4, False), (64, 64, 1, False)])
 def test_hierarchical_sampling_vs_oracle(n, m, steps, perturb):
     """z_vals of renderer.py:385-446. The SDF used for importance sampling comes from the fp16 tensor-core

@@ -254,3 +254,84 @@ def test_two_frame_maintain_shape_iteration_eager_and_graphed():
         if graphed:
             assert len(gts.graphs) == 2
     np.testing.assert_allclose(res[1], res[0], rtol=2e-3)
+
+
+def test_bench_configuration_8192_rays_vs_fp32_oracle_on_the_gpu():
+    """Parity AT THE BENCHMARKED CONFIGURATION (bench.py defaults: 8192 rays x (64+64) samples, SegLearnPose, mask_weight 5):
+    the oracle — fp32 PyTorch autograd with the double backward through sdf_network.gradient — runs on the same device in
+    2048-ray chunks against whole-batch normalisers, on the z samples the CUDA path drew.  north_star tolerances: colour
+    <= 2e-3, SDF <= 1e-3, every parameter / pose gradient rel <= 1e-2."""
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import TrainStep
+    import torch.nn.functional as F
+    B, n, m, up, img = 8192, 64, 64, 4, 3
+    scene = synthetic.build_scene(device=DEV, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
+    ts = TrainStep(scene, igr_weight=0.1, mask_weight=5.0, optimizer=False)
+    g = torch.Generator().manual_seed(1234)
+    px = torch.randint(140, 500, [B], generator=g).to(DEV)
+    py = torch.randint(60, 420, [B], generator=g).to(DEV)
+    tr = torch.rand(B, 1, generator=g).to(DEV)
+    ls, out = ts.forward_backward(img, B, pixels=(px, py), t_rand=tr)
+    torch.cuda.synchronize()
+    ds = scene["dataset"]
+    with torch.device(DEV):          # the oracle's factory calls follow the default device
+        leaf = lambda v: v.detach().clone().requires_grad_(v.requires_grad)
+        sdf_p = {k: leaf(v) for k, v in scene["sdf_network"].named_parameters()}
+        col_p = {k: leaf(v) for k, v in scene["color_network"].named_parameters()}
+        var = leaf(scene["deviation_network"].variance)
+        pose = ts.pose_of(img).detach().clone().requires_grad_(True)
+        rgb = ds.images[img][(py, px)].to(DEV)
+        mask = (ds.masks[img][(py, px)][:, :1].to(DEV) > 0.5).float()
+        z = out["z_vals"].detach()
+        S = z.shape[1]
+        sd = 2.0 / n
+        with torch.no_grad():
+            ro, rd = O.gen_rays(pose, ds.intrinsics_all_inv[img], px, py)
+            dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full_like(z[:, :1], sd)], -1)
+            pts = ro[:, None] + rd[:, None] * (z + 0.5 * dists)[..., None]
+            relax_total = (torch.linalg.norm(pts, dim=-1) < 1.2).float().sum()
+        mask_sum = mask.sum() + 1e-5
+        tot = torch.zeros(4, device=DEV)
+        col_err = sdf_err = 0.0
+        for i in range(0, B, 2048):
+            sl = slice(i, i + 2048)
+            ro, rd = O.gen_rays(pose, ds.intrinsics_all_inv[img], px[sl], py[sl])
+            nr, fr = O.near_far_from_sphere(ro, rd)
+            ref = O.render(sdf_p, col_p, var, ro, rd, nr, fr, n_samples=n, n_importance=m, up_sample_steps=up,
+                           cos_anneal_ratio=1.0, z_vals=z[sl])
+            relax = (torch.linalg.norm(ref["pts"].detach().reshape(-1, S, 3), dim=-1) < 1.2).float()
+            eik = (relax * (torch.linalg.norm(ref["gradients"], dim=-1) - 1.0) ** 2).sum() / (relax_total + 1e-5)
+            col = ((ref["color_fine"] - rgb[sl]) * mask[sl]).abs().sum() / mask_sum
+            bce = F.binary_cross_entropy(ref["weight_sum"].clip(1e-3, 1 - 1e-3), mask[sl], reduction="sum") / B
+            loss = col + 0.1 * eik + 5.0 * bce
+            loss.backward()
+            tot += torch.stack([loss.detach(), col.detach(), eik.detach(), bce.detach()])
+            col_err = max(col_err, float((out["color_fine"][sl] - ref["color_fine"]).abs().max()))
+            sdf_err = max(sdf_err, float((out["sdf"].reshape(B, S)[sl] - ref["sdf"].reshape(-1, S)).abs().max()))
+            del ref, loss
+    assert col_err <= 2e-3, col_err
+    assert sdf_err <= 1e-3, sdf_err
+    for k, v in zip(("loss", "color_loss", "eikonal_loss", "mask_loss"), tot.tolist()):
+        assert abs(float(ls[k]) - v) <= 2e-3 * max(1.0, abs(v)), (k, float(ls[k]), v)
+    worst = 0.0
+    for net, pd in ((scene["sdf_network"], sdf_p), (scene["color_network"], col_p)):
+        for k, p in net.named_parameters():
+            if pd[k].grad is None or p.grad is None:
+                assert pd[k].grad is None or float(pd[k].grad.abs().max()) == 0.0 or p.grad is not None, k
+                continue
+            e = float((p.grad.double() - pd[k].grad.double()).norm() / (pd[k].grad.double().norm() + 1e-30))
+            worst = max(worst, e)
+            assert e <= 1e-2, (k, e)
+    e = float((scene["deviation_network"].variance.grad - var.grad).abs() / var.grad.abs())
+    assert e <= 1e-2, ("variance", e)
+    # pose: the oracle's d loss / d c2w pushed through the pose module == the step's pose-parameter gradients
+    got = {k: p.grad.detach().clone() for k, p in scene["pose_network"].named_parameters() if p.grad is not None}
+    assert got, "the rendered frame's pose MLP must receive gradients"
+    for p in scene["pose_network"].parameters():
+        p.grad = None
+    ts.pose_of(img).backward(pose.grad)
+    for k, p in scene["pose_network"].named_parameters():
+        if k in got:
+            e = float((got[k].double() - p.grad.double()).norm() / (p.grad.double().norm() + 1e-30))
+            assert e <= 1e-2, ("pose", k, e)
+    print(f"bench-config parity: colour {col_err:.2e} sdf {sdf_err:.2e} worst param-grad rel {worst:.2e}")

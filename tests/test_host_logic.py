@@ -118,18 +118,21 @@ def _worker(rank, world, port, ret):
         lin.weight.copy_(torch.eye(3)); lin.bias.zero_()
 
     class _R:
-        process_group = None
+        pass
+    # a "pose MLP" of a frame that no rank renders: it must come out of the gradient all-reduce WITHOUT a gradient, so that
+    # an optimiser skips it as on one GPU (exp_runner.py:785-816 steps only the pose optimisers of the rendered frames)
+    idle = torch.nn.Linear(2, 2)
     scene = dict(renderer=_R(), sdf_network=lin, deviation_network=torch.nn.Module(), color_network=torch.nn.Module(),
-                 pose_network=None)
+                 pose_network=idle)
     # single-process reference on the union batch
-    ts1 = TrainStep(scene, mask_weight=5.0, group=None, optimizer=False)
+    ts1 = TrainStep(scene, mask_weight=5.0, group=None, optimizer=False, fused_loss=False)
     out = dict(color_fine=lin(color), weight_sum=wsum, gradient_error=torch.tensor(0.25))
     l1 = ts1.losses(out, rgb, mask)
     l1["loss"].backward()
     g_full = lin.weight.grad.clone()
     lin.weight.grad = None; lin.bias.grad = None
     # sharded
-    ts2 = TrainStep(scene, mask_weight=5.0, group=dist.group.WORLD, optimizer=False)
+    ts2 = TrainStep(scene, mask_weight=5.0, group=dist.group.WORLD, optimizer=False, fused_loss=False)
     sl = slice(rank * B // world, (rank + 1) * B // world)
     out2 = dict(color_fine=lin(color[sl]), weight_sum=wsum[sl], gradient_error=torch.tensor(0.25))
     l2 = ts2.losses(out2, rgb[sl], mask[sl])
@@ -139,7 +142,8 @@ def _worker(rank, world, port, ret):
     (l2["color_loss"] + 5.0 * l2["mask_loss"]).backward()
     ts2.allreduce_grads()
     ok = (abs(parts[0].item() - l1["color_loss"].item()) < 1e-6 and abs(parts[1].item() - l1["mask_loss"].item()) < 1e-6
-          and torch.allclose(lin.weight.grad, g_full, atol=1e-6))
+          and torch.allclose(lin.weight.grad, g_full, atol=1e-6)
+          and idle.weight.grad is None and idle.bias.grad is None and lin.bias.grad is not None)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 
@@ -214,7 +218,7 @@ def test_lr_schedule_matches_the_reference_function(tag):
         process_group = None
     scene = dict(renderer=_R(), sdf_network=torch.nn.Linear(3, 3), deviation_network=torch.nn.Module(),
                  color_network=torch.nn.Module(), pose_network=_Pose())
-    ts = TrainStep(scene, lr=0.0, pose_lr=0.0)
+    ts = TrainStep(scene, lr=0.0, pose_lr=0.0, optimizer="torch")          # host-side LR logic; FlatAdam needs a GPU
     assert len(ts.optimizer.param_groups) == 4 and ts.pose_group_of == {0: 1, 1: 2, 2: 3}
     net, pose = [], []
     for it in d[tag + ".iters"]:
