@@ -89,6 +89,8 @@ constexpr uint8_t CHF_A_OTHER = 1;     // A operand = the OTHER tile slot's ACT 
 constexpr uint8_t CHF_ACCUM = 2;       // continue on the previous step's accumulator: no operand wait, never zero-initialise
 constexpr uint8_t CHF_NO_COMMIT = 4;   // more passes follow: do not signal the epilogue after this step
 constexpr uint8_t CHF_W2 = 8;          // weights come from ChainPtrs::weights2 (residual images)
+constexpr uint8_t CHF_DUAL_A = 16;     // every weight slice multiplies BOTH slots' A operands (hi, then the residuals) before
+                                       // it is released: two passes for one weight stream
 struct ChainTable {
   int n_steps;
   int slots;            // tiles in flight per CTA: 0 -> CH_SLOTS; 1 for chains that use slot 1's buffers for residuals
@@ -127,9 +129,9 @@ __device__ __forceinline__ uint8_t* chain_smem_base(uint8_t* raw) {
   return reinterpret_cast<uint8_t*>(p);
 }
 
-__device__ __forceinline__ void chain_init_barriers(ChainSmem* s) {
+__device__ __forceinline__ void chain_init_barriers(ChainSmem* s, int epi_threads = EPI_THREADS) {
   for (int i = 0; i < CH_SLOTS; ++i) {
-    mbar_init(&s->act_ready[i], EPI_THREADS);
+    mbar_init(&s->act_ready[i], epi_threads);
     mbar_init(&s->acc_ready[i], 1);
   }
   for (int i = 0; i < CH_WSTAGES; ++i) {
@@ -200,6 +202,8 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
         }
         for (int kb = 0; kb < nkb; ++kb) {
           const uint32_t a_base = smem_u32(kb < st.nkb_a ? act + kb * BLK_BYTES : aux + (kb - st.nkb_a) * BLK_BYTES);
+          const uint32_t a_base2 = smem_u32(kb < st.nkb_a ? act0 + (aslot ^ 1) * 4 * BLK_BYTES + kb * BLK_BYTES
+                                                          : aux0 + (aslot ^ 1) * BLK_BYTES + (kb - st.nkb_a) * BLK_BYTES);
 #pragma unroll
           for (int part = 0; part < CH_WSPLIT; ++part, ++it) {
             const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
@@ -212,6 +216,9 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
               umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
                        umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
                        ((kb | ks) != 0 ? 1u : 0u) | accum);
+              if (st.flags & CHF_DUAL_A)
+                umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base2 + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                         umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc, 1u);
             }
             umma_commit(&s->w_empty[stage]);   // slot reusable once these MMAs have read it
           }

@@ -40,7 +40,9 @@ constexpr int RQ_PH = 2;                 // prefetch distance (8-column pieces) 
 //            fine_bwd 7.72 -> 7.16 ms, stash 203 -> 172 blocks per tile (27 -> 23 GB per 8192 rays)
 //   dropped  eviction hints in fine_fwd (5.17 -> 5.4 ms), bulk L2 prefetch from the producer warp, thread-issued prefetch
 //            one step ahead, PFD = 2 (spills at 96 registers), double-buffered TMEM loads and peeled special-case layers,
-//            setmaxnreg re-balancing (ptxas 12.9 compiles the epilogue region against the smaller budget)
+//            setmaxnreg re-balancing (re-checked in round 2 with ptxas 12.9 -v: a setmaxnreg.dec anywhere in the kernel caps
+//            the WHOLE kernel at the dec value — 3.6 KB of spills at dec 40 with or without the epilogue's inc, with or
+//            without separate kernel tails per role — and an inc alone frees nothing: 'Used 96 registers' either way)
 // -18 % fine_bwd traffic bought -7 % time: the epilogues are latency bound (16 warps, long-scoreboard 9.9 cycles per
 // issue), not bandwidth bound — see DESIGN.md §3.
 #define FINE_BOUNDS __launch_bounds__(CH_THREADS, 1)

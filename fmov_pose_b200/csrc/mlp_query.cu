@@ -131,9 +131,8 @@ __device__ __forceinline__ void pe6_half_to_block_hilo(uint8_t* blk_hi, uint8_t*
     const float f = (float)(1 << k);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      // the residual image carries what fp16 drops, so the encoding itself must be accurate: libm sincosf
       float s, co;
-      sincosf(x[c] * f, &s, &co);
+      fast_sincos(x[c] * f, &s, &co);      // abs error ~1e-6: far below the 1e-4 the split-precision chain is held to
       e[3 + 6 * k + c] = s;
       e[6 + 6 * k + c] = co;
     }
@@ -148,12 +147,6 @@ __device__ __forceinline__ void pe6_half_to_block_hilo(uint8_t* blk_hi, uint8_t*
   pack4(lo, false, q);
   row_half_store(blk_lo + row * 16, h, q);
 }
-// softplus(beta = 100) to fp32 accuracy (the fast polynomial's 4e-7 is fine for fp16 tiles, not for hi/lo pairs)
-__device__ __forceinline__ float softplus100_precise(float z) {
-  const float t = z * SP_BETA;
-  return t > 20.f ? z : log1pf(expf(t)) * (1.0f / SP_BETA);
-}
-
 template <bool PRECISE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
@@ -169,7 +162,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
   const long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
   const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
-  if (threadIdx.x == 0) chain_init_barriers(s);
+  if (threadIdx.x == 0) chain_init_barriers(s, PRECISE ? 2 * EPI_THREADS : EPI_THREADS);
   if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
@@ -182,23 +175,90 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
     } else if (warp == ISSUER_WARP) {
       if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
     }
-  } else {
+  } else if (PRECISE) {
+    // Split-precision chain: ONE tile in flight.  Slot 1's ACT / AUX hold the fp16 residuals of slot 0's operands, and all
+    // 16 epilogue warps work on the one accumulator: column group cg = warp / 4 owns columns [64 cg, 64 cg + 64).
+    static_assert(CH_WGS == 2, "the split-precision epilogue is written for 16 epilogue warps");
     EpiCtx c;
     epi_init(c, s, act0, aux0, tmem);
-    const float b8 = __ldg(a.b8);
-    // PRECISE: one tile in flight (slot 0); slot 1's ACT / AUX hold the fp16 residuals of slot 0's operands
+    const int cg = (warp - EPI_WARP0) >> 2;                     // 0..3
+    c.slot = 0;
+    c.act = act0;
+    c.aux = aux0;
+    c.tmem = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint8_t* const act_lo = act0 + 4 * BLK_BYTES;
     uint8_t* const aux_lo = aux0 + BLK_BYTES;
-    if (PRECISE && c.slot != 0) goto epilogue_done;
-    for (int k = c.slot; k < n_my; k += (PRECISE ? 1 : CH_SLOTS)) {
+    float* const part = reinterpret_cast<float*>(aux0);          // [4][128] partial dot products (AUX is free after layer 4)
+    const float b8 = __ldg(a.b8);
+    for (int k = 0; k < n_my; ++k) {
       const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
       const long long p = tile * TILE_M + c.row;
       const bool valid = p < a.P;
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) load_point(a, p, x);
       x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
-      if (PRECISE) pe6_half_to_block_hilo(c.aux, aux_lo, c.row, x, c.wg);
-      else if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
+      if (cg < 2) pe6_half_to_block_hilo(c.aux, aux_lo, c.row, x, cg);
+      epi_signal_act(c);
+      float sdf = 0.f;
+#pragma unroll 1
+      for (int l = 0; l < 8; ++l) {
+        const float* bias = a.bias + l * 256;
+        const int n_mma = (l == 3) ? 224 : 256;
+        uint8_t* actp = c.act + c.row * 16;
+        epi_wait_acc(c);
+#pragma unroll 2
+        for (int i = 0; i < 4; ++i) {
+          const int ck = cg * 4 + i;
+          if (ck * 16 >= n_mma) break;
+          float v[16];
+          acc_load16(c, ck * 16, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
+            v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
+            v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
+            v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
+            v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
+          }
+          if (l == 7) {
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w8 + ck * 16) + j4);
+              sdf = fmaf(v[j4 * 4 + 0], w4.x, sdf); sdf = fmaf(v[j4 * 4 + 1], w4.y, sdf);
+              sdf = fmaf(v[j4 * 4 + 2], w4.z, sdf); sdf = fmaf(v[j4 * 4 + 3], w4.w, sdf);
+            }
+          } else {
+            uint4 q2[2];
+            pack2(v, false, q2);
+            chunk_store(actp, ck, q2);
+            float lo[16];
+            split16(v, lo);
+            pack2(lo, false, q2);
+            chunk_store(act_lo + c.row * 16, ck, q2);
+          }
+        }
+        if (l < 7) epi_signal_act(c);
+        else tc_fence_before();
+      }
+      // combine the four column groups of the lin8-row-0 dot product
+      part[cg * 128 + c.row] = sdf;
+      named_bar_sync(3, 2 * EPI_THREADS);
+      if (cg == 0 && valid)
+        a.out[p] = (part[c.row] + part[128 + c.row] + part[256 + c.row] + part[384 + c.row] + b8) * a.out_scale;
+      named_bar_sync(3, 2 * EPI_THREADS);          // `part` aliases AUX, which the next tile's encoding overwrites
+    }
+  } else {
+    EpiCtx c;
+    epi_init(c, s, act0, aux0, tmem);
+    const float b8 = __ldg(a.b8);
+    for (int k = c.slot; k < n_my; k += CH_SLOTS) {
+      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
+      const long long p = tile * TILE_M + c.row;
+      const bool valid = p < a.P;
+      float x[3] = {0.f, 0.f, 0.f};
+      if (valid) load_point(a, p, x);
+      x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
+      if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
       else pe6_to_block(c.aux, c.row, x);
       epi_signal_act(c);
       float sdf = 0.f;
@@ -217,17 +277,10 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
-            if (PRECISE) {
-              v[j4 * 4 + 0] = softplus100_precise(v[j4 * 4 + 0] + b4.x);
-              v[j4 * 4 + 1] = softplus100_precise(v[j4 * 4 + 1] + b4.y);
-              v[j4 * 4 + 2] = softplus100_precise(v[j4 * 4 + 2] + b4.z);
-              v[j4 * 4 + 3] = softplus100_precise(v[j4 * 4 + 3] + b4.w);
-            } else {
-              v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
-              v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
-              v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
-              v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
-            }
+            v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
+            v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
+            v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
+            v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
           }
           if (l == 7) {
 #pragma unroll
@@ -240,12 +293,6 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
             uint4 q2[2];
             pack2(v, false, q2);
             chunk_store(actp, ck, q2);
-            if (PRECISE) {
-              float lo[16];
-              split16(v, lo);
-              pack2(lo, false, q2);
-              chunk_store(act_lo + c.row * 16, ck, q2);
-            }
           }
         }
         if (l < 7) epi_signal_act(c);
@@ -260,7 +307,6 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
       }
       if (c.wg == CH_WGS - 1 && valid) a.out[p] = (sdf + b8) * a.out_scale;
     }
-  epilogue_done:;
   }
   __syncthreads();
   if (warp == ISSUER_WARP) {
@@ -292,21 +338,21 @@ static void build_query_table(ChainTable& tb) {
   }
 }
 
-// Split-precision chain: per layer three passes into one accumulator, hi*W_hi + lo*W_hi + hi*W_lo (the residual images
-// have the layout of the forward blob), one tile in flight.  Result error ~1e-6 instead of the fp16 chain's ~1e-3.
+// Split-precision chain: per layer three products into one accumulator, hi*W_hi + lo*W_hi + hi*W_lo (the residual images
+// have the layout of the forward blob), one tile in flight.  The first two share one pass over W_hi (CHF_DUAL_A), so a
+// layer streams two weight images instead of three.  Result error ~1e-5 instead of the fp16 chain's ~1e-3.
 static void build_query_table_precise(ChainTable& tb) {
   ChainTable f;
   build_query_table(f);
   memset(&tb, 0, sizeof(tb));
-  tb.n_steps = 24;
+  tb.n_steps = 16;
   tb.slots = 1;
   for (int l = 0; l < 8; ++l) {
-    for (int pass = 0; pass < 3; ++pass) {
-      ChainStep st = f.step[l];
-      st.flags = (pass == 0 ? 0 : CHF_ACCUM) | (pass == 2 ? 0 : CHF_NO_COMMIT) | (pass == 1 ? CHF_A_OTHER : 0) |
-                 (pass == 2 ? CHF_W2 : 0);
-      tb.step[l * 3 + pass] = st;
-    }
+    ChainStep st = f.step[l];
+    st.flags = CHF_DUAL_A | CHF_NO_COMMIT;          // (hi + lo) * W_hi
+    tb.step[l * 2] = st;
+    st.flags = CHF_ACCUM | CHF_W2;                  // + hi * W_lo, then signal the epilogue
+    tb.step[l * 2 + 1] = st;
   }
 }
 

@@ -71,12 +71,12 @@ def build_step(B, n_samples, n_importance, up_sample_steps, device="cpu", n_imag
     rend = Renderer(None, sdf, var, col, n_samples=n_samples, n_importance=n_importance, n_outside=0,
                     up_sample_steps=up_sample_steps, perturb=1.0)
     g = torch.Generator(device="cpu").manual_seed(1)
-    images = torch.rand(n_images, H, W, 3, generator=g)
+    images = torch.rand(n_images, H, W, 3, generator=g, device="cpu")
     ys, xs = torch.meshgrid(torch.arange(H, device="cpu"), torch.arange(W, device="cpu"), indexing="ij")
     disc = (((xs - W // 2) ** 2 + (ys - H // 2) ** 2) < 150 ** 2).float()
     masks = disc[None, :, :, None].repeat(n_images, 1, 1, 3)
-    K4 = torch.eye(4)
-    K4[:3, :3] = torch.tensor(INTRINSICS)
+    K4 = torch.eye(4, device="cpu")
+    K4[:3, :3] = torch.tensor(INTRINSICS, device="cpu")
     intr_inv = torch.inverse(K4)[None].repeat(n_images, 1, 1).to(dev)
     ds = None
     if gpu:           # the reference's own ray functions on a Dataset shell (its __init__ is the disk loader: not run)
@@ -93,8 +93,8 @@ def build_step(B, n_samples, n_importance, up_sample_steps, device="cpu", n_imag
     def rays_cpu(img_id, n, pose):
         # models/dataset.py:656-671 restated (the original moves its tensors to 'cuda:0'); mask-bbox pixel range as
         # mask_guided_sampling draws it for the synthetic disc mask
-        px = torch.randint(170, 470, [n], generator=g)
-        py = torch.randint(90, 390, [n], generator=g)
+        px = torch.randint(170, 470, [n], generator=g, device="cpu")
+        py = torch.randint(90, 390, [n], generator=g, device="cpu")
         color, mask = images[img_id][(py, px)], masks[img_id][(py, px)]
         p = torch.stack([px, py, torch.ones_like(py)], dim=-1).float()
         p = torch.matmul(intr_inv[img_id, None, :3, :3], p[:, :, None]).squeeze()

@@ -47,7 +47,16 @@ if what == "flow":
           f"flow_bwd: {b_ms * 1e3:.1f} us  {bb / b_ms / 1e6:.0f} GB/s algorithmic")
     sys.exit(0)
 scene = synthetic.build_scene(device=dev, n_images=4, H=120, W=160)
-if what == "query":
+if what == "grid":
+    # config C5 per-GPU slab through both value chains: plain fp16 and split-precision (extract_fields' default)
+    rend = scene["renderer"]
+    bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
+    count = 512 ** 3 // 64
+    for precise in (False, True, True):
+        rend.extract_fields(bmin, bmax, 512, first=0, count=count, precise=precise)
+    torch.cuda.synchronize()
+    print("grid ok")
+elif what == "query":
     W, b = scene["sdf_network"].effective_weights()
     qw = packing.SdfQueryWeights(W, b)
     pts = torch.rand(rays * 128, 3, device=dev) * 2 - 1
