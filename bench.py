@@ -640,6 +640,77 @@ def main():
             extras["c5_marching_cubes_512"] = measure_in_child("--mc_only")
         except Exception as e:
             extras["c5_marching_cubes_512"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+    if world > 1 and not args.no_extras:          # collective sections: every rank takes part
+        extras_mg = {}
+        # (1) attribution of the N-GPU step: the SAME step without any collective (group=None), all ranks running it at the
+        # same time.  max over ranks = what the slowest GPU needs on its own under the node's concurrent load (power cap,
+        # clock spread); N-GPU step time minus that = cost of the two collectives + the waiting they impose.
+        try:
+            sc_solo = synthetic.build_scene(device=dev, n_samples=n, n_importance=m, up_sample_steps=up, pose_type="seg")
+            ts_solo = TrainStep(sc_solo, igr_weight=0.1, mask_weight=5.0, group=None, capturable=use_graph)
+            g_solo = GraphedTrainStep(ts_solo, B)
+            for i in range(2 * total_steps):
+                if ts_solo.graph_key(img_ids[i]) not in {k[0] for k in g_solo.graphs}:
+                    g_solo.step(img_ids[i], px_d[i], py_d[i], tr_d[i])
+            for i in range(args.warmup):
+                g_solo.step(img_ids[i], px_d[i], py_d[i], tr_d[i])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(args.steps):
+                g_solo.step(img_ids[args.warmup + i], px_d[args.warmup + i], py_d[args.warmup + i], tr_d[args.warmup + i])
+            e1.record()
+            torch.cuda.synchronize()
+            solo = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            allsolo = [torch.zeros_like(solo) for _ in range(world)]
+            torch.distributed.all_gather(allsolo, solo)
+            solo_ms = [float(t.item()) for t in allsolo]
+            step_ms_n = ms_dev / args.steps
+            extras_mg["step_attribution"] = {
+                "n_gpu_step_ms": step_ms_n, "solo_step_ms_per_rank": solo_ms, "solo_max_ms": max(solo_ms),
+                "solo_min_ms": min(solo_ms), "collectives_and_waiting_ms": step_ms_n - max(solo_ms),
+                "note": "solo = the identical captured step with group=None (no all-reduce), all ranks running it concurrently; "
+                        "the N-GPU step cannot be faster than the slowest rank's solo step, the remainder is the two "
+                        "collectives (4-float normaliser pack inside the forward, flat gradient buffer after dw) and the "
+                        "waiting they impose"}
+            g_solo.graphs.clear()
+            del g_solo, ts_solo, sc_solo
+        except Exception as e:
+            extras_mg["step_attribution"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        # (2) config C3 as BASELINE.json states it: a 65,536-ray GLOBAL batch sharded over the N GPUs (32 K / 16 K rays per
+        # GPU at N = 2 / 4), each rank running its shard as micro-batches of 8192 rays inside ONE captured graph
+        try:
+            per = 65536 // world
+            if per > B:
+                g3 = GraphedTrainStep(ts, per, micro_batch=B)
+                gg = torch.Generator().manual_seed(99 + rank)
+                px3 = torch.randint(140, 500, [per], generator=gg).to(dev)
+                py3 = torch.randint(60, 420, [per], generator=gg).to(dev)
+                tr3 = torch.rand(per, 1, generator=gg).to(dev)
+                for i in range(2):
+                    g3.step(3, px3, py3, tr3)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(4):
+                    g3.step(3, px3, py3, tr3)
+                e1.record()
+                barrier()
+                ms3 = torch.tensor([e0.elapsed_time(e1) / 4], device=dev)
+                torch.distributed.all_reduce(ms3, op=torch.distributed.ReduceOp.MAX)
+                extras_mg["c3_65536_global_rays"] = {
+                    "ms_per_step": ms3.item(), "rays_per_s": 65536 / ms3.item() * 1e3, "rays_per_gpu": per,
+                    "micro_batches_per_gpu": per // B,
+                    "note": "config C3 as stated (strong-scaled 64 K-ray global batch): graph replay of the micro-batched "
+                            "step, one normaliser all-reduce + one gradient all-reduce per step; max over ranks"}
+                g3.graphs.clear()
+                del g3
+            else:
+                extras_mg["c3_65536_global_rays"] = {"note": f"at N = {world} config C3 is {per} rays per GPU = the headline line"}
+        except Exception as e:
+            extras_mg["c3_65536_global_rays"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        if rank == 0:
+            extras = dict(extras or {}, **extras_mg)
     if not args.no_extras:              # collective (all ranks): config C5 across the N GPUs of this run
         try:
             grid = measure_grid_sharded(scene, dev, group, world)

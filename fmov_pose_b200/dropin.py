@@ -62,7 +62,10 @@ def main(argv=None):
         return 2
     script = os.path.abspath(argv[0])
     root = os.path.dirname(script)
-    install(root)
+    # `python -m fmov_pose_b200.dropin` runs this file as __main__; the models package imports the CANONICAL module
+    # (fmov_pose_b200.dropin), so the aliases and the checkout location are installed there
+    import fmov_pose_b200.dropin as canonical
+    canonical.install(root)
     sys.path.insert(0, root)                 # `utils.*` and friends resolve as if the script had been started directly
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")

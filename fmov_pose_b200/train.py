@@ -284,7 +284,12 @@ class TrainStep:
         ds, rend = s["dataset"], s["renderer"]
         dev = self.params[0].device
         pose = self.pose_of(img_id, img_t)
-        data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
+        nf_k = None
+        if self.fused_rays:      # the one-shot step samples from the ray-generation kernel's near / far: so does this one
+            r = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t, with_near_far=True)
+            data, nf_k = r[0], (r[2].detach(), r[3].detach())
+        else:
+            data, _ = ds.gen_random_rays_at(img_id, batch_size, pose, pixels=pixels, img_idx_t=img_t)
         rays_o, rays_d, true_rgb, mask = data[:, :3], data[:, 3:6], data[:, 6:9], data[:, 9:10]
         true_rgb, mask = true_rgb.detach(), mask.detach()      # slices of the same cat() as the rays
         ro = rays_o.detach().contiguous().requires_grad_(rays_o.requires_grad)      # cut: per-chunk backward stops here
@@ -293,7 +298,7 @@ class TrainStep:
             t_rand = torch.rand([batch_size, 1], device=dev)
         sd = 2.0 / rend.n_samples
         with torch.no_grad():
-            near, far = ds.near_far_from_sphere(ro, rd)
+            near, far = nf_k if nf_k is not None else ds.near_far_from_sphere(ro, rd)
             z_all = rend.sample_z(ro, rd, near, far, t_rand)
             dists = torch.cat([z_all[:, 1:] - z_all[:, :-1], torch.full_like(z_all[:, :1], sd)], dim=-1)
             pts = ro[:, None, :] + rd[:, None, :] * (z_all + 0.5 * dists)[:, :, None]
@@ -433,13 +438,17 @@ class GraphedTrainStep:
     scalars (`TrainStep.set_lr`), the activation stash is the recycled Stash pool buffer.  Nothing in the step reads
     back to the host, so one replay == one reference iteration (exp_runner.py:497-599, 772-816)."""
 
-    def __init__(self, ts, batch_size, cos_anneal_ratio=1.0, two_frames=False):
+    def __init__(self, ts, batch_size, cos_anneal_ratio=1.0, two_frames=False, micro_batch=None):
         """`two_frames`: the maintain_shape iteration of the shipped confs (exp_runner.py:512-548): `batch_size` rays
         of the current frame + `batch_size` rays of an earlier frame in one render; `step()` then also takes the second
-        frame's index and pixels, and t_rand has 2*batch_size rows."""
+        frame's index and pixels, and t_rand has 2*batch_size rows.  `micro_batch`: ray batches whose activation stash
+        does not fit HBM at once (config C3: 32 K / 16 K rays per GPU at N = 2 / 4) are captured as ONE graph of
+        TrainStep's micro-batched step (whole-batch sampling and normalisers, fine stage + backward per micro-batch)."""
         assert ts.optimizer is None or ts.capturable, "build the TrainStep with capturable=True (or the default FlatAdam)"
         self.ts, self.B, self.car = ts, int(batch_size), float(cos_anneal_ratio)
         self.two = bool(two_frames)
+        self.micro_batch = micro_batch
+        assert not (self.two and micro_batch), "micro-batching takes one frame per step"
         dev = ts.params[0].device
         self.dev = dev
         self.px = torch.zeros(self.B, dtype=torch.int64, device=dev)
@@ -462,6 +471,8 @@ class GraphedTrainStep:
 
     def _kw(self, add_img_id):
         kw = dict(pixels=(self.px, self.py), t_rand=self.tr, cos_anneal_ratio=self.car, img_t=self.img)
+        if self.micro_batch:
+            kw.update(micro_batch=self.micro_batch)
         if self.two:
             kw.update(additional_img_id=add_img_id, add_pixels=(self.px2, self.py2), add_img_t=self.img2)
         return kw

@@ -77,7 +77,16 @@ else:
     runner.renderer.render = render
     p0 = [p.detach().clone() for p in runner.sdf_network.parameters()]
     pose0 = [p.detach().clone() for p in runner.pose_network.parameters()]
-    runner.train()
+    ref_bug = None
+    try:
+        runner.train()
+    except NameError as e:
+        # the reference's own bug: the last statement of train() (exp_runner.py:976-980) calls extract_camera_poses, which
+        # uses `csv` without importing it (exp_runner.py:57) — reached only after the last iteration
+        if "csv" not in str(e) or runner.iter_step < runner.end_iter:
+            raise
+        ref_bug = str(e)
+    res["reference_bug_after_last_iteration"] = ref_bug
     moved = max(float((a - b.detach()).abs().max()) for a, b in zip(p0, runner.sdf_network.parameters()))
     pose_moved = max(float((a - b.detach()).abs().max()) for a, b in zip(pose0, runner.pose_network.parameters()))
     res.update(parity=parity, scalars=scalars, iter_step=int(runner.iter_step), sdf_param_moved=moved,
