@@ -8,6 +8,7 @@
 //   (host: exclusive prefix sum over the chunks — torch.cumsum; the totals size the outputs)
 //   fmov_mc_vertices   vertex positions (index or world coordinates) + the vertex id of every crossed edge (vid3)
 //   fmov_mc_triangles  case lookup, three vid3 reads per triangle corner
+//   (both skip chunks whose prefix-sum entry shows nothing to emit: chunk_voff / chunk_toff have n_chunks + 1 entries)
 // Output order is deterministic: vertices by (grid point x-major, axis), triangles by (cell x-major, table order).
 // Corner / edge numbering and the case table: fmov_pose_b200/mc_tables.py (uploaded once with fmov_mc_set_tables).
 #include "fmov_common.cuh"
@@ -44,16 +45,21 @@ __device__ __forceinline__ int mc_block_exscan(int v, int* total) {
   return base + inc - v;
 }
 
+// A chunk without any crossing (the vast majority: the surface is a 2-D set in a 3-D grid) is recognised with one
+// block-wide vote and skips both prefix sums; vertex and triangle counts share ONE scan (packed 16 + 16 bits: <= 3 * 256
+// and <= 5 * 256 per chunk).
+__device__ __forceinline__ int mc_pack(int nv, int nt) { return nv | (nt << 16); }
+
 __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int* __restrict__ chunk_nv,
                                                             int* __restrict__ chunk_nt) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
     const McPoint q = mc_point(g, ch * MC_CHUNK + threadIdx.x, true);
-    int tv, tt;
-    mc_block_exscan(mc_vertex_count(q), &tv);
-    mc_block_exscan(q.ntri, &tt);
+    const int v = mc_pack(mc_vertex_count(q), q.ntri);
+    int tot = 0;
+    if (__syncthreads_or(v)) mc_block_exscan(v, &tot);
     if (threadIdx.x == 0) {
-      chunk_nv[ch] = tv;
-      chunk_nt[ch] = tt;
+      chunk_nv[ch] = tot & 0xFFFF;
+      chunk_nt[ch] = tot >> 16;
     }
   }
 }
@@ -62,6 +68,7 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_vertices_kernel(const McGrid g, c
                                                                const McXform xf, float* __restrict__ verts,
                                                                int* __restrict__ vid3) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
+    if (chunk_voff[ch + 1] == chunk_voff[ch]) continue;          // no crossed edge starts in this chunk (block-uniform)
     const long long p = ch * MC_CHUNK + threadIdx.x;
     const McPoint q = mc_point(g, p, false);
     const int nv = mc_vertex_count(q);
@@ -74,6 +81,7 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_vertices_kernel(const McGrid g, c
 __global__ void __launch_bounds__(MC_CHUNK) mc_triangles_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
                                                                 const int* __restrict__ vid3, int* __restrict__ tris) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
+    if (chunk_toff[ch + 1] == chunk_toff[ch]) continue;          // no triangle in this chunk's cells (block-uniform)
     const long long p = ch * MC_CHUNK + threadIdx.x;
     const McPoint q = mc_point(g, p, true);
     int tt;

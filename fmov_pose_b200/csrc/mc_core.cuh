@@ -46,9 +46,12 @@ MC_HD McPoint mc_point(const McGrid& g, long long p, bool want_case) {
   q.cross[0] = q.cross[1] = q.cross[2] = false;
   q.f1[0] = q.f1[1] = q.f1[2] = 0.f;
   if (!q.valid) return q;
-  const long long YZ = (long long)g.Y * g.Z;
-  q.i = (int)(p / YZ);
-  const int r = (int)(p - (long long)q.i * YZ);
+  // the grid has fewer than 2^31 points (checked by the launcher): 32-bit index arithmetic (64-bit division is ~5x the
+  // instructions, and these kernels are issue-bound, not bandwidth-bound — ncu: 68 % issue-active at 0.7 TB/s)
+  const int YZ = g.Y * g.Z;
+  const unsigned int pu = (unsigned int)p;
+  q.i = (int)(pu / (unsigned int)YZ);
+  const int r = (int)(pu - (unsigned int)q.i * (unsigned int)YZ);
   q.j = r / g.Z;
   q.k = r - q.j * g.Z;
   const bool hx = q.i + 1 < g.X, hy = q.j + 1 < g.Y, hz = q.k + 1 < g.Z;

@@ -37,9 +37,11 @@ def marching_cubes(u, isovalue=0.0, scale=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0
     counts = torch.empty(2, nch, dtype=torch.int32, device=dev)
     L.check(lib.fmov_mc_count(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(counts[0]), L.ptr(counts[1]), L.stream()),
             "fmov_mc_count")
-    incl = torch.cumsum(counts, dim=1, dtype=torch.int64)
-    excl = (incl - counts).contiguous()
-    n_v, n_t = (int(v) for v in incl[:, -1].tolist())          # the one host sync: output sizes are data dependent
+    # exclusive prefix sums with the totals appended ([2, n_chunks + 1]): chunk c emits [off[c], off[c + 1]), and the emit
+    # kernels skip chunks whose range is empty
+    excl = torch.zeros(2, nch + 1, dtype=torch.int64, device=dev)
+    excl[:, 1:] = torch.cumsum(counts, dim=1, dtype=torch.int64)
+    n_v, n_t = (int(v) for v in excl[:, -1].tolist())          # the one host sync: output sizes are data dependent
     verts = torch.empty(n_v, 3, dtype=torch.float32, device=dev)
     tris = torch.empty(n_t, 3, dtype=torch.int32, device=dev)
     if n_v == 0:

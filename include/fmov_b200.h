@@ -231,7 +231,8 @@ int fmov_adam_step(float* const* param, const long long* off, const int* numel, 
  * per crossed grid edge, ordered by (grid point x-major, axis); triangles ordered by (cell x-major, case-table order).
  *   1. fmov_mc_set_tables (once): HOST case table [256][15] + triangle counts [256] (fmov_pose_b200/mc_tables.py)
  *   2. fmov_mc_count: per 256-point chunk (fmov_mc_chunk_count of them) the number of vertices / triangles
- *   3. caller: exclusive prefix sums (int64) over the chunks; totals size the outputs
+ *   3. caller: exclusive prefix sums (int64) over the chunks WITH the total appended (n_chunks + 1 entries: chunk c emits
+ *      [off[c], off[c+1]), empty chunks are skipped); totals size the outputs
  *   4. fmov_mc_vertices: verts [V,3] = index coordinate * (sx,sy,sz) + (ox,oy,oz); vid3 [X*Y*Z,3] int32 scratch receives the
  *      vertex id of every crossed edge (other entries stay unwritten and are never read)
  *   5. fmov_mc_triangles: tris [T,3] int32 vertex ids                                                                    */
