@@ -88,7 +88,7 @@ else:
         ref_bug = str(e)
     res["reference_bug_after_last_iteration"] = ref_bug
     moved = max(float((a - b.detach()).abs().max()) for a, b in zip(p0, runner.sdf_network.parameters()))
-    pose_moved = max(float((a - b.detach()).abs().max()) for a, b in zip(pose0, runner.pose_network.parameters()))
+    pose_moved = max(float((a.float() - b.detach().float()).abs().max()) for a, b in zip(pose0, runner.pose_network.parameters()))
     res.update(parity=parity, scalars=scalars, iter_step=int(runner.iter_step), sdf_param_moved=moved,
                pose_param_moved=pose_moved, current_image=int(runner.current_image),
                current_pose_mlp_index=int(runner.current_pose_mlp_index),
