@@ -92,14 +92,19 @@ def main():
             ts_a.step(fr[rank], Bh, pixels=(px[mine], py[mine]), t_rand=tr[mine])
         ts_b.step(fr[0], Bh, pixels=(px[sl0], py[sl0]), t_rand=tr[:2 * Bh], additional_img_id=fr[1], add_pixels=(px[sl1], py[sl1]))
     if world == 2:
-        worst_o = 0.0
+        worst_o, mean_o, cnt = 0.0, 0.0, 0
         for a, b in zip(ts_a.all_params, ts_b.all_params):
             worst_o = max(worst_o, float((a - b).abs().max()))
+            mean_o += float((a - b).abs().sum())
+            cnt += a.numel()
+        mean_o /= cnt
         steps_a = [float(v) for v in ts_a.optimizer.step_count]
         steps_b = [float(v) for v in ts_b.optimizer.step_count]
-        print(f"rank {rank}: FlatAdam 2 steps, frames differ per rank: max |param diff| vs single process {worst_o:.2e}; "
+        print(f"rank {rank}: FlatAdam 2 steps, frames differ per rank: |param diff| vs single process max {worst_o:.2e} mean {mean_o:.2e}; "
               f"group step counters {steps_a} vs {steps_b}")
-        ok = ok and worst_o < 2e-4 and steps_a == steps_b and steps_a[4] == 0.0      # pose MLP 3 was never rendered
+        # Adam's first steps are sign-like (lr per step whatever the gradient's size): where a gradient is fp16-rounding noise
+        # around zero the two runs may step in opposite directions, so the bound is one step (lr = 5e-4) and a tiny mean
+        ok = ok and worst_o < 1e-3 and mean_o < 2e-5 and steps_a == steps_b and steps_a[4] == 0.0      # pose MLP 3 was never rendered
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
