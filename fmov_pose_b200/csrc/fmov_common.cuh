@@ -281,6 +281,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // folded in: log1p(w)/100 = w*P(w) on w in (0,1], max abs error 4.1e-07 on the activation (fp16 storage rounds at
 // >= 1e-6 there); the reference's threshold branch (beta*z > 20 -> z) differs from this by < 2.1e-11.
 // Branch-free (8 instructions) so that the evaluations of an epilogue chunk interleave.
+constexpr int PE_RES_COL = 39;          // first of the three residual columns (x, y, z) in the encoded-input k-block
 __device__ __forceinline__ float softplus100(float z) {
   const float w = ex2_approx(fabsf(z) * (-SP_BETA * 1.4426950408889634f));
   float p = fmaf(w, 4.1551113827e-04f, -1.5783837298e-03f);

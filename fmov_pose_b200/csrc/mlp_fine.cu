@@ -173,6 +173,13 @@ __device__ __forceinline__ void pe_eval(const float x[3], float* e) {
     }
   }
 }
+// columns PE_RES_COL..+2 of the 64-wide encoded-input block: what fp16 drops of the raw coordinates (|x| up to ~1.75 has an
+// fp16 spacing of 9.8e-4, and d sdf / d x ~ 1: the largest single contribution to the SDF error of the fp16 chain)
+__device__ __forceinline__ void pe_with_residual(const float x[3], float* e64) {
+  pe_eval<6>(x, e64);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e64[PE_RES_COL + c] = x[c] - __half2float(__float2half_rn(x[c]));
+}
 // n = J_e^T g   (g has 3+6L entries)
 template <int L>
 __device__ __forceinline__ void pe_jt(const float x[3], const float* g, float n[3]) {
@@ -266,7 +273,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         float e[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
-        pe_eval<6>(pc.x, e);
+        pe_with_residual(pc.x, e);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (CH_WGS == 2 && h != c.wg) continue;        // each warpgroup stores one 32-column half
@@ -803,7 +810,7 @@ struct PackSpec {
   int src_rows, src_cols;
   int transpose;       // image row n <-> source column
   int row_off, n_valid;
-  int nseg, seg_dst[2], seg_src[2], seg_len[2];
+  int nseg, seg_dst[3], seg_src[3], seg_len[3];
   float scale;
   int bf16;
   int chunk0;          // first 16-byte chunk of this image in the global chunk numbering
@@ -924,11 +931,13 @@ static void build_bwd_table(ChainTable& tb) {
 
 // ---- fused packing -----------------------------------------------------------------------------------------
 static void add_spec(PackAllArgs& a, int img, int src, int rows, int cols, bool tr, int row_off, int n_valid, int nseg,
-                     int d0, int s0, int l0, int d1, int s1, int l1, float scale, bool bf16) {
+                     int d0, int s0, int l0, int d1, int s1, int l1, float scale, bool bf16, int d2 = 0, int s2 = 0,
+                     int l2 = 0) {
   PackSpec& sp = a.spec[a.n_spec++];
   sp.img = img; sp.src = src; sp.src_rows = rows; sp.src_cols = cols; sp.transpose = tr ? 1 : 0; sp.row_off = row_off;
   sp.n_valid = n_valid; sp.nseg = nseg; sp.seg_dst[0] = d0; sp.seg_src[0] = s0; sp.seg_len[0] = l0;
-  sp.seg_dst[1] = d1; sp.seg_src[1] = s1; sp.seg_len[1] = l1; sp.scale = scale; sp.bf16 = bf16 ? 1 : 0;
+  sp.seg_dst[1] = d1; sp.seg_src[1] = s1; sp.seg_len[1] = l1; sp.seg_dst[2] = d2; sp.seg_src[2] = s2; sp.seg_len[2] = l2;
+  sp.scale = scale; sp.bf16 = bf16 ? 1 : 0;
   const ImgInfo ii = img_info(img);
   sp.chunk0 = a.total_chunks;
   a.total_chunks += ii.npad * ii.kblocks * 8;
@@ -938,8 +947,10 @@ static void build_pack_specs(PackAllArgs& a, bool backward) {
   const float rs2 = 0.70710678118654752f;
   static const int so[9] = {256, 256, 256, 217, 256, 256, 256, 256, 257}, si[9] = {39, 256, 256, 256, 256, 256, 256, 256, 256};
   auto fwd_img = [&](int img, int l, bool bf) {
-    if (l == 0) add_spec(a, img, 0, so[0], si[0], false, 0, 256, 1, 0, 0, 39, 0, 0, 0, 1.f, bf);
-    else if (l == 4) add_spec(a, img, 4, 256, 256, false, 0, 256, 2, 0, 0, 217, 256, 217, 39, rs2, bf);
+    // the encoded-input k-block carries the fp16 residuals of the raw coordinates in columns 39..41 (pe_with_residual): the
+    // images repeat the weight columns of x, y, z there, so x enters the first layer and the skip layer to ~2^-22
+    if (l == 0) add_spec(a, img, 0, so[0], si[0], false, 0, 256, 2, 0, 0, 39, PE_RES_COL, 0, 3, 1.f, bf);
+    else if (l == 4) add_spec(a, img, 4, 256, 256, false, 0, 256, 3, 0, 0, 217, 256, 217, 39, rs2, bf, 256 + PE_RES_COL, 217, 3);
     else if (l == 8) add_spec(a, img, 8, 257, 256, false, 1, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
     else add_spec(a, img, l, so[l], si[l], false, 0, so[l], 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
   };

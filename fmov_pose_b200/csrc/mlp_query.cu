@@ -89,6 +89,8 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
     }
   }
 #pragma unroll
+  for (int c = 0; c < 3; ++c) e[PE_RES_COL + c] = x[c] - __half2float(__float2half_rn(x[c]));      // see pe_with_residual
+#pragma unroll
   for (int h = 0; h < 2; ++h) {
     uint4 q[4];
     pack4(e + 32 * h, false, q);
@@ -111,6 +113,8 @@ __device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const f
       e[6 + 6 * k + c] = co;
     }
   }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) e[PE_RES_COL + c] = x[c] - __half2float(__float2half_rn(x[c]));      // see pe_with_residual
   uint4 q[4];
   if (h == 0) pack4(e, false, q); else pack4(e + 32, false, q);
   row_half_store(blk + row * 16, h, q);

@@ -83,11 +83,11 @@ class SdfQueryWeights:
                 off = int(lib.fmov_sdf_fwd_blob_offset(l))
                 Wl = W[l].detach().float()
                 if l == 0:
-                    pack_image(Wl, blob, off, 256, 1, [(0, 0, 39)], bf16=fmt)
+                    pack_image(Wl, blob, off, 256, 1, [(0, 0, 39), (39, 0, 3)], bf16=fmt)          # 39..41: residuals of x, y, z
                 elif l == 3:
                     pack_image(Wl, blob, off, 224, 4, [(0, 0, 256)], bf16=fmt)
                 elif l == 4:
-                    pack_image(Wl, blob, off, 256, 5, [(0, 0, 217), (256, 217, 39)], scale=1.0 / SQ2, bf16=fmt)
+                    pack_image(Wl, blob, off, 256, 5, [(0, 0, 217), (256, 217, 39), (295, 217, 3)], scale=1.0 / SQ2, bf16=fmt)
                 else:
                     pack_image(Wl, blob, off, 256, 4, [(0, 0, 256)], bf16=fmt)
         self.bias = torch.zeros(8, 256, dtype=torch.float32, device=dev)
