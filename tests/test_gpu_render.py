@@ -96,10 +96,11 @@ def test_render_train_step_vs_reference_and_oracle(name):
 
     # ---- (a) reference golden (own sampling): colour / losses / gradient norms ---------------------------
     col_err = np.abs(c(out["color_fine"]) - d["out.color_fine"])
-    assert np.median(col_err) <= 2e-3 and (col_err > 2e-3).mean() <= 0.05, (np.median(col_err), col_err.max())
-    assert abs(losses["loss"].item() - d["loss"][0]) <= 1e-2 * abs(d["loss"][0])
+    # measured on B200 (round 2): colour max 1.0e-4, loss rel 3e-5, rays_d gradient rel 4.2e-3, gradient norms rel <= 1.2e-3
+    assert col_err.max() <= 2e-3 and np.median(col_err) <= 1e-5, (np.median(col_err), col_err.max())
+    assert abs(losses["loss"].item() - d["loss"][0]) <= 1e-3 * abs(d["loss"][0])
     g_rd = rel(c(rays_d.grad), d["grad.rays_d"])
-    assert g_rd <= 5e-2, g_rd
+    assert g_rd <= 1e-2, g_rd
     worst_gn = 0.0
     for k, v in d.items():
         if k.startswith("gnorm.") and ".lin" in k:
@@ -107,7 +108,7 @@ def test_render_train_step_vs_reference_and_oracle(name):
             p = dict(net.named_parameters())[k.split(".", 2)[2]]
             got = float(np.linalg.norm(c(p.grad).astype(np.float64)))
             worst_gn = max(worst_gn, abs(got - float(v)) / (float(v) + 1e-30))
-            assert abs(got - float(v)) <= 5e-2 * float(v) + 1e-9, (k, got, float(v))
+            assert abs(got - float(v)) <= 1e-2 * float(v) + 1e-9, (k, got, float(v))
     print(f"{name}: vs reference golden (own sampling): colour median {np.median(col_err):.2e} max {col_err.max():.2e} "
           f"frac>2e-3 {(col_err > 2e-3).mean():.4f}; loss rel {abs(losses['loss'].item() - d['loss'][0]) / abs(d['loss'][0]):.2e}; "
           f"rays_d grad rel {g_rd:.2e}; worst gradient-norm rel {worst_gn:.2e}; (same-z oracle) worst param grad rel {worst:.2e}")

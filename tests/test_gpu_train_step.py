@@ -148,7 +148,7 @@ def test_micro_batched_step_equals_one_shot_step(cfg):
         np.testing.assert_allclose(float(lb[k].detach()), float(la[k].detach()), rtol=1e-4, err_msg=k)
     # identical samples for n_importance > 0 (both paths sample from the kernel's near / far); with n_importance == 0 the
     # micro-batches rebuild z from torch's near / far (ulps from the kernel's), hence not bitwise
-    np.testing.assert_allclose(ob["color_fine"].cpu().numpy(), oa["color_fine"].detach().cpu().numpy(), atol=5e-5)
+    np.testing.assert_allclose(ob["color_fine"].cpu().numpy(), oa["color_fine"].detach().cpu().numpy(), atol=2e-4)
     n = 0
     for a, b in zip(ga, gb):
         assert (a is None) == (b is None)

@@ -181,7 +181,8 @@ def test_fused_ray_path_step_equals_the_default_step(cfg):
     # as isolated colour differences far inside north_star's 2e-3 bar
     dc = (cb - ca).abs()
     if cfg["n_importance"] == 0:
-        assert float(dc.max()) <= 2e-5, float(dc.max())
+        # z = near + (far - near) * t: up to 3 ulp of |mid| ~ 3 (7e-7) in z, times a colour slope of up to ~1e2 at a surface
+        assert float(dc.max()) <= 2e-4 and float(dc.mean()) <= 5e-6, (float(dc.max()), float(dc.mean()))
     else:
         assert float(dc.max()) <= 5e-4 and float(dc.mean()) <= 5e-6, (float(dc.max()), float(dc.mean()))
     n_net_checked = n_pose_checked = 0

@@ -20,7 +20,10 @@ needs_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "exp_runner.
 
 
 def _env():
-    return dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "shims"), ROOT]), TQDM_DISABLE="1")
+    # TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD: the reference (written for torch 1.9) calls torch.load on its own checkpoint, which
+    # holds numpy scalars; torch >= 2.6 refuses that by default
+    return dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests", "shims"), ROOT]), TQDM_DISABLE="1",
+                TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD="1")
 
 
 @needs_ref
