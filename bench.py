@@ -274,7 +274,40 @@ def measure_extras(scene, dev, use_graph=True):
         note = "oracle port of the reference (oracle/_ref absent) on the same B200"
     out["reference_pytorch_on_this_gpu"] = dict(tg, note=note)
     out["c2_literal_1024rays_32+0"] = measure_literal(dev, use_graph)
+    out["c4_barf_gf_512rays_64+64"] = measure_c4(dev, use_graph)
     return out
+
+
+def measure_c4(dev, use_graph=True):
+    """BASELINE config C4: the confs/ho3d_barf.conf iteration — BarfSDFNetwork / BarfRenderingNetwork (the BARF embedder
+    never applies its coarse-to-fine weights), ONE LearnPoseGF pose MLP for all frames (pose_type gf),
+    512 rays, 64+64 samples, mask_weight 1 — as a replayed graph."""
+    import torch
+    from fmov_pose_b200 import synthetic
+    from fmov_pose_b200.train import GraphedTrainStep, TrainStep
+    sc = synthetic.build_scene(device=dev, n_samples=64, n_importance=64, up_sample_steps=4, pose_type="gf")
+    ts = TrainStep(sc, mask_weight=1.0)
+    B, n_it = 512, 24
+    g = torch.Generator().manual_seed(5)
+    px = torch.randint(140, 500, [n_it, B], generator=g).to(dev)
+    py = torch.randint(60, 420, [n_it, B], generator=g).to(dev)
+    tr = torch.rand(n_it, B, 1, generator=g).to(dev)
+    gts = GraphedTrainStep(ts, B) if use_graph else None
+    step = (lambda i: gts.step(i % 20, px[i], py[i], tr[i])) if use_graph else \
+        (lambda i: ts.step(i % 20, B, pixels=(px[i], py[i]), t_rand=tr[i]))
+    for i in range(8):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(8, n_it):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (n_it - 8)
+    return {"ms_per_step": ms, "rays_per_s": B / ms * 1e3,
+            "note": "confs/ho3d_barf.conf iteration (pose_type gf, 512 rays, 64+64 samples, mask_weight 1); " +
+                    ("CUDA-graph replay" if use_graph else "eager")}
 
 
 def measure_literal(dev, use_graph=True):

@@ -47,7 +47,8 @@ def write_conf(ref_root, work, end_iter=6, batch_size=128, name="ho3d_virtual.co
     def sub(key, val):
         nonlocal text
         text, n = re.subn(rf"(\n\s*{key}\s*=\s*)[^\n]+", rf"\g<1>{val}", text, count=1)
-        assert n == 1, key
+        assert n == 1 or key in optional, key
+    optional = ("max_pro_iteration", "pro_warm_up_end", "mesh_warmup_step")          # absent from the non-progressive confs
     for key, val in dict(end_iter=end_iter, batch_size=batch_size, save_freq=end_iter, val_freq=100000, val_mesh_freq=100000,
                          report_freq=1, pose_freq=100000, mesh_warmup_step=0, max_pro_iteration=2, pro_warm_up_end=1,
                          warm_up_end=2).items():
