@@ -16,9 +16,9 @@ import importlib.util
 import os
 import runpy
 import sys
+import types
 
-_SUBMODULES = ("fields", "renderer", "barf_fields", "camera", "picture_pose", "pixel_pose", "dataset", "embedder",
-               "barf_embedder", "batch_lie_group_helper")
+_SUBMODULES = ("fields", "renderer", "barf_fields", "camera", "picture_pose", "dataset", "embedder", "batch_lie_group_helper")
 reference_root = os.environ.get("FMOV_REFERENCE_ROOT")          # where the reference's own models/dataset.py lives
 
 
@@ -31,7 +31,29 @@ def install(root=None):
     sys.modules["models"] = pkg
     for name in _SUBMODULES:
         sys.modules["models." + name] = importlib.import_module("fmov_pose_b200.models." + name)
+    # two module names of the reference have no file of their own in the mirror:
+    #  * models.barf_embedder (models/barf_embedder.py:6-75): `get_embedder` there is the mirror's get_barf_embedder — the
+    #    BARF embedder computes its coarse-to-fine weights and never applies them
+    #  * models.pixel_pose (models/pixel_pose.py:28-388): exp_runner.py:25 imports SegDeepPixelPose unconditionally, but the
+    #    per-pixel pose MLPs are only built with model.pixel_level = True (no shipped conf; out of scope, SURVEY.md §2 row
+    #    18): the names resolve to a class that fails loudly on construction
+    emb = sys.modules["models.embedder"]
+    be = types.ModuleType("models.barf_embedder")
+    be.Embedder, be.get_embedder = emb.Embedder, emb.get_barf_embedder
+    sys.modules["models.barf_embedder"] = be
+    pp = types.ModuleType("models.pixel_pose")
+    for cls_name in ("PixelPose", "DeepPixelPose", "SegDeepPixelPose"):
+        setattr(pp, cls_name, type(cls_name, (_UnsupportedPixelPose,), {"__module__": "fmov_pose_b200.models.pixel_pose"}))
+    sys.modules["models.pixel_pose"] = pp
+    pkg.barf_embedder, pkg.pixel_pose = be, pp
     return pkg
+
+
+class _UnsupportedPixelPose:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError(
+            f"{type(self).__name__} (model.pixel_level = True) is not part of the B200 train-step path: every shipped conf "
+            "uses the per-frame pose modules of models/picture_pose.py (LearnPoseGF / SegLearnPose)")
 
 
 def load_reference_module(relpath, alias):
