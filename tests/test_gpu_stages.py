@@ -135,6 +135,20 @@ def test_hierarchical_sampling_vs_oracle(n, m, steps, perturb):
         sdf = gpu_sdf((o[:, None] + dd[:, None] * z_ref[..., None]).reshape(-1, 3)).reshape(B, n)
         for i in range(steps):
             new_z = O.up_sample(o, dd, z_ref, sdf, m // steps, 64 * 2 ** i)
+            # (a0) every round IN ISOLATION: the kernel on exactly the oracle's state of this round (same z, same sdf), so
+            # that no flip of an earlier round can cascade.  The inverse CDF is discontinuous where denom < 1e-5 toggles
+            # (renderer.py:81-82): a sample can then move, but only inside its own bin
+            S_i = z_ref.shape[1]
+            zz = torch.zeros(B, S_i + m // steps)
+            zz[:, :S_i] = z_ref
+            ss = torch.zeros(B, S_i + m // steps)
+            ss[:, :S_i] = sdf
+            zz, ss = zz.to(DEV), ss.to(DEV)
+            ops.sample_round(o.to(DEV), dd.to(DEV), zz, ss, S_i, 0, True, m // steps, float(64 * 2 ** i))
+            dz = (zz[:, S_i:].cpu() - new_z).abs()
+            widest_bin = (z_ref[:, 1:] - z_ref[:, :-1]).max(dim=1, keepdim=True)[0]
+            assert bool((dz <= widest_bin + 1e-5).all()), (i, dz.max().item())
+            assert (dz > 2e-5).float().mean().item() <= 0.02, (i, (dz > 2e-5).float().mean().item(), dz.max().item())
             z_ref, sdf = O.cat_z_vals(gpu_sdf, o, dd, z_ref, new_z, sdf, last=(i + 1 == steps))
     # The reference's inverse CDF is discontinuous where a bin's pdf sits at the `denom < 1e-5` switch
     # (renderer.py:81-82): empty bins have pdf ~ 1e-5/sum, so ulp-level differences (expf, scan order) move
@@ -144,12 +158,12 @@ def test_hierarchical_sampling_vs_oracle(n, m, steps, perturb):
     # transport cost: mean |diff| tiny, max bounded by a coarse bin)
     print(f"hierarchical sampling n={n} m={m} steps={steps}: vs oracle-with-GPU-sdf mean |dz| {diff.mean().item():.2e} "
           f"max {diff.max().item():.2e}, rays with any |dz| > 1e-4: {(diff.max(dim=1)[0] > 1e-4).float().mean().item():.3f}")
-    # measured on B200 (round 2, two library builds): 64+64 / 4 rounds mean 2.2e-4 .. 4.0e-4, max 4.6e-2; 16+32 / 2 rounds
-    # 1.1e-5, 2.3e-2; 64+64 / 1 round 3.1e-6, 6.0e-3; 32+0 exactly 0.  A flipped sample moves by at most its (refined) bin
-    # and the flips cascade over the rounds (which samples flip depends on ulps, so the mean varies between builds): the
-    # bounds are a few refined bins for the max (a coarse bin at n = 16 is 0.125) and 1e-3 for the mean
+    # measured on B200 (round 2, three library builds): 64+64 / 4 rounds mean 2.2e-4 .. 4.0e-4, max 4.6e-2 .. 1.6e-1; 16+32 /
+    # 2 rounds 1.1e-5, 2.3e-2; 64+64 / 1 round 3.1e-6, 6.0e-3; 32+0 exactly 0.  Which samples flip depends on ulps, and a
+    # flip re-weights every later round (the per-round check (a0) above is the strict one; this end-to-end comparison can
+    # only bound the cascade): mean below 1e-3, max below two coarse bins of n = 16
     assert diff.mean().item() < 1e-3, diff.mean().item()
-    assert diff.max().item() < 0.1, diff.max().item()
+    assert diff.max().item() < 0.25, diff.max().item()
     # (b) against the fp32 oracle end to end: samples are positions along the ray, tolerance 2e-3
     z32 = O.sample_z(p, o, dd, near, far, n, m, steps, t_rand)
     # (a sample that flips bins in an early round re-weights the later rounds, so only the bulk statistics are
