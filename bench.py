@@ -585,11 +585,12 @@ def main():
     # per-kernel CUDA-event profile (roofline of the dominant kernel): eager launches of the same step, outside the
     # timed regions (events cannot be recorded inside a graph replay)
     L.profile_reset(True)
-    calls0 = L.n_calls
+    calls0, k0 = L.n_calls, L.kernel_launches()
     n_prof = max(3, min(args.steps, 10))
     for i in range(n_prof):
         run(i, False, eager=True)
     calls_per_step = (L.n_calls - calls0) // n_prof
+    kernels_per_step = (L.kernel_launches() - k0) // n_prof      # counted inside libfmov_b200.so at every launch site
     prof = L.profile_summary()
     L.profile_reset(False)
     barrier()
@@ -611,7 +612,11 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
     roof = None
-    launches = calls_per_step * args.steps       # C-ABI kernel-launching calls of libfmov_b200.so in the timed region
+    # kernels of libfmov_b200.so executed in the timed region: what one graph replay holds (counted by the library while the
+    # step was captured; equal to the eager count) x steps
+    if gts is not None and gts.kernels_per_step:
+        kernels_per_step = gts.kernels_per_step
+    launches = kernels_per_step * args.steps
     mlp = {k: v for k, v in prof.items() if k in KERNEL_FLOPS_PER_POINT}
     if mlp:
         top = max(mlp, key=lambda k: mlp[k]["ms"])
@@ -774,7 +779,9 @@ def main():
                            "algorithmic_flops_per_ray": flops_per_ray(n, m)},
                 "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": launches, "gpu_launches_note": f"{kernels_per_step} kernels of libfmov_b200.so per step "
+                f"(fmov_launch_count: counted inside the library at every launch site; {calls_per_step} C-ABI calls), "
+                "torch glue kernels not included", "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
                 "extras": extras,
                 "tensor_frac_whole_step": flops_per_ray(n, m) * value / world / 1e12 / peak_tf}
         emit(line)

@@ -27,10 +27,17 @@ def lib():
         _lib.fmov_sdf_fwd_blob_offset.restype = c_ll
         for name in ("fmov_fine_blob_bytes", "fmov_grad_offset", "fmov_grad_floats", "fmov_mc_chunk_count"):
             getattr(_lib, name).restype = c_ll
+        _lib.fmov_launch_count.restype = ctypes.c_ulonglong
     return _lib
 
 
-n_calls = 0      # successful C-ABI calls (each launches >= 1 kernel); bench.py reports it as gpu_launches
+n_calls = 0      # successful C-ABI calls (each launches >= 1 kernel)
+
+
+def kernel_launches():
+    """kernels of libfmov_b200.so launched by this process so far (counted inside the library at every launch site; a
+    launch recorded into a CUDA graph counts once, when it is captured) — bench.py's `gpu_launches`"""
+    return int(lib().fmov_launch_count())
 
 
 def check(status, what):

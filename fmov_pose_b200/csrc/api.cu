@@ -15,6 +15,8 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+static unsigned long long g_launches = 0;
+void note_launch() { ++g_launches; }
 int cuda_fail(cudaError_t e, const char* what) {
   set_last_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
   return ERR_CUDA;
@@ -24,6 +26,9 @@ using namespace fmov;
 
 extern "C" const char* fmov_last_error(void) { return g_err; }
 extern "C" int fmov_version(void) { return 100; }
+/* kernels of this library launched so far by this process (every launch site counts itself; launches recorded during a
+ * CUDA-graph capture are counted once, at capture) */
+extern "C" unsigned long long fmov_launch_count(void) { return fmov::g_launches; }
 
 // ----------------------------------------------------------------------------------------
 // Weight image packing: fp32 matrix -> [npad rows x 64*kblocks] fp16/bf16 no-swizzle operand image.

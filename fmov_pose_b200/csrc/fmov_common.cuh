@@ -37,6 +37,7 @@ enum Status : int {
 };
 void set_last_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void note_launch();          // one kernel of this library was launched (fmov_launch_count)
 
 #define FMOV_CUDA(call)                                        \
   do {                                                         \
@@ -54,6 +55,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                   \
     cudaError_t e__ = cudaGetLastError();                \
     if (e__ != cudaSuccess) return fmov::cuda_fail(e__, name); \
+    fmov::note_launch();                                 \
   } while (0)
 
 constexpr int TILE_M = 128;          // points per tile

@@ -461,6 +461,7 @@ class GraphedTrainStep:
         self.graphs = {}
         self.pool = None
         self.launches_per_step = 0
+        self.kernels_per_step = 0
         self._keep = []
 
     def set_cos_anneal_ratio(self, ratio):
@@ -496,11 +497,12 @@ class GraphedTrainStep:
             p.grad = None
         self._keep = [b for lst in Stash._pool.values() for b in lst]      # keep the stash buffer alive with the graph
         g = torch.cuda.CUDAGraph()
-        n0 = L.n_calls
+        n0, k0 = L.n_calls, L.kernel_launches()
         # thread_local: other threads (NCCL watchdog, autograd workers) may keep calling the CUDA runtime during capture
         with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
             ls, out = self._body(img_id, add_img_id)
-        self.launches_per_step = L.n_calls - n0
+        self.launches_per_step = L.n_calls - n0                  # C-ABI calls recorded into the graph
+        self.kernels_per_step = L.kernel_launches() - k0         # kernels of this library that one replay executes
         if self.pool is None:
             self.pool = g.pool()
         self.graphs[key] = (g, ls, out)

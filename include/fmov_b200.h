@@ -24,6 +24,8 @@ extern "C" {
 /* ---- library ------------------------------------------------------------------------- */
 const char* fmov_last_error(void);
 int fmov_version(void);
+/* number of kernels this library has launched in this process (a launch recorded into a CUDA graph counts once) */
+unsigned long long fmov_launch_count(void);
 
 /* ---- weight / tile images (host glue for the MLP kernels) ----------------------------- */
 /* fp32 matrix -> no-swizzle operand image [npad x 64*kblocks]; see api.cu. seg_* are HOST arrays.
