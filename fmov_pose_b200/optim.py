@@ -51,6 +51,7 @@ class FlatAdam:
         self.lr = torch.tensor([float(g["lr"]) for g in groups], dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(self.n_groups, dtype=torch.float32, device=dev)
         self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flag_cache = {}
         # device tables of fmov_adam_step
         ct, ce = [], []
         for i, n in enumerate(numels):
@@ -88,6 +89,22 @@ class FlatAdam:
         self.step_count.copy_(sd["step"])
         self.lr.copy_(sd["lr"])
 
+    def flags_for(self, active):
+        """device flag vector [n_groups] of an active set (only needed beyond 64 groups, where the launch-constant bit mask
+        does not reach).  Cached per set; creating one is a host-to-device copy, so a CUDA-graph capture must find it in
+        the cache (GraphedTrainStep calls this before capturing)."""
+        key = tuple(sorted(int(g) for g in active))
+        f = self._flag_cache.get(key)
+        if f is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("FlatAdam: the flag vector of this active set must exist before the capture "
+                                   "(call optimizer.flags_for(active_groups) first)")
+            host = torch.zeros(self.n_groups, dtype=torch.float32)
+            host[list(key)] = 1.0
+            f = host.to(self.device)
+            self._flag_cache[key] = f
+        return f
+
     # ---- the step ----------------------------------------------------------------------------------------------
     def gather(self, active_groups=None):
         """gradients of this rank's active groups -> G (zeroed first), flags of those groups set.  `active_groups`:
@@ -98,10 +115,13 @@ class FlatAdam:
         else:
             active = sorted(set(int(g) for g in active_groups))
             have = [(i, g) for i, g in have if self.group_of[i] in active]
-        assert all(0 <= g < min(self.n_groups, 64) for g in active) or not active
-        mask = 0
-        for g in active:
-            mask |= 1 << g
+        assert all(0 <= g < self.n_groups for g in active)
+        mask, flags = 0, None
+        if self.n_groups <= 64:
+            for g in active:
+                mask |= 1 << g
+        else:       # long sequences (one pose MLP per frame): the flags come from a cached device vector per active set
+            flags = self.flags_for(active)
         self.G.zero_()
         lib = L.lib()
         for s in range(0, max(len(have), 1), 160):
@@ -111,7 +131,7 @@ class FlatAdam:
             src = (ctypes.c_void_p * max(n, 1))(*[g.data_ptr() for g in grads])
             off = (ctypes.c_longlong * max(n, 1))(*[self.offs[i] for i, _ in part])
             num = (ctypes.c_int * max(n, 1))(*[self.numels[i] for i, _ in part])
-            L.check(lib.fmov_grad_gather(n, src, off, num, self.n_groups, ctypes.c_ulonglong(mask), L.c_void_p(0),
+            L.check(lib.fmov_grad_gather(n, src, off, num, self.n_groups, ctypes.c_ulonglong(mask), L.ptr(flags),
                                          L.ptr(self.G), L.c_ll(self.n_total), L.stream()), "fmov_grad_gather")
         return active
 

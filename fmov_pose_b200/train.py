@@ -496,6 +496,8 @@ class GraphedTrainStep:
         for p in ts.all_params:
             p.grad = None
         self._keep = [b for lst in Stash._pool.values() for b in lst]      # keep the stash buffer alive with the graph
+        if ts.own_optimizer and ts.optimizer.n_groups > 64:      # the active set's flag vector must pre-exist (H2D copy)
+            ts.optimizer.flags_for(ts.active_groups(img_id, add_img_id))
         g = torch.cuda.CUDAGraph()
         n0, k0 = L.n_calls, L.kernel_launches()
         # thread_local: other threads (NCCL watchdog, autograd workers) may keep calling the CUDA runtime during capture

@@ -90,3 +90,24 @@ def test_flat_adam_default_active_set_and_cuda_graph_replay():
         for a, b in zip(mine[gi], ref[gi]):
             np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
     assert [float(s) for s in opt.step_count] == [5.0, 5.0, 0.0]
+
+
+def test_flat_adam_beyond_64_groups():
+    """long sequences: one pose MLP per frame -> more parameter groups than the launch-constant bit mask holds"""
+    from fmov_pose_b200.optim import FlatAdam
+    g = torch.Generator().manual_seed(1)
+    groups = [[torch.randn(7, 5, generator=g).to(DEV).requires_grad_(True)] for _ in range(70)]
+    ref = [[p.detach().clone().requires_grad_(True) for p in ps] for ps in groups]
+    opt = FlatAdam([dict(params=ps, lr=1e-3) for ps in groups])
+    topt = [torch.optim.Adam(ps, lr=1e-3) for ps in ref]
+    for it, active in enumerate(([0, 3, 69], [0, 65], [0, 3, 69])):
+        for gi in active:
+            gr = torch.randn(7, 5, generator=g).to(DEV)
+            groups[gi][0].grad, ref[gi][0].grad = gr.clone(), gr.clone()
+        opt.step(active)
+        for gi in active:
+            topt[gi].step()
+    for gi in range(70):
+        np.testing.assert_allclose(groups[gi][0].detach().cpu().numpy(), ref[gi][0].detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
+    st = [float(v) for v in opt.step_count]
+    assert st[0] == 3.0 and st[3] == 2.0 and st[69] == 2.0 and st[65] == 1.0 and sum(st) == 8.0
