@@ -176,6 +176,10 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
 }
 
 // ---- warp 1 -----------------------------------------------------------------------------
+// SPLIT = false: the plain chains (no step flags are looked at: the single issuing thread's loop is on the critical path of
+// the MMA-bound value chain — the flag tests cost the query kernel 10 % when they were unconditional); SPLIT = true: the
+// split-precision chain (CHF_* flags honoured).
+template <bool SPLIT = false>
 __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
                                                  uint8_t* wst, uint32_t tmem, int n_my_tiles) {
   uint32_t it = 0;
@@ -189,10 +193,11 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
       const uint32_t idesc = umma_idesc(128, st.n, st.a_fmt, st.b_fmt, 0, 0);
       const int nkb = st.nkb_a + st.nkb_aux;
       for (int slot = 0; slot < nslot; ++slot) {
-        const int aslot = slot ^ (st.flags & CHF_A_OTHER);
+        const uint8_t fl = SPLIT ? st.flags : (uint8_t)0;
+        const int aslot = slot ^ (fl & CHF_A_OTHER);
         uint8_t* act = act0 + aslot * 4 * BLK_BYTES;
         uint8_t* aux = aux0 + aslot * BLK_BYTES;
-        const uint32_t accum = (st.flags & CHF_ACCUM) ? 1u : 0u;
+        const uint32_t accum = (fl & CHF_ACCUM) ? 1u : 0u;
         if (!accum) {
           FMOV_TR(1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
           mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
@@ -216,14 +221,14 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
               umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
                        umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
                        ((kb | ks) != 0 ? 1u : 0u) | accum);
-              if (st.flags & CHF_DUAL_A)
+              if (SPLIT && (fl & CHF_DUAL_A))
                 umma_f16(tmem + slot * 256, umma_desc_kmajor(a_base2 + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
                          umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc, 1u);
             }
             umma_commit(&s->w_empty[stage]);   // slot reusable once these MMAs have read it
           }
         }
-        if (!(st.flags & CHF_NO_COMMIT)) umma_commit(&s->acc_ready[slot]);
+        if (!(fl & CHF_NO_COMMIT)) umma_commit(&s->acc_ready[slot]);
         FMOV_TR(3, slot, nstep[slot] - 1);        // all MMAs of the step issued
       }
     }

@@ -177,7 +177,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
     if (warp == PRODUCER_WARP) {
       if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
     } else if (warp == ISSUER_WARP) {
-      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+      if (lane == 0) chain_mma_issuer<PRECISE>(tb, s, act0, aux0, wst, tmem, n_my);
     }
   } else if (PRECISE) {
     // Split-precision chain: ONE tile in flight.  Slot 1's ACT / AUX hold the fp16 residuals of slot 0's operands, and all
