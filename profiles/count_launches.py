@@ -15,7 +15,8 @@ dev = torch.device("cuda:0")
 for name, kw, B, two in (("literal 2x512 rays 32+0", dict(n_samples=32, n_importance=0), 512, True),
                          ("8192 rays 64+64", dict(n_samples=64, n_importance=64), 8192, False)):
     sc = synthetic.build_scene(device=dev, pose_type="seg", **kw)
-    ts = TrainStep(sc, mask_weight=5.0, fused_loss="--fused_loss" in sys.argv, fused_rays="--fused_rays" in sys.argv)
+    ts = TrainStep(sc, mask_weight=5.0, fused_loss="--torch_loss" not in sys.argv,
+                   fused_rays=None if "--torch_rays" not in sys.argv else False)
     g = torch.Generator().manual_seed(0)
     px = torch.randint(140, 500, [2 * B], generator=g).to(dev)
     py = torch.randint(60, 420, [2 * B], generator=g).to(dev)
