@@ -8,7 +8,7 @@
 //   (host: exclusive prefix sum over the chunks — torch.cumsum; the totals size the outputs)
 //   fmov_mc_vertices   vertex positions (index or world coordinates) + the vertex id of every crossed edge (vid3)
 //   fmov_mc_triangles  case lookup, three vid3 reads per triangle corner
-//   (both skip chunks whose prefix-sum entry shows nothing to emit: chunk_voff / chunk_toff have n_chunks + 1 entries)
+//   (both walk the list of non-empty chunks that fmov_mc_count appended to: ~2 % of the chunks at 512^3)
 // Output order is deterministic: vertices by (grid point x-major, axis), triangles by (cell x-major, table order).
 // Corner / edge numbering and the case table: fmov_pose_b200/mc_tables.py (uploaded once with fmov_mc_set_tables).
 #include "fmov_common.cuh"
@@ -50,128 +50,53 @@ __device__ __forceinline__ int mc_block_exscan(int v, int* total) {
 // and <= 5 * 256 per chunk).
 __device__ __forceinline__ int mc_pack(int nv, int nt) { return nv | (nt << 16); }
 
-// mc_point(g, p, true) for a warp of 32 consecutive points: every lane loads the four (x, y) corner rows at its own z and
-// takes the z + 1 values from lane + 1 by shuffle (lane 31 loads them), i.e. 4 instead of 8 loads per point.  Same values,
-// same marks, same case index as mc_core.cuh's mc_point (which the host emulation checks against the oracle).
-__device__ __forceinline__ McPoint mc_point_warp(const McGrid& g, long long p) {
-  McPoint q;
-  q.valid = p < g.n;
-  q.i = q.j = q.k = 0;
-  q.f0 = 0.f; q.b0 = false; q.ntri = 0; q.cubecase = 0;
-  q.cross[0] = q.cross[1] = q.cross[2] = false;
-  q.f1[0] = q.f1[1] = q.f1[2] = 0.f;
-  const int lane = threadIdx.x & 31;
-  const int YZ = g.Y * g.Z;
-  bool hx = false, hy = false, hz = false;
-  float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;          // u at (i,j,k) (i,j+1,k) (i+1,j,k) (i+1,j+1,k)
-  if (q.valid) {
-    const unsigned int pu = (unsigned int)p;
-    q.i = (int)(pu / (unsigned int)YZ);
-    const int r = (int)(pu - (unsigned int)q.i * (unsigned int)YZ);
-    q.j = r / g.Z;
-    q.k = r - q.j * g.Z;
-    hx = q.i + 1 < g.X; hy = q.j + 1 < g.Y; hz = q.k + 1 < g.Z;
-    a00 = g.u[p];
-    if (hy) a01 = g.u[p + g.Z];
-    if (hx) a10 = g.u[p + YZ];
-    if (hx && hy) a11 = g.u[p + YZ + g.Z];
-  }
-  // z + 1 neighbours: lane + 1 holds point p + 1 = (i, j, k + 1) whenever hz (same row); lane 31 loads its own
-  float b00 = __shfl_down_sync(0xffffffffu, a00, 1), b01 = __shfl_down_sync(0xffffffffu, a01, 1);
-  float b10 = __shfl_down_sync(0xffffffffu, a10, 1), b11 = __shfl_down_sync(0xffffffffu, a11, 1);
-  if (lane == 31 && q.valid && hz) {
-    b00 = g.u[p + 1];
-    if (hy) b01 = g.u[p + g.Z + 1];
-    if (hx) b10 = g.u[p + YZ + 1];
-    if (hx && hy) b11 = g.u[p + YZ + g.Z + 1];
-  }
-  if (!q.valid) return q;
-  q.f0 = a00;
-  q.b0 = a00 < g.iso;
-  if (hx) { q.f1[0] = a10; q.cross[0] = (a10 < g.iso) != q.b0; }
-  if (hy) { q.f1[1] = a01; q.cross[1] = (a01 < g.iso) != q.b0; }
-  if (hz) { q.f1[2] = b00; q.cross[2] = (b00 < g.iso) != q.b0; }
-  if (hx && hy && hz) {
-    // corners v0..v7 (mc_tables.py): (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
-    int c = q.b0 ? 1 : 0;
-    c |= (a10 < g.iso) ? 2 : 0;
-    c |= (a11 < g.iso) ? 4 : 0;
-    c |= (a01 < g.iso) ? 8 : 0;
-    c |= (b00 < g.iso) ? 16 : 0;
-    c |= (b10 < g.iso) ? 32 : 0;
-    c |= (b11 < g.iso) ? 64 : 0;
-    c |= (b01 < g.iso) ? 128 : 0;
-    q.cubecase = c;
-    q.ntri = (c == 0 || c == 255) ? 0 : g.ntri[c];
-  }
-  return q;
-}
-
 __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int* __restrict__ chunk_nv,
-                                                            int* __restrict__ chunk_nt) {
+                                                            int* __restrict__ chunk_nt, int* __restrict__ list,
+                                                            int* __restrict__ n_list) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
-    const McPoint q = mc_point_warp(g, ch * MC_CHUNK + threadIdx.x);
+    const McPoint q = mc_point(g, ch * MC_CHUNK + threadIdx.x, true);
     const int v = mc_pack(mc_vertex_count(q), q.ntri);
     int tot = 0;
     if (__syncthreads_or(v)) mc_block_exscan(v, &tot);
     if (threadIdx.x == 0) {
       chunk_nv[ch] = tot & 0xFFFF;
       chunk_nt[ch] = tot >> 16;
+      // the emit passes walk this list (about 2 % of the chunks at 512^3) instead of testing every chunk; its order is
+      // whatever the atomics give, the OUTPUT positions come from the prefix sums and do not depend on it
+      if (tot != 0) list[atomicAdd(n_list, 1)] = (int)ch;
     }
   }
 }
 
-// The emit passes only touch chunks that emit something (about 2 % of them at 512^3): a block looks at MC_CHUNK chunk
-// offsets at a time (one coalesced load per thread), compacts the non-empty ones into a shared list and walks that.
-__device__ __forceinline__ int mc_nonempty_list(const long long* __restrict__ off, long long n_chunks, long long batch,
-                                                int* list) {
-  __shared__ int n_list;
-  const long long ch = batch * MC_CHUNK + threadIdx.x;
-  const bool ne = ch < n_chunks && off[ch + 1] != off[ch];
-  if (threadIdx.x == 0) n_list = 0;
-  __syncthreads();
-  if (ne) list[atomicAdd(&n_list, 1)] = threadIdx.x;
-  __syncthreads();
-  const int n = n_list;
-  __syncthreads();          // n_list is reset by the next call
-  return n;
-}
-
 __global__ void __launch_bounds__(MC_CHUNK) mc_vertices_kernel(const McGrid g, const long long* __restrict__ chunk_voff,
+                                                               const int* __restrict__ list, const int* __restrict__ n_list,
                                                                const McXform xf, float* __restrict__ verts,
                                                                int* __restrict__ vid3) {
-  __shared__ int list[MC_CHUNK];
-  const long long n_batches = (g.n_chunks + MC_CHUNK - 1) / MC_CHUNK;
-  for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-    const int n = mc_nonempty_list(chunk_voff, g.n_chunks, batch, list);
-    for (int k = 0; k < n; ++k) {
-      const long long ch = batch * MC_CHUNK + list[k];
-      const long long p = ch * MC_CHUNK + threadIdx.x;
-      const McPoint q = mc_point(g, p, false);
-      const int nv = mc_vertex_count(q);
-      int tv;
-      const int local = mc_block_exscan(nv, &tv);
-      if (nv) mc_emit_vertices(g, xf, p, q, chunk_voff[ch] + local, verts, vid3);
-    }
-    __syncthreads();          // `list` is rewritten by the next batch
+  const int n = *n_list;
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    const long long ch = list[li];
+    if (chunk_voff[ch + 1] == chunk_voff[ch]) continue;          // triangles only (block-uniform)
+    const long long p = ch * MC_CHUNK + threadIdx.x;
+    const McPoint q = mc_point(g, p, false);
+    const int nv = mc_vertex_count(q);
+    int tv;
+    const int local = mc_block_exscan(nv, &tv);
+    if (nv) mc_emit_vertices(g, xf, p, q, chunk_voff[ch] + local, verts, vid3);
   }
 }
 
 __global__ void __launch_bounds__(MC_CHUNK) mc_triangles_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
+                                                                const int* __restrict__ list, const int* __restrict__ n_list,
                                                                 const int* __restrict__ vid3, int* __restrict__ tris) {
-  __shared__ int list[MC_CHUNK];
-  const long long n_batches = (g.n_chunks + MC_CHUNK - 1) / MC_CHUNK;
-  for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
-    const int n = mc_nonempty_list(chunk_toff, g.n_chunks, batch, list);
-    for (int k = 0; k < n; ++k) {
-      const long long ch = batch * MC_CHUNK + list[k];
-      const long long p = ch * MC_CHUNK + threadIdx.x;
-      const McPoint q = mc_point_warp(g, p);
-      int tt;
-      const int local = mc_block_exscan(q.ntri, &tt);
-      if (q.ntri) mc_emit_triangles(g, p, q, chunk_toff[ch] + local, vid3, tris);
-    }
-    __syncthreads();
+  const int n = *n_list;
+  for (int li = blockIdx.x; li < n; li += gridDim.x) {
+    const long long ch = list[li];
+    if (chunk_toff[ch + 1] == chunk_toff[ch]) continue;          // vertices only (block-uniform)
+    const long long p = ch * MC_CHUNK + threadIdx.x;
+    const McPoint q = mc_point(g, p, true);
+    int tt;
+    const int local = mc_block_exscan(q.ntri, &tt);
+    if (q.ntri) mc_emit_triangles(g, p, q, chunk_toff[ch] + local, vid3, tris);
   }
 }
 
@@ -181,6 +106,7 @@ static int mc_grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
   g.u = u; g.X = X; g.Y = Y; g.Z = Z; g.iso = iso;
   g.n = (long long)X * Y * Z;
   g.n_chunks = (g.n + MC_CHUNK - 1) / MC_CHUNK;
+  mc_set_shifts(g);
   FMOV_REQUIRE(g.n < (1LL << 31), "marching cubes: grid too large (vertex ids are 32-bit)");
   void *pt = nullptr, *pn = nullptr;
   FMOV_CUDA(cudaGetSymbolAddress(&pt, d_mc_tri));
@@ -218,36 +144,39 @@ extern "C" long long fmov_mc_chunk_count(int X, int Y, int Z) {
   return ((long long)X * Y * Z + MC_CHUNK - 1) / MC_CHUNK;
 }
 
-extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, void* stream) {
+extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list,
+                             int* n_list, void* stream) {
   McGrid g;
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
-  FMOV_REQUIRE(chunk_nv && chunk_nt, "fmov_mc_count: null output");
-  mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt);
+  FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list, "fmov_mc_count: null output");
+  FMOV_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int), (cudaStream_t)stream));
+  mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
   FMOV_LAUNCH_CHECK("mc_count_kernel");
   return OK;
 }
 
-extern "C" int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, float sx,
-                                float sy, float sz, float ox, float oy, float oz, float* verts, int* vid3, void* stream) {
+extern "C" int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, const int* list,
+                                const int* n_list, float sx, float sy, float sz, float ox, float oy, float oz, float* verts,
+                                int* vid3, void* stream) {
   McGrid g;
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
-  FMOV_REQUIRE(chunk_voff && verts && vid3, "fmov_mc_vertices: null argument");
+  FMOV_REQUIRE(chunk_voff && list && n_list && verts && vid3, "fmov_mc_vertices: null argument");
   McXform xf;
   xf.s[0] = sx; xf.s[1] = sy; xf.s[2] = sz; xf.o[0] = ox; xf.o[1] = oy; xf.o[2] = oz;
-  mc_vertices_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, xf, verts, vid3);
+  mc_vertices_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
   FMOV_LAUNCH_CHECK("mc_vertices_kernel");
   return OK;
 }
 
-extern "C" int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff,
-                                 const int* vid3, int* tris, void* stream) {
+extern "C" int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* list,
+                                 const int* n_list, const int* vid3, int* tris, void* stream) {
   McGrid g;
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
-  FMOV_REQUIRE(chunk_toff && vid3 && tris, "fmov_mc_triangles: null argument");
-  mc_triangles_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, vid3, tris);
+  FMOV_REQUIRE(chunk_toff && list && n_list && vid3 && tris, "fmov_mc_triangles: null argument");
+  mc_triangles_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
   FMOV_LAUNCH_CHECK("mc_triangles_kernel");
   return OK;
 }

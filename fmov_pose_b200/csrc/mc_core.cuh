@@ -23,7 +23,17 @@ struct McGrid {
   long long n_chunks;
   const signed char* tri;        // [256][3*MC_MAX_TRIS] case table (device memory in the kernels)
   const unsigned char* ntri;     // [256]
+  int sh_z, sh_yz;               // log2(Z), log2(Y*Z) when those are powers of two, else -1 (mc_set_shifts)
 };
+MC_HD int mc_log2_or_neg(long long v) {
+  int s = 0;
+  while ((1LL << s) < v) ++s;
+  return ((1LL << s) == v) ? s : -1;
+}
+MC_HD void mc_set_shifts(McGrid& g) {
+  g.sh_z = mc_log2_or_neg(g.Z);
+  g.sh_yz = mc_log2_or_neg((long long)g.Y * g.Z);
+}
 struct McXform { float s[3], o[3]; };     // output coordinate = index * s + o
 
 struct McPoint {
@@ -50,10 +60,16 @@ MC_HD McPoint mc_point(const McGrid& g, long long p, bool want_case) {
   // instructions, and these kernels are issue-bound, not bandwidth-bound — ncu: 68 % issue-active at 0.7 TB/s)
   const int YZ = g.Y * g.Z;
   const unsigned int pu = (unsigned int)p;
-  q.i = (int)(pu / (unsigned int)YZ);
-  const int r = (int)(pu - (unsigned int)q.i * (unsigned int)YZ);
-  q.j = r / g.Z;
-  q.k = r - q.j * g.Z;
+  if (g.sh_z >= 0 && g.sh_yz >= 0) {          // power-of-two Z and Y*Z (the 512^3 validate_mesh grid): shifts and masks
+    q.k = (int)(pu & (unsigned int)(g.Z - 1));
+    q.j = (int)((pu & (unsigned int)(YZ - 1)) >> g.sh_z);
+    q.i = (int)(pu >> g.sh_yz);
+  } else {
+    q.i = (int)(pu / (unsigned int)YZ);
+    const int r = (int)(pu - (unsigned int)q.i * (unsigned int)YZ);
+    q.j = r / g.Z;
+    q.k = r - q.j * g.Z;
+  }
   const bool hx = q.i + 1 < g.X, hy = q.j + 1 < g.Y, hz = q.k + 1 < g.Z;
   q.f0 = g.u[p];
   q.b0 = q.f0 < g.iso;

@@ -35,8 +35,10 @@ def marching_cubes(u, isovalue=0.0, scale=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0
     _ensure_tables(dev)
     nch = int(lib.fmov_mc_chunk_count(X, Y, Z))
     counts = torch.empty(2, nch, dtype=torch.int32, device=dev)
-    L.check(lib.fmov_mc_count(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(counts[0]), L.ptr(counts[1]), L.stream()),
-            "fmov_mc_count")
+    work = torch.empty(nch + 1, dtype=torch.int32, device=dev)          # [n_list | list of non-empty chunks]
+    n_list, lst = work[:1], work[1:]
+    L.check(lib.fmov_mc_count(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(counts[0]), L.ptr(counts[1]), L.ptr(lst),
+                              L.ptr(n_list), L.stream()), "fmov_mc_count")
     # exclusive prefix sums with the totals appended ([2, n_chunks + 1]): chunk c emits [off[c], off[c + 1]), and the emit
     # kernels skip chunks whose range is empty
     excl = torch.zeros(2, nch + 1, dtype=torch.int64, device=dev)
@@ -48,12 +50,13 @@ def marching_cubes(u, isovalue=0.0, scale=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0
         return verts, tris
     vid3 = torch.empty(X * Y * Z * 3, dtype=torch.int32, device=dev)          # written only where an edge is crossed
     s, o = [float(v) for v in scale], [float(v) for v in offset]
-    L.check(lib.fmov_mc_vertices(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(excl[0]), L.c_float(s[0]), L.c_float(s[1]),
+    L.check(lib.fmov_mc_vertices(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(excl[0]), L.ptr(lst), L.ptr(n_list),
+                                 L.c_float(s[0]), L.c_float(s[1]),
                                  L.c_float(s[2]), L.c_float(o[0]), L.c_float(o[1]), L.c_float(o[2]), L.ptr(verts),
                                  L.ptr(vid3), L.stream()), "fmov_mc_vertices")
     if n_t:
-        L.check(lib.fmov_mc_triangles(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(excl[1]), L.ptr(vid3), L.ptr(tris),
-                                      L.stream()), "fmov_mc_triangles")
+        L.check(lib.fmov_mc_triangles(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(excl[1]), L.ptr(lst), L.ptr(n_list),
+                                      L.ptr(vid3), L.ptr(tris), L.stream()), "fmov_mc_triangles")
     return verts, tris
 
 

@@ -240,11 +240,15 @@ int fmov_adam_step(float* const* param, const long long* off, const int* numel, 
  *   5. fmov_mc_triangles: tris [T,3] int32 vertex ids                                                                    */
 int fmov_mc_set_tables(const signed char* tri_table, const unsigned char* n_tris);
 long long fmov_mc_chunk_count(int X, int Y, int Z);
-int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, void* stream);
-int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, float sx, float sy,
-                     float sz, float ox, float oy, float oz, float* verts, int* vid3, void* stream);
-int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* vid3,
-                      int* tris, void* stream);
+/* list [n_chunks] int32 + n_list [1] int32 (device): fmov_mc_count appends the index of every chunk that emits something
+ * (n_list is zeroed by the call); the emit passes walk that list */
+int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
+                  void* stream);
+int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, const int* list,
+                     const int* n_list, float sx, float sy, float sz, float ox, float oy, float oz, float* verts, int* vid3,
+                     void* stream);
+int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* list,
+                      const int* n_list, const int* vid3, int* tris, void* stream);
 
 #ifdef __cplusplus
 }

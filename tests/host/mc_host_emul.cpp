@@ -30,6 +30,7 @@ int main(int argc, char** argv) {
   g.X = atoi(argv[1]); g.Y = atoi(argv[2]); g.Z = atoi(argv[3]); g.iso = (float)atof(argv[4]);
   g.n = (long long)g.X * g.Y * g.Z;
   g.n_chunks = (g.n + MC_CHUNK - 1) / MC_CHUNK;
+  mc_set_shifts(g);
   std::vector<float> u = slurp<float>(argv[5], (size_t)g.n);
   std::vector<signed char> tab = slurp<signed char>(argv[6], 256 * 15 + 256);
   g.u = u.data();

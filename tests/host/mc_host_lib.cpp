@@ -17,6 +17,7 @@ static bool grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
   g.u = u; g.X = X; g.Y = Y; g.Z = Z; g.iso = iso;
   g.n = (long long)X * Y * Z;
   g.n_chunks = (g.n + MC_CHUNK - 1) / MC_CHUNK;
+  mc_set_shifts(g);
   g.tri = g_tri; g.ntri = g_ntri;
   return true;
 }
@@ -30,10 +31,14 @@ int fmov_mc_set_tables(const signed char* tri, const unsigned char* ntri) {
   return 0;
 }
 long long fmov_mc_chunk_count(int X, int Y, int Z) { return ((long long)X * Y * Z + MC_CHUNK - 1) / MC_CHUNK; }
-int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, void*) {
+int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
+                  void*) {
   McGrid g;
-  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt) return -1;
-  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt || !list || !n_list) return -1;
+  *n_list = 0;
+  // the device appends in whatever order its atomics give: walk the chunks backwards here so that the glue and the emit
+  // passes are exercised with a list that is NOT in chunk order
+  for (long long ch = g.n_chunks - 1; ch >= 0; --ch) {
     int nv = 0, nt = 0;
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const McPoint q = mc_point(g, ch * MC_CHUNK + tid, true);
@@ -42,16 +47,19 @@ int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv,
     }
     chunk_nv[ch] = nv;
     chunk_nt[ch] = nt;
+    if (nv | nt) list[(*n_list)++] = (int)ch;
   }
   return 0;
 }
-int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, float sx, float sy, float sz,
-                     float ox, float oy, float oz, float* verts, int* vid3, void*) {
+int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, const int* list,
+                     const int* n_list, float sx, float sy, float sz, float ox, float oy, float oz, float* verts, int* vid3,
+                     void*) {
   McGrid g;
-  if (!grid(g, u, X, Y, Z, iso) || !chunk_voff || !verts || !vid3) return -1;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_voff || !list || !n_list || !verts || !vid3) return -1;
   McXform xf;
   xf.s[0] = sx; xf.s[1] = sy; xf.s[2] = sz; xf.o[0] = ox; xf.o[1] = oy; xf.o[2] = oz;
-  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+  for (int li = 0; li < *n_list; ++li) {
+    const long long ch = list[li];
     int local = 0;
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
@@ -63,11 +71,12 @@ int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long 
   }
   return 0;
 }
-int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* vid3, int* tris,
-                      void*) {
+int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long long* chunk_toff, const int* list,
+                      const int* n_list, const int* vid3, int* tris, void*) {
   McGrid g;
-  if (!grid(g, u, X, Y, Z, iso) || !chunk_toff || !vid3 || !tris) return -1;
-  for (long long ch = 0; ch < g.n_chunks; ++ch) {
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_toff || !list || !n_list || !vid3 || !tris) return -1;
+  for (int li = 0; li < *n_list; ++li) {
+    const long long ch = list[li];
     int local = 0;
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
