@@ -51,6 +51,14 @@ constexpr int EPI_THREADS = CH_WGS * 128;          // threads arriving per slot
 constexpr int CH_WSPLIT = FMOV_CH_WSPLIT;          // ring slots per 64-wide k-block: 1, 2 or 4
 constexpr int WSLOT_BYTES = 256 * 128 / CH_WSPLIT; // [256 rows x 64/CH_WSPLIT] 16-bit
 constexpr int CH_WSTAGES = 2 * CH_WSPLIT;
+// FMOV_SHARE_W = 1: the two tile slots of a CTA run every GEMM step in lockstep on ONE stream of weight slices (each slice
+// multiplies slot 0's and slot 1's A operand before it is released): half the L2 -> shared-memory weight traffic per tile.
+// The weight ring is latency bound (64 KiB per ~2.2 K-cycle round trip = 29 B/clk per SM, profiles/micro/l2_stream*.cu show
+// the SM itself can take 60-90 B/clk), so one step's 128 KiB take ~4.5 K cycles whether they feed one tile or two.
+#ifndef FMOV_SHARE_W
+#define FMOV_SHARE_W 0
+#endif
+constexpr bool CH_SHARE_W = FMOV_SHARE_W != 0;
 constexpr int MAX_STEPS = 40;
 constexpr int MAX_STASH = 56;
 
@@ -164,7 +172,8 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
       const uint8_t* __restrict__ wblob = (st.flags & CHF_W2) ? ptrs.weights2 : ptrs.weights;
       const uint32_t bytes = (uint32_t)st.n * (128u / CH_WSPLIT);
       const int nsl = (st.nkb_a + st.nkb_aux) * CH_WSPLIT;      // consecutive slices of this step's weight image
-      for (int slot = 0; slot < nslot; ++slot)
+      const int npass = (CH_SHARE_W && SL == CH_SLOTS) ? 1 : nslot;      // shared stream: one pass feeds both slots
+      for (int slot = 0; slot < npass; ++slot)
         for (int sl = 0; sl < nsl; ++sl, ++it) {
           const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
           mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
@@ -179,9 +188,64 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
 // SPLIT = false: the plain chains (no step flags are looked at: the single issuing thread's loop is on the critical path of
 // the MMA-bound value chain — the flag tests cost the query kernel 10 % when they were unconditional); SPLIT = true: the
 // split-precision chain (CHF_* flags honoured).
+// Shared weight stream (FMOV_SHARE_W): per step wait for BOTH slots' operands, then every weight slice multiplies slot 0's
+// and slot 1's A operand before its ring stage is released; both accumulators are committed at the end of the step.
+__device__ __forceinline__ void chain_mma_issuer_shared(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
+                                                        uint8_t* wst, uint32_t tmem, int n_my_tiles) {
+  uint32_t it = 0;
+  uint32_t nstep[CH_SLOTS] = {0, 0};
+  for (int k0 = 0; k0 < n_my_tiles; k0 += CH_SLOTS) {
+    const int nslot = (n_my_tiles - k0 < CH_SLOTS) ? (n_my_tiles - k0) : CH_SLOTS;
+    for (int si = 0; si < tb.n_steps; ++si) {
+      const ChainStep st = tb.step[si];
+      if (st.no_mma) continue;
+      const uint32_t idesc = umma_idesc(128, st.n, st.a_fmt, st.b_fmt, 0, 0);
+      const int nkb = st.nkb_a + st.nkb_aux;
+      for (int slot = 0; slot < nslot; ++slot) {
+        FMOV_TR(1, slot, nstep[slot]);
+        mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
+        FMOV_TR(2, slot, nstep[slot]);
+        ++nstep[slot];
+      }
+      tc_fence_after();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const uint32_t a_off = kb < st.nkb_a ? (uint32_t)(kb * BLK_BYTES) : 0u;
+        const uint32_t a_base0 = smem_u32(kb < st.nkb_a ? act0 + a_off : aux0 + (kb - st.nkb_a) * BLK_BYTES);
+        const uint32_t a_step = kb < st.nkb_a ? 4u * BLK_BYTES : (uint32_t)BLK_BYTES;      // slot 1's operand
+#pragma unroll
+        for (int part = 0; part < CH_WSPLIT; ++part, ++it) {
+          const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
+          mbar_wait_poll(&s->w_full[stage], n & 1);
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
+          for (int slot = 0; slot < nslot; ++slot) {
+#pragma unroll
+            for (int kk = 0; kk < 4 / CH_WSPLIT; ++kk) {
+              const int ks = part * (4 / CH_WSPLIT) + kk;
+              umma_f16(tmem + slot * 256,
+                       umma_desc_kmajor(a_base0 + slot * a_step + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                       umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
+                       (kb | ks) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&s->w_empty[stage]);
+        }
+      }
+      for (int slot = 0; slot < nslot; ++slot) {
+        umma_commit(&s->acc_ready[slot]);
+        FMOV_TR(3, slot, nstep[slot] - 1);
+      }
+    }
+  }
+}
+
 template <bool SPLIT = false>
 __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
                                                  uint8_t* wst, uint32_t tmem, int n_my_tiles) {
+  if (CH_SHARE_W && !SPLIT && tb.slots <= 0) {
+    chain_mma_issuer_shared(tb, s, act0, aux0, wst, tmem, n_my_tiles);
+    return;
+  }
   uint32_t it = 0;
   uint32_t nstep[CH_SLOTS] = {0, 0};
   const int SL = tb.slots > 0 ? tb.slots : CH_SLOTS;
@@ -343,6 +407,13 @@ __device__ __forceinline__ void tile_prefetch_l2(const uint8_t* tilep, int ck_fi
       prefetch_l2(p + TI_CHUNK_STRIDE);
     }
   }
+}
+
+// read-only 16-byte load that the compiler may not move (software-pipelined bias fetch)
+__device__ __forceinline__ float4 ldg_f4_volatile(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
 
 // ---- L2 eviction-priority hints: a kernel that reads a stash tensor twice marks the first

@@ -124,10 +124,10 @@ struct FineArgs {
   const float* bc4;        // [3]
   const float* wc4;        // [3][256]  colour lin4 (effective), fp32 (backward only)
   // per-sample fp32 tensors
-  float* sdf; float* nrm; float* rgb; float* ge;              // fwd outputs: [P],[P,3],[P,3],[P,40]
+  float* sdf; float* nrm; float* rgb; float* ge;              // fwd outputs: [P],[P,3],[P,3], g_e scratch (row40)
   const float* d_sdf; const float* d_nrm; const float* d_rgb; // bwd inputs
   float* d_pts; float* d_dirs; float* zc4;                    // bwd outputs: [P,3],[P,3],[P,4]
-  float* eb;                                                  // bwd scratch [P,40]
+  float* eb;                                                  // bwd scratch (row40)
   const float* amax;                                          // bwd: device scalar, max |upstream gradient|
 };
 
@@ -136,6 +136,11 @@ __device__ __forceinline__ uint8_t* stash_tile(const ChainPtrs& ptrs, int id, lo
 }
 
 struct PointCtx { bool valid; long long p; float x[3]; float d[3]; };
+// per-sample scratch rows of 40 floats (g_e of the forward, e-bar of the backward) live tile-major and column-major inside a
+// tile, [tile][40][128]: entry i of row r of tile t is at (t*40 + i)*128 + r, so the 32 lanes of a warp (consecutive rows)
+// touch 128 contiguous bytes per access instead of 32 sectors (the row-major [P,40] layout cost fine_fwd's normal step
+// 27 K cycles per tile).  The buffers hold 40*128*ceil(P/128) floats and are opaque to the caller.
+__device__ __forceinline__ long long row40(long long tile, int row, int i) { return (tile * 40 + i) * TILE_M + row; }
 __device__ __forceinline__ PointCtx load_sample(const FineArgs& a, long long tile, int row) {
   PointCtx c;
   c.p = tile * TILE_M + row;
@@ -291,6 +296,11 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         const int n_valid = (l == 3) ? 217 : 256;
         const int n_mma = (l == 3) ? 224 : 256;
         const float* bias = a.bias_sdf + l * 256;
+        // the chunk's 16 biases are fetched one chunk ahead (the first before the accumulator wait): the broadcast loads are
+        // L1 hits, but issued next to their use they still cost ~25 % of this loop in long-scoreboard stalls (ncu source view)
+        float4 bb[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + ck0 * 16) + j4);
         epi_wait_acc(c);
         // 16-column chunks; the TMEM load of chunk i+1 is in flight while chunk i is evaluated (two register buffers)
         uint8_t* actp = c.act + c.row * 16;
@@ -306,12 +316,14 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           if (ck * 16 < n_mma) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
-              v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
-              v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
-              v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
-              v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
+              v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
             }
+            if (i + 1 < NCK) {
+#pragma unroll
+              for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = softplus100(v[j]);
             if (ck * 16 + 16 > n_valid) {           // lin3: columns 217..223 are padding
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) v[jj] = (ck * 16 + jj < n_valid) ? v[jj] : 0.f;
@@ -382,11 +394,11 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             // columns 217..255 of v_4 are the PE part of the skip input (1/sqrt2 folded into the image): parked in
             // the g_e output row until the W_0^T delta_0 term arrives (keeps 39 registers free across the sweep)
 #pragma unroll
-            for (int j = 25; j < 32; ++j) a.ge[pc.p * 40 + (j - 25)] = v[j];
+            for (int j = 25; j < 32; ++j) a.ge[row40(tile, c.row, j - 25)] = v[j];
           }
           if (l == 4 && hb == 7 && pc.valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) a.ge[pc.p * 40 + 7 + j] = v[j];
+            for (int j = 0; j < 32; ++j) a.ge[row40(tile, c.row, 7 + j)] = v[j];
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= sigma_from_h(h[j]);    // H_4 is zero beyond col 216 -> delta_3 too
@@ -407,13 +419,13 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         acc_load16(c, 32, v + 32);
         ge[39] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 39; ++i) ge[i] = v[i] + (pc.valid ? a.ge[pc.p * 40 + i] : 0.f);
+        for (int i = 0; i < 39; ++i) ge[i] = v[i] + (pc.valid ? a.ge[row40(tile, c.row, i)] : 0.f);
         pe_jt<6>(pc.x, ge, nrm);
         if (pc.valid) {
 #pragma unroll
           for (int i = 0; i < 3; ++i) a.nrm[pc.p * 3 + i] = nrm[i];
 #pragma unroll
-          for (int i = 0; i < 40; ++i) a.ge[pc.p * 40 + i] = ge[i];
+          for (int i = 0; i < 40; ++i) a.ge[row40(tile, c.row, i)] = ge[i];
         }
         // extras = [pts(3), PE4(dirs)(27), normals(3)]   (models/fields.py:172-175)
         float e[64];
@@ -629,7 +641,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
             e[3 + 6 * kk + ci] = nbar[ci] * f * co;
             e[6 + 6 * kk + ci] = -nbar[ci] * f * sn;
             if (pc.valid) {
-              const float gs = a.ge[pc.p * 40 + 3 + 6 * kk + ci], gc = a.ge[pc.p * 40 + 6 + 6 * kk + ci];
+              const float gs = a.ge[row40(tile, c.row, 3 + 6 * kk + ci)], gc = a.ge[row40(tile, c.row, 6 + 6 * kk + ci)];
               xbar[ci] -= (gs * sn + gc * co) * f * f * nbar[ci];
             }
           }
@@ -745,7 +757,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
               for (int jj = 0; jj < 16; ++jj) {
                 const int col = ck * 16 + jj;
-                if (col >= 217) a.eb[pc.p * 40 + (col - 217)] = v[jj];
+                if (col >= 217) a.eb[row40(tile, c.row, col - 217)] = v[jj];
               }
             }
           }
@@ -782,7 +794,7 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         acc_load16(c, 32, v + 32);
         eb[39] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 39; ++i) eb[i] = v[i] + (pc.valid ? a.eb[pc.p * 40 + i] : 0.f);
+        for (int i = 0; i < 39; ++i) eb[i] = v[i] + (pc.valid ? a.eb[row40(tile, c.row, i)] : 0.f);
         float xe[3];
         pe_jt<6>(pc.x, eb, xe);
         if (pc.valid) {

@@ -271,6 +271,10 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
         const float* bias = a.bias + l * 256;
         const int n_mma = (l == 3) ? 224 : 256;       // lin3 has 217 outputs; columns 217.. meet zero weights next
         uint8_t* actp = c.act + c.row * 16;
+        // the chunk's 16 biases are fetched one chunk ahead (the first before the accumulator wait), see fine_fwd_kernel
+        float4 bb[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + c.wg * CH_CHUNKS * 16) + j4);
         epi_wait_acc(c);
 #pragma unroll 2
         for (int i = 0; i < CH_CHUNKS; ++i) {
@@ -280,12 +284,14 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
           acc_load16(c, ck * 16, v);
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + ck * 16) + j4);
-            v[j4 * 4 + 0] = softplus100(v[j4 * 4 + 0] + b4.x);
-            v[j4 * 4 + 1] = softplus100(v[j4 * 4 + 1] + b4.y);
-            v[j4 * 4 + 2] = softplus100(v[j4 * 4 + 2] + b4.z);
-            v[j4 * 4 + 3] = softplus100(v[j4 * 4 + 3] + b4.w);
+            v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
           }
+          if (i + 1 < CH_CHUNKS) {          // (the bias rows are padded to 256 floats: the read past n_mma is in bounds)
+#pragma unroll
+            for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = softplus100(v[j]);
           if (l == 7) {
 #pragma unroll
             for (int j4 = 0; j4 < 4; ++j4) {

@@ -129,7 +129,7 @@ def fine_forward(fw, stash, rays_o, rays_d, z, sample_dist):
     sdf = torch.empty(P, dtype=torch.float32, device=dev)
     nrm = torch.empty(P, 3, dtype=torch.float32, device=dev)
     rgb = torch.empty(P, 3, dtype=torch.float32, device=dev)
-    ge = torch.empty(P, 40, dtype=torch.float32, device=dev)
+    ge = torch.empty(-(-P // 128) * 128 * 40, dtype=torch.float32, device=dev)      # opaque: [tile][40][128]
     with L.timed("fine_fwd"):
       L.check(L.lib().fmov_fine_fwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),
@@ -145,7 +145,7 @@ def fine_backward(fw, stash, rays_o, rays_d, z, sample_dist, rgb, ge, d_sdf, d_n
     d_pts = torch.empty(P, 3, dtype=torch.float32, device=dev)
     d_dirs = torch.empty(P, 3, dtype=torch.float32, device=dev)
     zc4 = torch.empty(P, 4, dtype=torch.float32, device=dev)
-    eb = torch.empty(P, 40, dtype=torch.float32, device=dev)
+    eb = torch.empty(-(-P // 128) * 128 * 40, dtype=torch.float32, device=dev)      # scratch: [tile][40][128]
     with L.timed("fine_bwd"):
       L.check(L.lib().fmov_fine_bwd(L.c_ll(B), S, L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_float(sample_dist),
                                   L.ptr(fw.blob), stash.ptrs, L.ptr(fw.bias_sdf), L.ptr(fw.b8), L.ptr(fw.w8row),

@@ -196,6 +196,8 @@ int fmov_side_offset(int which);
 int fmov_fine_stash_count(void);
 int fmov_fine_stash_blocks(int id);
 int fmov_fine_stash_is_forward(int id);   /* 1: written by fmov_fine_fwd (a forward-only render needs only these) */
+/* ge (fwd -> bwd) and eb_scratch (bwd) are opaque per-sample scratch buffers of 40 * 128 * ceil(B*S / 128) floats
+ * (tile-major, [tile][40][128]) */
 int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z, float sample_dist,
                   const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
                   const float* bias_col, const float* bc4, float* sdf, float* nrm, float* rgb, float* ge, void* stream);
@@ -203,7 +205,7 @@ int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, 
                   const void* wblob, void* const* stash, const float* bias_sdf, const float* b8, const float* w8row,
                   const float* bias_col, const float* bc4, const float* wc4, const float* rgb, const float* ge,
                   const float* d_sdf, const float* d_nrm, const float* d_rgb, const float* amax, float* d_pts, float* d_dirs,
-                  float* zc4, float* eb_scratch /* [P,40] */, void* stream);
+                  float* zc4, float* eb_scratch, void* stream);
 /* weight / bias gradients into one flat fp32 buffer (zeroed by the call); fmov_grad_offset(kind, layer):
  * kind 0 sdf weight [out,in], 1 sdf bias, 2 colour weight, 3 colour bias (effective weights, reference shapes) */
 long long fmov_grad_offset(int kind, int layer);
