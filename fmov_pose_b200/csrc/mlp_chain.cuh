@@ -22,6 +22,7 @@
 // acc_ready (tcgen05.commit) -> epilogue; weight ring full/empty.
 #pragma once
 #include "fmov_common.cuh"
+#include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace fmov {
 
@@ -51,32 +52,44 @@ constexpr int EPI_THREADS = CH_WGS * 128;          // threads arriving per slot
 constexpr int CH_WSPLIT = FMOV_CH_WSPLIT;          // ring slots per 64-wide k-block: 1, 2 or 4
 constexpr int WSLOT_BYTES = 256 * 128 / CH_WSPLIT; // [256 rows x 64/CH_WSPLIT] 16-bit
 constexpr int CH_WSTAGES = 2 * CH_WSPLIT;
-// FMOV_SHARE_W = 1: the two tile slots of a CTA run every GEMM step in lockstep on ONE stream of weight slices (each slice
-// multiplies slot 0's and slot 1's A operand before it is released): half the L2 -> shared-memory weight traffic per tile.
-// The weight ring is latency bound (64 KiB per ~2.2 K-cycle round trip = 29 B/clk per SM, profiles/micro/l2_stream*.cu show
-// the SM itself can take 60-90 B/clk), so one step's 128 KiB take ~4.5 K cycles whether they feed one tile or two.
-#ifndef FMOV_SHARE_W
-#define FMOV_SHARE_W 0
+// FMOV_CH_PAIR = 1 (set by the including kernel file): CTA-PAIR mode.  The kernel is launched in clusters of two CTAs
+// (one per SM of a TPC); every GEMM step of a tile slot is ONE tcgen05.mma.cta_group::2 stream issued by the even CTA
+// for both CTAs' 128-point tiles (M = 256), and each CTA stages only HALF of every weight slice (N/2 rows of B) in its
+// ring.  Why: the weight ring is latency bound (64 KiB in flight per ~2.5 K-cycle L2 round trip = 23-29 B/clk per SM,
+// profiles/micro/l2_stream*.cu, r2s2 traces), so a step's 128 KiB of weights took ~5.5 K cycles against 2 K of tensor
+// time and the single issuing thread was busy 11 K of every 16 K cycles; with half the bytes per SM the same ring feeds a
+// step in ~2.8 K.  Weight images used in this mode are stored half-major ([half][chunk column][N/2 rows][16 B] per
+// 64-wide k-block) so that a CTA's half of a k-block is one contiguous bulk copy.
+#ifndef FMOV_CH_PAIR
+#define FMOV_CH_PAIR 0
 #endif
-constexpr bool CH_SHARE_W = FMOV_SHARE_W != 0;
+constexpr bool CH_PAIR = FMOV_CH_PAIR != 0;
+constexpr int CH_PW_STAGES = 4;                     // pair mode: ring stages of one half k-block (N/2 rows x 64 K) each
+constexpr int CH_PW_STAGE_BYTES = 128 * 128;        // 16 KiB (N = 256)
+constexpr uint32_t CH_PEER_MASK = 0xFEFFFFFFu;      // shared::cluster address of the pair's EVEN CTA (cute::Sm100MmaPeerBitMask)
 constexpr int MAX_STEPS = 40;
 constexpr int MAX_STASH = 56;
 
-// ---- optional timeline trace (-DFMOV_TRACE): CTA 0 records (tag, clock64) pairs; read back with fmov_debug_trace ----
+// ---- optional timeline trace (-DFMOV_TRACE): the tracing lanes of CTA 0 record (tag, clock64) pairs into per-warp regions
+// of a device buffer (counters in shared memory, plain stores: ~50 cycles per event — the first tracer took its slot with a
+// global atomic, ~850 cycles per event, which inflated every interval it measured); read back with fmov_debug_trace ----
 #ifdef FMOV_TRACE
-__device__ long long g_trace[2 * 32768];
-__device__ unsigned int g_trace_n;
-__device__ __forceinline__ void trace_ev(int kind, int who, int idx) {
-  if (blockIdx.x != 0) return;
-  const unsigned int i = atomicAdd(&g_trace_n, 1u);
-  if (i < 32768u) {
-    g_trace[2 * i] = ((long long)kind << 32) | ((long long)who << 16) | (long long)(idx & 0xFFFF);
-    g_trace[2 * i + 1] = clock64();
-  }
-}
-#define FMOV_TR(kind, who, idx) trace_ev(kind, who, idx)
+constexpr int TR_WARPS = 24, TR_CAP = 16384;
+__device__ long long g_trace[TR_WARPS][TR_CAP][2];
+__device__ unsigned int g_trace_cnt[TR_WARPS];
+#define FMOV_TR(S, kind, who, idx)                                                                     \
+  do {                                                                                                 \
+    if (blockIdx.x == 0) {                                                                             \
+      const unsigned int w__ = threadIdx.x >> 5, n__ = (S)->tr_cnt[w__]++;                             \
+      if (n__ < (unsigned int)TR_CAP) {                                                                \
+        g_trace[w__][n__][0] = ((long long)(kind) << 32) | ((long long)(who) << 16) | (long long)((idx) & 0xFFFF); \
+        g_trace[w__][n__][1] = clock64();                                                              \
+        g_trace_cnt[w__] = n__ + 1;                                                                    \
+      }                                                                                                \
+    }                                                                                                  \
+  } while (0)
 #else
-#define FMOV_TR(kind, who, idx)
+#define FMOV_TR(S, kind, who, idx)
 #endif
 
 struct ChainStep {
@@ -117,6 +130,7 @@ struct ChainSmem {
   uint64_t w_empty[CH_WSTAGES];
   uint32_t tmem_base;
   uint32_t pad_;
+  uint32_t tr_cnt[24];            // FMOV_TRACE: events recorded per warp
   float scratch[CH_SLOTS][128];   // per-row partial sums exchanged between the two column warpgroups of a slot
 };
 
@@ -139,14 +153,78 @@ __device__ __forceinline__ uint8_t* chain_smem_base(uint8_t* raw) {
 
 __device__ __forceinline__ void chain_init_barriers(ChainSmem* s, int epi_threads = EPI_THREADS) {
   for (int i = 0; i < CH_SLOTS; ++i) {
-    mbar_init(&s->act_ready[i], epi_threads);
+    // pair mode: one elected arrival per epilogue warp of BOTH CTAs, on the even CTA's barrier
+    mbar_init(&s->act_ready[i], CH_PAIR ? 2 * (epi_threads / 32) : epi_threads);
     mbar_init(&s->acc_ready[i], 1);
   }
+  for (int i = 0; i < 24; ++i) s->tr_cnt[i] = 0;
   for (int i = 0; i < CH_WSTAGES; ++i) {
     mbar_init(&s->w_full[i], 1);
     mbar_init(&s->w_empty[i], 1);
   }
   fence_mbar_init();
+}
+
+// ---- cluster / CTA-pair primitives ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {          // every thread of both CTAs (warps may arrive diverged)
+  __syncwarp();
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+// arrive (release at cluster scope) on the barrier at the same shared-memory offset in the pair's EVEN CTA
+__device__ __forceinline__ void mbar_arrive_even_cta(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & CH_PEER_MASK) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0xFFF) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout_trap(bar, parity);
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {   // one full warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= [A_even; A_odd] * [B_even; B_odd]^T : M = 256 (128 rows per CTA), each CTA holds N/2 rows of B
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs when all previously issued pair MMAs have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}\n" ::"r"(
+          smem_u32(bar))
+      : "memory");
 }
 
 // Tiles of this CTA: global tile index = blockIdx.x + k*gridDim.x, k = 0..n_my-1; slot = k & 1.
@@ -172,11 +250,11 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
       const uint8_t* __restrict__ wblob = (st.flags & CHF_W2) ? ptrs.weights2 : ptrs.weights;
       const uint32_t bytes = (uint32_t)st.n * (128u / CH_WSPLIT);
       const int nsl = (st.nkb_a + st.nkb_aux) * CH_WSPLIT;      // consecutive slices of this step's weight image
-      const int npass = (CH_SHARE_W && SL == CH_SLOTS) ? 1 : nslot;      // shared stream: one pass feeds both slots
-      for (int slot = 0; slot < npass; ++slot)
+      for (int slot = 0; slot < nslot; ++slot)
         for (int sl = 0; sl < nsl; ++sl, ++it) {
           const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
           mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
+          FMOV_TR(s, 7, stage, it);
           mbar_expect_tx(&s->w_full[stage], bytes);
           bulk_g2s(wst + stage * WSLOT_BYTES, wblob + st.w_off + (size_t)sl * bytes, bytes, &s->w_full[stage]);
         }
@@ -188,64 +266,9 @@ __device__ __forceinline__ void chain_weight_producer(const ChainTable& tb, cons
 // SPLIT = false: the plain chains (no step flags are looked at: the single issuing thread's loop is on the critical path of
 // the MMA-bound value chain — the flag tests cost the query kernel 10 % when they were unconditional); SPLIT = true: the
 // split-precision chain (CHF_* flags honoured).
-// Shared weight stream (FMOV_SHARE_W): per step wait for BOTH slots' operands, then every weight slice multiplies slot 0's
-// and slot 1's A operand before its ring stage is released; both accumulators are committed at the end of the step.
-__device__ __forceinline__ void chain_mma_issuer_shared(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
-                                                        uint8_t* wst, uint32_t tmem, int n_my_tiles) {
-  uint32_t it = 0;
-  uint32_t nstep[CH_SLOTS] = {0, 0};
-  for (int k0 = 0; k0 < n_my_tiles; k0 += CH_SLOTS) {
-    const int nslot = (n_my_tiles - k0 < CH_SLOTS) ? (n_my_tiles - k0) : CH_SLOTS;
-    for (int si = 0; si < tb.n_steps; ++si) {
-      const ChainStep st = tb.step[si];
-      if (st.no_mma) continue;
-      const uint32_t idesc = umma_idesc(128, st.n, st.a_fmt, st.b_fmt, 0, 0);
-      const int nkb = st.nkb_a + st.nkb_aux;
-      for (int slot = 0; slot < nslot; ++slot) {
-        FMOV_TR(1, slot, nstep[slot]);
-        mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
-        FMOV_TR(2, slot, nstep[slot]);
-        ++nstep[slot];
-      }
-      tc_fence_after();
-      for (int kb = 0; kb < nkb; ++kb) {
-        const uint32_t a_off = kb < st.nkb_a ? (uint32_t)(kb * BLK_BYTES) : 0u;
-        const uint32_t a_base0 = smem_u32(kb < st.nkb_a ? act0 + a_off : aux0 + (kb - st.nkb_a) * BLK_BYTES);
-        const uint32_t a_step = kb < st.nkb_a ? 4u * BLK_BYTES : (uint32_t)BLK_BYTES;      // slot 1's operand
-#pragma unroll
-        for (int part = 0; part < CH_WSPLIT; ++part, ++it) {
-          const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
-          mbar_wait_poll(&s->w_full[stage], n & 1);
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
-          for (int slot = 0; slot < nslot; ++slot) {
-#pragma unroll
-            for (int kk = 0; kk < 4 / CH_WSPLIT; ++kk) {
-              const int ks = part * (4 / CH_WSPLIT) + kk;
-              umma_f16(tmem + slot * 256,
-                       umma_desc_kmajor(a_base0 + slot * a_step + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
-                       umma_desc_kmajor(b_base + kk * 2 * ((uint32_t)st.n * 16), (uint32_t)st.n * 16), idesc,
-                       (kb | ks) != 0 ? 1u : 0u);
-            }
-          }
-          umma_commit(&s->w_empty[stage]);
-        }
-      }
-      for (int slot = 0; slot < nslot; ++slot) {
-        umma_commit(&s->acc_ready[slot]);
-        FMOV_TR(3, slot, nstep[slot] - 1);
-      }
-    }
-  }
-}
-
 template <bool SPLIT = false>
 __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
                                                  uint8_t* wst, uint32_t tmem, int n_my_tiles) {
-  if (CH_SHARE_W && !SPLIT && tb.slots <= 0) {
-    chain_mma_issuer_shared(tb, s, act0, aux0, wst, tmem, n_my_tiles);
-    return;
-  }
   uint32_t it = 0;
   uint32_t nstep[CH_SLOTS] = {0, 0};
   const int SL = tb.slots > 0 ? tb.slots : CH_SLOTS;
@@ -263,9 +286,9 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
         uint8_t* aux = aux0 + aslot * BLK_BYTES;
         const uint32_t accum = (fl & CHF_ACCUM) ? 1u : 0u;
         if (!accum) {
-          FMOV_TR(1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
+          FMOV_TR(s, 1, slot, nstep[slot]);            // issuer starts waiting for this slot's operand
           mbar_wait_poll(&s->act_ready[slot], nstep[slot] & 1);
-          FMOV_TR(2, slot, nstep[slot]);            // operand ready seen
+          FMOV_TR(s, 2, slot, nstep[slot]);            // operand ready seen
           ++nstep[slot];
           tc_fence_after();
         }
@@ -276,7 +299,9 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
 #pragma unroll
           for (int part = 0; part < CH_WSPLIT; ++part, ++it) {
             const uint32_t stage = it % CH_WSTAGES, n = it / CH_WSTAGES;
+            FMOV_TR(s, 8, stage, it);
             mbar_wait_poll(&s->w_full[stage], n & 1);
+            FMOV_TR(s, 9, stage, it);
             tc_fence_after();
             const uint32_t b_base = smem_u32(wst + stage * WSLOT_BYTES);
 #pragma unroll
@@ -293,7 +318,91 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
           }
         }
         if (!(fl & CHF_NO_COMMIT)) umma_commit(&s->acc_ready[slot]);
-        FMOV_TR(3, slot, nstep[slot] - 1);        // all MMAs of the step issued
+        FMOV_TR(s, 3, slot, nstep[slot] - 1);        // all MMAs of the step issued
+      }
+    }
+  }
+}
+
+// Tensor maps over the weight blob viewed as rows of 256 bytes, one per half-k-block size (N = 256 / 224 / 48 / 16 ->
+// boxes of 64 / 56 / 12 / 4 rows): in pair mode the weight copies are cp.async.bulk.tensor.2d.cta_group::2, the only bulk
+// copy whose completion may be signalled on the PARTNER CTA's mbarrier (a plain cp.async.bulk with a remote mbarrier
+// never completes: measured, r2s2) — so both CTAs' halves count into the even CTA's w_full and no hop is needed.
+struct PairMaps { CUtensorMap m[4]; };
+__host__ __device__ inline int pair_map_index(int n) { return n == 256 ? 0 : n == 224 ? 1 : n == 48 ? 2 : n == 16 ? 3 : -1; }
+__device__ __forceinline__ void tma2_load_rows(void* smem_dst, const CUtensorMap* map, int row, uint32_t bar_even) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(smem_u32(smem_dst)), "l"(map), "r"(0), "r"(row), "r"(bar_even)
+      : "memory");
+}
+
+// ---- CTA-pair mode (FMOV_CH_PAIR): producer / issuer ------------------------------------------------
+// Both walk (tile pair, step, slot, k-block) in the same order; ring stage = it % CH_PW_STAGES holds this CTA's half
+// (rows [rank*N/2, (rank+1)*N/2)) of one 64-wide k-block.  n_pair_tiles = tiles per CTA of the pair (the odd CTA pads
+// with a dummy tile when it has one less).
+__device__ __forceinline__ void chain_weight_producer_pair(const ChainTable& tb, const PairMaps& maps, ChainSmem* s,
+                                                           uint8_t* wst, int n_pair_tiles, uint32_t rank) {
+  uint32_t it = 0;
+  for (int k0 = 0; k0 < n_pair_tiles; k0 += CH_SLOTS) {
+    const int nslot = (n_pair_tiles - k0 < CH_SLOTS) ? (n_pair_tiles - k0) : CH_SLOTS;
+    for (int si = 0; si < tb.n_steps; ++si) {
+      const ChainStep st = tb.step[si];
+      if (st.no_mma) continue;
+      const uint32_t half = (uint32_t)st.n * 64u;                  // bytes of N/2 rows x 64 K
+      const CUtensorMap* map = &maps.m[pair_map_index(st.n)];
+      const int row0 = (int)((st.w_off + rank * half) >> 8);       // this CTA's half of k-block 0, in rows of 256 bytes
+      const int nkb = st.nkb_a + st.nkb_aux;
+      for (int slot = 0; slot < nslot; ++slot)
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t stage = it % CH_PW_STAGES, n = it / CH_PW_STAGES;
+          mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
+          FMOV_TR(s, 7, stage, it);                       // ring stage seen free: the copy is issued now
+          // both CTAs' copies complete on the EVEN CTA's barrier (the issuer lives there); it expects both halves
+          if (rank == 0) mbar_expect_tx(&s->w_full[stage], 2u * half);
+          tma2_load_rows(wst + stage * CH_PW_STAGE_BYTES, map, row0 + kb * (int)((2u * half) >> 8),
+                         smem_u32(&s->w_full[stage]) & CH_PEER_MASK);
+        }
+    }
+  }
+}
+// even CTA: one thread issues every MMA of the pair
+__device__ __forceinline__ void chain_mma_issuer_pair(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
+                                                      uint8_t* wst, uint32_t tmem, int n_pair_tiles) {
+  uint32_t it = 0;
+  uint32_t nstep[CH_SLOTS] = {0, 0};
+  for (int k0 = 0; k0 < n_pair_tiles; k0 += CH_SLOTS) {
+    const int nslot = (n_pair_tiles - k0 < CH_SLOTS) ? (n_pair_tiles - k0) : CH_SLOTS;
+    for (int si = 0; si < tb.n_steps; ++si) {
+      const ChainStep st = tb.step[si];
+      if (st.no_mma) continue;
+      const uint32_t idesc = umma_idesc(256, st.n, st.a_fmt, st.b_fmt, 0, 0);
+      const uint32_t b_chunk = (uint32_t)st.n * 8u;                // (N/2 rows) x 16 B: distance between chunk columns of B
+      const int nkb = st.nkb_a + st.nkb_aux;
+      for (int slot = 0; slot < nslot; ++slot) {
+        uint8_t* act = act0 + slot * 4 * BLK_BYTES;
+        uint8_t* aux = aux0 + slot * BLK_BYTES;
+        FMOV_TR(s, 1, slot, nstep[slot]);
+        mbar_wait_poll_cluster(&s->act_ready[slot], nstep[slot] & 1);     // both CTAs' operands written, accumulators drained
+        FMOV_TR(s, 2, slot, nstep[slot]);
+        ++nstep[slot];
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const uint32_t a_base = smem_u32(kb < st.nkb_a ? act + kb * BLK_BYTES : aux + (kb - st.nkb_a) * BLK_BYTES);
+          const uint32_t stage = it % CH_PW_STAGES, n = it / CH_PW_STAGES;
+          FMOV_TR(s, 8, stage, it);                       // issuer starts waiting for the stage
+          mbar_wait_poll_cluster(&s->w_full[stage], n & 1);      // both halves landed (each in its own CTA's ring)
+          FMOV_TR(s, 9, stage, it);                       // stage seen full
+          tc_fence_after();
+          const uint32_t b_base = smem_u32(wst + stage * CH_PW_STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma2_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                      umma_desc_kmajor(b_base + ks * 2 * b_chunk, b_chunk), idesc, (kb | ks) != 0 ? 1u : 0u);
+          umma2_commit_both(&s->w_empty[stage]);       // both CTAs' ring stages reusable once these MMAs have read them
+        }
+        umma2_commit_both(&s->acc_ready[slot]);
+        FMOV_TR(s, 3, slot, nstep[slot] - 1);
       }
     }
   }
@@ -324,9 +433,9 @@ __device__ __forceinline__ void epi_init(EpiCtx& c, ChainSmem* s, uint8_t* act0,
   c.acc_n = 0;
 }
 __device__ __forceinline__ void epi_wait_acc(EpiCtx& c) {
-  if ((threadIdx.x & 31) == 0) FMOV_TR(4, threadIdx.x >> 5, c.acc_n);      // epilogue warp starts waiting
+  if ((threadIdx.x & 31) == 0) FMOV_TR(c.s, 4, threadIdx.x >> 5, c.acc_n);      // epilogue warp starts waiting
   mbar_wait(&c.s->acc_ready[c.slot], c.acc_n & 1);
-  if ((threadIdx.x & 31) == 0) FMOV_TR(5, threadIdx.x >> 5, c.acc_n);      // accumulator ready
+  if ((threadIdx.x & 31) == 0) FMOV_TR(c.s, 5, threadIdx.x >> 5, c.acc_n);      // accumulator ready
   ++c.acc_n;
   tc_fence_after();
 }
@@ -334,8 +443,13 @@ __device__ __forceinline__ void epi_wait_acc(EpiCtx& c) {
 __device__ __forceinline__ void epi_signal_act(EpiCtx& c) {
   tc_fence_before();
   fence_proxy_async();
-  mbar_arrive(&c.s->act_ready[c.slot]);
-  if ((threadIdx.x & 31) == 0) FMOV_TR(6, threadIdx.x >> 5, c.acc_n);      // epilogue warp done with the step
+  if (CH_PAIR) {          // one arrival per warp, on the even CTA's barrier (its issuer serves both CTAs)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_even_cta(&c.s->act_ready[c.slot]);
+  } else {
+    mbar_arrive(&c.s->act_ready[c.slot]);
+  }
+  if ((threadIdx.x & 31) == 0) FMOV_TR(c.s, 6, threadIdx.x >> 5, c.acc_n);      // epilogue warp done with the step
 }
 // 32 accumulator columns [col0, col0+32) of this thread's row
 __device__ __forceinline__ void acc_load32(const EpiCtx& c, int col0, float* v) {

@@ -23,6 +23,12 @@
 #define FMOV_FINE_WGS 2
 #endif
 #define FMOV_CH_WGS FMOV_FINE_WGS
+// CTA-pair mode of the chain engine (mlp_chain.cuh): clusters of two CTAs, tcgen05.mma.cta_group::2, each CTA stages half of
+// every weight slice.  -DFMOV_FINE_PAIR=0 builds the one-CTA engine of rounds 1-2 (kept for A/B measurements).
+#ifndef FMOV_FINE_PAIR
+#define FMOV_FINE_PAIR 1
+#endif
+#define FMOV_CH_PAIR FMOV_FINE_PAIR
 #include "mlp_chain.cuh"
 #include "../../include/fmov_b200.h"
 
@@ -63,7 +69,8 @@ enum ImgId {
   IMG_CT0A = 22, IMG_CT0B = 23, IMG_CT1 = 24, IMG_CT2 = 25, IMG_CT3 = 26,   // colour transposed (bf16)
   IMG_FB0 = 27,        // FB0..FB7 forward images in bf16 (adjoint pass)
   IMG_TB0 = 35,        // TB0..TB8 transposed images in bf16 (backward pass; TB8 = lin8 feature rows^T)
-  IMG_COUNT = 44
+  IMG_FP0 = 44,        // FP0..FP7 copies of F0..F7 for the fine kernels (F0..F7 themselves are the sampling queries' blob)
+  IMG_COUNT = 52
 };
 struct ImgInfo { int npad, kblocks; };
 __host__ __device__ inline ImgInfo img_info(int id) {
@@ -80,6 +87,7 @@ __host__ __device__ inline ImgInfo img_info(int id) {
   if (id >= IMG_CT0A && id <= IMG_CT3) return ImgInfo{256, 4};
   if (id >= IMG_FB0 && id < IMG_FB0 + 8) return img_info(IMG_F0 + (id - IMG_FB0));
   if (id >= IMG_TB0 && id < IMG_TB0 + 9) return (id - IMG_TB0) == 0 ? ImgInfo{48, 4} : ImgInfo{256, 4};
+  if (id >= IMG_FP0 && id < IMG_FP0 + 8) return img_info(IMG_F0 + (id - IMG_FP0));
   return ImgInfo{0, 0};
 }
 __constant__ long long c_img_offset[IMG_COUNT + 1];
@@ -92,6 +100,11 @@ static long long img_offset(int id) {
   }
   return off;
 }
+
+// Layout of an image's 64-wide k-block: row-interleaved [8 chunk columns][N rows][16 B] (F0..F7: shared with the sampling
+// queries), or — every image only the fine kernels read, in CTA-pair mode — half-major [2 halves][8 chunk columns][N/2 rows]
+// [16 B], so that the N/2 rows one CTA of a pair stages are contiguous.
+__host__ __device__ inline bool img_half_major(int id) { return CH_PAIR && !(id >= IMG_F0 && id < IMG_F0 + 8); }
 
 // ---- stash tensors --------------------------------------------------------------------------------
 enum StashId {
@@ -239,7 +252,7 @@ __device__ __forceinline__ void get_chunk_raw(const EpiCtx& c, const ChainPtrs& 
 // =====================================================================================================
 __global__ void FINE_BOUNDS
 fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
-                const __grid_constant__ FineArgs a) {
+                const __grid_constant__ FineArgs a, const __grid_constant__ PairMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
@@ -249,20 +262,33 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long P = a.B * a.S;
   const long long n_tiles = (P + TILE_M - 1) / TILE_M;
-  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // pair mode: both CTAs of a pair walk as many tiles as the even one has (the odd CTA pads with a dummy tile)
+  const uint32_t rank = CH_PAIR ? cluster_ctarank() : 0u;
+  const long long first_tile = CH_PAIR ? (long long)(blockIdx.x & ~1u) : (long long)blockIdx.x;
+  const int n_my = (int)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) chain_init_barriers(s);
-  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
+  if (warp == ISSUER_WARP) {
+    if (CH_PAIR) tmem_alloc_pair(&s->tmem_base, 512);
+    else tmem_alloc(&s->tmem_base, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CH_PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp >= CTRL_WARP0) {
     if (warp == PRODUCER_WARP) {
-      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      if (lane == 0) {
+        if (CH_PAIR) chain_weight_producer_pair(tb, maps, s, wst, n_my, rank);
+        else chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      }
     } else if (warp == ISSUER_WARP) {
-      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+      if (lane == 0) {
+        if (!CH_PAIR) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+        else if (rank == 0) chain_mma_issuer_pair(tb, s, act0, aux0, wst, tmem, n_my);
+      }
     }
   } else {
     EpiCtx c;
@@ -271,8 +297,10 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
     const int ck0 = c.wg * NCK;
     const bool owner = c.wg == CH_WGS - 1;      // warpgroup that owns the per-row state and the narrow steps
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
-      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
-      const PointCtx pc = load_sample(a, tile, c.row);
+      const long long tile_raw = (long long)blockIdx.x + (long long)k * gridDim.x;
+      // dummy tile of the odd CTA (pair mode): every point invalid, stash traffic goes to the padding tile n_tiles
+      const long long tile = tile_raw < n_tiles ? tile_raw : n_tiles;
+      const PointCtx pc = load_sample(a, tile_raw, c.row);
       // ---- input: PE6(x) -> AUX + stash ----------------------------------------------------------------
       {
         float e[64];
@@ -493,10 +521,12 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       }
     }
   }
-  __syncthreads();
+  if (CH_PAIR) cluster_sync_all();      // neither CTA may leave while its partner still signals its barriers / reads its smem
+  else __syncthreads();
   if (warp == ISSUER_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (CH_PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -505,7 +535,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 // =====================================================================================================
 __global__ void FINE_BOUNDS
 fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
-                const __grid_constant__ FineArgs a) {
+                const __grid_constant__ FineArgs a, const __grid_constant__ PairMaps maps) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
@@ -515,20 +545,33 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long P = a.B * a.S;
   const long long n_tiles = (P + TILE_M - 1) / TILE_M;
-  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // pair mode: both CTAs of a pair walk as many tiles as the even one has (the odd CTA pads with a dummy tile)
+  const uint32_t rank = CH_PAIR ? cluster_ctarank() : 0u;
+  const long long first_tile = CH_PAIR ? (long long)(blockIdx.x & ~1u) : (long long)blockIdx.x;
+  const int n_my = (int)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
 
   if (threadIdx.x == 0) chain_init_barriers(s);
-  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
+  if (warp == ISSUER_WARP) {
+    if (CH_PAIR) tmem_alloc_pair(&s->tmem_base, 512);
+    else tmem_alloc(&s->tmem_base, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CH_PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp >= CTRL_WARP0) {
     if (warp == PRODUCER_WARP) {
-      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      if (lane == 0) {
+        if (CH_PAIR) chain_weight_producer_pair(tb, maps, s, wst, n_my, rank);
+        else chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      }
     } else if (warp == ISSUER_WARP) {
-      if (lane == 0) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+      if (lane == 0) {
+        if (!CH_PAIR) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
+        else if (rank == 0) chain_mma_issuer_pair(tb, s, act0, aux0, wst, tmem, n_my);
+      }
     }
   } else {
     EpiCtx c;
@@ -540,8 +583,10 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
     const float ginv = 1.0f / gscale;
     const uint64_t pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     for (int k = c.slot; k < n_my; k += CH_SLOTS) {
-      const long long tile = (long long)blockIdx.x + (long long)k * gridDim.x;
-      const PointCtx pc = load_sample(a, tile, c.row);
+      const long long tile_raw = (long long)blockIdx.x + (long long)k * gridDim.x;
+      // dummy tile of the odd CTA (pair mode): every point invalid, stash traffic goes to the padding tile n_tiles
+      const long long tile = tile_raw < n_tiles ? tile_raw : n_tiles;
+      const PointCtx pc = load_sample(a, tile_raw, c.row);
       float sbar = 0.f, nbar[3] = {0.f, 0.f, 0.f}, zc4[3] = {0.f, 0.f, 0.f}, xbar[3] = {0.f, 0.f, 0.f};
       if (pc.valid) {
         sbar = a.d_sdf[pc.p] * gscale;
@@ -805,10 +850,12 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
       tc_fence_before();
     }
   }
-  __syncthreads();
+  if (CH_PAIR) cluster_sync_all();      // neither CTA may leave while its partner still signals its barriers / reads its smem
+  else __syncthreads();
   if (warp == ISSUER_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (CH_PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -878,7 +925,12 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAllArgs a) {
     uint4 q4;
     if (sp.bf16) { q4.x = pack_bf2(v[0], v[1]); q4.y = pack_bf2(v[2], v[3]); q4.z = pack_bf2(v[4], v[5]); q4.w = pack_bf2(v[6], v[7]); }
     else { q4.x = pack_h2(v[0], v[1]); q4.y = pack_h2(v[2], v[3]); q4.z = pack_h2(v[4], v[5]); q4.w = pack_h2(v[6], v[7]); }
-    *reinterpret_cast<uint4*>(a.blob + img_offset_dev(sp.img) + (size_t)kb * ii.npad * 128 + (size_t)ch * ii.npad * 16 + (size_t)n * 16) = q4;
+    size_t in_kb = (size_t)ch * ii.npad * 16 + (size_t)n * 16;
+    if (img_half_major(sp.img)) {
+      const int hn = ii.npad / 2, h = n / hn;
+      in_kb = (size_t)h * hn * 128 + (size_t)ch * hn * 16 + (size_t)(n - h * hn) * 16;
+    }
+    *reinterpret_cast<uint4*>(a.blob + img_offset_dev(sp.img) + (size_t)kb * ii.npad * 128 + in_kb) = q4;
   }
 }
 }  // namespace fmov
@@ -903,7 +955,7 @@ static void set_pf(ChainStep& st, int t0, int t1 = 0xFF) { st.pf[0] = (uint8_t)t
 static void build_fwd_table(ChainTable& tb) {
   init_table(tb);
   int n = 0;
-  for (int l = 0; l < 8; ++l) set_step(tb.step[n++], IMG_F0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_F16, FMT_F16);
+  for (int l = 0; l < 8; ++l) set_step(tb.step[n++], IMG_FP0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_F16, FMT_F16);
   set_step(tb.step[n++], IMG_F0 + 8, 4, 0, FMT_F16, FMT_F16);                 // lin8 feature rows
   for (int l = 7; l >= 1; --l) {                                                // reverse sweep: reads H_l
     set_pf(tb.step[n], ST_H1 + (l - 1));
@@ -930,7 +982,7 @@ static void build_bwd_table(ChainTable& tb) {
   set_step(tb.step[n++], IMG_CT0A, 4, 0, kGradFmt, kGradFmt);
   for (int l = 0; l < 8; ++l) {                                                 // adjoint pass: reads H_{l+1}, delta_l
     set_pf(tb.step[n], ST_H1 + l, ST_D0 + l);
-    set_step(tb.step[n++], (kGradBf16 ? IMG_FB0 : IMG_F0) + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, kGradFmt, kGradFmt);
+    set_step(tb.step[n++], (kGradBf16 ? IMG_FB0 : IMG_FP0) + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, kGradFmt, kGradFmt);
   }
   for (int l = 8; l >= 1; --l) {                                                // ordinary backward: reads H_l, q_{l-1}
     set_pf(tb.step[n], ST_H1 + (l - 1), ST_Q0 + (l - 1));
@@ -974,6 +1026,7 @@ static void build_pack_specs(PackAllArgs& a, bool backward) {
     else add_spec(a, img, l, 256, 256, true, 0, 256, 1, 0, 0, 256, 0, 0, 0, 1.f, bf);
   };
   for (int l = 0; l < 9; ++l) fwd_img(IMG_F0 + l, l, false);
+  for (int l = 0; l < 8; ++l) fwd_img(IMG_FP0 + l, l, false);
   for (int l = 0; l < 8; ++l) tr_img(IMG_T0 + l, l, false);
   // colour net: kernel K order is [feat(256) | extras(33)], reference order is [extras(33) | feat(256)]
   add_spec(a, IMG_C0 + 0, 18, 256, 289, false, 0, 256, 2, 0, 33, 256, 256, 0, 33, 1.f, false);
@@ -1028,17 +1081,23 @@ extern "C" int fmov_pack_all(const float* const* srcs, void* blob, float* side, 
 }
 
 #ifdef FMOV_TRACE
-/* debug builds only: copies the CTA-0 timeline of the last fine kernels to the host and resets it */
+/* debug builds only: copies the CTA-0 timeline of the last fine kernel to the host ([event][tag, clock], warp regions
+ * concatenated) and resets it */
 extern "C" int fmov_debug_trace(long long* host, int max_events) {
-  unsigned int n = 0;
+  unsigned int cnt[TR_WARPS];
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
-  if ((int)n > max_events) n = max_events;
-  if (n > 32768u) n = 32768u;
-  cudaMemcpyFromSymbol(host, g_trace, (size_t)n * 2 * sizeof(long long));
-  unsigned int zero = 0;
-  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
-  return (int)n;
+  cudaMemcpyFromSymbol(cnt, g_trace_cnt, sizeof(cnt));
+  int n = 0;
+  for (int w = 0; w < TR_WARPS; ++w) {
+    int c = (int)cnt[w];
+    if (c > TR_CAP) c = TR_CAP;
+    if (n + c > max_events) c = max_events - n;
+    if (c > 0) cudaMemcpyFromSymbol(host + 2 * (size_t)n, g_trace, (size_t)c * 2 * sizeof(long long), (size_t)w * TR_CAP * 2 * sizeof(long long));
+    n += c > 0 ? c : 0;
+  }
+  memset(cnt, 0, sizeof(cnt));
+  cudaMemcpyToSymbol(g_trace_cnt, cnt, sizeof(cnt));
+  return n;
 }
 #endif
 
@@ -1080,6 +1139,86 @@ static int grid_for(long long P, int max_ctas) {
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   return grid;
 }
+// One persistent CTA per SM; in CTA-pair mode clusters of two CTAs (as many pairs as can be resident at once: a pair that
+// had to wait for another to finish would double the kernel time, the tile assignment is static).
+// tensor maps of a weight blob (pair mode); the last few blobs are cached (a train loop re-packs into the same buffer)
+static int pair_maps_for(const void* blob, PairMaps& out) {
+  memset(&out, 0, sizeof(out));
+  if (!CH_PAIR) return OK;
+  struct Entry { const void* blob; PairMaps maps; };
+  static Entry cache[8];
+  static int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i)
+    if (cache[i].blob == blob) { out = cache[i].maps; return OK; }
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FMOV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    FMOV_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = (EncodeFn)fn;
+  }
+  const long long bytes = img_offset(IMG_COUNT);
+  FMOV_REQUIRE(bytes % 256 == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0, "fine: weight blob must be 16-byte aligned");
+  static const int ns[4] = {256, 224, 48, 16};
+  Entry e;
+  e.blob = blob;
+  for (int i = 0; i < 4; ++i) {
+    cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)};
+    cuuint64_t gstr[1] = {256};
+    cuuint32_t box[2] = {256, (cuuint32_t)(ns[i] * 64 / 256)};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FMOV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the %d-row weight box", (int)r, ns[i] / 4);
+  }
+  cache[next] = e;
+  next = (next + 1) % 8;
+  if (n_cached < 8) ++n_cached;
+  out = e.maps;
+  return OK;
+}
+template <typename Kernel>
+static int launch_fine(Kernel kernel, long long P, const ChainTable& tb, const ChainPtrs& ptrs, const FineArgs& a,
+                       cudaStream_t stream, const char* name) {
+  int grid = grid_for(P, 0);
+  PairMaps maps;
+  int st = pair_maps_for(ptrs.weights, maps);
+  if (st) return st;
+  if (!CH_PAIR) {
+    kernel<<<grid, CH_THREADS, FL::DYN_BYTES, stream>>>(tb, ptrs, a, maps);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(CH_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = FL::DYN_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs[2] = {0, 0};          // per kernel (fwd / bwd)
+    int& mp = max_pairs[name[5] == 'f' ? 0 : 1];
+    if (mp == 0) {
+      cfg.gridDim = dim3(2 * 74, 1, 1);
+      int n = 0;
+      FMOV_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+      FMOV_REQUIRE(n > 0, "%s: no CTA pair fits on this device", name);
+      mp = n;
+    }
+    grid = (grid + 1) & ~1;                    // pairs; the odd CTA of the last pair may only have a dummy tile
+    if (grid > 2 * mp) grid = 2 * mp;
+    cfg.gridDim = dim3(grid, 1, 1);
+    FMOV_CUDA(cudaLaunchKernelEx(&cfg, kernel, tb, ptrs, a, maps));
+  }
+  FMOV_LAUNCH_CHECK(name);
+  return OK;
+}
 
 /* stash: HOST array of ST_COUNT device pointers (tile-image tensors, fmov_fine_stash_blocks(id) blocks per tile) */
 extern "C" int fmov_fine_fwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z,
@@ -1101,9 +1240,7 @@ extern "C" int fmov_fine_fwd(long long B, int S, const float* rays_o, const floa
   for (int i = 0; i < ST_COUNT; ++i)
     if (stash_is_forward(i)) FMOV_REQUIRE(stash[i], "fmov_fine_fwd: stash tensor %d is null", i);
   a.sdf = sdf; a.nrm = nrm; a.rgb = rgb; a.ge = ge;
-  fine_fwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
-  FMOV_LAUNCH_CHECK("fine_fwd_kernel");
-  return OK;
+  return launch_fine(fine_fwd_kernel, B * S, tb, ptrs, a, (cudaStream_t)stream, "fine_fwd_kernel");
 }
 
 extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const float* rays_d, const float* z,
@@ -1128,7 +1265,5 @@ extern "C" int fmov_fine_bwd(long long B, int S, const float* rays_o, const floa
     if (stash_kb(i) > 0) FMOV_REQUIRE(stash[i], "fmov_fine_bwd: stash tensor %d is null", i);      // 0 blocks: never touched
   a.rgb = const_cast<float*>(rgb); a.ge = const_cast<float*>(ge);
   a.d_sdf = d_sdf; a.d_nrm = d_nrm; a.d_rgb = d_rgb; a.d_pts = d_pts; a.d_dirs = d_dirs; a.zc4 = zc4; a.eb = eb_scratch; a.amax = amax;
-  fine_bwd_kernel<<<grid_for(B * S, 0), CH_THREADS, FL::DYN_BYTES, (cudaStream_t)stream>>>(tb, ptrs, a);
-  FMOV_LAUNCH_CHECK("fine_bwd_kernel");
-  return OK;
+  return launch_fine(fine_bwd_kernel, B * S, tb, ptrs, a, (cudaStream_t)stream, "fine_bwd_kernel");
 }

@@ -71,7 +71,8 @@ class Stash:
     def __init__(self, P, device, with_backward=True):
         lib = L.lib()
         n = lib.fmov_fine_stash_count()
-        self.nt = (P + 127) // 128
+        # + 1: the padding tile that the odd CTA of a pair writes when it has one tile less than its partner (csrc/mlp_fine.cu)
+        self.nt = (P + 127) // 128 + 1
         self.device = device
         self.blocks = [lib.fmov_fine_stash_blocks(i) for i in range(n)]
         # buffer order: the tensors the forward kernel writes first, so that a forward-only stash is a prefix

@@ -29,7 +29,7 @@ g = torch.Generator().manual_seed(0)
 px = torch.randint(30, 130, [rays], generator=g).to(dev)
 py = torch.randint(10, 110, [rays], generator=g).to(dev)
 tr = torch.rand(rays, 1, generator=g).to(dev)
-NEV = 32768
+NEV = 24 * 16384
 buf = (ctypes.c_longlong * (2 * NEV))()
 lib = L.lib()
 orig_fwd, orig_bwd = fine.fine_forward, fine.fine_backward

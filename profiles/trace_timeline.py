@@ -18,16 +18,17 @@ g = torch.Generator().manual_seed(0)
 px = torch.randint(30, 130, [rays], generator=g).to(dev)
 py = torch.randint(10, 110, [rays], generator=g).to(dev)
 tr = torch.rand(rays, 1, generator=g).to(dev)
-buf = (ctypes.c_longlong * (2 * 32768))()
+NEV = 24 * 16384
+buf = (ctypes.c_longlong * (2 * NEV))()
 lib = L.lib()
 from fmov_pose_b200 import fine
 orig_fwd, orig_bwd = fine.fine_forward, fine.fine_backward
 traces = {}
 def wrap(name, fn):
     def f(*a, **k):
-        lib.fmov_debug_trace(buf, 32768)
+        lib.fmov_debug_trace(buf, NEV)
         r = fn(*a, **k)
-        n = lib.fmov_debug_trace(buf, 32768)
+        n = lib.fmov_debug_trace(buf, NEV)
         traces[name] = np.array(buf[: 2 * n], dtype=np.int64).reshape(n, 2).copy()
         return r
     return f

@@ -44,7 +44,7 @@ def test_static_queries_without_a_gpu(lib):
     lib.fmov_sdf_fwd_blob_bytes.restype = ctypes.c_longlong
     assert lib.fmov_version() >= 100
     assert lib.fmov_fine_stash_count() == 54          # 53 tile tensors + the ReLU sign words of C1..C4
-    assert lib.fmov_fine_image_count() == 44
+    assert lib.fmov_fine_image_count() == 52
     # flat gradient buffer = effective weights + biases of both MLPs (reference shapes)
     sdf_w = 256 * 39 + 2 * 256 * 256 + 217 * 256 + 4 * 256 * 256 + 257 * 256
     sdf_b = 7 * 256 + 217 + 257

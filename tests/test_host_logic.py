@@ -298,26 +298,27 @@ def test_stash_layout_follows_the_library_directory(monkeypatch):
     for lib in (default, variant):
         monkeypatch.setattr(L, "lib", lambda lib=lib: lib)
         fine.Stash._pool.clear()
-        P = 128 * 5 + 3                                     # 6 tiles
+        P = 128 * 5 + 3                                     # 6 tiles + the padding tile of the CTA-pair engine
+        NT = 7
         full = fine.Stash(P, torch.device("cpu"), with_backward=True)
         n = len(lib.blocks)
-        assert full.nt == 6 and len(full.tensors) == n
+        assert full.nt == NT and len(full.tensors) == n
         spans = []
         for i, t in enumerate(full.tensors):
-            assert t is not None and t.numel() == lib.blocks[i] * 6 * 16384, i
+            assert t is not None and t.numel() == lib.blocks[i] * NT * 16384, i
             off = t.data_ptr() - full.buf.data_ptr()
             spans.append((off, off + t.numel(), i))
         used = sorted(s for s in spans if s[1] > s[0])
         assert all(a[1] == b[0] for a, b in zip(used, used[1:])) and used[0][0] == 0          # contiguous, no overlap
-        assert used[-1][1] == sum(lib.blocks) * 6 * 16384 == full.buf.numel()
-        n_fwd_bytes = sum(lib.blocks[i] for i in lib.fwd) * 6 * 16384
+        assert used[-1][1] == sum(lib.blocks) * NT * 16384 == full.buf.numel()
+        n_fwd_bytes = sum(lib.blocks[i] for i in lib.fwd) * NT * 16384
         assert all((s[1] <= n_fwd_bytes) == (s[2] in lib.fwd) for s in used)                  # forward tensors = prefix
         full.buf = None                                      # do not recycle: the next stash must size itself
         fwd_only = fine.Stash(P, torch.device("cpu"), with_backward=False)
         assert fwd_only.buf.numel() == n_fwd_bytes
         assert all((t is not None) == (i in lib.fwd) for i, t in enumerate(fwd_only.tensors) if lib.blocks[i] > 0)
         fwd_only.ensure_backward(P, torch.device("cpu"))
-        assert all(t is not None for t in fwd_only.tensors) and fwd_only.buf.numel() == sum(lib.blocks) * 6 * 16384
+        assert all(t is not None for t in fwd_only.tensors) and fwd_only.buf.numel() == sum(lib.blocks) * NT * 16384
         fwd_only.buf = None
     fine.Stash._pool.clear()
 
