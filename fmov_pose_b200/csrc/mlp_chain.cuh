@@ -103,7 +103,10 @@ struct ChainStep {
   uint8_t pf[2];        // stash tensors (4-block tiles) this step's epilogue reads from HBM; 0xFF = none.
                         // The producer warp bulk-prefetches them into L2 one step ahead.
   uint8_t flags;        // CHF_* bits (0 for an ordinary step)
-  uint8_t pad[2];
+  uint8_t bias16;       // pair mode: one more K = 16 MMA after the k-blocks, A = columns 48..63 of the slot's AUX block (1.0 in
+                        // columns 48 / 49), B = the [N x 16] slice appended to the step's weight image (bias as fp16 hi + lo):
+                        // the layer's bias is added by the tensor core instead of 4 broadcast loads + 16 adds per chunk
+  uint8_t pad[1];
 };
 // Step flags: let several GEMM passes share one accumulator (split-precision chains: hi*W_hi + lo*W_hi + hi*W_lo).
 constexpr uint8_t CHF_A_OTHER = 1;     // A operand = the OTHER tile slot's ACT / AUX region (holds the fp16 residuals)
@@ -328,8 +331,10 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
 // boxes of 64 / 56 / 12 / 4 rows): in pair mode the weight copies are cp.async.bulk.tensor.2d.cta_group::2, the only bulk
 // copy whose completion may be signalled on the PARTNER CTA's mbarrier (a plain cp.async.bulk with a remote mbarrier
 // never completes: measured, r2s2) — so both CTAs' halves count into the even CTA's w_full and no hop is needed.
-struct PairMaps { CUtensorMap m[4]; };
+struct PairMaps { CUtensorMap m[6]; };      // half k-blocks of N = 256 / 224 / 48 / 16, half bias slices of N = 256 / 224
 __host__ __device__ inline int pair_map_index(int n) { return n == 256 ? 0 : n == 224 ? 1 : n == 48 ? 2 : n == 16 ? 3 : -1; }
+__host__ __device__ inline int pair_bias_map_index(int n) { return n == 256 ? 4 : n == 224 ? 5 : -1; }
+constexpr int AUX_ONE_COL = 48;             // columns 48 / 49 of an AUX block hold 1.0 where a bias16 step follows
 __device__ __forceinline__ void tma2_load_rows(void* smem_dst, const CUtensorMap* map, int row, uint32_t bar_even) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
@@ -341,6 +346,8 @@ __device__ __forceinline__ void tma2_load_rows(void* smem_dst, const CUtensorMap
 // Both walk (tile pair, step, slot, k-block) in the same order; ring stage = it % CH_PW_STAGES holds this CTA's half
 // (rows [rank*N/2, (rank+1)*N/2)) of one 64-wide k-block.  n_pair_tiles = tiles per CTA of the pair (the odd CTA pads
 // with a dummy tile when it has one less).
+// BIAS: the table may contain bias16 steps (the backward kernel's does not: its instantiation carries no code for them)
+template <bool BIAS>
 __device__ __forceinline__ void chain_weight_producer_pair(const ChainTable& tb, const PairMaps& maps, ChainSmem* s,
                                                            uint8_t* wst, int n_pair_tiles, uint32_t rank) {
   uint32_t it = 0;
@@ -353,7 +360,7 @@ __device__ __forceinline__ void chain_weight_producer_pair(const ChainTable& tb,
       const CUtensorMap* map = &maps.m[pair_map_index(st.n)];
       const int row0 = (int)((st.w_off + rank * half) >> 8);       // this CTA's half of k-block 0, in rows of 256 bytes
       const int nkb = st.nkb_a + st.nkb_aux;
-      for (int slot = 0; slot < nslot; ++slot)
+      for (int slot = 0; slot < nslot; ++slot) {
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const uint32_t stage = it % CH_PW_STAGES, n = it / CH_PW_STAGES;
           mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
@@ -363,10 +370,22 @@ __device__ __forceinline__ void chain_weight_producer_pair(const ChainTable& tb,
           tma2_load_rows(wst + stage * CH_PW_STAGE_BYTES, map, row0 + kb * (int)((2u * half) >> 8),
                          smem_u32(&s->w_full[stage]) & CH_PEER_MASK);
         }
+        if (BIAS && st.bias16) {          // this CTA's N/2 rows of the [N x 16] bias slice behind the k-blocks
+          const uint32_t bhalf = (uint32_t)st.n * 16u;
+          const uint32_t stage = it % CH_PW_STAGES, n = it / CH_PW_STAGES;
+          mbar_wait_poll(&s->w_empty[stage], (n & 1) ^ 1);
+          if (rank == 0) mbar_expect_tx(&s->w_full[stage], 2u * bhalf);
+          tma2_load_rows(wst + stage * CH_PW_STAGE_BYTES, &maps.m[pair_bias_map_index(st.n)],
+                         (int)((st.w_off + (uint32_t)nkb * 2u * half + rank * bhalf) >> 8),
+                         smem_u32(&s->w_full[stage]) & CH_PEER_MASK);
+          ++it;
+        }
+      }
     }
   }
 }
 // even CTA: one thread issues every MMA of the pair
+template <bool BIAS>
 __device__ __forceinline__ void chain_mma_issuer_pair(const ChainTable& tb, ChainSmem* s, uint8_t* act0, uint8_t* aux0,
                                                       uint8_t* wst, uint32_t tmem, int n_pair_tiles) {
   uint32_t it = 0;
@@ -400,6 +419,15 @@ __device__ __forceinline__ void chain_mma_issuer_pair(const ChainTable& tb, Chai
             umma2_f16(tmem + slot * 256, umma_desc_kmajor(a_base + ks * 2 * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
                       umma_desc_kmajor(b_base + ks * 2 * b_chunk, b_chunk), idesc, (kb | ks) != 0 ? 1u : 0u);
           umma2_commit_both(&s->w_empty[stage]);       // both CTAs' ring stages reusable once these MMAs have read them
+        }
+        if (BIAS && st.bias16) {          // + 1.0 * bias_hi + 2^-12 * (2^12 bias_lo): K = 16 slice of the AUX block x the bias slice
+          const uint32_t stage = it % CH_PW_STAGES, n = it / CH_PW_STAGES;
+          mbar_wait_poll_cluster(&s->w_full[stage], n & 1);
+          tc_fence_after();
+          umma2_f16(tmem + slot * 256, umma_desc_kmajor(smem_u32(aux) + (AUX_ONE_COL / 8) * TI_CHUNK_STRIDE, TI_CHUNK_STRIDE),
+                    umma_desc_kmajor(smem_u32(wst + stage * CH_PW_STAGE_BYTES), b_chunk), idesc, 1u);
+          umma2_commit_both(&s->w_empty[stage]);
+          ++it;
         }
         umma2_commit_both(&s->acc_ready[slot]);
         FMOV_TR(s, 3, slot, nstep[slot] - 1);

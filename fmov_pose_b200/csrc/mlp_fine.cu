@@ -90,21 +90,30 @@ __host__ __device__ inline ImgInfo img_info(int id) {
   if (id >= IMG_FP0 && id < IMG_FP0 + 8) return img_info(IMG_F0 + (id - IMG_FP0));
   return ImgInfo{0, 0};
 }
-__constant__ long long c_img_offset[IMG_COUNT + 1];
-__device__ __forceinline__ long long img_offset_dev(int id) { return c_img_offset[id]; }
-static long long img_offset(int id) {
-  long long off = 0;
-  for (int i = 0; i < id; ++i) {
-    const ImgInfo ii = img_info(i);
-    off += (long long)ii.npad * 128 * ii.kblocks;
-  }
-  return off;
-}
-
 // Layout of an image's 64-wide k-block: row-interleaved [8 chunk columns][N rows][16 B] (F0..F7: shared with the sampling
 // queries), or — every image only the fine kernels read, in CTA-pair mode — half-major [2 halves][8 chunk columns][N/2 rows]
 // [16 B], so that the N/2 rows one CTA of a pair stages are contiguous.
 __host__ __device__ inline bool img_half_major(int id) { return CH_PAIR && !(id >= IMG_F0 && id < IMG_F0 + 8); }
+// Images of the biased forward layers carry, behind their k-blocks, a [N x 16] slice (half-major like the k-blocks) whose
+// K columns 0 / 1 hold the layer's bias as fp16 hi + fp16 residual (x 2^12, so that it is a normal fp16 number): the chain's bias16 step multiplies it with the 1.0
+// columns of the AUX block (pair mode only; the one-CTA engine adds the fp32 bias in the epilogue).
+constexpr bool FINE_BIAS_MMA = CH_PAIR;
+constexpr float BIAS_LO_SCALE = 4096.0f;      // AUX column 48 = 1, column 49 = 1 / 4096: z += 1 * b_hi + 2^-12 * (2^12 b_lo)
+__host__ __device__ inline bool img_has_bias(int id) {
+  return FINE_BIAS_MMA && (id == IMG_F0 + 8 || (id >= IMG_C0 && id < IMG_C0 + 4) || (id >= IMG_FP0 && id < IMG_FP0 + 8));
+}
+__host__ __device__ inline long long img_bytes(int id) {
+  const ImgInfo ii = img_info(id);
+  return (long long)ii.npad * 128 * ii.kblocks + (img_has_bias(id) ? (long long)ii.npad * 32 : 0);
+}
+__constant__ long long c_img_offset[IMG_COUNT + 1];
+__device__ __forceinline__ long long img_offset_dev(int id) { return c_img_offset[id]; }
+static long long img_offset(int id) {
+  long long off = 0;
+  for (int i = 0; i < id; ++i) off += img_bytes(i);
+  return off;
+}
+
 
 // ---- stash tensors --------------------------------------------------------------------------------
 enum StashId {
@@ -281,13 +290,13 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   if (warp >= CTRL_WARP0) {
     if (warp == PRODUCER_WARP) {
       if (lane == 0) {
-        if (CH_PAIR) chain_weight_producer_pair(tb, maps, s, wst, n_my, rank);
+        if (CH_PAIR) chain_weight_producer_pair<FINE_BIAS_MMA>(tb, maps, s, wst, n_my, rank);
         else chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
       }
     } else if (warp == ISSUER_WARP) {
       if (lane == 0) {
         if (!CH_PAIR) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
-        else if (rank == 0) chain_mma_issuer_pair(tb, s, act0, aux0, wst, tmem, n_my);
+        else if (rank == 0) chain_mma_issuer_pair<FINE_BIAS_MMA>(tb, s, act0, aux0, wst, tmem, n_my);
       }
     }
   } else {
@@ -307,6 +316,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 64; ++i) e[i] = 0.f;
         pe_with_residual(pc.x, e);
+        if (FINE_BIAS_MMA) { e[AUX_ONE_COL] = 1.0f; e[AUX_ONE_COL + 1] = 1.0f / BIAS_LO_SCALE; }      // x the bias slices of lin0..lin8
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (CH_WGS == 2 && h != c.wg) continue;        // each warpgroup stores one 32-column half
@@ -327,8 +337,10 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         // the chunk's 16 biases are fetched one chunk ahead (the first before the accumulator wait): the broadcast loads are
         // L1 hits, but issued next to their use they still cost ~25 % of this loop in long-scoreboard stalls (ncu source view)
         float4 bb[4];
+        if (!FINE_BIAS_MMA) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + ck0 * 16) + j4);
+          for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + ck0 * 16) + j4);
+        }
         epi_wait_acc(c);
         // 16-column chunks; the TMEM load of chunk i+1 is in flight while chunk i is evaluated (two register buffers)
         uint8_t* actp = c.act + c.row * 16;
@@ -342,13 +354,15 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           tmem_ld_wait();
           if (i + 1 < NCK && (ck + 1) * 16 < n_mma) tmem_ld16(c.tmem + (ck + 1) * 16, vbuf[(i + 1) & 1]);
           if (ck * 16 < n_mma) {
+            if (!FINE_BIAS_MMA) {          // (pair mode: the accumulator already holds W u + b)
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
-            }
-            if (i + 1 < NCK) {
+              for (int j4 = 0; j4 < 4; ++j4) {
+                v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
+              }
+              if (i + 1 < NCK) {
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+                for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+              }
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = softplus100(v[j]);
@@ -394,7 +408,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int col = hb * 32 + j;
-          v[j] += __ldg(a.b8 + 1 + col);
+          if (!FINE_BIAS_MMA) v[j] += __ldg(a.b8 + 1 + col);
           h[j] = __ldg(a.w8row + col) * sigma_from_h(h[j]);
         }
         put_chunk(c, ptrs, false, ST_F, tile, hb, false, v);
@@ -462,6 +476,7 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
         e[0] = pc.x[0]; e[1] = pc.x[1]; e[2] = pc.x[2];
         pe_eval<4>(pc.d, e + 3);
         e[30] = nrm[0]; e[31] = nrm[1]; e[32] = nrm[2];
+        if (FINE_BIAS_MMA) { e[AUX_ONE_COL] = 1.0f; e[AUX_ONE_COL + 1] = 1.0f / BIAS_LO_SCALE; }      // x the bias slices of colour lin0..lin3
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint4 q[4];
@@ -492,7 +507,8 @@ fine_fwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
           acc_load32(c, hb * 32, v);
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (!FINE_BIAS_MMA) b4 = __ldg(reinterpret_cast<const float4*>(bias + hb * 32) + j4);
             v[j4 * 4 + 0] = fmaxf(v[j4 * 4 + 0] + b4.x, 0.f);
             v[j4 * 4 + 1] = fmaxf(v[j4 * 4 + 1] + b4.y, 0.f);
             v[j4 * 4 + 2] = fmaxf(v[j4 * 4 + 2] + b4.z, 0.f);
@@ -564,13 +580,13 @@ fine_bwd_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ C
   if (warp >= CTRL_WARP0) {
     if (warp == PRODUCER_WARP) {
       if (lane == 0) {
-        if (CH_PAIR) chain_weight_producer_pair(tb, maps, s, wst, n_my, rank);
+        if (CH_PAIR) chain_weight_producer_pair<false>(tb, maps, s, wst, n_my, rank);
         else chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
       }
     } else if (warp == ISSUER_WARP) {
       if (lane == 0) {
         if (!CH_PAIR) chain_mma_issuer(tb, s, act0, aux0, wst, tmem, n_my);
-        else if (rank == 0) chain_mma_issuer_pair(tb, s, act0, aux0, wst, tmem, n_my);
+        else if (rank == 0) chain_mma_issuer_pair<false>(tb, s, act0, aux0, wst, tmem, n_my);
       }
     }
   } else {
@@ -881,6 +897,8 @@ struct PackAllArgs {
   float* side;                 // [bias_sdf 8x256 | b8 257(+pad to 264) | w8row 256 | bias_col 4x256 | bc4 4 | wc4 3x256]
   int n_spec;
   int total_chunks;
+  int n_bias;                  // bias slices (FINE_BIAS_MMA): image, source tensor (index into src), first source row, valid rows
+  int bias_img[13], bias_src[13], bias_row_off[13], bias_nvalid[13];
   PackSpec spec[PACK_MAX];
 };
 constexpr int SIDE_BIAS_SDF = 0, SIDE_B8 = 2048, SIDE_W8ROW = 2048 + 264, SIDE_BIAS_COL = SIDE_W8ROW + 256,
@@ -932,6 +950,22 @@ __global__ void pack_all_kernel(const __grid_constant__ PackAllArgs a) {
     }
     *reinterpret_cast<uint4*>(a.blob + img_offset_dev(sp.img) + (size_t)kb * ii.npad * 128 + in_kb) = q4;
   }
+  // ---- bias slices: [half][2 chunk columns][N/2 rows][16 B]; K column 0 = fp16(b), 1 = fp16(b - fp16(b)), rest 0 -------
+  for (int bi = 0; bi < a.n_bias; ++bi) {
+    const ImgInfo ii = img_info(a.bias_img[bi]);
+    const int hn = ii.npad / 2;
+    uint8_t* dst = a.blob + img_offset_dev(a.bias_img[bi]) + (size_t)ii.kblocks * ii.npad * 128;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * ii.npad; i += gridDim.x * blockDim.x) {
+      const int ch = i / ii.npad, n = i - ch * ii.npad, h = n / hn;
+      uint4 q4 = make_uint4(0u, 0u, 0u, 0u);
+      if (ch == 0 && n < a.bias_nvalid[bi]) {
+        const float b = a.src[a.bias_src[bi]][n + a.bias_row_off[bi]];
+        const float hi = __half2float(__float2half_rn(b));
+        q4.x = pack_h2(hi, (b - hi) * BIAS_LO_SCALE);          // the residual scaled into fp16's normal range
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)h * hn * 32 + (size_t)ch * hn * 16 + (size_t)(n - h * hn) * 16) = q4;
+    }
+  }
 }
 }  // namespace fmov
 using namespace fmov;
@@ -957,12 +991,14 @@ static void build_fwd_table(ChainTable& tb) {
   int n = 0;
   for (int l = 0; l < 8; ++l) set_step(tb.step[n++], IMG_FP0 + l, l == 0 ? 0 : 4, (l == 0 || l == 4) ? 1 : 0, FMT_F16, FMT_F16);
   set_step(tb.step[n++], IMG_F0 + 8, 4, 0, FMT_F16, FMT_F16);                 // lin8 feature rows
+  for (int i = 0; i < 9; ++i) tb.step[i].bias16 = FINE_BIAS_MMA ? 1 : 0;       // biases of lin0..lin8 by the tensor core
   for (int l = 7; l >= 1; --l) {                                                // reverse sweep: reads H_l
     set_pf(tb.step[n], ST_H1 + (l - 1));
     set_step(tb.step[n++], IMG_T0 + l, 4, 0, FMT_F16, FMT_F16);
   }
   set_pf(tb.step[n], ST_F);                                                     // F goes back into ACT here
   set_step(tb.step[n++], IMG_T0 + 0, 4, 0, FMT_F16, FMT_F16);                  // W_0^T delta_0 (N = 48)
+  for (int l = 0; l < 4; ++l) tb.step[n + l].bias16 = FINE_BIAS_MMA ? 1 : 0;   // colour lin0..lin3
   set_step(tb.step[n++], IMG_C0 + 0, 4, 1, FMT_F16, FMT_F16);                  // colour lin0: feat + extras
   for (int l = 1; l < 4; ++l) set_step(tb.step[n++], IMG_C0 + l, 4, 0, FMT_F16, FMT_F16);
   set_step(tb.step[n++], IMG_C0 + 4, 4, 0, FMT_F16, FMT_F16);                  // colour lin4 (N = 16)
@@ -1007,7 +1043,16 @@ static void add_spec(PackAllArgs& a, int img, int src, int rows, int cols, bool 
   a.total_chunks += ii.npad * ii.kblocks * 8;
 }
 static void build_pack_specs(PackAllArgs& a, bool backward) {
-  a.n_spec = 0; a.total_chunks = 0;
+  a.n_spec = 0; a.total_chunks = 0; a.n_bias = 0;
+  auto add_bias = [&](int img, int src, int row_off, int n_valid) {
+    if (!img_has_bias(img)) return;
+    const int i = a.n_bias++;
+    a.bias_img[i] = img; a.bias_src[i] = src; a.bias_row_off[i] = row_off; a.bias_nvalid[i] = n_valid;
+  };
+  static const int so_b[8] = {256, 256, 256, 217, 256, 256, 256, 256};
+  for (int l = 0; l < 8; ++l) add_bias(IMG_FP0 + l, 9 + l, 0, so_b[l]);
+  add_bias(IMG_F0 + 8, 17, 1, 256);                      // lin8 feature rows 1..256
+  for (int l = 0; l < 4; ++l) add_bias(IMG_C0 + l, 23 + l, 0, 256);
   const float rs2 = 0.70710678118654752f;
   static const int so[9] = {256, 256, 256, 217, 256, 256, 256, 256, 257}, si[9] = {39, 256, 256, 256, 256, 256, 256, 256, 256};
   auto fwd_img = [&](int img, int l, bool bf) {
@@ -1163,18 +1208,19 @@ static int pair_maps_for(const void* blob, PairMaps& out) {
   }
   const long long bytes = img_offset(IMG_COUNT);
   FMOV_REQUIRE(bytes % 256 == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0, "fine: weight blob must be 16-byte aligned");
-  static const int ns[4] = {256, 224, 48, 16};
+  static const int box_rows[6] = {256 * 64 / 256, 224 * 64 / 256, 48 * 64 / 256, 16 * 64 / 256,      // half k-blocks
+                                 256 * 16 / 256, 224 * 16 / 256};                                     // half bias slices
   Entry e;
   e.blob = blob;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 6; ++i) {
     cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)};
     cuuint64_t gstr[1] = {256};
-    cuuint32_t box[2] = {256, (cuuint32_t)(ns[i] * 64 / 256)};
+    cuuint32_t box[2] = {256, (cuuint32_t)box_rows[i]};
     cuuint32_t estr[2] = {1, 1};
     const CUresult r = encode(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FMOV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the %d-row weight box", (int)r, ns[i] / 4);
+    FMOV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the %d-row weight box", (int)r, box_rows[i]);
   }
   cache[next] = e;
   next = (next + 1) % 8;
