@@ -60,6 +60,9 @@ constexpr int CH_WSTAGES = 2 * CH_WSPLIT;
 // time and the single issuing thread was busy 11 K of every 16 K cycles; with half the bytes per SM the same ring feeds a
 // step in ~2.8 K.  Weight images used in this mode are stored half-major ([half][chunk column][N/2 rows][16 B] per
 // 64-wide k-block) so that a CTA's half of a k-block is one contiguous bulk copy.
+#ifndef FMOV_FINE_PAIR
+#define FMOV_FINE_PAIR 1          // the fine-stage kernels and the train step's sampling queries use the pair engine
+#endif
 #ifndef FMOV_CH_PAIR
 #define FMOV_CH_PAIR 0
 #endif
@@ -154,10 +157,10 @@ __device__ __forceinline__ uint8_t* chain_smem_base(uint8_t* raw) {
   return reinterpret_cast<uint8_t*>(p);
 }
 
-__device__ __forceinline__ void chain_init_barriers(ChainSmem* s, int epi_threads = EPI_THREADS) {
+__device__ __forceinline__ void chain_init_barriers(ChainSmem* s, int epi_threads = EPI_THREADS, bool pair = CH_PAIR) {
   for (int i = 0; i < CH_SLOTS; ++i) {
     // pair mode: one elected arrival per epilogue warp of BOTH CTAs, on the even CTA's barrier
-    mbar_init(&s->act_ready[i], CH_PAIR ? 2 * (epi_threads / 32) : epi_threads);
+    mbar_init(&s->act_ready[i], pair ? 2 * (epi_threads / 32) : epi_threads);
     mbar_init(&s->acc_ready[i], 1);
   }
   for (int i = 0; i < 24; ++i) s->tr_cnt[i] = 0;
@@ -334,12 +337,59 @@ __device__ __forceinline__ void chain_mma_issuer(const ChainTable& tb, ChainSmem
 struct PairMaps { CUtensorMap m[6]; };      // half k-blocks of N = 256 / 224 / 48 / 16, half bias slices of N = 256 / 224
 __host__ __device__ inline int pair_map_index(int n) { return n == 256 ? 0 : n == 224 ? 1 : n == 48 ? 2 : n == 16 ? 3 : -1; }
 __host__ __device__ inline int pair_bias_map_index(int n) { return n == 256 ? 4 : n == 224 ? 5 : -1; }
-constexpr int AUX_ONE_COL = 48;             // columns 48 / 49 of an AUX block hold 1.0 where a bias16 step follows
+// bias16 steps: column 48 of the AUX block holds 1.0 and column 49 holds 2^-12; the bias slice holds fp16(b) and
+// 2^12 (b - fp16(b)) in its K columns 0 / 1 — the residual is scaled into fp16's NORMAL range (an unscaled residual is a
+// subnormal fp16 number for |b| < 0.12, and with those the tensor core lost it: colour-net gradient parity 8e-3 -> 1.6e-2)
+constexpr int AUX_ONE_COL = 48;
+constexpr float BIAS_LO_SCALE = 4096.0f;
 __device__ __forceinline__ void tma2_load_rows(void* smem_dst, const CUtensorMap* map, int row, uint32_t bar_even) {
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
           "r"(smem_u32(smem_dst)), "l"(map), "r"(0), "r"(row), "r"(bar_even)
       : "memory");
+}
+
+// Host side: the six tensor maps of a weight blob of `bytes` bytes; the last few blobs are cached per translation unit
+// (a train loop re-packs into the same buffer, and the maps only encode address and extent).
+static int chain_pair_maps(const void* blob, long long bytes, PairMaps& out) {
+  struct Entry { const void* blob; long long bytes; PairMaps maps; };
+  static Entry cache[8];
+  static int n_cached = 0, next = 0;
+  for (int i = 0; i < n_cached; ++i)
+    if (cache[i].blob == blob && cache[i].bytes == bytes) { out = cache[i].maps; return OK; }
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FMOV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    FMOV_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = (EncodeFn)fn;
+  }
+  FMOV_REQUIRE(bytes > 0 && bytes % 256 == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0,
+               "weight blob must be 16-byte aligned and a multiple of 256 bytes (%lld)", bytes);
+  static const int box_rows[6] = {256 * 64 / 256, 224 * 64 / 256, 48 * 64 / 256, 16 * 64 / 256,      // half k-blocks
+                                 256 * 16 / 256, 224 * 16 / 256};                                     // half bias slices
+  Entry e;
+  e.blob = blob;
+  e.bytes = bytes;
+  for (int i = 0; i < 6; ++i) {
+    cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)};
+    cuuint64_t gstr[1] = {256};
+    cuuint32_t box[2] = {256, (cuuint32_t)box_rows[i]};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FMOV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the %d-row weight box", (int)r, box_rows[i]);
+  }
+  cache[next] = e;
+  next = (next + 1) % 8;
+  if (n_cached < 8) ++n_cached;
+  out = e.maps;
+  return OK;
 }
 
 // ---- CTA-pair mode (FMOV_CH_PAIR): producer / issuer ------------------------------------------------
@@ -468,10 +518,11 @@ __device__ __forceinline__ void epi_wait_acc(EpiCtx& c) {
   tc_fence_after();
 }
 // A operand for the next step is written (or nothing to write) and this slot's accumulator is drained.
+template <bool PAIR = CH_PAIR>
 __device__ __forceinline__ void epi_signal_act(EpiCtx& c) {
   tc_fence_before();
   fence_proxy_async();
-  if (CH_PAIR) {          // one arrival per warp, on the even CTA's barrier (its issuer serves both CTAs)
+  if (PAIR) {          // one arrival per warp, on the even CTA's barrier (its issuer serves both CTAs)
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive_even_cta(&c.s->act_ready[c.slot]);
   } else {

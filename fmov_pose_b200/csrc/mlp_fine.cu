@@ -24,10 +24,8 @@
 #endif
 #define FMOV_CH_WGS FMOV_FINE_WGS
 // CTA-pair mode of the chain engine (mlp_chain.cuh): clusters of two CTAs, tcgen05.mma.cta_group::2, each CTA stages half of
-// every weight slice.  -DFMOV_FINE_PAIR=0 builds the one-CTA engine of rounds 1-2 (kept for A/B measurements).
-#ifndef FMOV_FINE_PAIR
-#define FMOV_FINE_PAIR 1
-#endif
+// every weight slice.  -DFMOV_FINE_PAIR=0 builds the one-CTA engine of rounds 1-2 (kept for A/B measurements; the default
+// lives in mlp_chain.cuh).
 #define FMOV_CH_PAIR FMOV_FINE_PAIR
 #include "mlp_chain.cuh"
 #include "../../include/fmov_b200.h"
@@ -98,7 +96,6 @@ __host__ __device__ inline bool img_half_major(int id) { return CH_PAIR && !(id 
 // K columns 0 / 1 hold the layer's bias as fp16 hi + fp16 residual (x 2^12, so that it is a normal fp16 number): the chain's bias16 step multiplies it with the 1.0
 // columns of the AUX block (pair mode only; the one-CTA engine adds the fp32 bias in the epilogue).
 constexpr bool FINE_BIAS_MMA = CH_PAIR;
-constexpr float BIAS_LO_SCALE = 4096.0f;      // AUX column 48 = 1, column 49 = 1 / 4096: z += 1 * b_hi + 2^-12 * (2^12 b_lo)
 __host__ __device__ inline bool img_has_bias(int id) {
   return FINE_BIAS_MMA && (id == IMG_F0 + 8 || (id >= IMG_C0 && id < IMG_C0 + 4) || (id >= IMG_FP0 && id < IMG_FP0 + 8));
 }
@@ -1186,47 +1183,10 @@ static int grid_for(long long P, int max_ctas) {
 }
 // One persistent CTA per SM; in CTA-pair mode clusters of two CTAs (as many pairs as can be resident at once: a pair that
 // had to wait for another to finish would double the kernel time, the tile assignment is static).
-// tensor maps of a weight blob (pair mode); the last few blobs are cached (a train loop re-packs into the same buffer)
 static int pair_maps_for(const void* blob, PairMaps& out) {
   memset(&out, 0, sizeof(out));
   if (!CH_PAIR) return OK;
-  struct Entry { const void* blob; PairMaps maps; };
-  static Entry cache[8];
-  static int n_cached = 0, next = 0;
-  for (int i = 0; i < n_cached; ++i)
-    if (cache[i].blob == blob) { out = cache[i].maps; return OK; }
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    FMOV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-    FMOV_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-    encode = (EncodeFn)fn;
-  }
-  const long long bytes = img_offset(IMG_COUNT);
-  FMOV_REQUIRE(bytes % 256 == 0 && (reinterpret_cast<uintptr_t>(blob) & 15) == 0, "fine: weight blob must be 16-byte aligned");
-  static const int box_rows[6] = {256 * 64 / 256, 224 * 64 / 256, 48 * 64 / 256, 16 * 64 / 256,      // half k-blocks
-                                 256 * 16 / 256, 224 * 16 / 256};                                     // half bias slices
-  Entry e;
-  e.blob = blob;
-  for (int i = 0; i < 6; ++i) {
-    cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)};
-    cuuint64_t gstr[1] = {256};
-    cuuint32_t box[2] = {256, (cuuint32_t)box_rows[i]};
-    cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(&e.maps.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(blob), gdim, gstr, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    FMOV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for the %d-row weight box", (int)r, box_rows[i]);
-  }
-  cache[next] = e;
-  next = (next + 1) % 8;
-  if (n_cached < 8) ++n_cached;
-  out = e.maps;
-  return OK;
+  return chain_pair_maps(blob, img_offset(IMG_COUNT), out);
 }
 template <typename Kernel>
 static int launch_fine(Kernel kernel, long long P, const ChainTable& tb, const ChainPtrs& ptrs, const FineArgs& a,

@@ -97,7 +97,7 @@ __device__ __forceinline__ void pe6_to_block(uint8_t* blk, int row, const float 
     row_half_store(blk + row * 16, h, q);
   }
 }
-__device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const float x[3], int h) {
+__device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const float x[3], int h, bool bias_cols = false) {
   float e[64];
 #pragma unroll
   for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -115,6 +115,7 @@ __device__ __forceinline__ void pe6_half_to_block(uint8_t* blk, int row, const f
   }
 #pragma unroll
   for (int c = 0; c < 3; ++c) e[PE_RES_COL + c] = x[c] - __half2float(__float2half_rn(x[c]));      // see pe_with_residual
+  if (bias_cols) { e[AUX_ONE_COL] = 1.0f; e[AUX_ONE_COL + 1] = 1.0f / BIAS_LO_SCALE; }              // x the bias slices (bias16 steps)
   uint4 q[4];
   if (h == 0) pack4(e, false, q); else pack4(e + 32, false, q);
   row_half_store(blk + row * 16, h, q);
@@ -151,10 +152,16 @@ __device__ __forceinline__ void pe6_half_to_block_hilo(uint8_t* blk_hi, uint8_t*
   pack4(lo, false, q);
   row_half_store(blk_lo + row * 16, h, q);
 }
-template <bool PRECISE>
+// MODE 0: one-CTA engine, row-interleaved weight images, biases added in the epilogue (any caller's stand-alone blob)
+// MODE 1: split-precision chain (one-CTA engine)
+// MODE 2: CTA-pair engine (clusters of two, tcgen05.mma.cta_group::2, half-major images with bias slices: the FP0..FP7 images
+//         of the fine-stage blob) — the hierarchical-sampling queries of the train step
+constexpr int QM_SINGLE = 0, QM_PRECISE = 1, QM_PAIR = 2;
+template <int MODE>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ ChainPtrs ptrs,
-                 const __grid_constant__ QueryArgs a) {
+                 const __grid_constant__ QueryArgs a, const __grid_constant__ PairMaps maps) {
+  constexpr bool PRECISE = MODE == QM_PRECISE, PAIR = MODE == QM_PAIR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = chain_smem_base(smem_raw);
   ChainSmem* s = reinterpret_cast<ChainSmem*>(base);
@@ -164,20 +171,33 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
-  const int n_my = (int)((n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  // pair mode: both CTAs of a pair walk as many tiles as the even one has (the odd CTA pads with an all-invalid tile)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const long long first_tile = PAIR ? (long long)(blockIdx.x & ~1u) : (long long)blockIdx.x;
+  const int n_my = (int)((n_tiles - first_tile + gridDim.x - 1) / gridDim.x);
 
-  if (threadIdx.x == 0) chain_init_barriers(s, PRECISE ? 2 * EPI_THREADS : EPI_THREADS);
-  if (warp == ISSUER_WARP) tmem_alloc(&s->tmem_base, 512);
+  if (threadIdx.x == 0) chain_init_barriers(s, PRECISE ? 2 * EPI_THREADS : EPI_THREADS, PAIR);
+  if (warp == ISSUER_WARP) {
+    if (PAIR) tmem_alloc_pair(&s->tmem_base, 512);
+    else tmem_alloc(&s->tmem_base, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s->tmem_base;
 
   if (warp >= CTRL_WARP0) {
     if (warp == PRODUCER_WARP) {
-      if (lane == 0) chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      if (lane == 0) {
+        if (PAIR) chain_weight_producer_pair<true>(tb, maps, s, wst, n_my, rank);
+        else chain_weight_producer(tb, ptrs, s, wst, n_my, blockIdx.x, gridDim.x);
+      }
     } else if (warp == ISSUER_WARP) {
-      if (lane == 0) chain_mma_issuer<PRECISE>(tb, s, act0, aux0, wst, tmem, n_my);
+      if (lane == 0) {
+        if (!PAIR) chain_mma_issuer<PRECISE>(tb, s, act0, aux0, wst, tmem, n_my);
+        else if (rank == 0) chain_mma_issuer_pair<true>(tb, s, act0, aux0, wst, tmem, n_my);
+      }
     }
   } else if (PRECISE) {
     // Split-precision chain: ONE tile in flight.  Slot 1's ACT / AUX hold the fp16 residuals of slot 0's operands, and all
@@ -262,9 +282,9 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
       float x[3] = {0.f, 0.f, 0.f};
       if (valid) load_point(a, p, x);
       x[0] *= a.in_scale; x[1] *= a.in_scale; x[2] *= a.in_scale;
-      if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg);   // warpgroup wg writes PE columns [32wg, 32wg+32)
+      if (CH_WGS == 2) pe6_half_to_block(c.aux, c.row, x, c.wg, PAIR);   // warpgroup wg writes PE columns [32wg, 32wg+32)
       else pe6_to_block(c.aux, c.row, x);
-      epi_signal_act(c);
+      epi_signal_act<PAIR>(c);
       float sdf = 0.f;
 #pragma unroll 1
       for (int l = 0; l < 8; ++l) {
@@ -273,8 +293,10 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
         uint8_t* actp = c.act + c.row * 16;
         // the chunk's 16 biases are fetched one chunk ahead (the first before the accumulator wait), see fine_fwd_kernel
         float4 bb[4];
+        if (!PAIR) {
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + c.wg * CH_CHUNKS * 16) + j4);
+          for (int j4 = 0; j4 < 4; ++j4) bb[j4] = __ldg(reinterpret_cast<const float4*>(bias + c.wg * CH_CHUNKS * 16) + j4);
+        }
         epi_wait_acc(c);
 #pragma unroll 2
         for (int i = 0; i < CH_CHUNKS; ++i) {
@@ -282,13 +304,15 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
           if (ck * 16 >= n_mma) break;
           float v[16];
           acc_load16(c, ck * 16, v);
+          if (!PAIR) {          // (pair mode: bias16 steps, the accumulator already holds W u + b)
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
-          }
-          if (i + 1 < CH_CHUNKS) {          // (the bias rows are padded to 256 floats: the read past n_mma is in bounds)
+            for (int j4 = 0; j4 < 4; ++j4) {
+              v[j4 * 4 + 0] += bb[j4].x; v[j4 * 4 + 1] += bb[j4].y; v[j4 * 4 + 2] += bb[j4].z; v[j4 * 4 + 3] += bb[j4].w;
+            }
+            if (i + 1 < CH_CHUNKS) {          // (the bias rows are padded to 256 floats: the read past n_mma is in bounds)
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+              for (int j4 = 0; j4 < 4; ++j4) bb[j4] = ldg_f4_volatile(reinterpret_cast<const float4*>(bias + (ck + 1) * 16) + j4);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = softplus100(v[j]);
@@ -305,7 +329,7 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
             chunk_store(actp, ck, q2);
           }
         }
-        if (l < 7) epi_signal_act(c);
+        if (l < 7) epi_signal_act<PAIR>(c);
         else tc_fence_before();
       }
       // combine the two column halves of the lin8-row-0 dot product
@@ -318,10 +342,12 @@ sdf_query_kernel(const __grid_constant__ ChainTable tb, const __grid_constant__ 
       if (c.wg == CH_WGS - 1 && valid) a.out[p] = (sdf + b8) * a.out_scale;
     }
   }
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA may leave while its partner still signals its barriers / reads its smem
+  else __syncthreads();
   if (warp == ISSUER_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    if (PAIR) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
   }
 }
 
@@ -346,6 +372,26 @@ static void build_query_table(ChainTable& tb) {
     st.pf[0] = st.pf[1] = 0xFF;
     off += (uint32_t)st.n * 128u * (st.nkb_a + st.nkb_aux);
   }
+}
+
+// CTA-pair chain: the half-major images FP0..FP7 of the fine-stage blob, each followed by its bias slice (mlp_fine.cu,
+// img_bytes); offsets relative to FP0.
+static void build_query_table_pair(ChainTable& tb) {
+  build_query_table(tb);
+  uint32_t off = 0;
+  for (int l = 0; l < 8; ++l) {
+    ChainStep& st = tb.step[l];
+    st.w_off = off;
+    st.bias16 = 1;
+    off += (uint32_t)st.n * 128u * (st.nkb_a + st.nkb_aux) + (uint32_t)st.n * 32u;
+  }
+}
+extern "C" long long fmov_sdf_pair_blob_bytes(void) {
+  if (!FMOV_FINE_PAIR) return 0;          // built without the pair engine: FP0..FP7 are plain copies of F0..F7
+  ChainTable tb;
+  build_query_table_pair(tb);
+  const ChainStep& st = tb.step[7];
+  return (long long)st.w_off + (long long)st.n * 128 * (st.nkb_a + st.nkb_aux) + (long long)st.n * 32;
 }
 
 // Split-precision chain: per layer three products into one accumulator, hi*W_hi + lo*W_hi + hi*W_lo (the residual images
@@ -380,10 +426,11 @@ extern "C" long long fmov_sdf_fwd_blob_offset(int layer) {
   return tb.step[layer].w_off;
 }
 
-static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cudaStream_t stream, const void* wblob_lo = nullptr) {
-  static ChainTable tb, tbp;
+static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cudaStream_t stream, const void* wblob_lo = nullptr,
+                        bool pair = false) {
+  static ChainTable tb, tbp, tb2;
   static bool init = false;
-  if (!init) { build_query_table(tb); build_query_table_precise(tbp); init = true; }
+  if (!init) { build_query_table(tb); build_query_table_precise(tbp); build_query_table_pair(tb2); init = true; }
   ChainPtrs ptrs;
   memset(&ptrs, 0, sizeof(ptrs));
   ptrs.weights = reinterpret_cast<const uint8_t*>(wblob);
@@ -393,16 +440,47 @@ static int launch_query(const QueryArgs& a, const void* wblob, int max_ctas, cud
   FMOV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   static bool attr_set = false;
   if (!attr_set) {
-    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
-    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<QM_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<QM_PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
+    FMOV_CUDA(cudaFuncSetAttribute(sdf_query_kernel<QM_PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, QL::DYN_BYTES));
     attr_set = true;
   }
   long long n_tiles = (a.P + TILE_M - 1) / TILE_M;
   if (n_tiles == 0) return OK;
   int grid = (int)(n_tiles < sms ? n_tiles : sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  if (wblob_lo) sdf_query_kernel<true><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tbp, ptrs, a);
-  else sdf_query_kernel<false><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tb, ptrs, a);
+  PairMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (pair) {
+    int st = chain_pair_maps(wblob, fmov_sdf_pair_blob_bytes(), maps);
+    if (st) return st;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(CH_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = QL::DYN_BYTES;
+    cfg.stream = stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs = 0;
+    if (max_pairs == 0) {
+      cfg.gridDim = dim3(2 * 74, 1, 1);
+      int n = 0;
+      FMOV_CUDA(cudaOccupancyMaxActiveClusters(&n, sdf_query_kernel<QM_PAIR>, &cfg));
+      FMOV_REQUIRE(n > 0, "sdf_query_kernel: no CTA pair fits on this device");
+      max_pairs = n;
+    }
+    grid = (grid + 1) & ~1;
+    if (grid > 2 * max_pairs) grid = 2 * max_pairs;
+    cfg.gridDim = dim3(grid, 1, 1);
+    FMOV_CUDA(cudaLaunchKernelEx(&cfg, sdf_query_kernel<QM_PAIR>, tb2, ptrs, a, maps));
+  } else if (wblob_lo) {
+    sdf_query_kernel<QM_PRECISE><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tbp, ptrs, a, maps);
+  } else {
+    sdf_query_kernel<QM_SINGLE><<<grid, CH_THREADS, QL::DYN_BYTES, stream>>>(tb, ptrs, a, maps);
+  }
   FMOV_LAUNCH_CHECK("sdf_query_kernel");
   return OK;
 }
@@ -430,6 +508,21 @@ extern "C" int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, con
   a.mode = 1; a.P = B * S; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.S = S; a.z_stride = z_stride; a.z_off = z_off;
   a.in_scale = in_scale; a.out_scale = out_scale; a.bias = bias8x256; a.w8 = w8_row0; a.b8 = b8; a.out = out;
   return launch_query(a, wblob, 0, (cudaStream_t)stream);
+}
+
+/* same query on the CTA-pair engine: `wblob_pair` = the half-major images FP0..FP7 with their bias slices
+ * (fmov_sdf_pair_blob_bytes() bytes: the FP0.. region of the blob fmov_pack_all writes); biases come from the slices */
+extern "C" int fmov_sdf_query_rays_pair(const float* rays_o, const float* rays_d, const float* z, long long B, int S,
+                                        int z_stride, int z_off, const void* wblob_pair, const float* w8_row0, const float* b8,
+                                        float in_scale, float out_scale, float* out, void* stream) {
+  FMOV_REQUIRE(B >= 0 && S > 0 && z_stride >= S + z_off, "fmov_sdf_query_rays_pair: bad shape B=%lld S=%d stride=%d off=%d", B,
+               S, z_stride, z_off);
+  FMOV_REQUIRE(B == 0 || (rays_o && rays_d && z && out && wblob_pair && w8_row0), "fmov_sdf_query_rays_pair: null argument");
+  QueryArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = 1; a.P = B * S; a.rays_o = rays_o; a.rays_d = rays_d; a.z = z; a.S = S; a.z_stride = z_stride; a.z_off = z_off;
+  a.in_scale = in_scale; a.out_scale = out_scale; a.bias = nullptr; a.w8 = w8_row0; a.b8 = b8; a.out = out;
+  return launch_query(a, wblob_pair, 0, (cudaStream_t)stream, nullptr, true);
 }
 
 extern "C" int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,

@@ -15,6 +15,7 @@ SQ2 = math.sqrt(2.0)
 IMG_F0, IMG_T0, IMG_C0 = 0, 9, 17
 IMG_CT0A, IMG_CT0B, IMG_CT1, IMG_CT2, IMG_CT3 = 22, 23, 24, 25, 26
 IMG_FB0, IMG_TB0 = 27, 35
+IMG_FP0 = 44
 
 
 def _img_info(i):
@@ -60,6 +61,10 @@ class FineWeights:
         self.bc4 = self.side[o[4]: o[4] + 3]
         self.wc4 = self.side[o[5]: o[5] + 768]
         self.query = packing.SdfQueryWeights.from_views(self.blob, self.bias_sdf, self.w8row, self.b8)
+        nb = int(lib.fmov_sdf_pair_blob_bytes())
+        if nb > 0:          # half-major copies FP0..FP7 (+ bias slices): the sampling queries run on the CTA-pair engine
+            off = _img_info(IMG_FP0)[0]
+            self.query.blob_pair = self.blob[off: off + nb]
 
 
 class Stash:

@@ -30,7 +30,12 @@ def sdf_query_rays(qw, rays_o, rays_d, z, S, z_off=0, in_scale=1.0, out_scale=1.
     B = rays_o.shape[0]
     assert z.is_contiguous() and z.dtype == torch.float32
     out = torch.empty(B, S, dtype=torch.float32, device=z.device)
-    if B:
+    if B and getattr(qw, "blob_pair", None) is not None:          # train step: CTA-pair engine, biases in the weight images
+        with L.timed("sdf_query"):
+            L.check(L.lib().fmov_sdf_query_rays_pair(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), S, z.shape[1], z_off,
+                                                     L.ptr(qw.blob_pair), L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(in_scale),
+                                                     L.c_float(out_scale), L.ptr(out), L.stream()), "fmov_sdf_query_rays_pair")
+    elif B:
         L.check(L.lib().fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), S, z.shape[1], z_off,
                                             L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
                                             L.c_float(in_scale), L.c_float(out_scale), L.ptr(out), L.stream()),
@@ -101,12 +106,20 @@ def hierarchical_sample(qw, rays_o, rays_d, near, far, t_rand, n_samples, n_impo
     sdf = torch.empty(B, S, dtype=torch.float32, device=z.device)
     lib = L.lib()
 
+    pair = getattr(qw, "blob_pair", None)          # FineWeights: half-major images -> the CTA-pair engine
+
     def query(z_off, cnt):
       with L.timed("sdf_query"):
-        L.check(lib.fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), cnt, S, z_off,
-                                        L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
-                                        L.c_float(scale), L.c_float(1.0 / scale), L.ptr(sdf_tmp), L.stream()),
-                "fmov_sdf_query_rays")
+        if pair is not None:
+            L.check(lib.fmov_sdf_query_rays_pair(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), cnt, S, z_off,
+                                                 L.ptr(pair), L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(scale),
+                                                 L.c_float(1.0 / scale), L.ptr(sdf_tmp), L.stream()),
+                    "fmov_sdf_query_rays_pair")
+        else:
+            L.check(lib.fmov_sdf_query_rays(L.ptr(rays_o), L.ptr(rays_d), L.ptr(z), L.c_ll(B), cnt, S, z_off,
+                                            L.ptr(qw.blob), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
+                                            L.c_float(scale), L.c_float(1.0 / scale), L.ptr(sdf_tmp), L.stream()),
+                    "fmov_sdf_query_rays")
 
     # sdf is kept [B,S] row-aligned with z; queries write a dense [B,cnt] block that is scattered in
     sdf_tmp = torch.empty(B * max(n_samples, m), dtype=torch.float32, device=z.device)

@@ -65,6 +65,7 @@ class SdfQueryWeights:
         self = cls.__new__(cls)
         self.blob, self.bias, self.w8, self.b8 = blob, bias, w8, b8
         self.blob_lo = None
+        self.blob_pair = None
         return self
 
     def __init__(self, W, b, precise=False):
@@ -76,6 +77,7 @@ class SdfQueryWeights:
             "kernels are built for the 8x256, multires=6, skip_in=(4,) SDF network of the shipped confs"
         self.blob = torch.zeros(int(lib.fmov_sdf_fwd_blob_bytes()), dtype=torch.uint8, device=dev)
         self.blob_lo = torch.zeros_like(self.blob) if precise else None
+        self.blob_pair = None          # only FineWeights carries the half-major images of the CTA-pair engine
         for fmt, blob in ((0, self.blob), (2, self.blob_lo)):
             if blob is None:
                 continue

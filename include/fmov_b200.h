@@ -62,6 +62,13 @@ int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z
                         int z_off, const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8,
                         float in_scale, float out_scale, float* out, void* stream);
 /* bmin3/bmax3 are HOST float[3]; points first..first+count of the x-major res^3 grid. */
+/* fmov_sdf_query_rays on the CTA-pair engine (clusters of two CTAs, tcgen05.mma.cta_group::2): the hierarchical-sampling
+ * queries of the train step.  wblob_pair = the FP0..FP7 region of the fine-stage blob (fmov_fine_image_info(44), fmov_sdf_pair_blob_bytes()
+ * bytes; 0 bytes when the library was built without the pair engine): half-major images, biases in their bias slices. */
+long long fmov_sdf_pair_blob_bytes(void);
+int fmov_sdf_query_rays_pair(const float* rays_o, const float* rays_d, const float* z, long long B, int S, int z_stride,
+                             int z_off, const void* wblob_pair, const float* w8_row0, const float* b8, float in_scale,
+                             float out_scale, float* out, void* stream);
 int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long long first, long long count,
                         const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
                         float out_scale, float* out, void* stream);

@@ -53,6 +53,13 @@ def test_static_queries_without_a_gpu(lib):
     assert lib.fmov_grad_floats() == sdf_w + sdf_b + col_w + col_b
     assert lib.fmov_grad_offset(1, 0) == sdf_w
     assert lib.fmov_sdf_fwd_blob_bytes() == 128 * (256 * 1 + 256 * 4 * 2 + 224 * 4 + 256 * 5 + 256 * 4 * 3)
+    # CTA-pair engine: the same eight images half-major, each followed by its [N x 16] bias slice; FP0 is image 44
+    lib.fmov_sdf_pair_blob_bytes.restype = ctypes.c_longlong
+    assert lib.fmov_sdf_pair_blob_bytes() == lib.fmov_sdf_fwd_blob_bytes() + 32 * (7 * 256 + 224)
+    off, off2, npad, kb = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+    assert lib.fmov_fine_image_info(44, ctypes.byref(off), ctypes.byref(npad), ctypes.byref(kb)) == 0
+    assert lib.fmov_fine_image_info(52, ctypes.byref(off2), ctypes.byref(npad), ctypes.byref(kb)) != 0      # no such image
+    assert off.value + lib.fmov_sdf_pair_blob_bytes() == lib.fmov_fine_blob_bytes()                          # FP0..FP7 close the blob
 
 
 def test_errors_are_status_codes_not_exceptions(lib):

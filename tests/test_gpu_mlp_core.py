@@ -127,3 +127,35 @@ def test_sdf_query_rays_and_grid_vs_oracle():
     pts = o[:, None] + dd[:, None] * z[:, 3:3 + S, None]
     ref = O.sdf_value(p, pts.reshape(-1, 3)).reshape(B, S)
     assert (got.cpu() - ref).abs().max().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,S", [(1, 64), (37, 64), (777, 16), (148 * 2 * 2 + 3, 64)])
+def test_pair_engine_query_vs_single_engine_and_oracle(B, S):
+    """fmov_sdf_query_rays_pair (clusters of two CTAs, tcgen05.mma.cta_group::2, half-major images FP0..FP7 of the fine blob,
+    biases added by the tensor core) against fmov_sdf_query_rays on the same network and rays, and against the fp32 oracle
+    (SDFNetwork.sdf, models/fields.py:88-107).  Odd tile counts exercise the padding tile of the odd CTA."""
+    from fmov_pose_b200 import fine, ops
+    d = load_golden("full_6464_gf")
+    p, W, b = _sdf_weights(d, _dev())
+    cp = params_from(d, "col.")
+    Wc = [O.eff_weight(cp, "", l).to(_dev()) for l in range(5)]
+    bc = [cp[f"lin{l}.bias"].to(_dev()) for l in range(5)]
+    fw = fine.FineWeights(W, b, Wc, bc, need_backward=False)
+    if fw.query.blob_pair is None:
+        pytest.skip("library built without the CTA-pair engine (-DFMOV_FINE_PAIR=0)")
+    g = torch.Generator().manual_seed(B)
+    o = torch.tensor([0.0, 0.0, -3.0]).repeat(B, 1) + torch.randn(B, 3, generator=g) * 0.05
+    dd = torch.nn.functional.normalize(torch.tensor([0.0, 0.0, 1.0]).repeat(B, 1) + torch.randn(B, 3, generator=g) * 0.1, dim=-1)
+    z = torch.sort(torch.rand(B, S + 5, generator=g) * 2 + 2, dim=-1)[0]
+    od, ddd, zd = o.to(_dev()), dd.to(_dev()), z.to(_dev()).contiguous()
+    got_pair = ops.sdf_query_rays(fw.query, od, ddd, zd, S, z_off=3)
+    pair_blob, fw.query.blob_pair = fw.query.blob_pair, None
+    got_single = ops.sdf_query_rays(fw.query, od, ddd, zd, S, z_off=3)
+    fw.query.blob_pair = pair_blob
+    torch.cuda.synchronize()
+    pts = o[:, None] + dd[:, None] * z[:, 3:3 + S, None]
+    ref = O.sdf_value(p, pts.reshape(-1, 3)).reshape(B, S)
+    # both chains round every activation to fp16; they differ in where the bias enters the fp32 sum (measured: <= 2e-4)
+    assert (got_pair - got_single).abs().max().item() <= 5e-4
+    assert (got_pair.cpu() - ref).abs().max().item() <= 1e-3          # north_star: SDF <= 1e-3
