@@ -1154,6 +1154,8 @@ extern "C" int fmov_fine_image_info(int id, long long* offset, int* npad, int* k
   return OK;
 }
 extern "C" long long fmov_fine_blob_bytes(void) { return img_offset(IMG_COUNT); }
+/* byte offset, inside the fine blob, of the images the pair-engine queries read (FP0..FP7, fmov_sdf_pair_blob_bytes() bytes) */
+extern "C" long long fmov_sdf_pair_blob_offset(void) { return img_offset(IMG_FP0); }
 extern "C" int fmov_grad_is_bf16(void) { return kGradBf16 ? 1 : 0; }
 extern "C" int fmov_fine_stash_count(void) { return ST_COUNT; }
 extern "C" int fmov_fine_stash_blocks(int id) { return (id >= 0 && id < ST_COUNT) ? stash_kb(id) : -1; }

@@ -15,7 +15,6 @@ SQ2 = math.sqrt(2.0)
 IMG_F0, IMG_T0, IMG_C0 = 0, 9, 17
 IMG_CT0A, IMG_CT0B, IMG_CT1, IMG_CT2, IMG_CT3 = 22, 23, 24, 25, 26
 IMG_FB0, IMG_TB0 = 27, 35
-IMG_FP0 = 44
 
 
 def _img_info(i):
@@ -63,7 +62,7 @@ class FineWeights:
         self.query = packing.SdfQueryWeights.from_views(self.blob, self.bias_sdf, self.w8row, self.b8)
         nb = int(lib.fmov_sdf_pair_blob_bytes())
         if nb > 0:          # half-major copies FP0..FP7 (+ bias slices): the sampling queries run on the CTA-pair engine
-            off = _img_info(IMG_FP0)[0]
+            off = int(lib.fmov_sdf_pair_blob_offset())
             self.query.blob_pair = self.blob[off: off + nb]
 
 

@@ -63,9 +63,10 @@ int fmov_sdf_query_rays(const float* rays_o, const float* rays_d, const float* z
                         float in_scale, float out_scale, float* out, void* stream);
 /* bmin3/bmax3 are HOST float[3]; points first..first+count of the x-major res^3 grid. */
 /* fmov_sdf_query_rays on the CTA-pair engine (clusters of two CTAs, tcgen05.mma.cta_group::2): the hierarchical-sampling
- * queries of the train step.  wblob_pair = the FP0..FP7 region of the fine-stage blob (fmov_fine_image_info(44), fmov_sdf_pair_blob_bytes()
- * bytes; 0 bytes when the library was built without the pair engine): half-major images, biases in their bias slices. */
+ * queries of the train step.  wblob_pair = the FP0..FP7 region of the fine-stage blob (fmov_sdf_pair_blob_offset(),
+ * fmov_sdf_pair_blob_bytes() bytes; 0 bytes when the library was built without the pair engine): half-major images, biases in their bias slices. */
 long long fmov_sdf_pair_blob_bytes(void);
+long long fmov_sdf_pair_blob_offset(void);   /* where that region starts inside the fmov_pack_all blob */
 int fmov_sdf_query_rays_pair(const float* rays_o, const float* rays_d, const float* z, long long B, int S, int z_stride,
                              int z_off, const void* wblob_pair, const float* w8_row0, const float* b8, float in_scale,
                              float out_scale, float* out, void* stream);

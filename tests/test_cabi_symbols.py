@@ -56,10 +56,12 @@ def test_static_queries_without_a_gpu(lib):
     # CTA-pair engine: the same eight images half-major, each followed by its [N x 16] bias slice; FP0 is image 44
     lib.fmov_sdf_pair_blob_bytes.restype = ctypes.c_longlong
     assert lib.fmov_sdf_pair_blob_bytes() == lib.fmov_sdf_fwd_blob_bytes() + 32 * (7 * 256 + 224)
-    off, off2, npad, kb = ctypes.c_longlong(), ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
+    lib.fmov_sdf_pair_blob_offset.restype = ctypes.c_longlong
+    off, npad, kb = ctypes.c_longlong(), ctypes.c_int(), ctypes.c_int()
     assert lib.fmov_fine_image_info(44, ctypes.byref(off), ctypes.byref(npad), ctypes.byref(kb)) == 0
-    assert lib.fmov_fine_image_info(52, ctypes.byref(off2), ctypes.byref(npad), ctypes.byref(kb)) != 0      # no such image
-    assert off.value + lib.fmov_sdf_pair_blob_bytes() == lib.fmov_fine_blob_bytes()                          # FP0..FP7 close the blob
+    assert off.value == lib.fmov_sdf_pair_blob_offset() and (npad.value, kb.value) == (256, 1)
+    assert lib.fmov_fine_image_info(52, ctypes.byref(off), ctypes.byref(npad), ctypes.byref(kb)) != 0       # no such image
+    assert lib.fmov_sdf_pair_blob_offset() + lib.fmov_sdf_pair_blob_bytes() == lib.fmov_fine_blob_bytes()    # FP0..FP7 close the blob
 
 
 def test_errors_are_status_codes_not_exceptions(lib):
