@@ -198,9 +198,9 @@ HBM_KERNEL_BYTES_PER_RAY = {
 
 def measured_traffic(kernel, rays):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` summary of
-    this very configuration (profiles/r2_ncu_traffic.json, keyed by rays per launch); None when not captured"""
+    this very configuration (profiles/r2b_ncu_traffic.json, keyed by rays per launch); None when not captured"""
     try:
-        tab = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        tab = json.load(open(os.path.join(ROOT, "profiles", "r2b_ncu_traffic.json")))
         return float(tab[str(rays)][kernel])
     except Exception:
         return None
@@ -628,8 +628,8 @@ def main():
         roof = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": traffic,
                 "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of one launch at this batch size, ncu --set full "
-                                 "(profiles/r2_ncu_traffic.json)" if traffic else
-                                 "no ncu --set full capture committed for this batch size (profiles/r2_ncu_traffic.json)"),
+                                 "(profiles/r2b_ncu_traffic.json)" if traffic else
+                                 "no ncu --set full capture committed for this batch size (profiles/r2b_ncu_traffic.json)"),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms,
                 "timing_note": "per-kernel times: CUDA events around each launch in an eager pass of the same step, outside "
                                "the timed graph replay (events cannot be recorded inside a replay)",
