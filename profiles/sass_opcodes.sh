@@ -13,7 +13,7 @@ for sym in $(cuobjdump -elf $LIB 2>/dev/null | grep -oE "_ZN4fmov[A-Za-z0-9_]+" 
   echo
 done
 echo "# CTA-pair engine: full mnemonics of the tensor / TMA / cluster instructions (2CTA = cta_group::2)"
-for sym in $(cuobjdump -elf $LIB 2>/dev/null | grep -oE "_ZN4fmov[A-Za-z0-9_]+" | grep -E "fine_fwd_kernel|fine_bwd_kernel|sdf_query_kernelILi2" | sort -u); do
+for sym in $(cuobjdump -elf $LIB 2>/dev/null | grep -oE "_ZN4fmov[A-Za-z0-9_]+" | grep -E "fine_fwd_kernel|fine_bwd_kernel|sdf_query_kernelILi2" | grep -v "_param_" | sort -u); do
   printf "%-34s " "$(echo $sym | c++filt | sed 's/(.*//; s/fmov:://; s/void //')"
   cuobjdump -sass -fun "$sym" $LIB 2>/dev/null | grep -oE "UTCHMMA[.A-Z0-9_]*|UTMALDG[.A-Z0-9_]*|UTCBAR[.A-Z0-9_]*|UCGABAR[.A-Z_]*|UTCATOMSWS[.A-Z0-9_]*" | sort | uniq -c | awk '{printf "%s %s  ", $1, $2}'
   echo
