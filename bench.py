@@ -218,7 +218,11 @@ def measure_extras(scene, dev, use_graph=True):
     buf = torch.empty(count, dtype=torch.float32, device=dev)
     bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for tag, precise in (("c5_grid_query", True), ("c5_grid_query_fast_fp16_chain", False)):
+    notes = {"act": "activation-split chain (default of extract_fields: activations and encoded inputs as fp16 hi + lo, SDF within "
+                    "3.6e-4 of the reference's own grid on the whole box; 2 MMA passes per layer over one weight stream, one tile in flight)",
+             True: "full split-precision chain (weights split too: 1.3e-5; 3 MMA passes per layer over two weight streams)",
+             False: "plain fp16 chain (6.7e-4 on the +-1.01 box, two tiles in flight)"}
+    for tag, precise in (("c5_grid_query", "act"), ("c5_grid_query_full_split", True), ("c5_grid_query_fast_fp16_chain", False)):
         for _ in range(2):
             rend.extract_fields(bmin, bmax, res, first=0, count=count, out=buf, precise=precise)
         torch.cuda.synchronize()
@@ -230,10 +234,7 @@ def measure_extras(scene, dev, use_graph=True):
         ms = e0.elapsed_time(e1) / 3
         out[tag] = {"points": count, "ms": ms, "sdf_queries_per_s": count / ms * 1e3,
                     "tflops_algorithmic": count * F_S / ms / 1e9,
-                    "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing; " +
-                            ("split-precision chain (default of extract_fields: SDF within 1e-4 of fp32 on the whole box; "
-                             "3 MMA passes per layer, one tile in flight)" if precise else
-                             "plain fp16 chain (1.3e-3 at the box corners)")}
+                    "note": "1/8 slab of the 512^3 grid (config C5 per-GPU share), includes weight packing; " + notes[precise]}
     # whole-frame forward-only render (validate_image shape: 640x480 = 307,200 rays, 64+64 samples)
     ds = scene["dataset"]
     with torch.no_grad():

@@ -35,7 +35,7 @@ def gather_slabs(local, resolution, group=None):
     return torch.cat(parts)
 
 
-def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=None, to_host=False, precise=True):
+def extract_fields_sharded(renderer, bound_min, bound_max, resolution, group=None, to_host=False, precise="act"):
     """u = -sdf on the res^3 grid with the x-planes partitioned across the ranks of `group`.
     -> [res,res,res] tensor on every rank (device; pinned host memory when to_host: what validate_mesh hands to
     marching cubes, exp_runner.py:1630-1640)."""

@@ -209,14 +209,15 @@ class NeuSRenderer:
                 "depth_fine": depth.reshape(*shape, 1), "weight_sum": wsum.reshape(*shape, 1)}
 
     # ------------------------------------------------------------------------------------------------
-    def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None, precise=True):
+    def extract_fields(self, bound_min, bound_max, resolution, first=0, count=None, out=None, precise="act"):
         """u = -sdf on the res^3 grid (models/renderer.py:9-37 with query_func of :506) in one launch.
         `first`/`count` select a contiguous x-major range (grid partitioning across ranks).
-        `precise` (default): split-precision chain, within ~1e-5 of the fp32 network on the whole +-1.01 box (the plain
-        fp16 chain is 1.3e-3 off at the box corners, above north_star's 1e-3)."""
+        `precise`: "act" (default) = activation-split chain, 3.6e-4 of the reference's own grid on the whole +-1.01 box
+        (north_star: SDF <= 1e-3) at 0.40 G queries/s; True = full split-precision chain, 1.3e-5 at 0.30 G/s; False = plain
+        fp16 chain, 6.7e-4 at 0.74 G/s (profiles/r2b_grid_modes.txt)."""
         with torch.no_grad():
             W, b = self.sdf_network.effective_weights()
-            qw = _packing.SdfQueryWeights(W, b, precise=precise)
+            qw = _packing.SdfQueryWeights(W, b, precise=precise is True)
             total = resolution ** 3
             if count is None:
                 count = total - first
@@ -227,7 +228,7 @@ class NeuSRenderer:
                                 count, out, in_scale=sc, out_scale=-1.0 / sc, precise=precise)
         return out
 
-    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0, precise=True):
+    def extract_geometry(self, bound_min, bound_max, resolution, threshold=0.0, precise="act"):
         """models/renderer.py:500-507: the 512^3 grid query and the marching cubes both run on the device; only the
         mesh crosses to the host (the reference copies 512 chunks of the grid to the host and runs PyMCubes there)."""
         u = self.extract_fields(bound_min, bound_max, resolution, precise=precise).reshape(resolution, resolution, resolution)

@@ -13,8 +13,9 @@ def sdf_query_points(qw, pts, in_scale=1.0, out_scale=1.0, precise=False):
     P = pts.shape[0]
     out = torch.empty(P, 1, dtype=torch.float32, device=pts.device)
     if P and precise:
-        assert qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the split-precision chain"
-        L.check(L.lib().fmov_sdf_query_points_precise(L.ptr(pts), L.c_ll(P), L.ptr(qw.blob), L.ptr(qw.blob_lo),
+        # precise=True: full split (needs the residual images blob_lo); precise="act": activation-split chain (blob_lo = NULL)
+        assert precise == "act" or qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the full split"
+        L.check(L.lib().fmov_sdf_query_points_precise(L.ptr(pts), L.c_ll(P), L.ptr(qw.blob), L.ptr(None if precise == "act" else qw.blob_lo),
                                                       L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8), L.c_float(in_scale),
                                                       L.c_float(out_scale), L.ptr(out), L.stream()),
                 "fmov_sdf_query_points_precise")
@@ -48,10 +49,10 @@ def sdf_query_grid(qw, bmin, bmax, res, first, count, out, in_scale=1.0, out_sca
     bm = (ctypes.c_float * 3)(*[float(v) for v in bmin])
     bx = (ctypes.c_float * 3)(*[float(v) for v in bmax])
     if precise:
-        assert qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the split-precision chain"
+        assert precise == "act" or qw.blob_lo is not None, "SdfQueryWeights(..., precise=True) is needed for the full split"
         with L.timed("sdf_query_grid_precise"):
             L.check(L.lib().fmov_sdf_query_grid_precise(bm, bx, int(res), L.c_ll(first), L.c_ll(count), L.ptr(qw.blob),
-                                                        L.ptr(qw.blob_lo), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
+                                                        L.ptr(None if precise == "act" else qw.blob_lo), L.ptr(qw.bias), L.ptr(qw.w8), L.ptr(qw.b8),
                                                         L.c_float(in_scale), L.c_float(out_scale), L.ptr(out),
                                                         L.stream()), "fmov_sdf_query_grid_precise")
         return out

@@ -48,11 +48,11 @@ if what == "flow":
     sys.exit(0)
 scene = synthetic.build_scene(device=dev, n_images=4, H=120, W=160)
 if what == "grid":
-    # config C5 per-GPU slab through both value chains: plain fp16 and split-precision (extract_fields' default)
+    # config C5 per-GPU slab through the value chains: plain fp16, activation-split (extract_fields' default), full split
     rend = scene["renderer"]
     bmin, bmax = torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3)
     count = 512 ** 3 // 64
-    for precise in (False, True, True):
+    for precise in (False, "act", True):
         rend.extract_fields(bmin, bmax, 512, first=0, count=count, precise=precise)
     torch.cuda.synchronize()
     print("grid ok")

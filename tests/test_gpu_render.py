@@ -130,7 +130,8 @@ def test_direct_field_calls_and_grid():
     ref = O.sdf_forward(p, pts)
     ref_n = O.sdf_gradient(p, pts, create_graph=False)
     x = pts.to(DEV)
-    assert (sdf_net.sdf(x).cpu() - ref[:, :1]).abs().max().item() <= 1e-4          # split-precision chain (default)
+    assert (sdf_net.sdf(x).cpu() - ref[:, :1]).abs().max().item() <= 5e-4          # activation-split chain (default; measured 3e-4)
+    assert (sdf_net.sdf(x, precise=True).cpu() - ref[:, :1]).abs().max().item() <= 1e-4          # full split-precision chain
     assert (sdf_net.sdf(x, precise=False).cpu() - ref[:, :1]).abs().max().item() <= 1e-3
     full = sdf_net(x).cpu()
     assert (full[:, :1] - ref[:, :1]).abs().max().item() <= 1e-3
@@ -141,9 +142,11 @@ def test_direct_field_calls_and_grid():
     res = 24
     u = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res).reshape(res, res, res).cpu()
     u_ref = O.extract_fields(p, [-1.01] * 3, [1.01] * 3, res)
-    assert (u - u_ref).abs().max().item() <= 1e-4          # north_star: SDF <= 1e-3 on the whole +-1.01 box
+    assert (u - u_ref).abs().max().item() <= 5e-4          # north_star: SDF <= 1e-3 on the whole +-1.01 box (measured 3.6e-4)
+    u_full = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, precise=True).reshape(res, res, res).cpu()
+    assert (u_full - u_ref).abs().max().item() <= 1e-4
     u_fast = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, precise=False).reshape(res, res, res).cpu()
-    assert (u_fast - u_ref).abs().max().item() <= 2e-3
+    assert (u_fast - u_ref).abs().max().item() <= 1e-3          # (measured 6.7e-4 since the encoded inputs carry the coordinate residuals)
     # partitioned query (2 "ranks") equals the full one
     half = res ** 3 // 2
     a = rend.extract_fields(torch.tensor([-1.01] * 3), torch.tensor([1.01] * 3), res, first=0, count=half)
