@@ -74,11 +74,14 @@ int fmov_sdf_query_grid(const float* bmin3, const float* bmax3, int res, long lo
                         const void* wblob, const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
                         float out_scale, float* out, void* stream);
 
-/* split-precision ("precise") value chain for SDFNetwork.sdf / extract_fields (models/fields.py:106-107,
- * models/renderer.py:9-37, :506): every layer accumulates hi*W_hi + lo*W_hi + hi*W_lo with hi = fp16(v), lo = fp16(v - hi),
- * so the result is within ~1e-5 of the fp32 network everywhere in the +-1.01 box (north_star: SDF <= 1e-3; the plain
- * fp16 chain reaches 1.3e-3 at |x| ~ 1.75).  wblob_lo: residual images W - fp16(W) in wblob's layout
- * (fmov_pack_image with bf16 = 2).  About 3x the cost of the plain chain. */
+/* split-precision value chains for SDFNetwork.sdf / extract_fields (models/fields.py:106-107, models/renderer.py:9-37, :506),
+ * measured against the reference's own 40^3 grid on the +-1.01 box (north_star: SDF <= 1e-3; profiles/r2b_grid_modes.txt):
+ *   wblob_lo != NULL  full split: every layer accumulates hi*W_hi + lo*W_hi + hi*W_lo with hi = fp16(v), lo = fp16(v - hi):
+ *                     1.3e-5, 0.30 G queries/s per GPU.  wblob_lo = residual images W - fp16(W) in wblob's layout
+ *                     (fmov_pack_image with bf16 = 2)
+ *   wblob_lo == NULL  activation split: (hi + lo)*W with plain fp16 weights, one pass over the weight stream: 3.6e-4,
+ *                     0.40 G queries/s (the default of the Python mirror's sdf() / extract_fields)
+ * (the plain chain, fmov_sdf_query_points / _grid: 6.7e-4 on that box, 1e-3 at |x| ~ 2, 0.74 G queries/s) */
 int fmov_sdf_query_points_precise(const float* pts, long long P, const void* wblob, const void* wblob_lo,
                                   const float* bias8x256, const float* w8_row0, const float* b8, float in_scale,
                                   float out_scale, float* out, void* stream);
