@@ -4,6 +4,7 @@
 #   bash profiles/r2_capture.sh bench     bench.py defaults -> gpurun_out/${TAG}_bench.json
 #   bash profiles/r2_capture.sh launches  ncu launch list (gpu__time_duration) of the bench command
 #   bash profiles/r2_capture.sh full      ncu --set full of every kernel of one 8192-ray step + marching cubes, summarised
+#   bash profiles/r2_capture.sh fullstep  (the step part of `full` only)
 # Summaries are written to gpurun_out/ (copied into profiles/ by hand after review); the .ncu-rep files stay in /tmp.
 set -u
 TAG=${TAG:-r2b}          # r2 = first session of round 2, r2b = final tree of round 2 (CTA-pair engine)
@@ -21,6 +22,12 @@ launches)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no_extras --no_cpu_baseline > gpurun_out/${TAG}_launches_run.log 2>&1
   echo "launches rc=$?"; python profiles/summarize.py launches gpurun_out/${TAG}_launches.csv > gpurun_out/${TAG}_launches_8192rays.txt 2>&1; head -30 gpurun_out/${TAG}_launches_8192rays.txt ;;
+fullstep)
+  timeout 300 python profiles/run_kernels.py step 8192 > gpurun_out/${TAG}_step_plain.log 2>&1 && \
+  timeout 1500 ncu --set full --clock-control none --import-source on -k "$KREGEX" --launch-skip 40 -c 45 -o /tmp/${TAG}_step8192 -f \
+    python profiles/run_kernels.py step 8192 > gpurun_out/${TAG}_ncu_step.log 2>&1
+  echo "ncu step rc=$?"; tail -2 gpurun_out/${TAG}_ncu_step.log
+  python profiles/summarize.py full /tmp/${TAG}_step8192.ncu-rep > gpurun_out/${TAG}_ncu_full_8192rays.txt 2>&1 ;;
 full)
   timeout 300 python profiles/run_kernels.py step 8192 > gpurun_out/${TAG}_step_plain.log 2>&1 && \
   timeout 1500 ncu --set full --clock-control none --import-source on -k "$KREGEX" --launch-skip 40 -c 45 -o /tmp/${TAG}_step8192 -f \
