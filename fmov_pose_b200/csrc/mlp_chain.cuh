@@ -187,11 +187,7 @@ __device__ __forceinline__ void cluster_sync_all() {          // every thread of
 // before its warp elects the arriving lane.  (`.release.cluster` here compiled to a MEMBAR that also waited for the thread's
 // outstanding global stash stores: 9 % of fine_fwd's and 5 % of fine_bwd's warp samples were `membar` stalls on it.)
 __device__ __forceinline__ void mbar_arrive_even_cta(uint64_t* bar) {
-#ifdef FMOV_ARRIVE_RELEASE_CLUSTER
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & CH_PEER_MASK) : "memory");
-#else
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & CH_PEER_MASK) : "memory");
-#endif
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
