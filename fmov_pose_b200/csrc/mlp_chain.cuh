@@ -1,25 +1,31 @@
-// Fused MLP "chain" engine (v2): a persistent CTA walks 128-point tiles through a table of GEMM steps
-// with the activation tile resident in shared memory, weights streamed from L2 by TMA bulk copies,
-// accumulators in TMEM and a per-kernel epilogue between steps.  TWO tiles are in flight per CTA so that
-// the tensor core works on one tile while the other tile's epilogue runs.
+// Fused MLP "chain" engine: a persistent CTA walks 128-point tiles through a table of GEMM steps with the activation
+// tile resident in shared memory, weights streamed from L2 into a ring, accumulators in TMEM and a per-kernel epilogue
+// between steps.  TWO tiles are in flight per CTA so that the tensor core works on one tile while the other tile's
+// epilogue runs.  Two forms:
+//   one-CTA engine   tcgen05.mma.cta_group::1 (M = 128); weight k-slices by cp.async.bulk into a 4 x 16 KiB ring
+//   CTA-pair engine  clusters of two CTAs; ONE tcgen05.mma.cta_group::2 stream (M = 256) issued by the even CTA for both
+//                    CTAs' tiles; each CTA stages half of every weight k-block by cta_group::2 tensor-map TMA; commits
+//                    multicast to both CTAs; optional bias16 steps add the layer bias by one extra K = 16 MMA
 //
 // Warp roles (CH_WGS = 2: 20 warps, 640 threads):
 //   warps 0..7    epilogue of tile slot 0: two warpgroups, columns 0..127 and 128..255 of the tile
 //   warps 8..15   epilogue of tile slot 1        (tcgen05.ld -> fp32 math -> st.shared next A operand
 //                                                 + st.global / ld.global of the stash rows)
-//   warp 16       weight producer   cp.async.bulk  weight-image k-blocks -> WST ring            (1 lane)
-//   warp 17       MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage        (1 lane) + TMEM alloc
-//   warps 18,19   idle (complete the control warpgroup for setmaxnreg)
-// 4 epilogue warps per scheduler: the epilogues are latency bound (TMEM / HBM loads, MUFU chains), measured
-// 0.24 eligible warps per cycle with 8 epilogue warps.
+//   warp 16       weight producer   bulk / tensor-map copies of weight k-blocks -> WST ring          (1 lane)
+//   warp 17       MMA issuer        tcgen05.mma    A = ACT[slot]/AUX[slot], B = WST stage            (1 lane) + TMEM alloc
+//                 (pair engine: only the even CTA's issuer issues; the odd CTA's is idle)
+//   warps 18,19   idle
+// What bounds the kernels built on it was measured in round 2b (knock-out builds): with the pair engine the
+// weight stream and the tensor core are off the critical path; the epilogue warps' instruction and memory work is it.
 //
 // Stash traffic is done by the row-owning thread: in the tile-image layout a tile row is 128 contiguous
 // bytes per 64-feature block, so a warp reads/writes 4 KiB contiguous per block (fully coalesced), and a
 // thread only ever re-reads rows it wrote itself (program-order coherence, no fences).  Cross-thread
 // visibility is only needed for operands of the MMA (shared memory: fence.proxy.async + mbarrier).
 //
-// mbarriers (per tile slot): act_ready (128 arrivals: A operand written + TMEM drained) -> MMA issuer;
-// acc_ready (tcgen05.commit) -> epilogue; weight ring full/empty.
+// mbarriers (per tile slot): act_ready (A operand written + TMEM drained: one arrival per epilogue thread, or one per
+// epilogue warp of both CTAs on the even CTA's barrier in pair mode) -> MMA issuer; acc_ready (tcgen05.commit) ->
+// epilogue; weight ring full/empty.
 #pragma once
 #include "fmov_common.cuh"
 #include <cuda.h>          // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
@@ -32,10 +38,10 @@ constexpr int CH_SLOTS = 2;
 #endif
 constexpr int CH_WGS = FMOV_CH_WGS;                // epilogue warpgroups (column ranges) per tile slot: 1 or 2
 constexpr int CH_CHUNKS = 16 / CH_WGS;             // 16-column chunks handled by one warpgroup
-// Warp layout: epilogue warps first (whole warpgroups, so that setmaxnreg can be applied per role), then one control
-// warpgroup whose warps 0/1 are the weight producer / MMA issuer (warps 2/3 idle).  Registers are allocated per SM
-// sub-partition (16 K each, warp w lives in partition w % 4): with 5 warps per partition the launch allocation is
-// <= 96 registers/thread; the control warpgroup then shrinks to 24 and the epilogue warps grow (chain_regs_*).
+// Warp layout: epilogue warps first (whole warpgroups), then one control warpgroup whose warps 0/1 are the weight producer /
+// MMA issuer (warps 2/3 idle).  Registers are allocated per SM sub-partition (16 K each, warp w lives in partition w % 4):
+// with 5 warps per partition the launch allocation is <= 96 registers/thread (setmaxnreg cannot re-balance it with
+// ptxas 12.9: a .dec anywhere caps the whole kernel).
 constexpr int EPI_WARP0 = 0;
 constexpr int CTRL_WARP0 = CH_SLOTS * CH_WGS * 4;
 constexpr int PRODUCER_WARP = CTRL_WARP0;
@@ -43,9 +49,9 @@ constexpr int ISSUER_WARP = CTRL_WARP0 + 1;
 constexpr int CH_THREADS = (CTRL_WARP0 + 4) * 32;           // 640 (two warpgroups per slot) / 384
 constexpr int EPI_THREADS = CH_WGS * 128;          // threads arriving per slot
 // Weight ring: 64 KiB of shared memory in CH_WSTAGES slots of 1/CH_WSPLIT k-block each (a K = 64/CH_WSPLIT slice of
-// all N rows is contiguous in the weight image).  The ring is refilled from L2 with ~1.5 us latency per slot; with two
-// 32 KiB slots the MMA issuer waited on weights for half of every step (measured: 5.1 K cycles per 128x256x256 step
-// against 2 K of tensor time); four 16 KiB slots keep three copies in flight behind the one being read.
+// all N rows is contiguous in the weight image).  One-CTA engine: the ring is latency bound — 48 KiB in flight behind the
+// stage being read, per ~2-2.5 K-cycle L2 round trip under load = 23-29 B/clk per SM, although the SM itself can take
+// 60-90 B/clk (profiles/micro/l2_stream*.cu); 2 x 32 KiB was worse (one copy in flight), 8 x 8 KiB too (per-request cost).
 #ifndef FMOV_CH_WSPLIT
 #define FMOV_CH_WSPLIT 2
 #endif
@@ -103,8 +109,8 @@ struct ChainStep {
   uint8_t a_fmt;        // FMT_F16 / FMT_BF16 (A and B must match: tcgen05 kind::f16 cannot mix them)
   uint8_t b_fmt;
   uint8_t no_mma;       // epilogue-only step (no weights / MMA / accumulator)
-  uint8_t pf[2];        // stash tensors (4-block tiles) this step's epilogue reads from HBM; 0xFF = none.
-                        // The producer warp bulk-prefetches them into L2 one step ahead.
+  uint8_t pf[2];        // stash tensors (4-block tiles) this step's epilogue reads from HBM; 0xFF = none (documentation of the
+                        // tile program: the epilogue threads prefetch their own rows, see tile_prefetch_l2)
   uint8_t flags;        // CHF_* bits (0 for an ordinary step)
   uint8_t bias16;       // pair mode: one more K = 16 MMA after the k-blocks, A = columns 48..63 of the slot's AUX block (1.0 in
                         // columns 48 / 49), B = the [N x 16] slice appended to the step's weight image (bias as fp16 hi + lo):
@@ -239,11 +245,6 @@ __device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
 
 // Tiles of this CTA: global tile index = blockIdx.x + k*gridDim.x, k = 0..n_my-1; slot = k & 1.
 // Producer and issuer walk (pair, step, slot, k-block) in the same order.
-
-template <int N>
-__device__ __forceinline__ void chain_regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void chain_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 // ---- producer warp -------------------------------------------------------------------------
 // (measured on B200 and removed: a bulk L2 prefetch of the next step's stash tiles from this warp — fine_bwd 12.3 -> 14.1 ms

@@ -78,7 +78,7 @@ def test_sdf_query_points_vs_oracle(P):
     qw = packing.SdfQueryWeights(W, b)
     g = torch.Generator().manual_seed(P)
     # points in the unit ball: the region the renderer's SDF values matter in (fp16 operands give
-    # ~6e-4 there; the far field |x|~2 reaches 1.3e-3 — see DESIGN.md "precision")
+    # ~6e-4 there; the far field |x| ~ 2 reaches 1.0e-3 since the encoded inputs carry the coordinate residuals — DESIGN.md "Precision")
     v = torch.randn(P, 3, generator=g)
     pts = v / v.norm(dim=1, keepdim=True) * torch.rand(P, 1, generator=g) ** (1 / 3)
     out = ops.sdf_query_points(qw, pts.to(_dev()))
