@@ -380,7 +380,7 @@ def measure_marching_cubes_child():
     print(json.dumps({"grid": "512^3", "ms": ms, "vertices": int(v.shape[0]), "triangles": int(t.shape[0]),
                       "radius_min_max": [float(r.min()), float(r.max())],
                       "algorithmic_gb_per_s": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / hbm,
-                      "note": "fmov_mc_count + cumsum + fmov_mc_vertices + fmov_mc_triangles incl. the host sync for the "
+                      "note": "fmov_mc_count + fmov_mc_scan + fmov_mc_vertices + fmov_mc_triangles incl. the host sync for the "
                               "output sizes; the reference copies the grid to the host and runs PyMCubes on one core"}))
 
 

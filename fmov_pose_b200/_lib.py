@@ -27,7 +27,7 @@ def lib():
         _lib.fmov_sdf_fwd_blob_offset.restype = c_ll
         _lib.fmov_sdf_pair_blob_bytes.restype = c_ll
         _lib.fmov_sdf_pair_blob_offset.restype = c_ll
-        for name in ("fmov_fine_blob_bytes", "fmov_grad_offset", "fmov_grad_floats", "fmov_mc_chunk_count"):
+        for name in ("fmov_fine_blob_bytes", "fmov_grad_offset", "fmov_grad_floats", "fmov_mc_chunk_count", "fmov_mc_group_count"):
             getattr(_lib, name).restype = c_ll
         _lib.fmov_launch_count.restype = ctypes.c_ulonglong
     return _lib

@@ -2,13 +2,15 @@
 // `mcubes.marching_cubes(u, threshold)` of PyMCubes 0.1.4 — CPU, third-party).  Produces the same INDEXED mesh: one
 // vertex per crossed grid edge (shared by the cells around it), triangles from a 256-case table over the 12 cell edges.
 //
-// Three passes over the grid, all HBM-bound streaming kernels (thread per grid point, z fastest => coalesced rows;
-// the +1 / +Z / +YZ neighbours come from L1/L2, so each pass reads u once from HBM: 4 B per point):
-//   fmov_mc_count      per 256-point chunk: number of crossed edges starting at its points and of triangles of its cells
-//   (host: exclusive prefix sum over the chunks — torch.cumsum; the totals size the outputs)
+// Three passes over the grid (z fastest => coalesced rows; the +Z / +YZ neighbour rows come from L1/L2, so each pass reads u
+// once from HBM: 4 B per point) and a scan between them:
+//   fmov_mc_count      per 256-point chunk: number of crossed edges starting at its points and of triangles of its cells.
+//                      Z % 4 == 0 (every validate_mesh grid): warp per chunk on 16-byte quads and bit masks
+//                      (mc_count_quad_kernel); else thread per point (mc_count_kernel)
+//   fmov_mc_scan       exclusive 64-bit prefix sums over the chunks, totals appended; the totals size the outputs
 //   fmov_mc_vertices   vertex positions (index or world coordinates) + the vertex id of every crossed edge (vid3)
 //   fmov_mc_triangles  case lookup, three vid3 reads per triangle corner
-//   (both walk the list of non-empty chunks that fmov_mc_count appended to: ~2 % of the chunks at 512^3)
+//   (both walk the list of non-empty chunks that fmov_mc_count appended to)
 // Output order is deterministic: vertices by (grid point x-major, axis), triangles by (cell x-major, table order).
 // Corner / edge numbering and the case table: fmov_pose_b200/mc_tables.py (uploaded once with fmov_mc_set_tables).
 #include "fmov_common.cuh"
@@ -52,7 +54,8 @@ __device__ __forceinline__ int mc_pack(int nv, int nt) { return nv | (nt << 16);
 
 __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int* __restrict__ chunk_nv,
                                                             int* __restrict__ chunk_nt, int* __restrict__ list,
-                                                            int* __restrict__ n_list) {
+                                                            int* __restrict__ n_list,
+                                                            unsigned long long* __restrict__ group_sums) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
     const McPoint q = mc_point(g, ch * MC_CHUNK + threadIdx.x, true);
     const int v = mc_pack(mc_vertex_count(q), q.ntri);
@@ -63,8 +66,109 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int*
       chunk_nt[ch] = tot >> 16;
       // the emit passes walk this list (about 2 % of the chunks at 512^3) instead of testing every chunk; its order is
       // whatever the atomics give, the OUTPUT positions come from the prefix sums and do not depend on it
-      if (tot != 0) list[atomicAdd(n_list, 1)] = (int)ch;
+      if (tot != 0) {
+        list[atomicAdd(n_list, 1)] = (int)ch;
+        atomicAdd(&group_sums[ch >> MC_GROUP_SHIFT], (unsigned long long)(tot & 0xFFFF) | ((unsigned long long)(tot >> 16) << 32));
+      }
     }
+  }
+}
+
+// The same counts on quads (mc_core.cuh: Z % 4 == 0): one WARP per chunk, lane = two quads (16-byte loads of the four rows
+// around them), chunk totals by one warp reduction — no shared memory, no block barrier, a quarter of the load
+// instructions and ~1/6 of the issue slots of the per-point kernel (which was issue-bound at 0.7 TB/s).
+__global__ void __launch_bounds__(MC_CHUNK) mc_count_quad_kernel(const McGrid g, int* __restrict__ chunk_nv,
+                                                                 int* __restrict__ chunk_nt, int* __restrict__ list,
+                                                                 int* __restrict__ n_list,
+                                                                 unsigned long long* __restrict__ group_sums) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = (long long)gridDim.x * (MC_CHUNK / 32);
+  for (long long ch = (long long)blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); ch < g.n_chunks; ch += n_warps) {
+    // both halves' loads (8 x 16 B + 8 x 4 B per lane) are in flight before the first comparison; n is a multiple of 4, so a
+    // quad is inside the grid or not at all (then it re-reads quad 0 and counts nothing)
+    const long long p0 = ch * MC_CHUNK + lane * 4, p1 = p0 + MC_CHUNK / 2;
+    const bool in0 = p0 < g.n, in1 = p1 < g.n;
+    const McQuadRows q0 = mc_quad_load(g, in0 ? (unsigned int)p0 : 0u), q1 = mc_quad_load(g, in1 ? (unsigned int)p1 : 0u);
+    int packed = in0 ? mc_quad_eval(g, q0) : 0;
+    packed += in1 ? mc_quad_eval(g, q1) : 0;
+    const int tot = (int)__reduce_add_sync(0xffffffffu, (unsigned int)packed);          // <= 768 | 1280 << 16 per chunk
+    if (lane == 0) {
+      chunk_nv[ch] = tot & 0xFFFF;
+      chunk_nt[ch] = tot >> 16;
+      if (tot != 0) {
+        list[atomicAdd(n_list, 1)] = (int)ch;
+        atomicAdd(&group_sums[ch >> MC_GROUP_SHIFT], (unsigned long long)(tot & 0xFFFF) | ((unsigned long long)(tot >> 16) << 32));
+      }
+    }
+  }
+}
+
+// Exclusive prefix sums of the chunk counts (64-bit, totals appended).  group_sums (written by the count pass with integer
+// atomics, so order-independent) holds vertices | triangles << 32 per group of 4096 chunks; block b adds up the groups
+// before its own and scans its 4096 chunks in four rounds of 1024.
+constexpr int MC_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(MC_SCAN_THREADS) mc_scan_kernel(const int* __restrict__ chunk_nv,
+                                                                  const int* __restrict__ chunk_nt,
+                                                                  const unsigned long long* __restrict__ group_sums,
+                                                                  long long n_chunks, long long* __restrict__ voff,
+                                                                  long long* __restrict__ toff, long long* __restrict__ totals) {
+  __shared__ unsigned long long warp_sum[MC_SCAN_THREADS / 32];
+  __shared__ long long base_v, base_t;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // groups before this block (32 + 32 bits would overflow over many groups: two 64-bit sums)
+  long long sv = 0, st = 0;
+  for (int b = threadIdx.x; b < (int)blockIdx.x; b += MC_SCAN_THREADS) {
+    const unsigned long long s = group_sums[b];
+    sv += (long long)(s & 0xFFFFFFFFull);
+    st += (long long)(s >> 32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    st += __shfl_xor_sync(0xffffffffu, st, o);
+  }
+  if (threadIdx.x == 0) { base_v = 0; base_t = 0; }
+  __syncthreads();
+  if (lane == 0 && (sv | st)) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&base_v), (unsigned long long)sv);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&base_t), (unsigned long long)st);
+  }
+  __syncthreads();
+  long long run_v = base_v, run_t = base_t;
+  const long long first = (long long)blockIdx.x << MC_GROUP_SHIFT;
+  for (int r = 0; r < (1 << MC_GROUP_SHIFT) / MC_SCAN_THREADS; ++r) {
+    const long long c = first + r * MC_SCAN_THREADS + threadIdx.x;
+    const bool in = c < n_chunks;
+    // within a group both sums stay below 2^23: one packed 64-bit scan
+    const unsigned long long v = in ? ((unsigned long long)chunk_nv[c] | ((unsigned long long)chunk_nt[c] << 32)) : 0ull;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();                       // warp_sum of the previous round is no longer read
+    if (lane == 31) warp_sum[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < MC_SCAN_THREADS / 32; ++w) {
+      const unsigned long long s = warp_sum[w];
+      if (w < warp) before += s;
+      total += s;
+    }
+    const unsigned long long ex = before + inc - v;
+    if (in) {
+      voff[c] = run_v + (long long)(ex & 0xFFFFFFFFull);
+      toff[c] = run_t + (long long)(ex >> 32);
+      if (c == n_chunks - 1) {
+        const long long tv = run_v + (long long)((ex + v) & 0xFFFFFFFFull), tt = run_t + (long long)((ex + v) >> 32);
+        voff[n_chunks] = tv; toff[n_chunks] = tt;
+        totals[0] = tv; totals[1] = tt;
+      }
+    }
+    run_v += (long long)(total & 0xFFFFFFFFull);
+    run_t += (long long)(total >> 32);
   }
 }
 
@@ -144,15 +248,39 @@ extern "C" long long fmov_mc_chunk_count(int X, int Y, int Z) {
   return ((long long)X * Y * Z + MC_CHUNK - 1) / MC_CHUNK;
 }
 
+extern "C" long long fmov_mc_group_count(int X, int Y, int Z) {
+  return (fmov_mc_chunk_count(X, Y, Z) + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT;
+}
+
 extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list,
-                             int* n_list, void* stream) {
+                             int* n_list, unsigned long long* group_sums, void* stream) {
   McGrid g;
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
-  FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list, "fmov_mc_count: null output");
+  FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list && group_sums, "fmov_mc_count: null output");
   FMOV_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int), (cudaStream_t)stream));
-  mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
-  FMOV_LAUNCH_CHECK("mc_count_kernel");
+  FMOV_CUDA(cudaMemsetAsync(group_sums, 0, sizeof(unsigned long long) * (size_t)fmov_mc_group_count(X, Y, Z), (cudaStream_t)stream));
+  if (mc_quads_ok(g)) {
+    // a warp per chunk: the same number of resident warps as the per-point kernel
+    const long long want = (g.n_chunks + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32);
+    const int blocks = (int)(want < mc_blocks(g) ? want : mc_blocks(g));
+    mc_count_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list, group_sums);
+    FMOV_LAUNCH_CHECK("mc_count_quad_kernel");
+  } else {
+    mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list, group_sums);
+    FMOV_LAUNCH_CHECK("mc_count_kernel");
+  }
+  return OK;
+}
+
+extern "C" int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+                            long long* chunk_voff, long long* chunk_toff, long long* totals, void* stream) {
+  FMOV_REQUIRE(chunk_nv && chunk_nt && group_sums && chunk_voff && chunk_toff && totals, "fmov_mc_scan: null argument");
+  FMOV_REQUIRE(n_chunks >= 1 && n_chunks <= (1LL << 31) / MC_CHUNK, "fmov_mc_scan: bad chunk count %lld", n_chunks);
+  const int groups = (int)((n_chunks + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT);
+  mc_scan_kernel<<<groups, MC_SCAN_THREADS, 0, (cudaStream_t)stream>>>(chunk_nv, chunk_nt, group_sums, n_chunks, chunk_voff,
+                                                                        chunk_toff, totals);
+  FMOV_LAUNCH_CHECK("mc_scan_kernel");
   return OK;
 }
 

@@ -14,6 +14,7 @@ namespace fmov {
 
 constexpr int MC_CHUNK = 256;          // grid points per chunk = threads per block
 constexpr int MC_MAX_TRIS = 5;
+constexpr int MC_GROUP_SHIFT = 12;      // the offsets scan works on groups of 4096 chunks (fmov_mc_scan)
 
 struct McGrid {
   const float* u;
@@ -47,6 +48,21 @@ struct McPoint {
   int cubecase;
 };
 
+// linear index -> (i, j, k)
+MC_HD void mc_split(const McGrid& g, unsigned int pu, int& i, int& j, int& k) {
+  const int YZ = g.Y * g.Z;
+  if (g.sh_z >= 0 && g.sh_yz >= 0) {          // power-of-two Z and Y*Z (the 512^3 validate_mesh grid): shifts and masks
+    k = (int)(pu & (unsigned int)(g.Z - 1));
+    j = (int)((pu & (unsigned int)(YZ - 1)) >> g.sh_z);
+    i = (int)(pu >> g.sh_yz);
+  } else {
+    i = (int)(pu / (unsigned int)YZ);
+    const int r = (int)(pu - (unsigned int)i * (unsigned int)YZ);
+    j = r / g.Z;
+    k = r - j * g.Z;
+  }
+}
+
 // values and marks around point p (all loads are row-contiguous across the warp)
 MC_HD McPoint mc_point(const McGrid& g, long long p, bool want_case) {
   McPoint q;
@@ -59,17 +75,7 @@ MC_HD McPoint mc_point(const McGrid& g, long long p, bool want_case) {
   // the grid has fewer than 2^31 points (checked by the launcher): 32-bit index arithmetic (64-bit division is ~5x the
   // instructions, and these kernels are issue-bound, not bandwidth-bound — ncu: 68 % issue-active at 0.7 TB/s)
   const int YZ = g.Y * g.Z;
-  const unsigned int pu = (unsigned int)p;
-  if (g.sh_z >= 0 && g.sh_yz >= 0) {          // power-of-two Z and Y*Z (the 512^3 validate_mesh grid): shifts and masks
-    q.k = (int)(pu & (unsigned int)(g.Z - 1));
-    q.j = (int)((pu & (unsigned int)(YZ - 1)) >> g.sh_z);
-    q.i = (int)(pu >> g.sh_yz);
-  } else {
-    q.i = (int)(pu / (unsigned int)YZ);
-    const int r = (int)(pu - (unsigned int)q.i * (unsigned int)YZ);
-    q.j = r / g.Z;
-    q.k = r - q.j * g.Z;
-  }
+  mc_split(g, (unsigned int)p, q.i, q.j, q.k);
   const bool hx = q.i + 1 < g.X, hy = q.j + 1 < g.Y, hz = q.k + 1 < g.Z;
   q.f0 = g.u[p];
   q.b0 = q.f0 < g.iso;
@@ -92,6 +98,85 @@ MC_HD McPoint mc_point(const McGrid& g, long long p, bool want_case) {
   return q;
 }
 MC_HD int mc_vertex_count(const McPoint& q) { return (q.cross[0] ? 1 : 0) + (q.cross[1] ? 1 : 0) + (q.cross[2] ? 1 : 0); }
+
+// ---- the count pass on QUADS: four z-consecutive points k0 .. k0+3 (k0 % 4 == 0, Z % 4 == 0: a quad never straddles a
+// row and is one 16-byte load).  Everything is done on 5-bit "below the iso-value" masks of the four rows around the quad:
+// bit t = u(row, k0 + t) < iso, t = 0..4 (bit 4 = first point of the next quad; absent at the row end).
+MC_HD unsigned int mc_quad_mask(float a, float b, float c, float d, float e, float iso) {
+  return (a < iso ? 1u : 0u) | (b < iso ? 2u : 0u) | (c < iso ? 4u : 0u) | (d < iso ? 8u : 0u) | (e < iso ? 16u : 0u);
+}
+MC_HD int mc_popc4(unsigned int m) { return (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u)); }
+// crossed edges starting at the quad's points | triangles of their cells << 16: the sums of mc_vertex_count / ntri that
+// mc_point(.., true) gives for the four points.  m00 m01 m10 m11 = masks of rows (i,j) (i,j+1) (i+1,j) (i+1,j+1);
+// hx / hy: i + 1 < X, j + 1 < Y (masks of absent rows are ignored); hz4: k0 + 4 < Z (bit 4 present).
+MC_HD int mc_quad_counts(const McGrid& g, unsigned int m00, unsigned int m01, unsigned int m10, unsigned int m11, bool hx,
+                         bool hy, bool hz4) {
+  const unsigned int zmask = hz4 ? 0xFu : 0x7u;          // points whose +z neighbour exists
+  int nv = mc_popc4((m00 ^ (m00 >> 1)) & zmask);
+  if (hy) nv += mc_popc4(m00 ^ m01);
+  if (hx) nv += mc_popc4(m00 ^ m10);
+  int nt = 0;
+  if (hx && hy) {
+    // cell t is empty when its eight corners agree: bits t and t+1 all clear or all set in the four rows
+    const unsigned int any = m00 | m01 | m10 | m11, all = m00 & m01 & m10 & m11;
+    const unsigned int mixed = ~((~any & ~(any >> 1)) | (all & (all >> 1))) & zmask;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int t = 0; t < 4; ++t) {
+      if (!((mixed >> t) & 1u)) continue;
+      // corners v0..v7 as in mc_point: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
+      const unsigned int c = ((m00 >> t) & 1u) | (((m10 >> t) & 1u) << 1) | (((m11 >> t) & 1u) << 2) |
+                             (((m01 >> t) & 1u) << 3) | (((m00 >> (t + 1)) & 1u) << 4) | (((m10 >> (t + 1)) & 1u) << 5) |
+                             (((m11 >> (t + 1)) & 1u) << 6) | (((m01 >> (t + 1)) & 1u) << 7);
+      nt += g.ntri[c];
+    }
+  }
+  return nv | (nt << 16);
+}
+// the loads of one quad, all issued before anything looks at them: p = linear index of its first point (a multiple of 4)
+struct McQuadRows {
+  float v[4][5];          // rows (i,j) (i,j+1) (i+1,j) (i+1,j+1) at k0 .. k0+4; an absent row repeats row (i,j)
+  bool hx, hy, hz4;
+};
+MC_HD McQuadRows mc_quad_load(const McGrid& g, unsigned int p) {
+  McQuadRows q;
+  int i, j, k0;
+  mc_split(g, p, i, j, k0);
+  const int YZ = g.Y * g.Z;
+  q.hx = i + 1 < g.X; q.hy = j + 1 < g.Y; q.hz4 = k0 + 4 < g.Z;
+  // an absent row never counts (hx / hy in mc_quad_counts): it reads row (i,j) again, so there is no branch between the loads
+  const unsigned int off[4] = {0u, q.hy ? (unsigned int)g.Z : 0u, q.hx ? (unsigned int)YZ : 0u,
+                               (q.hx && q.hy) ? (unsigned int)(YZ + g.Z) : 0u};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 4; ++r) {
+    const float* row = g.u + (p + off[r]);
+#if defined(__CUDA_ARCH__)
+    const float4 f = *reinterpret_cast<const float4*>(row);
+    q.v[r][0] = f.x; q.v[r][1] = f.y; q.v[r][2] = f.z; q.v[r][3] = f.w;
+#else
+    for (int t = 0; t < 4; ++t) q.v[r][t] = row[t];
+#endif
+    q.v[r][4] = q.hz4 ? row[4] : 0.f;
+  }
+  return q;
+}
+MC_HD int mc_quad_eval(const McGrid& g, const McQuadRows& q) {
+  const unsigned int full = q.hz4 ? 31u : 15u;          // bit 4 only where that point exists
+  unsigned int m[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 4; ++r) m[r] = mc_quad_mask(q.v[r][0], q.v[r][1], q.v[r][2], q.v[r][3], q.v[r][4], g.iso) & full;
+  // nearly every quad is far from the surface: all of its (up to) 20 values on one side
+  if ((m[0] | m[1] | m[2] | m[3]) == 0u || (m[0] & m[1] & m[2] & m[3]) == full) return 0;
+  return mc_quad_counts(g, m[0], m[1], m[2], m[3], q.hx, q.hy, q.hz4);
+}
+MC_HD int mc_quad(const McGrid& g, unsigned int p) { return mc_quad_eval(g, mc_quad_load(g, p)); }
+// the quad path needs whole quads per row and 16-byte loads
+MC_HD bool mc_quads_ok(const McGrid& g) { return (g.Z & 3) == 0 && (reinterpret_cast<unsigned long long>(g.u) & 15ull) == 0; }
 
 // vertices of the crossed edges that start at point p; `id` = id of the first one
 MC_HD void mc_emit_vertices(const McGrid& g, const McXform& xf, long long p, const McPoint& q, long long id, float* verts,

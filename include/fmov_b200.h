@@ -246,17 +246,22 @@ int fmov_adam_step(float* const* param, const long long* off, const int* numel, 
  * per crossed grid edge, ordered by (grid point x-major, axis); triangles ordered by (cell x-major, case-table order).
  *   1. fmov_mc_set_tables (once): HOST case table [256][15] + triangle counts [256] (fmov_pose_b200/mc_tables.py)
  *   2. fmov_mc_count: per 256-point chunk (fmov_mc_chunk_count of them) the number of vertices / triangles
- *   3. caller: exclusive prefix sums (int64) over the chunks WITH the total appended (n_chunks + 1 entries: chunk c emits
- *      [off[c], off[c+1]), empty chunks are skipped); totals size the outputs
+ *   3. fmov_mc_scan: exclusive prefix sums (int64) over the chunks WITH the total appended (n_chunks + 1 entries: chunk c
+ *      emits [off[c], off[c+1]), empty chunks are skipped); totals [2] = (V, T) size the outputs (the caller's one
+ *      device->host read)
  *   4. fmov_mc_vertices: verts [V,3] = index coordinate * (sx,sy,sz) + (ox,oy,oz); vid3 [X*Y*Z,3] int32 scratch receives the
  *      vertex id of every crossed edge (other entries stay unwritten and are never read)
  *   5. fmov_mc_triangles: tris [T,3] int32 vertex ids                                                                    */
 int fmov_mc_set_tables(const signed char* tri_table, const unsigned char* n_tris);
 long long fmov_mc_chunk_count(int X, int Y, int Z);
-/* list [n_chunks] int32 + n_list [1] int32 (device): fmov_mc_count appends the index of every chunk that emits something
- * (n_list is zeroed by the call); the emit passes walk that list */
+long long fmov_mc_group_count(int X, int Y, int Z);          /* groups of 4096 chunks: entries of group_sums */
+/* list [n_chunks] int32 + n_list [1] int32 (device): fmov_mc_count appends the index of every chunk that emits something;
+ * the emit passes walk that list.  group_sums [fmov_mc_group_count] (device): vertices | triangles << 32 per group of
+ * chunks, the starting points of fmov_mc_scan's blocks.  n_list and group_sums are zeroed by the call. */
 int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
-                  void* stream);
+                  unsigned long long* group_sums, void* stream);
+int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+                 long long* chunk_voff, long long* chunk_toff, long long* totals, void* stream);
 int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, const int* list,
                      const int* n_list, float sx, float sy, float sz, float ox, float oy, float oz, float* verts, int* vid3,
                      void* stream);

@@ -45,6 +45,17 @@ int main(int argc, char** argv) {
       nv += mc_vertex_count(q);
       nt += q.ntri;
     }
+    if (mc_quads_ok(g)) {          // mc_count_quad_kernel must count what the per-point code counts
+      long long qv = 0, qt = 0;
+      for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {
+        const long long p = ch * MC_CHUNK + q4 * 4;
+        if (p >= g.n) continue;
+        const int packed = mc_quad(g, (unsigned int)p);
+        qv += packed & 0xFFFF;
+        qt += packed >> 16;
+      }
+      if (qv != nv || qt != nt) { fprintf(stderr, "quad counts differ in chunk %lld: %lld %lld vs %lld %lld\n", ch, qv, qt, nv, nt); return 3; }
+    }
     voff[ch + 1] = voff[ch] + nv;
     toff[ch + 1] = toff[ch] + nt;
   }

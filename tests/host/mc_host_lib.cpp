@@ -1,4 +1,4 @@
-// Host stand-in for the five marching-cubes entry points of libfmov_b200.so (same C signatures, host pointers): the
+// Host stand-in for the marching-cubes entry points of libfmov_b200.so (same C signatures, host pointers): the
 // kernels' per-point code (csrc/mc_core.cuh) driven chunk by chunk.  Lets the Python glue of fmov_pose_b200/mcubes_gpu.py
 // (argument marshalling, prefix sums, output sizing) run on the CPU in tests/test_marching_cubes_host_emulation.py.
 // Test infrastructure, never shipped.
@@ -31,23 +31,58 @@ int fmov_mc_set_tables(const signed char* tri, const unsigned char* ntri) {
   return 0;
 }
 long long fmov_mc_chunk_count(int X, int Y, int Z) { return ((long long)X * Y * Z + MC_CHUNK - 1) / MC_CHUNK; }
+long long fmov_mc_group_count(int X, int Y, int Z) {
+  return (fmov_mc_chunk_count(X, Y, Z) + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT;
+}
 int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
-                  void*) {
+                  unsigned long long* group_sums, void*) {
   McGrid g;
-  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt || !list || !n_list) return -1;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt || !list || !n_list || !group_sums) return -1;
   *n_list = 0;
+  for (long long b = 0; b < fmov_mc_group_count(X, Y, Z); ++b) group_sums[b] = 0;
   // the device appends in whatever order its atomics give: walk the chunks backwards here so that the glue and the emit
   // passes are exercised with a list that is NOT in chunk order
   for (long long ch = g.n_chunks - 1; ch >= 0; --ch) {
     int nv = 0, nt = 0;
-    for (int tid = 0; tid < MC_CHUNK; ++tid) {
-      const McPoint q = mc_point(g, ch * MC_CHUNK + tid, true);
-      nv += mc_vertex_count(q);
-      nt += q.ntri;
+    if (mc_quads_ok(g)) {          // mc_count_quad_kernel: 32 lanes x 2 quads
+      for (int h = 0; h < 2; ++h)
+        for (int lane = 0; lane < 32; ++lane) {
+          const long long p = ch * MC_CHUNK + h * (MC_CHUNK / 2) + lane * 4;
+          if (p >= g.n) continue;
+          const int packed = mc_quad(g, (unsigned int)p);
+          nv += packed & 0xFFFF;
+          nt += packed >> 16;
+        }
+    } else {
+      for (int tid = 0; tid < MC_CHUNK; ++tid) {
+        const McPoint q = mc_point(g, ch * MC_CHUNK + tid, true);
+        nv += mc_vertex_count(q);
+        nt += q.ntri;
+      }
     }
     chunk_nv[ch] = nv;
     chunk_nt[ch] = nt;
-    if (nv | nt) list[(*n_list)++] = (int)ch;
+    if (nv | nt) {
+      list[(*n_list)++] = (int)ch;
+      group_sums[ch >> MC_GROUP_SHIFT] += (unsigned long long)nv | ((unsigned long long)nt << 32);
+    }
+  }
+  return 0;
+}
+int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+                 long long* voff, long long* toff, long long* totals, void*) {
+  if (!chunk_nv || !chunk_nt || !group_sums || !voff || !toff || !totals || n_chunks < 1) return -1;
+  // like the device: each group of 4096 chunks starts from the sums of the groups before it
+  const long long groups = (n_chunks + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT;
+  for (long long b = 0; b < groups; ++b) {
+    long long v = 0, t = 0;
+    for (long long a = 0; a < b; ++a) { v += (long long)(group_sums[a] & 0xFFFFFFFFull); t += (long long)(group_sums[a] >> 32); }
+    const long long end = ((b + 1) << MC_GROUP_SHIFT) < n_chunks ? ((b + 1) << MC_GROUP_SHIFT) : n_chunks;
+    for (long long c = b << MC_GROUP_SHIFT; c < end; ++c) {
+      voff[c] = v; toff[c] = t;
+      v += chunk_nv[c]; t += chunk_nt[c];
+    }
+    if (end == n_chunks) { voff[n_chunks] = v; toff[n_chunks] = t; totals[0] = v; totals[1] = t; }
   }
   return 0;
 }

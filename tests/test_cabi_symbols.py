@@ -28,7 +28,7 @@ def test_header_declares_the_documented_entry_points():
                  "fmov_sample_round", "fmov_sdf_query_points", "fmov_sdf_query_rays", "fmov_sdf_query_grid",
                  "fmov_fine_fwd", "fmov_fine_bwd", "fmov_dw", "fmov_composite_fwd", "fmov_composite_bwd",
                  "fmov_loss_fwd_bwd", "fmov_ray_reduce_bwd", "fmov_last_error", "fmov_mc_set_tables", "fmov_mc_count",
-                 "fmov_mc_vertices", "fmov_mc_triangles", "fmov_weight_norm_fwd", "fmov_pose_gf_fwd", "fmov_flow_fwd"]:
+                 "fmov_mc_scan", "fmov_mc_vertices", "fmov_mc_triangles", "fmov_weight_norm_fwd", "fmov_pose_gf_fwd", "fmov_flow_fwd"]:
         assert must in names, must
 
 
@@ -72,13 +72,16 @@ def test_errors_are_status_codes_not_exceptions(lib):
     st = lib.fmov_pose_fwd(7, None, None, None, None, None, None, None)
     assert st == -1
     # marching cubes: null grid / degenerate sizes / tables not uploaded are argument errors, not crashes
-    assert lib.fmov_mc_count(None, 8, 8, 8, ctypes.c_float(0.0), None, None, None, None, None) == -1
+    assert lib.fmov_mc_count(None, 8, 8, 8, ctypes.c_float(0.0), None, None, None, None, None, None) == -1
     buf = (ctypes.c_float * 8)()
-    assert lib.fmov_mc_count(buf, 1, 2, 2, ctypes.c_float(0.0), None, None, None, None, None) == -1 and b"bad grid" in lib.fmov_last_error()
-    assert lib.fmov_mc_count(buf, 2, 2, 2, ctypes.c_float(0.0), None, None, None, None, None) == -1 and b"fmov_mc_set_tables" in lib.fmov_last_error()
+    assert lib.fmov_mc_count(buf, 1, 2, 2, ctypes.c_float(0.0), None, None, None, None, None, None) == -1 and b"bad grid" in lib.fmov_last_error()
+    assert lib.fmov_mc_count(buf, 2, 2, 2, ctypes.c_float(0.0), None, None, None, None, None, None) == -1 and b"fmov_mc_set_tables" in lib.fmov_last_error()
     assert lib.fmov_mc_set_tables(None, None) == -1
     lib.fmov_mc_chunk_count.restype = ctypes.c_longlong
     assert lib.fmov_mc_chunk_count(512, 512, 512) == 512 ** 3 // 256 and lib.fmov_mc_chunk_count(3, 3, 3) == 1
+    lib.fmov_mc_group_count.restype = ctypes.c_longlong
+    assert lib.fmov_mc_group_count(512, 512, 512) == 128 and lib.fmov_mc_group_count(3, 3, 3) == 1
+    assert lib.fmov_mc_scan(None, None, None, ctypes.c_longlong(1), None, None, None, None) == -1
 
 
 def test_product_package_never_imports_the_oracle():

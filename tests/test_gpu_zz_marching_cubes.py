@@ -28,7 +28,11 @@ def _field(kind, shape, seed=0):
 
 @pytest.mark.parametrize("kind,shape,iso", [("sphere", (33, 29, 31), 0.0), ("torus", (40, 40, 24), 0.0),
                                             ("waves", (37, 18, 50), 0.05), ("noise", (17, 16, 19), 0.0),
-                                            ("noise", (2, 2, 2), 0.0), ("sphere", (9, 300, 7), 0.0)])
+                                            ("noise", (2, 2, 2), 0.0), ("sphere", (9, 300, 7), 0.0),
+                                            # Z % 4 == 0: quad count kernel; the last two span 2 and 3 scan groups
+                                            ("noise", (9, 7, 4), 0.0), ("noise", (2, 2, 8), 0.1), ("waves", (21, 18, 52), 0.05),
+                                            ("noise", (30, 31, 32), 0.2), ("sphere", (104, 101, 100), 0.0),
+                                            ("waves", (131, 127, 129), 0.05)])
 def test_mesh_equals_the_oracle(kind, shape, iso):
     from fmov_pose_b200 import mcubes_gpu
     u = _field(kind, shape)
@@ -38,6 +42,19 @@ def test_mesh_equals_the_oracle(kind, shape, iso):
     assert tuple(v.shape) == v_ref.shape and tuple(t.shape) == t_ref.shape
     np.testing.assert_allclose(v.cpu().numpy(), v_ref, rtol=0, atol=2e-5)          # fp32 interpolation vs fp64
     np.testing.assert_array_equal(t.cpu().numpy().astype(np.int64), t_ref)         # indices: bit-exact
+
+
+def test_count_kernels_agree_on_a_misaligned_grid():
+    """the same Z % 4 == 0 grid at a 16-byte aligned and at a 4-byte aligned address: quad and per-point count kernels"""
+    from fmov_pose_b200 import mcubes_gpu
+    u = _field("noise", (24, 20, 36))
+    buf = torch.empty(u.size + 1, dtype=torch.float32, device=DEV)
+    shifted = buf[1:].view(u.shape)
+    shifted.copy_(torch.from_numpy(u))
+    assert shifted.data_ptr() % 16 == 4
+    v0, t0 = mcubes_gpu.marching_cubes(torch.from_numpy(u).to(DEV), 0.1)
+    v1, t1 = mcubes_gpu.marching_cubes(shifted, 0.1)
+    assert torch.equal(v0, v1) and torch.equal(t0, t1) and t0.shape[0] > 1000
 
 
 def test_empty_and_world_coordinates():

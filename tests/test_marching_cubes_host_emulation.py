@@ -45,7 +45,11 @@ def _field(kind, shape, seed=0):
 
 @pytest.mark.parametrize("kind,shape,iso", [("sphere", (33, 29, 31), 0.0), ("waves", (37, 18, 50), 0.05),
                                             ("noise", (17, 16, 19), 0.0), ("noise", (2, 2, 2), 0.0),
-                                            ("noise", (3, 129, 2), 0.25), ("sphere", (9, 300, 7), 0.0)])
+                                            ("noise", (3, 129, 2), 0.25), ("sphere", (9, 300, 7), 0.0),
+                                            # Z % 4 == 0: the count pass works on quads (mc_count_quad_kernel's code)
+                                            ("sphere", (30, 31, 32), 0.0), ("waves", (21, 18, 52), 0.05),
+                                            ("noise", (9, 7, 4), 0.0), ("noise", (2, 2, 8), 0.1),
+                                            ("noise", (5, 67, 12), -0.2)])
 def test_device_logic_equals_the_oracle(emul, kind, shape, iso):
     u = _field(kind, shape)
     v, t = emul(u, iso)
@@ -72,6 +76,7 @@ def test_python_glue_end_to_end_on_a_host_stand_in(tmp_path, monkeypatch):
                     os.path.join(ROOT, "tests", "host", "mc_host_lib.cpp"), "-o", so], check=True)
     fake = ctypes.CDLL(so)
     fake.fmov_mc_chunk_count.restype = ctypes.c_longlong
+    fake.fmov_mc_group_count.restype = ctypes.c_longlong
     fake.fmov_last_error.restype = ctypes.c_char_p
     monkeypatch.setattr(L, "lib", lambda: fake)
     monkeypatch.setattr(L, "ptr", lambda t: ctypes.c_void_p(0 if t is None else t.data_ptr()))
@@ -82,7 +87,8 @@ def test_python_glue_end_to_end_on_a_host_stand_in(tmp_path, monkeypatch):
     class _AsCuda(torch.Tensor):          # a CPU tensor that answers is_cuda like device memory would
         is_cuda = True
 
-    for kind, shape, iso in (("sphere", (33, 29, 31), 0.0), ("noise", (17, 16, 19), 0.1), ("noise", (2, 2, 2), 0.0)):
+    for kind, shape, iso in (("sphere", (33, 29, 31), 0.0), ("noise", (17, 16, 19), 0.1), ("noise", (2, 2, 2), 0.0),
+                             ("noise", (18, 17, 20), 0.1), ("sphere", (104, 101, 100), 0.0)):          # the last one spans two scan groups
         u = _field(kind, shape)
         ut = torch.from_numpy(u).as_subclass(_AsCuda)
         v, t = mcubes_gpu.marching_cubes(ut, iso)
