@@ -54,8 +54,7 @@ __device__ __forceinline__ int mc_pack(int nv, int nt) { return nv | (nt << 16);
 
 __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int* __restrict__ chunk_nv,
                                                             int* __restrict__ chunk_nt, int* __restrict__ list,
-                                                            int* __restrict__ n_list,
-                                                            unsigned long long* __restrict__ group_sums) {
+                                                            int* __restrict__ n_list) {
   for (long long ch = blockIdx.x; ch < g.n_chunks; ch += gridDim.x) {
     const McPoint q = mc_point(g, ch * MC_CHUNK + threadIdx.x, true);
     const int v = mc_pack(mc_vertex_count(q), q.ntri);
@@ -66,10 +65,7 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int*
       chunk_nt[ch] = tot >> 16;
       // the emit passes walk this list (about 2 % of the chunks at 512^3) instead of testing every chunk; its order is
       // whatever the atomics give, the OUTPUT positions come from the prefix sums and do not depend on it
-      if (tot != 0) {
-        list[atomicAdd(n_list, 1)] = (int)ch;
-        atomicAdd(&group_sums[ch >> MC_GROUP_SHIFT], (unsigned long long)(tot & 0xFFFF) | ((unsigned long long)(tot >> 16) << 32));
-      }
+      if (tot != 0) list[atomicAdd(n_list, 1)] = (int)ch;
     }
   }
 }
@@ -79,10 +75,12 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int*
 // instructions and ~1/6 of the issue slots of the per-point kernel (which was issue-bound at 0.7 TB/s).
 __global__ void __launch_bounds__(MC_CHUNK) mc_count_quad_kernel(const McGrid g, int* __restrict__ chunk_nv,
                                                                  int* __restrict__ chunk_nt, int* __restrict__ list,
-                                                                 int* __restrict__ n_list,
-                                                                 unsigned long long* __restrict__ group_sums) {
+                                                                 int* __restrict__ n_list) {
   const int lane = threadIdx.x & 31;
   const long long n_warps = (long long)gridDim.x * (MC_CHUNK / 32);
+  // non-empty chunks are appended to the list 32 at a time (lane k keeps the k-th one found): one atomic per 32 chunks
+  // instead of ~10^5 atomics on one address
+  int pending = 0, mine = 0;
   for (long long ch = (long long)blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); ch < g.n_chunks; ch += n_warps) {
     // both halves' loads (8 x 16 B + 8 x 4 B per lane) are in flight before the first comparison; n is a multiple of 4, so a
     // quad is inside the grid or not at all (then it re-reads quad 0 and counts nothing)
@@ -95,18 +93,51 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_quad_kernel(const McGrid g,
     if (lane == 0) {
       chunk_nv[ch] = tot & 0xFFFF;
       chunk_nt[ch] = tot >> 16;
-      if (tot != 0) {
-        list[atomicAdd(n_list, 1)] = (int)ch;
-        atomicAdd(&group_sums[ch >> MC_GROUP_SHIFT], (unsigned long long)(tot & 0xFFFF) | ((unsigned long long)(tot >> 16) << 32));
+    }
+    if (tot != 0) {          // warp-uniform
+      if (lane == pending) mine = (int)ch;
+      if (++pending == 32) {
+        int at = 0;
+        if (lane == 0) at = atomicAdd(n_list, 32);
+        at = __shfl_sync(0xffffffffu, at, 0);
+        list[at + lane] = mine;
+        pending = 0;
       }
     }
   }
+  if (pending) {
+    int at = 0;
+    if (lane == 0) at = atomicAdd(n_list, pending);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (lane < pending) list[at + lane] = mine;
+  }
 }
 
-// Exclusive prefix sums of the chunk counts (64-bit, totals appended).  group_sums (written by the count pass with integer
-// atomics, so order-independent) holds vertices | triangles << 32 per group of 4096 chunks; block b adds up the groups
-// before its own and scans its 4096 chunks in four rounds of 1024.
+// Sums of the chunk counts per group of 4096 chunks (vertices | triangles << 32): the starting points of the scan's blocks.
 constexpr int MC_SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(MC_SCAN_THREADS) mc_group_sums_kernel(const int* __restrict__ chunk_nv,
+                                                                        const int* __restrict__ chunk_nt, long long n_chunks,
+                                                                        unsigned long long* __restrict__ group_sums) {
+  __shared__ unsigned long long warp_sum[MC_SCAN_THREADS / 32];
+  const long long first = (long long)blockIdx.x << MC_GROUP_SHIFT;
+  unsigned long long s = 0;
+  for (int r = 0; r < (1 << MC_GROUP_SHIFT) / MC_SCAN_THREADS; ++r) {
+    const long long c = first + r * MC_SCAN_THREADS + threadIdx.x;
+    if (c < n_chunks) s += (unsigned long long)chunk_nv[c] | ((unsigned long long)chunk_nt[c] << 32);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < MC_SCAN_THREADS / 32; ++w) t += warp_sum[w];
+    group_sums[blockIdx.x] = t;          // both fields < 2^23
+  }
+}
+
+// Exclusive prefix sums of the chunk counts (64-bit, totals appended): block b adds up the groups before its own and scans
+// its 4096 chunks in four rounds of 1024.
 __global__ void __launch_bounds__(MC_SCAN_THREADS) mc_scan_kernel(const int* __restrict__ chunk_nv,
                                                                   const int* __restrict__ chunk_nt,
                                                                   const unsigned long long* __restrict__ group_sums,
@@ -204,6 +235,79 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_triangles_kernel(const McGrid g, 
   }
 }
 
+// The emit passes on quads (Z % 4 == 0): a WARP per listed chunk, the quad loads and masks of the count pass again, ids from
+// one packed warp scan (first half | second half << 16), and only the lanes whose quads cross the surface emit.
+struct McWarpChunk {
+  McQuadRows q0, q1;
+  unsigned int m0[4], m1[4];
+  unsigned int p0, p1;
+  int c0, c1;          // packed counts (vertices | triangles << 16) of this lane's two quads
+};
+__device__ __forceinline__ void mc_warp_chunk(const McGrid& g, long long ch, int lane, McWarpChunk& w) {
+  const long long p0 = ch * MC_CHUNK + lane * 4, p1 = p0 + MC_CHUNK / 2;
+  const bool in0 = p0 < g.n, in1 = p1 < g.n;
+  w.p0 = in0 ? (unsigned int)p0 : 0u;
+  w.p1 = in1 ? (unsigned int)p1 : 0u;
+  w.q0 = mc_quad_load(g, w.p0);
+  w.q1 = mc_quad_load(g, w.p1);
+  mc_quad_masks(g, w.q0, w.m0);
+  mc_quad_masks(g, w.q1, w.m1);
+  w.c0 = in0 ? mc_quad_eval_masks(g, w.q0, w.m0) : 0;
+  w.c1 = in1 ? mc_quad_eval_masks(g, w.q1, w.m1) : 0;
+}
+// exclusive offsets of this lane's two quads within the chunk (quads in point order: first half lanes 0..31, then second half)
+__device__ __forceinline__ void mc_warp_offsets(int n0, int n1, int lane, int& ex0, int& ex1) {
+  int inc = n0 | (n1 << 16);          // <= 640 per half: no carry between the fields
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int tot0 = __shfl_sync(0xffffffffu, inc, 31) & 0xFFFF;
+  ex0 = (inc & 0xFFFF) - n0;
+  ex1 = tot0 + (inc >> 16) - n1;
+}
+
+__global__ void __launch_bounds__(MC_CHUNK) mc_vertices_quad_kernel(const McGrid g, const long long* __restrict__ chunk_voff,
+                                                                    const int* __restrict__ list,
+                                                                    const int* __restrict__ n_list, const McXform xf,
+                                                                    float* __restrict__ verts, int* __restrict__ vid3) {
+  const int n = *n_list, lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * (MC_CHUNK / 32);
+  for (int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); li < n; li += n_warps) {
+    const long long ch = list[li];
+    const long long base = chunk_voff[ch];
+    if (chunk_voff[ch + 1] == base) continue;          // triangles only (warp-uniform)
+    McWarpChunk w;
+    mc_warp_chunk(g, ch, lane, w);
+    const int n0 = w.c0 & 0xFFFF, n1 = w.c1 & 0xFFFF;
+    int ex0, ex1;
+    mc_warp_offsets(n0, n1, lane, ex0, ex1);
+    if (n0) mc_quad_emit_vertices(g, xf, w.p0, w.q0, w.m0, base + ex0, verts, vid3);
+    if (n1) mc_quad_emit_vertices(g, xf, w.p1, w.q1, w.m1, base + ex1, verts, vid3);
+  }
+}
+
+__global__ void __launch_bounds__(MC_CHUNK) mc_triangles_quad_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
+                                                                     const int* __restrict__ list,
+                                                                     const int* __restrict__ n_list,
+                                                                     const int* __restrict__ vid3, int* __restrict__ tris) {
+  const int n = *n_list, lane = threadIdx.x & 31;
+  const int n_warps = gridDim.x * (MC_CHUNK / 32);
+  for (int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); li < n; li += n_warps) {
+    const long long ch = list[li];
+    const long long base = chunk_toff[ch];
+    if (chunk_toff[ch + 1] == base) continue;          // vertices only (warp-uniform)
+    McWarpChunk w;
+    mc_warp_chunk(g, ch, lane, w);
+    const int n0 = w.c0 >> 16, n1 = w.c1 >> 16;
+    int ex0, ex1;
+    mc_warp_offsets(n0, n1, lane, ex0, ex1);
+    if (n0) mc_quad_emit_triangles(g, w.p0, w.q0, w.m0, base + ex0, vid3, tris);
+    if (n1) mc_quad_emit_triangles(g, w.p1, w.q1, w.m1, base + ex1, vid3, tris);
+  }
+}
+
 static int mc_grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
   FMOV_REQUIRE(u && X >= 2 && Y >= 2 && Z >= 2, "marching cubes: bad grid %d x %d x %d", X, Y, Z);
   FMOV_REQUIRE(g_mc_tables_set, "marching cubes: call fmov_mc_set_tables first");
@@ -253,32 +357,33 @@ extern "C" long long fmov_mc_group_count(int X, int Y, int Z) {
 }
 
 extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list,
-                             int* n_list, unsigned long long* group_sums, void* stream) {
+                             int* n_list, void* stream) {
   McGrid g;
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
-  FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list && group_sums, "fmov_mc_count: null output");
+  FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list, "fmov_mc_count: null output");
   FMOV_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int), (cudaStream_t)stream));
-  FMOV_CUDA(cudaMemsetAsync(group_sums, 0, sizeof(unsigned long long) * (size_t)fmov_mc_group_count(X, Y, Z), (cudaStream_t)stream));
   if (mc_quads_ok(g)) {
     // a warp per chunk: the same number of resident warps as the per-point kernel
     const long long want = (g.n_chunks + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32);
     const int blocks = (int)(want < mc_blocks(g) ? want : mc_blocks(g));
-    mc_count_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list, group_sums);
+    mc_count_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
     FMOV_LAUNCH_CHECK("mc_count_quad_kernel");
   } else {
-    mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list, group_sums);
+    mc_count_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
     FMOV_LAUNCH_CHECK("mc_count_kernel");
   }
   return OK;
 }
 
-extern "C" int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+extern "C" int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, long long n_chunks, unsigned long long* group_scratch,
                             long long* chunk_voff, long long* chunk_toff, long long* totals, void* stream) {
-  FMOV_REQUIRE(chunk_nv && chunk_nt && group_sums && chunk_voff && chunk_toff && totals, "fmov_mc_scan: null argument");
+  FMOV_REQUIRE(chunk_nv && chunk_nt && group_scratch && chunk_voff && chunk_toff && totals, "fmov_mc_scan: null argument");
   FMOV_REQUIRE(n_chunks >= 1 && n_chunks <= (1LL << 31) / MC_CHUNK, "fmov_mc_scan: bad chunk count %lld", n_chunks);
   const int groups = (int)((n_chunks + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT);
-  mc_scan_kernel<<<groups, MC_SCAN_THREADS, 0, (cudaStream_t)stream>>>(chunk_nv, chunk_nt, group_sums, n_chunks, chunk_voff,
+  mc_group_sums_kernel<<<groups, MC_SCAN_THREADS, 0, (cudaStream_t)stream>>>(chunk_nv, chunk_nt, n_chunks, group_scratch);
+  FMOV_LAUNCH_CHECK("mc_group_sums_kernel");
+  mc_scan_kernel<<<groups, MC_SCAN_THREADS, 0, (cudaStream_t)stream>>>(chunk_nv, chunk_nt, group_scratch, n_chunks, chunk_voff,
                                                                         chunk_toff, totals);
   FMOV_LAUNCH_CHECK("mc_scan_kernel");
   return OK;
@@ -293,8 +398,13 @@ extern "C" int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, 
   FMOV_REQUIRE(chunk_voff && list && n_list && verts && vid3, "fmov_mc_vertices: null argument");
   McXform xf;
   xf.s[0] = sx; xf.s[1] = sy; xf.s[2] = sz; xf.o[0] = ox; xf.o[1] = oy; xf.o[2] = oz;
-  mc_vertices_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
-  FMOV_LAUNCH_CHECK("mc_vertices_kernel");
+  if (mc_quads_ok(g)) {
+    mc_vertices_quad_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
+    FMOV_LAUNCH_CHECK("mc_vertices_quad_kernel");
+  } else {
+    mc_vertices_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
+    FMOV_LAUNCH_CHECK("mc_vertices_kernel");
+  }
   return OK;
 }
 
@@ -304,7 +414,12 @@ extern "C" int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso,
   int st = mc_grid(g, u, X, Y, Z, iso);
   if (st) return st;
   FMOV_REQUIRE(chunk_toff && list && n_list && vid3 && tris, "fmov_mc_triangles: null argument");
-  mc_triangles_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
-  FMOV_LAUNCH_CHECK("mc_triangles_kernel");
+  if (mc_quads_ok(g)) {
+    mc_triangles_quad_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
+    FMOV_LAUNCH_CHECK("mc_triangles_quad_kernel");
+  } else {
+    mc_triangles_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
+    FMOV_LAUNCH_CHECK("mc_triangles_kernel");
+  }
   return OK;
 }

@@ -106,6 +106,17 @@ MC_HD unsigned int mc_quad_mask(float a, float b, float c, float d, float e, flo
   return (a < iso ? 1u : 0u) | (b < iso ? 2u : 0u) | (c < iso ? 4u : 0u) | (d < iso ? 8u : 0u) | (e < iso ? 16u : 0u);
 }
 MC_HD int mc_popc4(unsigned int m) { return (int)((m & 1u) + ((m >> 1) & 1u) + ((m >> 2) & 1u) + ((m >> 3) & 1u)); }
+// cells of the quad (bit t) whose eight corners do not all agree: bits t and t+1 neither all clear nor all set in the four rows
+MC_HD unsigned int mc_quad_mixed(unsigned int m00, unsigned int m01, unsigned int m10, unsigned int m11, unsigned int zmask) {
+  const unsigned int any = m00 | m01 | m10 | m11, all = m00 & m01 & m10 & m11;
+  return ~((~any & ~(any >> 1)) | (all & (all >> 1))) & zmask;
+}
+// case of cell t; corners v0..v7 as in mc_point: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
+MC_HD int mc_quad_case(unsigned int m00, unsigned int m01, unsigned int m10, unsigned int m11, int t) {
+  return (int)(((m00 >> t) & 1u) | (((m10 >> t) & 1u) << 1) | (((m11 >> t) & 1u) << 2) | (((m01 >> t) & 1u) << 3) |
+               (((m00 >> (t + 1)) & 1u) << 4) | (((m10 >> (t + 1)) & 1u) << 5) | (((m11 >> (t + 1)) & 1u) << 6) |
+               (((m01 >> (t + 1)) & 1u) << 7));
+}
 // crossed edges starting at the quad's points | triangles of their cells << 16: the sums of mc_vertex_count / ntri that
 // mc_point(.., true) gives for the four points.  m00 m01 m10 m11 = masks of rows (i,j) (i,j+1) (i+1,j) (i+1,j+1);
 // hx / hy: i + 1 < X, j + 1 < Y (masks of absent rows are ignored); hz4: k0 + 4 < Z (bit 4 present).
@@ -117,19 +128,13 @@ MC_HD int mc_quad_counts(const McGrid& g, unsigned int m00, unsigned int m01, un
   if (hx) nv += mc_popc4(m00 ^ m10);
   int nt = 0;
   if (hx && hy) {
-    // cell t is empty when its eight corners agree: bits t and t+1 all clear or all set in the four rows
-    const unsigned int any = m00 | m01 | m10 | m11, all = m00 & m01 & m10 & m11;
-    const unsigned int mixed = ~((~any & ~(any >> 1)) | (all & (all >> 1))) & zmask;
+    const unsigned int mixed = mc_quad_mixed(m00, m01, m10, m11, zmask);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int t = 0; t < 4; ++t) {
       if (!((mixed >> t) & 1u)) continue;
-      // corners v0..v7 as in mc_point: (0,0,0) (1,0,0) (1,1,0) (0,1,0) (0,0,1) (1,0,1) (1,1,1) (0,1,1)
-      const unsigned int c = ((m00 >> t) & 1u) | (((m10 >> t) & 1u) << 1) | (((m11 >> t) & 1u) << 2) |
-                             (((m01 >> t) & 1u) << 3) | (((m00 >> (t + 1)) & 1u) << 4) | (((m10 >> (t + 1)) & 1u) << 5) |
-                             (((m11 >> (t + 1)) & 1u) << 6) | (((m01 >> (t + 1)) & 1u) << 7);
-      nt += g.ntri[c];
+      nt += g.ntri[mc_quad_case(m00, m01, m10, m11, t)];
     }
   }
   return nv | (nt << 16);
@@ -163,16 +168,23 @@ MC_HD McQuadRows mc_quad_load(const McGrid& g, unsigned int p) {
   }
   return q;
 }
-MC_HD int mc_quad_eval(const McGrid& g, const McQuadRows& q) {
+MC_HD void mc_quad_masks(const McGrid& g, const McQuadRows& q, unsigned int m[4]) {
   const unsigned int full = q.hz4 ? 31u : 15u;          // bit 4 only where that point exists
-  unsigned int m[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int r = 0; r < 4; ++r) m[r] = mc_quad_mask(q.v[r][0], q.v[r][1], q.v[r][2], q.v[r][3], q.v[r][4], g.iso) & full;
+}
+MC_HD int mc_quad_eval_masks(const McGrid& g, const McQuadRows& q, const unsigned int m[4]) {
   // nearly every quad is far from the surface: all of its (up to) 20 values on one side
+  const unsigned int full = q.hz4 ? 31u : 15u;
   if ((m[0] | m[1] | m[2] | m[3]) == 0u || (m[0] & m[1] & m[2] & m[3]) == full) return 0;
   return mc_quad_counts(g, m[0], m[1], m[2], m[3], q.hx, q.hy, q.hz4);
+}
+MC_HD int mc_quad_eval(const McGrid& g, const McQuadRows& q) {
+  unsigned int m[4];
+  mc_quad_masks(g, q, m);
+  return mc_quad_eval_masks(g, q, m);
 }
 MC_HD int mc_quad(const McGrid& g, unsigned int p) { return mc_quad_eval(g, mc_quad_load(g, p)); }
 // the quad path needs whole quads per row and 16-byte loads
@@ -214,6 +226,58 @@ MC_HD void mc_emit_triangles(const McGrid& g, long long p, const McPoint& q, lon
       const long long pe = p + ox * YZ + (long long)oy * g.Z + oz;
       tris[(t0 + t) * 3 + c] = vid3[pe * 3 + axis];
     }
+  }
+}
+
+// ---- the emit passes on quads (same order and ids as the per-point functions above) ----
+// vertices of the crossed edges starting at the quad's four points, in (point, axis) order; `id` = id of the first one
+MC_HD void mc_quad_emit_vertices(const McGrid& g, const McXform& xf, unsigned int p, const McQuadRows& q,
+                                 const unsigned int m[4], long long id, float* verts, int* vid3) {
+  int i, j, k0;
+  mc_split(g, p, i, j, k0);
+  const unsigned int zmask = q.hz4 ? 0xFu : 0x7u;
+  const unsigned int cx = q.hx ? ((m[0] ^ m[2]) & 0xFu) : 0u, cy = q.hy ? ((m[0] ^ m[1]) & 0xFu) : 0u,
+                     cz = (m[0] ^ (m[0] >> 1)) & zmask;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < 4; ++t) {
+    if (!(((cx | cy | cz) >> t) & 1u)) continue;
+    const float f0 = q.v[0][t];
+    const float f1[3] = {q.v[2][t], q.v[1][t], q.v[0][t + 1]};          // other end along x, y, z
+    const bool cr[3] = {((cx >> t) & 1u) != 0u, ((cy >> t) & 1u) != 0u, ((cz >> t) & 1u) != 0u};
+    const float base[3] = {(float)i, (float)j, (float)(k0 + t)};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int a = 0; a < 3; ++a) {
+      if (!cr[a]) continue;
+      const float w = (g.iso - f0) / (f1[a] - f0);          // as mc_emit_vertices
+      float v[3] = {base[0], base[1], base[2]};
+      v[a] += w;
+      verts[id * 3 + 0] = fmaf(v[0], xf.s[0], xf.o[0]);
+      verts[id * 3 + 1] = fmaf(v[1], xf.s[1], xf.o[1]);
+      verts[id * 3 + 2] = fmaf(v[2], xf.s[2], xf.o[2]);
+      vid3[((long long)p + t) * 3 + a] = (int)id;
+      ++id;
+    }
+  }
+}
+// triangles of the quad's four cells; `t0` = index of the first one
+MC_HD void mc_quad_emit_triangles(const McGrid& g, unsigned int p, const McQuadRows& q, const unsigned int m[4], long long t0,
+                                  const int* vid3, int* tris) {
+  if (!(q.hx && q.hy)) return;
+  const unsigned int mixed = mc_quad_mixed(m[0], m[1], m[2], m[3], q.hz4 ? 0xFu : 0x7u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int t = 0; t < 4; ++t) {
+    if (!((mixed >> t) & 1u)) continue;
+    McPoint c;
+    c.cubecase = mc_quad_case(m[0], m[1], m[2], m[3], t);
+    c.ntri = g.ntri[c.cubecase];
+    mc_emit_triangles(g, (long long)p + t, c, t0, vid3, tris);
+    t0 += c.ntri;
   }
 }
 

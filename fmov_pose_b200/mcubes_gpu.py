@@ -37,14 +37,14 @@ def marching_cubes(u, isovalue=0.0, scale=(1.0, 1.0, 1.0), offset=(0.0, 0.0, 0.0
     counts = torch.empty(2, nch, dtype=torch.int32, device=dev)
     work = torch.empty(nch + 1, dtype=torch.int32, device=dev)          # [n_list | list of non-empty chunks]
     n_list, lst = work[:1], work[1:]
-    # int64: [group sums | totals (V, T) | vertex offsets | triangle offsets]; offsets are exclusive prefix sums with the
+    # int64: [scan scratch | totals (V, T) | vertex offsets | triangle offsets]; offsets are exclusive prefix sums with the
     # totals appended (chunk c emits [off[c], off[c + 1]), the emit kernels skip chunks whose range is empty)
     ng = int(lib.fmov_mc_group_count(X, Y, Z))
     w64 = torch.empty(ng + 2 + 2 * (nch + 1), dtype=torch.int64, device=dev)
     gsum, totals, excl = w64[:ng], w64[ng:ng + 2], w64[ng + 2:].view(2, nch + 1)
     L.check(lib.fmov_mc_count(L.ptr(u), X, Y, Z, L.c_float(isovalue), L.ptr(counts[0]), L.ptr(counts[1]), L.ptr(lst),
-                              L.ptr(n_list), L.ptr(gsum), L.stream()), "fmov_mc_count")
-    L.check(lib.fmov_mc_scan(L.ptr(counts[0]), L.ptr(counts[1]), L.ptr(gsum), L.c_ll(nch), L.ptr(excl[0]),
+                              L.ptr(n_list), L.stream()), "fmov_mc_count")
+    L.check(lib.fmov_mc_scan(L.ptr(counts[0]), L.ptr(counts[1]), L.c_ll(nch), L.ptr(gsum), L.ptr(excl[0]),
                              L.ptr(excl[1]), L.ptr(totals), L.stream()), "fmov_mc_scan")
     n_v, n_t = (int(v) for v in totals.tolist())          # the one host sync: output sizes are data dependent
     verts = torch.empty(n_v, 3, dtype=torch.float32, device=dev)

@@ -254,13 +254,13 @@ int fmov_adam_step(float* const* param, const long long* off, const int* numel, 
  *   5. fmov_mc_triangles: tris [T,3] int32 vertex ids                                                                    */
 int fmov_mc_set_tables(const signed char* tri_table, const unsigned char* n_tris);
 long long fmov_mc_chunk_count(int X, int Y, int Z);
-long long fmov_mc_group_count(int X, int Y, int Z);          /* groups of 4096 chunks: entries of group_sums */
-/* list [n_chunks] int32 + n_list [1] int32 (device): fmov_mc_count appends the index of every chunk that emits something;
- * the emit passes walk that list.  group_sums [fmov_mc_group_count] (device): vertices | triangles << 32 per group of
- * chunks, the starting points of fmov_mc_scan's blocks.  n_list and group_sums are zeroed by the call. */
+long long fmov_mc_group_count(int X, int Y, int Z);          /* groups of 4096 chunks: entries of fmov_mc_scan's scratch */
+/* list [n_chunks] int32 + n_list [1] int32 (device): fmov_mc_count appends the index of every chunk that emits something
+ * (n_list is zeroed by the call, the order of the list is unspecified); the emit passes walk that list */
 int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
-                  unsigned long long* group_sums, void* stream);
-int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+                  void* stream);
+/* group_scratch [fmov_mc_group_count] (device, no initialisation needed); chunk_voff / chunk_toff [n_chunks + 1]; totals [2] */
+int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, long long n_chunks, unsigned long long* group_scratch,
                  long long* chunk_voff, long long* chunk_toff, long long* totals, void* stream);
 int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long long* chunk_voff, const int* list,
                      const int* n_list, float sx, float sy, float sz, float ox, float oy, float oz, float* verts, int* vid3,

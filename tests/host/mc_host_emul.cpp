@@ -67,6 +67,19 @@ int main(int argc, char** argv) {
   // pass 2: vertices (mc_vertices_kernel)
   for (long long ch = 0; ch < g.n_chunks; ++ch) {
     int local = 0;
+    if (mc_quads_ok(g)) {          // mc_vertices_quad_kernel
+      for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {
+        const long long p = ch * MC_CHUNK + q4 * 4;
+        if (p >= g.n) continue;
+        const McQuadRows q = mc_quad_load(g, (unsigned int)p);
+        unsigned int m[4];
+        mc_quad_masks(g, q, m);
+        const int nv = mc_quad_eval_masks(g, q, m) & 0xFFFF;
+        if (nv) mc_quad_emit_vertices(g, xf, (unsigned int)p, q, m, voff[ch] + local, verts.data(), vid3.data());
+        local += nv;
+      }
+      continue;
+    }
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
       const McPoint q = mc_point(g, p, false);
@@ -78,6 +91,19 @@ int main(int argc, char** argv) {
   // pass 3: triangles (mc_triangles_kernel)
   for (long long ch = 0; ch < g.n_chunks; ++ch) {
     int local = 0;
+    if (mc_quads_ok(g)) {          // mc_triangles_quad_kernel
+      for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {
+        const long long p = ch * MC_CHUNK + q4 * 4;
+        if (p >= g.n) continue;
+        const McQuadRows q = mc_quad_load(g, (unsigned int)p);
+        unsigned int m[4];
+        mc_quad_masks(g, q, m);
+        const int nt = mc_quad_eval_masks(g, q, m) >> 16;
+        if (nt) mc_quad_emit_triangles(g, (unsigned int)p, q, m, toff[ch] + local, vid3.data(), tris.data());
+        local += nt;
+      }
+      continue;
+    }
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
       const McPoint q = mc_point(g, p, true);

@@ -35,11 +35,10 @@ long long fmov_mc_group_count(int X, int Y, int Z) {
   return (fmov_mc_chunk_count(X, Y, Z) + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT;
 }
 int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv, int* chunk_nt, int* list, int* n_list,
-                  unsigned long long* group_sums, void*) {
+                  void*) {
   McGrid g;
-  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt || !list || !n_list || !group_sums) return -1;
+  if (!grid(g, u, X, Y, Z, iso) || !chunk_nv || !chunk_nt || !list || !n_list) return -1;
   *n_list = 0;
-  for (long long b = 0; b < fmov_mc_group_count(X, Y, Z); ++b) group_sums[b] = 0;
   // the device appends in whatever order its atomics give: walk the chunks backwards here so that the glue and the emit
   // passes are exercised with a list that is NOT in chunk order
   for (long long ch = g.n_chunks - 1; ch >= 0; --ch) {
@@ -62,18 +61,20 @@ int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv,
     }
     chunk_nv[ch] = nv;
     chunk_nt[ch] = nt;
-    if (nv | nt) {
-      list[(*n_list)++] = (int)ch;
-      group_sums[ch >> MC_GROUP_SHIFT] += (unsigned long long)nv | ((unsigned long long)nt << 32);
-    }
+    if (nv | nt) list[(*n_list)++] = (int)ch;
   }
   return 0;
 }
-int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, const unsigned long long* group_sums, long long n_chunks,
+int fmov_mc_scan(const int* chunk_nv, const int* chunk_nt, long long n_chunks, unsigned long long* group_sums,
                  long long* voff, long long* toff, long long* totals, void*) {
   if (!chunk_nv || !chunk_nt || !group_sums || !voff || !toff || !totals || n_chunks < 1) return -1;
-  // like the device: each group of 4096 chunks starts from the sums of the groups before it
+  // like the device: sums per group of 4096 chunks first, then each group starts from the sums of the groups before it
   const long long groups = (n_chunks + (1LL << MC_GROUP_SHIFT) - 1) >> MC_GROUP_SHIFT;
+  for (long long b = 0; b < groups; ++b) {
+    group_sums[b] = 0;
+    for (long long c = b << MC_GROUP_SHIFT; c < ((b + 1) << MC_GROUP_SHIFT) && c < n_chunks; ++c)
+      group_sums[b] += (unsigned long long)chunk_nv[c] | ((unsigned long long)chunk_nt[c] << 32);
+  }
   for (long long b = 0; b < groups; ++b) {
     long long v = 0, t = 0;
     for (long long a = 0; a < b; ++a) { v += (long long)(group_sums[a] & 0xFFFFFFFFull); t += (long long)(group_sums[a] >> 32); }
@@ -96,6 +97,19 @@ int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, const long 
   for (int li = 0; li < *n_list; ++li) {
     const long long ch = list[li];
     int local = 0;
+    if (mc_quads_ok(g)) {          // mc_vertices_quad_kernel: quads in point order, ids from the running sum
+      for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {
+        const long long p = ch * MC_CHUNK + q4 * 4;
+        if (p >= g.n) continue;
+        const McQuadRows q = mc_quad_load(g, (unsigned int)p);
+        unsigned int m[4];
+        mc_quad_masks(g, q, m);
+        const int nv = mc_quad_eval_masks(g, q, m) & 0xFFFF;
+        if (nv) mc_quad_emit_vertices(g, xf, (unsigned int)p, q, m, chunk_voff[ch] + local, verts, vid3);
+        local += nv;
+      }
+      continue;
+    }
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
       const McPoint q = mc_point(g, p, false);
@@ -113,6 +127,19 @@ int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso, const long
   for (int li = 0; li < *n_list; ++li) {
     const long long ch = list[li];
     int local = 0;
+    if (mc_quads_ok(g)) {          // mc_triangles_quad_kernel
+      for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {
+        const long long p = ch * MC_CHUNK + q4 * 4;
+        if (p >= g.n) continue;
+        const McQuadRows q = mc_quad_load(g, (unsigned int)p);
+        unsigned int m[4];
+        mc_quad_masks(g, q, m);
+        const int nt = mc_quad_eval_masks(g, q, m) >> 16;
+        if (nt) mc_quad_emit_triangles(g, (unsigned int)p, q, m, chunk_toff[ch] + local, vid3, tris);
+        local += nt;
+      }
+      continue;
+    }
     for (int tid = 0; tid < MC_CHUNK; ++tid) {
       const long long p = ch * MC_CHUNK + tid;
       const McPoint q = mc_point(g, p, true);

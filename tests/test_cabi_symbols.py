@@ -72,16 +72,16 @@ def test_errors_are_status_codes_not_exceptions(lib):
     st = lib.fmov_pose_fwd(7, None, None, None, None, None, None, None)
     assert st == -1
     # marching cubes: null grid / degenerate sizes / tables not uploaded are argument errors, not crashes
-    assert lib.fmov_mc_count(None, 8, 8, 8, ctypes.c_float(0.0), None, None, None, None, None, None) == -1
+    assert lib.fmov_mc_count(None, 8, 8, 8, ctypes.c_float(0.0), None, None, None, None, None) == -1
     buf = (ctypes.c_float * 8)()
-    assert lib.fmov_mc_count(buf, 1, 2, 2, ctypes.c_float(0.0), None, None, None, None, None, None) == -1 and b"bad grid" in lib.fmov_last_error()
-    assert lib.fmov_mc_count(buf, 2, 2, 2, ctypes.c_float(0.0), None, None, None, None, None, None) == -1 and b"fmov_mc_set_tables" in lib.fmov_last_error()
+    assert lib.fmov_mc_count(buf, 1, 2, 2, ctypes.c_float(0.0), None, None, None, None, None) == -1 and b"bad grid" in lib.fmov_last_error()
+    assert lib.fmov_mc_count(buf, 2, 2, 2, ctypes.c_float(0.0), None, None, None, None, None) == -1 and b"fmov_mc_set_tables" in lib.fmov_last_error()
     assert lib.fmov_mc_set_tables(None, None) == -1
     lib.fmov_mc_chunk_count.restype = ctypes.c_longlong
     assert lib.fmov_mc_chunk_count(512, 512, 512) == 512 ** 3 // 256 and lib.fmov_mc_chunk_count(3, 3, 3) == 1
     lib.fmov_mc_group_count.restype = ctypes.c_longlong
     assert lib.fmov_mc_group_count(512, 512, 512) == 128 and lib.fmov_mc_group_count(3, 3, 3) == 1
-    assert lib.fmov_mc_scan(None, None, None, ctypes.c_longlong(1), None, None, None, None) == -1
+    assert lib.fmov_mc_scan(None, None, ctypes.c_longlong(1), None, None, None, None, None) == -1
 
 
 def test_product_package_never_imports_the_oracle():
