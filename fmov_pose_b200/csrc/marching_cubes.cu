@@ -19,7 +19,7 @@
 
 namespace fmov {
 
-__device__ signed char d_mc_tri[256 * 3 * MC_MAX_TRIS];       // case table, read through L1 (mostly case 0 / 255)
+__device__ __align__(16) signed char d_mc_tri[256 * MC_TRI_STRIDE];       // case table, one 16-byte row per case, read through L1
 __device__ unsigned char d_mc_ntri[256];
 static bool g_mc_tables_set = false;
 
@@ -274,37 +274,55 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_vertices_quad_kernel(const McGrid
                                                                     float* __restrict__ verts, int* __restrict__ vid3) {
   const int n = *n_list, lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * (MC_CHUNK / 32);
-  for (int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); li < n; li += n_warps) {
-    const long long ch = list[li];
-    const long long base = chunk_voff[ch];
-    if (chunk_voff[ch + 1] == base) continue;          // triangles only (warp-uniform)
+  int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5);
+  if (li >= n) return;
+  long long ch = list[li];
+  while (true) {
+    // the next list entry, this chunk's offsets and its grid values are all requested before anything is used: one
+    // memory latency per chunk in front of the emission instead of three dependent ones
+    const int li_next = li + n_warps;
+    const long long ch_next = li_next < n ? list[li_next] : 0;
+    const long long base = chunk_voff[ch], end = chunk_voff[ch + 1];
     McWarpChunk w;
     mc_warp_chunk(g, ch, lane, w);
-    const int n0 = w.c0 & 0xFFFF, n1 = w.c1 & 0xFFFF;
-    int ex0, ex1;
-    mc_warp_offsets(n0, n1, lane, ex0, ex1);
-    if (n0) mc_quad_emit_vertices(g, xf, w.p0, w.q0, w.m0, base + ex0, verts, vid3);
-    if (n1) mc_quad_emit_vertices(g, xf, w.p1, w.q1, w.m1, base + ex1, verts, vid3);
+    if (end != base) {          // else triangles only (warp-uniform)
+      const int n0 = w.c0 & 0xFFFF, n1 = w.c1 & 0xFFFF;
+      int ex0, ex1;
+      mc_warp_offsets(n0, n1, lane, ex0, ex1);
+      if (n0) mc_quad_emit_vertices(g, xf, w.p0, w.q0, w.m0, base + ex0, verts, vid3);
+      if (n1) mc_quad_emit_vertices(g, xf, w.p1, w.q1, w.m1, base + ex1, verts, vid3);
+    }
+    if (li_next >= n) break;
+    li = li_next;
+    ch = ch_next;
   }
 }
 
-__global__ void __launch_bounds__(MC_CHUNK) mc_triangles_quad_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
+__global__ void __launch_bounds__(MC_CHUNK, 3) mc_triangles_quad_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
                                                                      const int* __restrict__ list,
                                                                      const int* __restrict__ n_list,
                                                                      const int* __restrict__ vid3, int* __restrict__ tris) {
   const int n = *n_list, lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * (MC_CHUNK / 32);
-  for (int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5); li < n; li += n_warps) {
-    const long long ch = list[li];
-    const long long base = chunk_toff[ch];
-    if (chunk_toff[ch + 1] == base) continue;          // vertices only (warp-uniform)
+  int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5);
+  if (li >= n) return;
+  long long ch = list[li];
+  while (true) {
+    const int li_next = li + n_warps;          // as in mc_vertices_quad_kernel
+    const long long ch_next = li_next < n ? list[li_next] : 0;
+    const long long base = chunk_toff[ch], end = chunk_toff[ch + 1];
     McWarpChunk w;
     mc_warp_chunk(g, ch, lane, w);
-    const int n0 = w.c0 >> 16, n1 = w.c1 >> 16;
-    int ex0, ex1;
-    mc_warp_offsets(n0, n1, lane, ex0, ex1);
-    if (n0) mc_quad_emit_triangles(g, w.p0, w.q0, w.m0, base + ex0, vid3, tris);
-    if (n1) mc_quad_emit_triangles(g, w.p1, w.q1, w.m1, base + ex1, vid3, tris);
+    if (end != base) {          // else vertices only (warp-uniform)
+      const int n0 = w.c0 >> 16, n1 = w.c1 >> 16;
+      int ex0, ex1;
+      mc_warp_offsets(n0, n1, lane, ex0, ex1);
+      if (n0) mc_quad_emit_triangles(g, w.p0, w.q0, w.m0, base + ex0, vid3, tris);
+      if (n1) mc_quad_emit_triangles(g, w.p1, w.q1, w.m1, base + ex1, vid3, tris);
+    }
+    if (li_next >= n) break;
+    li = li_next;
+    ch = ch_next;
   }
 }
 
@@ -342,7 +360,10 @@ extern "C" int fmov_mc_set_tables(const signed char* tri_table, const unsigned c
     for (int i = 0; i < 3 * n_tris[c]; ++i)
       FMOV_REQUIRE(tri_table[c * 15 + i] >= 0 && tri_table[c * 15 + i] < 12, "fmov_mc_set_tables: bad edge in case %d", c);
   }
-  FMOV_CUDA(cudaMemcpyToSymbol(d_mc_tri, tri_table, 256 * 3 * MC_MAX_TRIS));
+  signed char rows[256 * MC_TRI_STRIDE];
+  for (int c = 0; c < 256; ++c)
+    for (int k = 0; k < MC_TRI_STRIDE; ++k) rows[c * MC_TRI_STRIDE + k] = k < 15 ? tri_table[c * 15 + k] : (signed char)-1;
+  FMOV_CUDA(cudaMemcpyToSymbol(d_mc_tri, rows, sizeof(rows)));
   FMOV_CUDA(cudaMemcpyToSymbol(d_mc_ntri, n_tris, 256));
   g_mc_tables_set = true;
   return OK;

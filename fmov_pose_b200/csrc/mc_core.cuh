@@ -14,6 +14,7 @@ namespace fmov {
 
 constexpr int MC_CHUNK = 256;          // grid points per chunk = threads per block
 constexpr int MC_MAX_TRIS = 5;
+constexpr int MC_TRI_STRIDE = 16;       // bytes per case in McGrid::tri: 15 cell-edge numbers + 1 pad (one 16-byte load)
 constexpr int MC_GROUP_SHIFT = 12;      // the offsets scan works on groups of 4096 chunks (fmov_mc_scan)
 
 struct McGrid {
@@ -22,7 +23,7 @@ struct McGrid {
   float iso;
   long long n;          // X*Y*Z
   long long n_chunks;
-  const signed char* tri;        // [256][3*MC_MAX_TRIS] case table (device memory in the kernels)
+  const signed char* tri;        // [256][MC_TRI_STRIDE] case table, 16-byte aligned (device memory in the kernels)
   const unsigned char* ntri;     // [256]
   int sh_z, sh_yz;               // log2(Z), log2(Y*Z) when those are powers of two, else -1 (mc_set_shifts)
 };
@@ -208,24 +209,56 @@ MC_HD void mc_emit_vertices(const McGrid& g, const McXform& xf, long long p, con
   }
 }
 
-// triangles of the cell whose lowest corner is point p; `t0` = index of the first one
+// cell edge e starts at point + origin(e) and runs along axis(e) (mc_tables.py EDGE_ORIGIN / EDGE_AXIS):
+//   e:      0   1   2   3   4   5   6   7   8   9   10  11
+//   axis:   x   y   x   y   x   y   x   y   z   z   z   z
+//   origin: 000 100 010 000 001 101 011 001 000 100 110 010
+// packed 5 bits per edge: axis | ox << 2 | oy << 3 | oz << 4
+MC_HD unsigned int mc_edge_code(int e) {
+  const unsigned long long lut = (0ull << 0) | (5ull << 5) | (8ull << 10) | (1ull << 15) | (16ull << 20) | (21ull << 25) |
+                                 (24ull << 30) | (17ull << 35) | (2ull << 40) | (6ull << 45) | (14ull << 50) | (10ull << 55);
+  return (unsigned int)(lut >> (5 * e)) & 31u;
+}
+// triangles of the cell whose lowest corner is point p; `t0` = index of the first one.  Reads first, stores after, so that
+// the vertex-id reads (scattered 4-byte reads, one DRAM latency each) are in flight together.
 MC_HD void mc_emit_triangles(const McGrid& g, long long p, const McPoint& q, long long t0, const int* vid3, int* tris) {
   const long long YZ = (long long)g.Y * g.Z;
-  const signed char* row = g.tri + q.cubecase * (3 * MC_MAX_TRIS);
-  for (int t = 0; t < q.ntri; ++t) {
-    for (int c = 0; c < 3; ++c) {
-      const int e = row[3 * t + c];
-      // cell edge e starts at point + origin(e) and runs along axis(e) (mc_tables.py EDGE_ORIGIN / EDGE_AXIS):
-      //   e:      0   1   2   3   4   5   6   7   8   9   10  11
-      //   axis:   x   y   x   y   x   y   x   y   z   z   z   z
-      //   origin: 000 100 010 000 001 101 011 001 000 100 110 010
-      const int axis = e >= 8 ? 2 : (e & 1);
-      const int ox = (e == 1 || e == 5 || e == 9 || e == 10) ? 1 : 0;
-      const int oy = (e == 2 || e == 6 || e == 10 || e == 11) ? 1 : 0;
-      const int oz = (e >= 4 && e <= 7) ? 1 : 0;
-      const long long pe = p + ox * YZ + (long long)oy * g.Z + oz;
-      tris[(t0 + t) * 3 + c] = vid3[pe * 3 + axis];
+  const signed char* row = g.tri + q.cubecase * MC_TRI_STRIDE;
+  // the row as two 64-bit words, edge k = byte k (no dynamically indexed array: that would live in local memory)
+  unsigned long long lo, hi;
+#if defined(__CUDA_ARCH__)
+  const int4 r = *reinterpret_cast<const int4*>(row);
+  lo = (unsigned long long)(unsigned int)r.x | ((unsigned long long)(unsigned int)r.y << 32);
+  hi = (unsigned long long)(unsigned int)r.z | ((unsigned long long)(unsigned int)r.w << 32);
+#else
+  lo = hi = 0;
+  for (int k = 0; k < 8; ++k) {
+    lo |= (unsigned long long)(unsigned char)row[k] << (8 * k);
+    hi |= (unsigned long long)(unsigned char)row[8 + k] << (8 * k);
+  }
+#endif
+  // batches of three triangles (most cells have no more): nine reads in flight, then nine stores
+  const int nc = 3 * q.ntri;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int k0 = 0; k0 < nc; k0 += 9) {
+    int id[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 9; ++k) {
+      if (k0 + k >= nc) continue;
+      const int kk = k0 + k;
+      const unsigned int code = mc_edge_code((int)((kk < 8 ? lo >> (8 * kk) : hi >> (8 * (kk - 8))) & 0xFFull));
+      const long long pe = p + ((code >> 2) & 1u) * YZ + (long long)((code >> 3) & 1u) * g.Z + ((code >> 4) & 1u);
+      id[k] = vid3[pe * 3 + (code & 3u)];
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 9; ++k)
+      if (k0 + k < nc) tris[t0 * 3 + k0 + k] = id[k];
   }
 }
 
@@ -269,7 +302,7 @@ MC_HD void mc_quad_emit_triangles(const McGrid& g, unsigned int p, const McQuadR
   if (!(q.hx && q.hy)) return;
   const unsigned int mixed = mc_quad_mixed(m[0], m[1], m[2], m[3], q.hz4 ? 0xFu : 0x7u);
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+#pragma unroll 1
 #endif
   for (int t = 0; t < 4; ++t) {
     if (!((mixed >> t) & 1u)) continue;

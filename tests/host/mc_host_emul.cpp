@@ -34,7 +34,10 @@ int main(int argc, char** argv) {
   std::vector<float> u = slurp<float>(argv[5], (size_t)g.n);
   std::vector<signed char> tab = slurp<signed char>(argv[6], 256 * 15 + 256);
   g.u = u.data();
-  g.tri = tab.data();
+  std::vector<signed char> rows(256 * MC_TRI_STRIDE, -1);          // 16-byte rows like the device copy
+  for (int c = 0; c < 256; ++c)
+    for (int k = 0; k < 15; ++k) rows[c * MC_TRI_STRIDE + k] = tab[c * 15 + k];
+  g.tri = rows.data();
   g.ntri = reinterpret_cast<const unsigned char*>(tab.data() + 256 * 15);
   // pass 1: per-chunk counts (mc_count_kernel)
   std::vector<long long> voff(g.n_chunks + 1, 0), toff(g.n_chunks + 1, 0);

@@ -8,7 +8,7 @@
 
 using namespace fmov;
 
-static signed char g_tri[256 * 15];
+static signed char g_tri[256 * MC_TRI_STRIDE];          // 16-byte rows like the device copy
 static unsigned char g_ntri[256];
 static bool g_set = false;
 
@@ -25,7 +25,8 @@ static bool grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
 extern "C" {
 int fmov_mc_set_tables(const signed char* tri, const unsigned char* ntri) {
   if (!tri || !ntri) return -1;
-  memcpy(g_tri, tri, sizeof(g_tri));
+  for (int c = 0; c < 256; ++c)
+    for (int k = 0; k < MC_TRI_STRIDE; ++k) g_tri[c * MC_TRI_STRIDE + k] = k < 15 ? tri[c * 15 + k] : (signed char)-1;
   memcpy(g_ntri, ntri, sizeof(g_ntri));
   g_set = true;
   return 0;
