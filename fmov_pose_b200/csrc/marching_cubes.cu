@@ -298,10 +298,36 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_vertices_quad_kernel(const McGrid
   }
 }
 
+// Triangles of ONE quad written by the whole warp: lane = (cell t = lane / 8, corner slot s = lane % 8 -> corners s and s + 8
+// of the cell's <= 15), so the scattered vertex-id reads of a quad are one round of parallel loads instead of a divergent
+// per-lane walk (the per-lane walk cost ~1100 issue slots per chunk, this ~100 per quad that has triangles).
+// p = first point of the quad, mpack = its four 5-bit row masks (m00 | m01 << 5 | m10 << 10 | m11 << 15) | hz4 << 20,
+// t0 = index of the quad's first triangle.  All arguments warp-uniform.
+__device__ __forceinline__ void mc_warp_emit_triangles(const McGrid& g, int lane, unsigned int p, unsigned int mpack,
+                                                       long long t0, const int* __restrict__ vid3, int* __restrict__ tris) {
+  const unsigned int m00 = mpack & 31u, m01 = (mpack >> 5) & 31u, m10 = (mpack >> 10) & 31u, m11 = (mpack >> 15) & 31u;
+  const unsigned int mixed = mc_quad_mixed(m00, m01, m10, m11, ((mpack >> 20) & 1u) ? 0xFu : 0x7u);
+  const int t = lane >> 3, s = lane & 7;
+  int c = 0, n = 0;
+  if ((mixed >> t) & 1u) {
+    c = mc_quad_case(m00, m01, m10, m11, t);
+    n = g.ntri[c];
+  }
+  // triangles of the quad's cells before mine
+  const int n0 = __shfl_sync(0xffffffffu, n, 0), n1 = __shfl_sync(0xffffffffu, n, 8), n2 = __shfl_sync(0xffffffffu, n, 16);
+  const long long first = t0 + (t > 0 ? n0 : 0) + (t > 1 ? n1 : 0) + (t > 2 ? n2 : 0);
+  const long long pc = (long long)p + t;
+  int id0 = 0, id1 = 0;
+  if (s < 3 * n) id0 = vid3[mc_corner_slot(g, pc, c, s)];
+  if (s + 8 < 3 * n) id1 = vid3[mc_corner_slot(g, pc, c, s + 8)];
+  if (s < 3 * n) tris[first * 3 + s] = id0;
+  if (s + 8 < 3 * n) tris[first * 3 + s + 8] = id1;
+}
+
 __global__ void __launch_bounds__(MC_CHUNK, 3) mc_triangles_quad_kernel(const McGrid g, const long long* __restrict__ chunk_toff,
-                                                                     const int* __restrict__ list,
-                                                                     const int* __restrict__ n_list,
-                                                                     const int* __restrict__ vid3, int* __restrict__ tris) {
+                                                                        const int* __restrict__ list,
+                                                                        const int* __restrict__ n_list,
+                                                                        const int* __restrict__ vid3, int* __restrict__ tris) {
   const int n = *n_list, lane = threadIdx.x & 31;
   const int n_warps = gridDim.x * (MC_CHUNK / 32);
   int li = blockIdx.x * (MC_CHUNK / 32) + (threadIdx.x >> 5);
@@ -317,8 +343,19 @@ __global__ void __launch_bounds__(MC_CHUNK, 3) mc_triangles_quad_kernel(const Mc
       const int n0 = w.c0 >> 16, n1 = w.c1 >> 16;
       int ex0, ex1;
       mc_warp_offsets(n0, n1, lane, ex0, ex1);
-      if (n0) mc_quad_emit_triangles(g, w.p0, w.q0, w.m0, base + ex0, vid3, tris);
-      if (n1) mc_quad_emit_triangles(g, w.p1, w.q1, w.m1, base + ex1, vid3, tris);
+      const unsigned int mp0 = w.m0[0] | (w.m0[1] << 5) | (w.m0[2] << 10) | (w.m0[3] << 15) | (w.q0.hz4 ? 1u << 20 : 0u);
+      const unsigned int mp1 = w.m1[0] | (w.m1[1] << 5) | (w.m1[2] << 10) | (w.m1[3] << 15) | (w.q1.hz4 ? 1u << 20 : 0u);
+      // quads with triangles, in point order (n > 0 implies hx && hy)
+      for (unsigned int owners = __ballot_sync(0xffffffffu, n0 != 0); owners; owners &= owners - 1) {
+        const int o = __ffs(owners) - 1;
+        mc_warp_emit_triangles(g, lane, __shfl_sync(0xffffffffu, w.p0, o), __shfl_sync(0xffffffffu, mp0, o),
+                               base + __shfl_sync(0xffffffffu, ex0, o), vid3, tris);
+      }
+      for (unsigned int owners = __ballot_sync(0xffffffffu, n1 != 0); owners; owners &= owners - 1) {
+        const int o = __ffs(owners) - 1;
+        mc_warp_emit_triangles(g, lane, __shfl_sync(0xffffffffu, w.p1, o), __shfl_sync(0xffffffffu, mp1, o),
+                               base + __shfl_sync(0xffffffffu, ex1, o), vid3, tris);
+      }
     }
     if (li_next >= n) break;
     li = li_next;
@@ -340,6 +377,18 @@ static int mc_grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
   g.tri = reinterpret_cast<const signed char*>(pt);
   g.ntri = reinterpret_cast<const unsigned char*>(pn);
   return OK;
+}
+// grid of a grid-stride kernel = exactly the blocks that are resident at once: all warps then sweep the grid as ONE window of
+// consecutive chunks, and the rows of plane i + 1 that a chunk reads are still in L2 when the window reaches them as plane i
+// (with more blocks than fit, the late blocks re-read what the first wave had already fetched: 1.5x the DRAM traffic)
+template <class K>
+static int mc_resident_blocks(K kernel, long long max_useful) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MC_CHUNK, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  const long long want = (long long)sms * per_sm;
+  return (int)(max_useful < want ? (max_useful < 1 ? 1 : max_useful) : want);
 }
 static int mc_blocks(const McGrid& g) {
   int dev = 0, sms = 0;
@@ -385,9 +434,7 @@ extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int
   FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list, "fmov_mc_count: null output");
   FMOV_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int), (cudaStream_t)stream));
   if (mc_quads_ok(g)) {
-    // a warp per chunk: the same number of resident warps as the per-point kernel
-    const long long want = (g.n_chunks + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32);
-    const int blocks = (int)(want < mc_blocks(g) ? want : mc_blocks(g));
+    const int blocks = mc_resident_blocks(mc_count_quad_kernel, (g.n_chunks + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32));
     mc_count_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
     FMOV_LAUNCH_CHECK("mc_count_quad_kernel");
   } else {
@@ -420,7 +467,8 @@ extern "C" int fmov_mc_vertices(const float* u, int X, int Y, int Z, float iso, 
   McXform xf;
   xf.s[0] = sx; xf.s[1] = sy; xf.s[2] = sz; xf.o[0] = ox; xf.o[1] = oy; xf.o[2] = oz;
   if (mc_quads_ok(g)) {
-    mc_vertices_quad_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
+    const int blocks = mc_resident_blocks(mc_vertices_quad_kernel, g.n_chunks);
+    mc_vertices_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
     FMOV_LAUNCH_CHECK("mc_vertices_quad_kernel");
   } else {
     mc_vertices_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_voff, list, n_list, xf, verts, vid3);
@@ -436,7 +484,8 @@ extern "C" int fmov_mc_triangles(const float* u, int X, int Y, int Z, float iso,
   if (st) return st;
   FMOV_REQUIRE(chunk_toff && list && n_list && vid3 && tris, "fmov_mc_triangles: null argument");
   if (mc_quads_ok(g)) {
-    mc_triangles_quad_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
+    const int blocks = mc_resident_blocks(mc_triangles_quad_kernel, g.n_chunks);
+    mc_triangles_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);
     FMOV_LAUNCH_CHECK("mc_triangles_quad_kernel");
   } else {
     mc_triangles_kernel<<<mc_blocks(g), MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_toff, list, n_list, vid3, tris);

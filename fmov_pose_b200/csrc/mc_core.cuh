@@ -219,25 +219,16 @@ MC_HD unsigned int mc_edge_code(int e) {
                                  (24ull << 30) | (17ull << 35) | (2ull << 40) | (6ull << 45) | (14ull << 50) | (10ull << 55);
   return (unsigned int)(lut >> (5 * e)) & 31u;
 }
-// triangles of the cell whose lowest corner is point p; `t0` = index of the first one.  Reads first, stores after, so that
-// the vertex-id reads (scattered 4-byte reads, one DRAM latency each) are in flight together.
+// where the vertex id of corner k (0 .. 3 * ntri - 1, case-table order) of the cell at point p lives in vid3
+MC_HD long long mc_corner_slot(const McGrid& g, long long p, int cubecase, int k) {
+  const unsigned int code = mc_edge_code(g.tri[cubecase * MC_TRI_STRIDE + k]);
+  const long long pe = p + (long long)((code >> 2) & 1u) * ((long long)g.Y * g.Z) + (long long)((code >> 3) & 1u) * g.Z +
+                       ((code >> 4) & 1u);
+  return pe * 3 + (code & 3u);
+}
+// triangles of the cell whose lowest corner is point p; `t0` = index of the first one.  Batches of three triangles (most
+// cells have no more), reads first and stores after: the vertex-id reads are scattered 4-byte reads, one DRAM latency each
 MC_HD void mc_emit_triangles(const McGrid& g, long long p, const McPoint& q, long long t0, const int* vid3, int* tris) {
-  const long long YZ = (long long)g.Y * g.Z;
-  const signed char* row = g.tri + q.cubecase * MC_TRI_STRIDE;
-  // the row as two 64-bit words, edge k = byte k (no dynamically indexed array: that would live in local memory)
-  unsigned long long lo, hi;
-#if defined(__CUDA_ARCH__)
-  const int4 r = *reinterpret_cast<const int4*>(row);
-  lo = (unsigned long long)(unsigned int)r.x | ((unsigned long long)(unsigned int)r.y << 32);
-  hi = (unsigned long long)(unsigned int)r.z | ((unsigned long long)(unsigned int)r.w << 32);
-#else
-  lo = hi = 0;
-  for (int k = 0; k < 8; ++k) {
-    lo |= (unsigned long long)(unsigned char)row[k] << (8 * k);
-    hi |= (unsigned long long)(unsigned char)row[8 + k] << (8 * k);
-  }
-#endif
-  // batches of three triangles (most cells have no more): nine reads in flight, then nine stores
   const int nc = 3 * q.ntri;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -247,13 +238,8 @@ MC_HD void mc_emit_triangles(const McGrid& g, long long p, const McPoint& q, lon
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int k = 0; k < 9; ++k) {
-      if (k0 + k >= nc) continue;
-      const int kk = k0 + k;
-      const unsigned int code = mc_edge_code((int)((kk < 8 ? lo >> (8 * kk) : hi >> (8 * (kk - 8))) & 0xFFull));
-      const long long pe = p + ((code >> 2) & 1u) * YZ + (long long)((code >> 3) & 1u) * g.Z + ((code >> 4) & 1u);
-      id[k] = vid3[pe * 3 + (code & 3u)];
-    }
+    for (int k = 0; k < 9; ++k)
+      if (k0 + k < nc) id[k] = vid3[mc_corner_slot(g, p, q.cubecase, k0 + k)];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -296,7 +282,9 @@ MC_HD void mc_quad_emit_vertices(const McGrid& g, const McXform& xf, unsigned in
     }
   }
 }
-// triangles of the quad's four cells; `t0` = index of the first one
+// triangles of the quad's four cells; `t0` = index of the first one.  This in-order walk is what the host stand-in runs; the
+// device hands the same (cell, corner) items to the lanes of a warp (marching_cubes.cu: mc_warp_emit_triangles) — same
+// mc_quad_mixed / mc_quad_case / mc_corner_slot, same output positions.
 MC_HD void mc_quad_emit_triangles(const McGrid& g, unsigned int p, const McQuadRows& q, const unsigned int m[4], long long t0,
                                   const int* vid3, int* tris) {
   if (!(q.hx && q.hy)) return;
