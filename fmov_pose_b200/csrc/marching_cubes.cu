@@ -113,6 +113,80 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_quad_kernel(const McGrid g,
   }
 }
 
+// The count pass marching along x (mc_core.cuh: Y * Z % 256 == 0, every validate_mesh grid): block = 8 adjacent chunk columns
+// (their j + 1 rows are each other's rows: L1), a contiguous range of (column group, i) items per block, i fastest.  Per
+// step a lane loads 2 rows x 2 quads of plane i + 1 and carries their four masks into the next step.
+__global__ void __launch_bounds__(MC_CHUNK) mc_count_march_kernel(const McGrid g, const int cpp, int* __restrict__ chunk_nv,
+                                                                  int* __restrict__ chunk_nt, int* __restrict__ list,
+                                                                  int* __restrict__ n_list) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int groups = (cpp + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32);
+  const int total = groups * g.X;          // < 2^31 / 256
+  const int per = (total + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int r0 = (int)blockIdx.x * per, r1 = r0 + per < total ? r0 + per : total;
+  if (r0 >= r1) return;
+  const unsigned int YZ = (unsigned int)(g.Y * g.Z);
+  int cg = r0 / g.X, i = r0 - cg * g.X;
+  bool fresh = true;          // the masks of plane i have to be loaded (first step of the block / of a column)
+  unsigned int q[2] = {0u, 0u}, zoff[2] = {0u, 0u}, m00[2] = {0u, 0u}, m01[2] = {0u, 0u};
+  bool hy[2] = {false, false}, hz4[2] = {false, false};
+  int pending = 0, mine = 0;
+  for (int r = r0; r < r1; ++r) {
+    const int col = cg * (MC_CHUNK / 32) + wi;
+    if (col < cpp) {          // warp-uniform
+      if (fresh) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          q[h] = (unsigned int)col * MC_CHUNK + h * (MC_CHUNK / 2) + lane * 4;          // offset of the quad in its plane
+          int pi, pj, pk;
+          mc_split(g, q[h], pi, pj, pk);          // pi == 0
+          hy[h] = pj + 1 < g.Y;
+          hz4[h] = pk + 4 < g.Z;
+          zoff[h] = hy[h] ? (unsigned int)g.Z : 0u;          // an absent row j + 1 repeats row j (never counted: hy)
+        }
+        const unsigned int base = (unsigned int)i * YZ;
+        const McRow5 a0 = mc_row_load(g, base + q[0], hz4[0]), b0 = mc_row_load(g, base + q[0] + zoff[0], hz4[0]);
+        const McRow5 a1 = mc_row_load(g, base + q[1], hz4[1]), b1 = mc_row_load(g, base + q[1] + zoff[1], hz4[1]);
+        m00[0] = mc_row_mask(g, a0, hz4[0]); m01[0] = mc_row_mask(g, b0, hz4[0]);
+        m00[1] = mc_row_mask(g, a1, hz4[1]); m01[1] = mc_row_mask(g, b1, hz4[1]);
+        fresh = false;
+      }
+      const bool hx = i + 1 < g.X;
+      const unsigned int next = (unsigned int)(hx ? i + 1 : i) * YZ;          // no plane i + 1: plane i again (never counted: hx)
+      const McRow5 a0 = mc_row_load(g, next + q[0], hz4[0]), b0 = mc_row_load(g, next + q[0] + zoff[0], hz4[0]);
+      const McRow5 a1 = mc_row_load(g, next + q[1], hz4[1]), b1 = mc_row_load(g, next + q[1] + zoff[1], hz4[1]);
+      const unsigned int m10[2] = {mc_row_mask(g, a0, hz4[0]), mc_row_mask(g, a1, hz4[1])};
+      const unsigned int m11[2] = {mc_row_mask(g, b0, hz4[0]), mc_row_mask(g, b1, hz4[1])};
+      const int packed = mc_quad_eval_flags(g, m00[0], m01[0], m10[0], m11[0], hx, hy[0], hz4[0]) +
+                         mc_quad_eval_flags(g, m00[1], m01[1], m10[1], m11[1], hx, hy[1], hz4[1]);
+      const int tot = (int)__reduce_add_sync(0xffffffffu, (unsigned int)packed);
+      const int ch = i * cpp + col;
+      if (lane == 0) {
+        chunk_nv[ch] = tot & 0xFFFF;
+        chunk_nt[ch] = tot >> 16;
+      }
+      if (tot != 0) {          // warp-uniform; appended 32 at a time as in mc_count_quad_kernel
+        if (lane == pending) mine = ch;
+        if (++pending == 32) {
+          int at = 0;
+          if (lane == 0) at = atomicAdd(n_list, 32);
+          at = __shfl_sync(0xffffffffu, at, 0);
+          list[at + lane] = mine;
+          pending = 0;
+        }
+      }
+      m00[0] = m10[0]; m00[1] = m10[1]; m01[0] = m11[0]; m01[1] = m11[1];
+    }
+    if (++i == g.X) { i = 0; ++cg; fresh = true; }
+  }
+  if (pending) {
+    int at = 0;
+    if (lane == 0) at = atomicAdd(n_list, pending);
+    at = __shfl_sync(0xffffffffu, at, 0);
+    if (lane < pending) list[at + lane] = mine;
+  }
+}
+
 // Sums of the chunk counts per group of 4096 chunks (vertices | triangles << 32): the starting points of the scan's blocks.
 constexpr int MC_SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(MC_SCAN_THREADS) mc_group_sums_kernel(const int* __restrict__ chunk_nv,
@@ -433,7 +507,13 @@ extern "C" int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int
   if (st) return st;
   FMOV_REQUIRE(chunk_nv && chunk_nt && list && n_list, "fmov_mc_count: null output");
   FMOV_CUDA(cudaMemsetAsync(n_list, 0, sizeof(int), (cudaStream_t)stream));
-  if (mc_quads_ok(g)) {
+  if (mc_march_ok(g)) {
+    const int cpp = (int)(((long long)Y * Z) / MC_CHUNK);
+    const long long items = (long long)((cpp + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32)) * X;
+    const int blocks = mc_resident_blocks(mc_count_march_kernel, items);
+    mc_count_march_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, cpp, chunk_nv, chunk_nt, list, n_list);
+    FMOV_LAUNCH_CHECK("mc_count_march_kernel");
+  } else if (mc_quads_ok(g)) {
     const int blocks = mc_resident_blocks(mc_count_quad_kernel, (g.n_chunks + MC_CHUNK / 32 - 1) / (MC_CHUNK / 32));
     mc_count_quad_kernel<<<blocks, MC_CHUNK, 0, (cudaStream_t)stream>>>(g, chunk_nv, chunk_nt, list, n_list);
     FMOV_LAUNCH_CHECK("mc_count_quad_kernel");

@@ -176,11 +176,15 @@ MC_HD void mc_quad_masks(const McGrid& g, const McQuadRows& q, unsigned int m[4]
 #endif
   for (int r = 0; r < 4; ++r) m[r] = mc_quad_mask(q.v[r][0], q.v[r][1], q.v[r][2], q.v[r][3], q.v[r][4], g.iso) & full;
 }
-MC_HD int mc_quad_eval_masks(const McGrid& g, const McQuadRows& q, const unsigned int m[4]) {
+MC_HD int mc_quad_eval_flags(const McGrid& g, unsigned int m00, unsigned int m01, unsigned int m10, unsigned int m11, bool hx,
+                             bool hy, bool hz4) {
   // nearly every quad is far from the surface: all of its (up to) 20 values on one side
-  const unsigned int full = q.hz4 ? 31u : 15u;
-  if ((m[0] | m[1] | m[2] | m[3]) == 0u || (m[0] & m[1] & m[2] & m[3]) == full) return 0;
-  return mc_quad_counts(g, m[0], m[1], m[2], m[3], q.hx, q.hy, q.hz4);
+  const unsigned int full = hz4 ? 31u : 15u;
+  if ((m00 | m01 | m10 | m11) == 0u || (m00 & m01 & m10 & m11) == full) return 0;
+  return mc_quad_counts(g, m00, m01, m10, m11, hx, hy, hz4);
+}
+MC_HD int mc_quad_eval_masks(const McGrid& g, const McQuadRows& q, const unsigned int m[4]) {
+  return mc_quad_eval_flags(g, m[0], m[1], m[2], m[3], q.hx, q.hy, q.hz4);
 }
 MC_HD int mc_quad_eval(const McGrid& g, const McQuadRows& q) {
   unsigned int m[4];
@@ -188,8 +192,29 @@ MC_HD int mc_quad_eval(const McGrid& g, const McQuadRows& q) {
   return mc_quad_eval_masks(g, q, m);
 }
 MC_HD int mc_quad(const McGrid& g, unsigned int p) { return mc_quad_eval(g, mc_quad_load(g, p)); }
+// ---- the count pass MARCHING along x (planes are whole numbers of chunks: Y * Z % 256 == 0): a warp keeps one chunk column,
+// the masks of plane i + 1 computed at step i are the masks of plane i at step i + 1, so every value is loaded and compared
+// once (the quad kernel above loads and compares each row four times: as row (i,j), (i,j+1), (i+1,j) and (i+1,j+1)).
+struct McRow5 { float v[5]; };
+MC_HD McRow5 mc_row_load(const McGrid& g, unsigned int p, bool hz4) {          // p = linear index of the quad (multiple of 4)
+  McRow5 r;
+  const float* row = g.u + p;
+#if defined(__CUDA_ARCH__)
+  const float4 f = *reinterpret_cast<const float4*>(row);
+  r.v[0] = f.x; r.v[1] = f.y; r.v[2] = f.z; r.v[3] = f.w;
+#else
+  for (int t = 0; t < 4; ++t) r.v[t] = row[t];
+#endif
+  r.v[4] = hz4 ? row[4] : 0.f;
+  return r;
+}
+MC_HD unsigned int mc_row_mask(const McGrid& g, const McRow5& r, bool hz4) {
+  return mc_quad_mask(r.v[0], r.v[1], r.v[2], r.v[3], r.v[4], g.iso) & (hz4 ? 31u : 15u);
+}
+
 // the quad path needs whole quads per row and 16-byte loads
 MC_HD bool mc_quads_ok(const McGrid& g) { return (g.Z & 3) == 0 && (reinterpret_cast<unsigned long long>(g.u) & 15ull) == 0; }
+MC_HD bool mc_march_ok(const McGrid& g) { return mc_quads_ok(g) && ((long long)g.Y * g.Z) % MC_CHUNK == 0; }
 
 // vertices of the crossed edges that start at point p; `id` = id of the first one
 MC_HD void mc_emit_vertices(const McGrid& g, const McXform& xf, long long p, const McPoint& q, long long id, float* verts,

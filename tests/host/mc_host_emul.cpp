@@ -24,6 +24,32 @@ static void dump(const char* path, const std::vector<T>& v) {
   fclose(f);
 }
 
+
+// mc_count_march_kernel on the host: every chunk column marched along x with the masks of plane i carried; returns the
+// packed counts (vertices | triangles << 16) of chunk (i, col) through `out[i * cpp + col]`
+static void march_counts(const McGrid& g, std::vector<int>& out) {
+  const int cpp = (int)(((long long)g.Y * g.Z) / MC_CHUNK);
+  const unsigned int YZ = (unsigned int)(g.Y * g.Z);
+  out.assign((size_t)cpp * g.X, 0);
+  for (int col = 0; col < cpp; ++col)
+    for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {          // lane x half
+      const unsigned int q = (unsigned int)col * MC_CHUNK + q4 * 4;
+      int pi, pj, pk;
+      mc_split(g, q, pi, pj, pk);
+      const bool hy = pj + 1 < g.Y, hz4 = pk + 4 < g.Z;
+      const unsigned int zoff = hy ? (unsigned int)g.Z : 0u;
+      unsigned int m00 = mc_row_mask(g, mc_row_load(g, q, hz4), hz4), m01 = mc_row_mask(g, mc_row_load(g, q + zoff, hz4), hz4);
+      for (int i = 0; i < g.X; ++i) {
+        const bool hx = i + 1 < g.X;
+        const unsigned int next = (unsigned int)(hx ? i + 1 : i) * YZ;
+        const unsigned int m10 = mc_row_mask(g, mc_row_load(g, next + q, hz4), hz4),
+                           m11 = mc_row_mask(g, mc_row_load(g, next + q + zoff, hz4), hz4);
+        out[(size_t)i * cpp + col] += mc_quad_eval_flags(g, m00, m01, m10, m11, hx, hy, hz4);
+        m00 = m10; m01 = m11;
+      }
+    }
+}
+
 int main(int argc, char** argv) {
   if (argc != 9) return 2;
   McGrid g;
@@ -39,6 +65,8 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 15; ++k) rows[c * MC_TRI_STRIDE + k] = tab[c * 15 + k];
   g.tri = rows.data();
   g.ntri = reinterpret_cast<const unsigned char*>(tab.data() + 256 * 15);
+  std::vector<int> marched;
+  if (mc_march_ok(g)) march_counts(g, marched);
   // pass 1: per-chunk counts (mc_count_kernel)
   std::vector<long long> voff(g.n_chunks + 1, 0), toff(g.n_chunks + 1, 0);
   for (long long ch = 0; ch < g.n_chunks; ++ch) {
@@ -56,6 +84,10 @@ int main(int argc, char** argv) {
         const int packed = mc_quad(g, (unsigned int)p);
         qv += packed & 0xFFFF;
         qt += packed >> 16;
+      }
+      if (mc_march_ok(g) && ((marched[ch] & 0xFFFF) != nv || (marched[ch] >> 16) != nt)) {
+        fprintf(stderr, "marched counts differ in chunk %lld\n", ch);
+        return 4;
       }
       if (qv != nv || qt != nt) { fprintf(stderr, "quad counts differ in chunk %lld: %lld %lld vs %lld %lld\n", ch, qv, qt, nv, nt); return 3; }
     }

@@ -22,6 +22,32 @@ static bool grid(McGrid& g, const float* u, int X, int Y, int Z, float iso) {
   return true;
 }
 
+
+// mc_count_march_kernel on the host: every chunk column marched along x with the masks of plane i carried; returns the
+// packed counts (vertices | triangles << 16) of chunk (i, col) through `out[i * cpp + col]`
+static void march_counts(const McGrid& g, std::vector<int>& out) {
+  const int cpp = (int)(((long long)g.Y * g.Z) / MC_CHUNK);
+  const unsigned int YZ = (unsigned int)(g.Y * g.Z);
+  out.assign((size_t)cpp * g.X, 0);
+  for (int col = 0; col < cpp; ++col)
+    for (int q4 = 0; q4 < MC_CHUNK / 4; ++q4) {          // lane x half
+      const unsigned int q = (unsigned int)col * MC_CHUNK + q4 * 4;
+      int pi, pj, pk;
+      mc_split(g, q, pi, pj, pk);
+      const bool hy = pj + 1 < g.Y, hz4 = pk + 4 < g.Z;
+      const unsigned int zoff = hy ? (unsigned int)g.Z : 0u;
+      unsigned int m00 = mc_row_mask(g, mc_row_load(g, q, hz4), hz4), m01 = mc_row_mask(g, mc_row_load(g, q + zoff, hz4), hz4);
+      for (int i = 0; i < g.X; ++i) {
+        const bool hx = i + 1 < g.X;
+        const unsigned int next = (unsigned int)(hx ? i + 1 : i) * YZ;
+        const unsigned int m10 = mc_row_mask(g, mc_row_load(g, next + q, hz4), hz4),
+                           m11 = mc_row_mask(g, mc_row_load(g, next + q + zoff, hz4), hz4);
+        out[(size_t)i * cpp + col] += mc_quad_eval_flags(g, m00, m01, m10, m11, hx, hy, hz4);
+        m00 = m10; m01 = m11;
+      }
+    }
+}
+
 extern "C" {
 int fmov_mc_set_tables(const signed char* tri, const unsigned char* ntri) {
   if (!tri || !ntri) return -1;
@@ -42,9 +68,14 @@ int fmov_mc_count(const float* u, int X, int Y, int Z, float iso, int* chunk_nv,
   *n_list = 0;
   // the device appends in whatever order its atomics give: walk the chunks backwards here so that the glue and the emit
   // passes are exercised with a list that is NOT in chunk order
+  std::vector<int> marched;
+  if (mc_march_ok(g)) march_counts(g, marched);
   for (long long ch = g.n_chunks - 1; ch >= 0; --ch) {
     int nv = 0, nt = 0;
-    if (mc_quads_ok(g)) {          // mc_count_quad_kernel: 32 lanes x 2 quads
+    if (mc_march_ok(g)) {          // mc_count_march_kernel
+      nv = marched[ch] & 0xFFFF;
+      nt = marched[ch] >> 16;
+    } else if (mc_quads_ok(g)) {          // mc_count_quad_kernel: 32 lanes x 2 quads
       for (int h = 0; h < 2; ++h)
         for (int lane = 0; lane < 32; ++lane) {
           const long long p = ch * MC_CHUNK + h * (MC_CHUNK / 2) + lane * 4;

@@ -32,7 +32,14 @@ def _field(kind, shape, seed=0):
                                             # Z % 4 == 0: quad count kernel; the last two span 2 and 3 scan groups
                                             ("noise", (9, 7, 4), 0.0), ("noise", (2, 2, 8), 0.1), ("waves", (21, 18, 52), 0.05),
                                             ("noise", (30, 31, 32), 0.2), ("sphere", (104, 101, 100), 0.0),
-                                            ("waves", (131, 127, 129), 0.05)])
+                                            ("waves", (131, 127, 129), 0.05),
+                                            # Y * Z % 256 == 0: marching count kernel (block ranges start mid-column in
+                                            # the larger ones; (4, 2, 512): one row is two chunks).  The iso-value of the
+                                            # large noise grid is exact in fp32: the C ABI takes a float, the oracle a
+                                            # double, and 1.2e-8 / |f1 - f0| would exceed atol on its flattest edges
+                                            ("noise", (5, 16, 16), 0.0), ("noise", (2, 8, 64), 0.1), ("noise", (4, 2, 512), 0.3),
+                                            ("waves", (19, 40, 32), 0.05), ("noise", (70, 64, 64), 0.25),
+                                            ("sphere", (129, 128, 128), 0.0)])
 def test_mesh_equals_the_oracle(kind, shape, iso):
     from fmov_pose_b200 import mcubes_gpu
     u = _field(kind, shape)

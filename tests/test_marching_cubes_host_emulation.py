@@ -49,7 +49,11 @@ def _field(kind, shape, seed=0):
                                             # Z % 4 == 0: the count pass works on quads (mc_count_quad_kernel's code)
                                             ("sphere", (30, 31, 32), 0.0), ("waves", (21, 18, 52), 0.05),
                                             ("noise", (9, 7, 4), 0.0), ("noise", (2, 2, 8), 0.1),
-                                            ("noise", (5, 67, 12), -0.2)])
+                                            ("noise", (5, 67, 12), -0.2),
+                                            # Y * Z % 256 == 0: the count pass marches along x (mc_count_march_kernel's code)
+                                            ("noise", (5, 16, 16), 0.0), ("noise", (2, 8, 64), 0.1), ("waves", (19, 40, 32), 0.05),
+                                            ("sphere", (33, 24, 32), 0.0), ("noise", (3, 2, 128), 0.0),
+                                            ("noise", (4, 2, 512), 0.3)])
 def test_device_logic_equals_the_oracle(emul, kind, shape, iso):
     u = _field(kind, shape)
     v, t = emul(u, iso)
@@ -88,7 +92,7 @@ def test_python_glue_end_to_end_on_a_host_stand_in(tmp_path, monkeypatch):
         is_cuda = True
 
     for kind, shape, iso in (("sphere", (33, 29, 31), 0.0), ("noise", (17, 16, 19), 0.1), ("noise", (2, 2, 2), 0.0),
-                             ("noise", (18, 17, 20), 0.1), ("sphere", (104, 101, 100), 0.0)):          # the last one spans two scan groups
+                             ("noise", (18, 17, 20), 0.1), ("noise", (6, 24, 32), 0.1), ("sphere", (104, 101, 100), 0.0)):          # the last one spans two scan groups
         u = _field(kind, shape)
         ut = torch.from_numpy(u).as_subclass(_AsCuda)
         v, t = mcubes_gpu.marching_cubes(ut, iso)
