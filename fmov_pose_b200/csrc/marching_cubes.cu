@@ -5,8 +5,9 @@
 // Three passes over the grid (z fastest => coalesced rows; the +Z / +YZ neighbour rows come from L1/L2, so each pass reads u
 // once from HBM: 4 B per point) and a scan between them:
 //   fmov_mc_count      per 256-point chunk: number of crossed edges starting at its points and of triangles of its cells.
-//                      Z % 4 == 0 (every validate_mesh grid): warp per chunk on 16-byte quads and bit masks
-//                      (mc_count_quad_kernel); else thread per point (mc_count_kernel)
+//                      Three kernels, the first that applies: mc_count_march_kernel (Z % 4 == 0 and Y * Z % 256 == 0, every
+//                      validate_mesh grid: warp per chunk column marching along x on 16-byte quads and bit masks, each value
+//                      loaded once), mc_count_quad_kernel (Z % 4 == 0: warp per chunk, quads), mc_count_kernel (thread per point)
 //   fmov_mc_scan       exclusive 64-bit prefix sums over the chunks, totals appended; the totals size the outputs
 //   fmov_mc_vertices   vertex positions (index or world coordinates) + the vertex id of every crossed edge (vid3)
 //   fmov_mc_triangles  case lookup, three vid3 reads per triangle corner
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(MC_CHUNK) mc_count_kernel(const McGrid g, int*
     if (threadIdx.x == 0) {
       chunk_nv[ch] = tot & 0xFFFF;
       chunk_nt[ch] = tot >> 16;
-      // the emit passes walk this list (about 2 % of the chunks at 512^3) instead of testing every chunk; its order is
+      // the emit passes walk this list (a quarter of the chunks at 512^3) instead of testing every chunk; its order is
       // whatever the atomics give, the OUTPUT positions come from the prefix sums and do not depend on it
       if (tot != 0) list[atomicAdd(n_list, 1)] = (int)ch;
     }
